@@ -1,0 +1,311 @@
+"""ORACLE (test infrastructure, never shipped, never timed as the product).
+
+CPU (torch, float32) restatement of the two third-party networks that diart's hot
+path calls through ``Model.from_pretrained`` (reference ``src/diart/models.py:50``)
+and ``LazyModel.__call__`` (``src/diart/models.py:131-133``):
+
+* ``PyanNet``         -- pyannote/segmentation  (SincNet -> 4x BiLSTM(128) -> 2x Linear(128) -> Linear(K) -> sigmoid)
+* ``XVectorSincNet``  -- pyannote/embedding     (SincNet -> 5x TDNN -> weighted StatsPool -> Linear(3000, 512))
+
+The arithmetic lives in the un-vendored dependency ``pyannote.audio`` (reference
+``setup.cfg:34``, ``pyannote.audio>=2.1.1``; ``models.py:15`` needs >=3.0) and
+``asteroid-filterbanks`` (``ParamSincFB``), neither of which is installed here and
+neither of which is under ``/root/reference``.  This file restates their published
+architectures with pyannote-compatible ``state_dict`` keys so
+a real checkpoint loads unchanged.  Parity status: **unpinned by the reference's own
+tests** (it has none); pinned here only by parameter counts
+(1 472 749 / 4 346 366) and frame counts (293 / 279).
+
+Call sites in the reference that define the contracts:
+  segmentation  ``src/diart/blocks/segmentation.py:42-48``   (B,1,S) -> (B,F,K)
+  embedding     ``src/diart/blocks/embedding.py:51-68``      (N,1,S),(N,F) -> (N,D)
+"""
+from __future__ import annotations
+
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class ParamSincFB(nn.Module):
+    """asteroid_filterbanks.ParamSincFB(80, 251, stride=10, sample_rate=16000, min_low_hz=50, min_band_hz=50).
+
+    Learnt: ``low_hz_`` (40,1), ``band_hz_`` (40,1).  ``filters()`` -> (80,1,251):
+    40 even (cos) band-pass filters then 40 odd (sin) ones, Hamming-windowed.
+    """
+
+    def __init__(self, n_filters: int = 80, kernel_size: int = 251, stride: int = 10,
+                 sample_rate: float = 16000.0, min_low_hz: float = 50, min_band_hz: float = 50):
+        super().__init__()
+        assert kernel_size % 2 == 1
+        self.n_filters, self.kernel_size, self.stride = n_filters, kernel_size, stride
+        self.sample_rate, self.min_low_hz, self.min_band_hz = sample_rate, min_low_hz, min_band_hz
+        self.half_kernel = kernel_size // 2
+        low_hz, high_hz = 30, sample_rate / 2 - (min_low_hz + min_band_hz)
+        mel = np.linspace(self.to_mel(low_hz), self.to_mel(high_hz), n_filters // 2 + 1, dtype="float32")
+        hz = self.to_hz(mel)
+        self.low_hz_ = nn.Parameter(torch.from_numpy(hz[:-1]).view(-1, 1))
+        self.band_hz_ = nn.Parameter(torch.from_numpy(np.diff(hz)).view(-1, 1))
+        window_ = np.hamming(kernel_size)[: self.half_kernel]
+        n_ = 2 * np.pi * (torch.arange(-self.half_kernel, 0.0).view(1, -1) / sample_rate)
+        self.register_buffer("window_", torch.from_numpy(window_).float())
+        self.register_buffer("n_", n_)
+
+    @staticmethod
+    def to_mel(hz):
+        return 2595 * np.log10(1 + hz / 700)
+
+    @staticmethod
+    def to_hz(mel):
+        return 700 * (10 ** (mel / 2595) - 1)
+
+    def _make(self, low, high, kind):
+        band = (high - low)[:, 0]
+        ft_low = torch.matmul(low, self.n_)
+        ft_high = torch.matmul(high, self.n_)
+        if kind == "cos":
+            left = ((torch.sin(ft_high) - torch.sin(ft_low)) / (self.n_ / 2)) * self.window_
+            center = 2 * band.view(-1, 1)
+            right = torch.flip(left, dims=[1])
+        else:
+            left = ((torch.cos(ft_low) - torch.cos(ft_high)) / (self.n_ / 2)) * self.window_
+            center = torch.zeros_like(band.view(-1, 1))
+            right = -torch.flip(left, dims=[1])
+        bp = torch.cat([left, center, right], dim=1) / (2 * band[:, None])
+        return bp.view(self.n_filters // 2, 1, self.kernel_size)
+
+    def filters(self) -> torch.Tensor:
+        low = self.min_low_hz + torch.abs(self.low_hz_)
+        high = torch.clamp(low + self.min_band_hz + torch.abs(self.band_hz_), self.min_low_hz, self.sample_rate / 2)
+        return torch.cat([self._make(low, high, "cos"), self._make(low, high, "sin")], dim=0)
+
+
+class Encoder(nn.Module):
+    """asteroid_filterbanks.Encoder: conv1d with the filterbank's filters, no bias."""
+
+    def __init__(self, filterbank: ParamSincFB):
+        super().__init__()
+        self.filterbank = filterbank
+
+    def forward(self, x):
+        return F.conv1d(x, self.filterbank.filters(), stride=self.filterbank.stride, padding=0)
+
+
+class SincNet(nn.Module):
+    """pyannote.audio.models.blocks.sincnet.SincNet(sample_rate=16000, stride=10) -> (B, 60, 293) for 80000 samples."""
+
+    def __init__(self, sample_rate: int = 16000, stride: int = 10):
+        super().__init__()
+        self.wav_norm1d = nn.InstanceNorm1d(1, affine=True)
+        self.conv1d = nn.ModuleList([
+            Encoder(ParamSincFB(80, 251, stride=stride, sample_rate=sample_rate, min_low_hz=50, min_band_hz=50)),
+            nn.Conv1d(80, 60, 5, stride=1),
+            nn.Conv1d(60, 60, 5, stride=1),
+        ])
+        self.pool1d = nn.ModuleList([nn.MaxPool1d(3, stride=3, padding=0, dilation=1) for _ in range(3)])
+        self.norm1d = nn.ModuleList([nn.InstanceNorm1d(80, affine=True), nn.InstanceNorm1d(60, affine=True),
+                                     nn.InstanceNorm1d(60, affine=True)])
+
+    def forward(self, waveforms: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        outputs = self.wav_norm1d(waveforms)
+        for c, (conv1d, pool1d, norm1d) in enumerate(zip(self.conv1d, self.pool1d, self.norm1d)):
+            outputs = conv1d(outputs)
+            if c == 0:
+                outputs = torch.abs(outputs)
+            outputs = pool1d(outputs)
+            if taps is not None:
+                taps[f"sinc_pool{c}"] = outputs
+            outputs = F.leaky_relu(norm1d(outputs))
+        return outputs
+
+
+class PyanNet(nn.Module):
+    """pyannote.audio.models.segmentation.PyanNet with the pyannote/segmentation hyper-parameters."""
+
+    def __init__(self, num_speakers: int = 3, sample_rate: int = 16000):
+        super().__init__()
+        self.sincnet = SincNet(sample_rate=sample_rate, stride=10)
+        self.lstm = nn.LSTM(60, 128, num_layers=4, bidirectional=True, batch_first=True, dropout=0.0)
+        self.linear = nn.ModuleList([nn.Linear(256, 128), nn.Linear(128, 128)])
+        self.classifier = nn.Linear(128, num_speakers)
+
+    def forward(self, waveforms: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        x = self.sincnet(waveforms, taps)                 # (B, 60, 293)
+        x = x.transpose(1, 2)                             # (B, 293, 60)
+        if taps is not None:
+            taps["sincnet"] = x
+        x, _ = self.lstm(x)
+        if taps is not None:
+            taps["lstm"] = x
+        for linear in self.linear:
+            x = F.leaky_relu(linear(x))
+        return torch.sigmoid(self.classifier(x))
+
+
+class StatsPool(nn.Module):
+    """pyannote.audio.models.blocks.pooling.StatsPool.
+
+    ``mode="3.1"``: nearest-neighbour weight resize and the two ``+1e-8`` guards
+    (pyannote.audio 3.1); ``mode="2.1"``: linear resize (align_corners=False), no guards
+    (pyannote.audio 2.1 / 3.0).  SURVEY.md Appendix A.5.
+    """
+
+    def __init__(self, mode: str = "3.1"):
+        super().__init__()
+        assert mode in ("3.1", "2.1")
+        self.mode = mode
+
+    def forward(self, sequences: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if weights is None:
+            return torch.cat([sequences.mean(dim=-1), sequences.std(dim=-1, unbiased=True)], dim=-1)
+        weights = weights.unsqueeze(dim=1)                # (N, 1, Tw)
+        num_frames, num_weights = sequences.shape[2], weights.shape[2]
+        if num_frames != num_weights:
+            if self.mode == "3.1":
+                weights = F.interpolate(weights, size=num_frames, mode="nearest")
+            else:
+                weights = F.interpolate(weights, size=num_frames, mode="linear", align_corners=False)
+        eps = 1e-8 if self.mode == "3.1" else 0.0
+        v1 = weights.sum(dim=2) + eps
+        mean = torch.sum(sequences * weights, dim=2) / v1
+        dx2 = torch.square(sequences - mean.unsqueeze(2))
+        v2 = torch.square(weights).sum(dim=2)
+        var = torch.sum(dx2 * weights, dim=2) / (v1 - v2 / v1 + eps)
+        return torch.cat([mean, torch.sqrt(var)], dim=1)
+
+
+class XVectorSincNet(nn.Module):
+    """pyannote.audio.models.embedding.XVectorSincNet (pyannote/embedding), dimension 512."""
+
+    def __init__(self, sample_rate: int = 16000, dimension: int = 512, pool_mode: str = "3.1"):
+        super().__init__()
+        self.sincnet = SincNet(sample_rate=sample_rate, stride=10)
+        self.tdnns = nn.ModuleList()
+        in_channel = 60
+        for out_channel, k, d in zip([512, 512, 512, 512, 1500], [5, 3, 3, 1, 1], [1, 2, 3, 1, 1]):
+            self.tdnns.extend([nn.Conv1d(in_channel, out_channel, k, dilation=d), nn.LeakyReLU(),
+                               nn.BatchNorm1d(out_channel)])
+            in_channel = out_channel
+        self.stats_pool = StatsPool(pool_mode)
+        self.embedding = nn.Linear(in_channel * 2, dimension)
+
+    def trunk(self, waveforms: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        x = self.sincnet(waveforms, taps)
+        for i, layer in enumerate(self.tdnns):
+            x = layer(x)
+            if taps is not None and i % 3 == 2:
+                taps[f"tdnn{i // 3}"] = x
+        return x                                          # (N, 1500, 279)
+
+    def forward(self, waveforms: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        return self.embedding(self.stats_pool(self.trunk(waveforms), weights))
+
+    def forward_dedup(self, waveforms: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+        """Trunk once per waveform, K pools.  ``weights`` (B, F, K) -> (B, K, D).
+
+        Arithmetically identical to the reference's K-fold repeat
+        (``src/diart/blocks/embedding.py:57-59``) because the weights only enter at pooling.
+        """
+        x = self.trunk(waveforms)
+        B, _, K = weights.shape
+        out = [self.embedding(self.stats_pool(x, weights[:, :, k])) for k in range(K)]
+        return torch.stack(out, dim=1)
+
+
+# --------------------------------------------------------------------------------------
+# Seeded synthetic weights: no checkpoints exist offline.
+# --------------------------------------------------------------------------------------
+
+def n_params(module: nn.Module) -> int:
+    return sum(p.numel() for p in module.parameters())
+
+
+def make_segmentation(seed: int = 4321, num_speakers: int = 3) -> PyanNet:
+    """PyTorch-default init under ``seed``; classifier rescaled so the sigmoid outputs
+    straddle tau_active instead of idling at 0.5 (otherwise clustering branches never fire)."""
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    net = PyanNet(num_speakers=num_speakers)
+    with torch.no_grad():
+        for p in net.sincnet.norm1d.parameters():
+            p.add_(0.1 * torch.randn(p.shape, generator=g))
+        net.sincnet.wav_norm1d.weight.fill_(1.25)
+        net.sincnet.wav_norm1d.bias.fill_(0.05)
+        net.classifier.weight.mul_(60.0)
+        net.classifier.bias.copy_(torch.tensor([0.3, -0.2, 0.1, -0.4][:num_speakers]))
+    return net.eval()
+
+
+def make_embedding(seed: int = 8765, pool_mode: str = "3.1") -> XVectorSincNet:
+    g = torch.Generator().manual_seed(seed)
+    torch.manual_seed(seed)
+    net = XVectorSincNet(pool_mode=pool_mode)
+    with torch.no_grad():
+        for p in net.sincnet.norm1d.parameters():
+            p.add_(0.1 * torch.randn(p.shape, generator=g))
+        net.sincnet.wav_norm1d.weight.fill_(0.8)
+        net.sincnet.wav_norm1d.bias.fill_(-0.02)
+        for m in net.tdnns:
+            if isinstance(m, nn.BatchNorm1d):
+                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
+                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
+                m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
+                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
+    return net.eval()
+
+
+def synth_audio(num_samples: int, seed: int = 1234, sample_rate: int = 16000, num_speakers: int = 4) -> np.ndarray:
+    """Mono float32 stream in [-1,1]: harmonic 'speakers' with formant-like envelopes gated by a
+    seeded two-state turn-taking chain with some overlap, plus -40 dB white noise."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(num_samples, dtype=np.float64) / sample_rate
+    out = np.zeros(num_samples, dtype=np.float64)
+    seg_len = int(0.25 * sample_rate)
+    n_seg = num_samples // seg_len + 1
+    for s in range(num_speakers):
+        f0 = rng.uniform(90, 250)
+        formants = rng.uniform([300, 900, 2200], [800, 2200, 3400])
+        vib = 1.0 + 0.02 * np.sin(2 * np.pi * rng.uniform(3, 6) * t + rng.uniform(0, 6.28))
+        phase = 2 * np.pi * np.cumsum(f0 * vib) / sample_rate
+        voice = np.zeros(num_samples)
+        for h in range(1, 30):
+            fh = f0 * h
+            if fh > 3800:
+                break
+            amp = sum(np.exp(-0.5 * ((fh - fc) / 180.0) ** 2) for fc in formants) + 0.02
+            voice += amp / h ** 0.5 * np.sin(h * phase + rng.uniform(0, 6.28))
+        voice /= np.max(np.abs(voice)) + 1e-9
+        state, gate = rng.random() < 0.4, np.zeros(n_seg)
+        for i in range(n_seg):
+            if rng.random() < (0.25 if state else 0.12):
+                state = not state
+            gate[i] = 1.0 if state else 0.0
+        g = np.repeat(gate, seg_len)[:num_samples]
+        k = np.hanning(int(0.05 * sample_rate))
+        g = np.convolve(g, k / k.sum(), mode="same")
+        out += rng.uniform(0.25, 0.5) * g * voice
+    out += 10 ** (-40 / 20) * rng.standard_normal(num_samples)
+    out = np.clip(out, -1, 1)
+    return out.astype(np.float32)
+
+
+def windows(stream: np.ndarray, n_chunks: int, chunk: int = 80000, step: int = 8000) -> np.ndarray:
+    """Chunk i = samples [step*i, step*i + chunk), exactly as ``rearrange_audio_stream``
+    (reference ``src/diart/operators.py:44-100``) emits them."""
+    idx = np.arange(chunk)[None, :] + step * np.arange(n_chunks)[:, None]
+    return stream[idx]
+
+
+if __name__ == "__main__":
+    seg, emb = make_segmentation(), make_embedding()
+    print("PyanNet params", n_params(seg), "XVectorSincNet params", n_params(emb))
+    x = torch.from_numpy(windows(synth_audio(80000 + 8000 * 3), 4))[:, None, :]
+    with torch.no_grad():
+        s = seg(x)
+        print("seg", tuple(s.shape), float(s.min()), float(s.max()), s.amax(dim=1))
+        e = emb(x, None)
+        print("emb", tuple(e.shape))
