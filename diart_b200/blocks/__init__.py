@@ -1,0 +1,8 @@
+from .aggregation import DelayedAggregation
+from .base import HyperParameter, Pipeline, PipelineConfig
+from .clustering import OnlineSpeakerClustering
+from .diarization import SpeakerDiarization, SpeakerDiarizationConfig
+from .embedding import (EmbeddingNormalization, OverlapAwareSpeakerEmbedding, OverlappedSpeechPenalty,
+                        SpeakerEmbedding)
+from .segmentation import SpeakerSegmentation
+from .utils import Binarize

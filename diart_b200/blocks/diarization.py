@@ -1,0 +1,206 @@
+"""``SpeakerDiarization`` pipeline (mirrors reference ``src/diart/blocks/diarization.py:21-234``).
+
+Lines 177-203 of the reference -- segmentation, overlapped-speech penalty, embedding, normalisation
+and the sequential clustering loop -- run as ONE fused device step (``dg_pipeline_step``): the
+waveform batch is uploaded once, nothing returns to the host in between, and only the
+(B,F,K) scores and the (B,K) speaker map come back.  Lines 205-232 (aggregation, binarisation,
+buffer bookkeeping) are host-side numpy for now ("next").
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from .. import _lib
+from .. import models as m
+from ..core import Annotation, Segment, SlidingWindow, SlidingWindowFeature
+from . import base
+from .aggregation import DelayedAggregation
+from .clustering import OnlineSpeakerClustering
+from .embedding import OverlapAwareSpeakerEmbedding
+from .segmentation import SpeakerSegmentation
+from .utils import Binarize
+
+
+class SpeakerDiarizationConfig(base.PipelineConfig):
+    def __init__(self, segmentation: Optional[m.SegmentationModel] = None,
+                 embedding: Optional[m.EmbeddingModel] = None, duration: float = 5, step: float = 0.5,
+                 latency=None, tau_active: float = 0.6, rho_update: float = 0.3, delta_new: float = 1,
+                 gamma: float = 3, beta: float = 10, max_speakers: int = 20,
+                 normalize_embedding_weights: bool = False, device: Optional[torch.device] = None,
+                 sample_rate: int = 16000, **kwargs):
+        self.segmentation = segmentation or m.SegmentationModel.from_pyannote("pyannote/segmentation")
+        self.embedding = embedding or m.EmbeddingModel.from_pyannote("pyannote/embedding")
+        self._duration, self._sample_rate, self._step = duration, sample_rate, step
+        self._latency = latency
+        if self._latency is None or self._latency == "min":
+            self._latency = self._step
+        elif self._latency == "max":
+            self._latency = self._duration
+        self.tau_active, self.rho_update, self.delta_new = tau_active, rho_update, delta_new
+        self.gamma, self.beta, self.max_speakers = gamma, beta, max_speakers
+        self.normalize_embedding_weights = normalize_embedding_weights
+        self.device = device or torch.device("cuda")
+
+    @property
+    def duration(self) -> float:
+        return self._duration
+
+    @property
+    def step(self) -> float:
+        return self._step
+
+    @property
+    def latency(self) -> float:
+        return self._latency
+
+    @property
+    def sample_rate(self) -> int:
+        return self._sample_rate
+
+
+class SpeakerDiarization(base.Pipeline):
+    def __init__(self, config: Optional[SpeakerDiarizationConfig] = None):
+        self._config = SpeakerDiarizationConfig() if config is None else config
+        msg = f"Latency should be in the range [{self._config.step}, {self._config.duration}]"
+        assert self._config.step <= self._config.latency <= self._config.duration, msg
+        self.segmentation = SpeakerSegmentation(self._config.segmentation, self._config.device)
+        self.embedding = OverlapAwareSpeakerEmbedding(
+            self._config.embedding, self._config.gamma, self._config.beta, norm=1,
+            normalize_weights=self._config.normalize_embedding_weights, device=self._config.device)
+        self.pred_aggregation = DelayedAggregation(self._config.step, self._config.latency,
+                                                   strategy="hamming", cropping_mode="loose")
+        self.audio_aggregation = DelayedAggregation(self._config.step, self._config.latency,
+                                                    strategy="first", cropping_mode="center")
+        self.binarize = Binarize(self._config.tau_active)
+        self.timestamp_shift = 0
+        self.clustering: Optional[OnlineSpeakerClustering] = None
+        self.chunk_buffer, self.pred_buffer = [], []
+        self._fused: Optional[C.c_void_p] = None
+        self._pinned: Optional[torch.Tensor] = None
+        self.reset()
+
+    @staticmethod
+    def get_config_class() -> type:
+        return SpeakerDiarizationConfig
+
+    @staticmethod
+    def suggest_metric():
+        from pyannote.metrics.diarization import DiarizationErrorRate  # optional dependency
+
+        return DiarizationErrorRate(collar=0, skip_overlap=False)
+
+    @staticmethod
+    def hyper_parameters() -> Sequence[base.HyperParameter]:
+        return [base.TauActive, base.RhoUpdate, base.DeltaNew]
+
+    @property
+    def config(self) -> SpeakerDiarizationConfig:
+        return self._config
+
+    def set_timestamp_shift(self, shift: float):
+        self.timestamp_shift = shift
+
+    def reset(self):
+        self.set_timestamp_shift(0)
+        self._drop_fused()
+        self.clustering = OnlineSpeakerClustering(self.config.tau_active, self.config.rho_update,
+                                                  self.config.delta_new, "cosine", self.config.max_speakers,
+                                                  device=self.segmentation.device)
+        self.chunk_buffer, self.pred_buffer = [], []
+
+    # ------------------------------------------------------------------ fused device step
+    def _drop_fused(self):
+        if self._fused is not None:
+            _lib.lib().dg_pipeline_destroy(self._fused)
+            self._fused = None
+
+    def __del__(self):
+        try:
+            self._drop_fused()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _native_models(self):
+        seg = getattr(self.segmentation.model, "model", None)
+        emb = self.embedding.embedding.native
+        scalar_norm = not isinstance(self.embedding.normalize.norm, torch.Tensor)
+        if isinstance(seg, m.B200PyanNet) and emb is not None and scalar_norm:
+            return seg, emb
+        return None
+
+    def device_step(self, batch: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """batch (B,S) float32 on the device -> (segmentation (B,F,K), embeddings (B,K,D), map (B,K) int32),
+        all on the device; clustering state advances by B chunks."""
+        native = self._native_models()
+        device = self.segmentation.device
+        if native is None:  # foreign models behind the loader API: block by block, still on the device
+            seg = self.segmentation.forward_device(batch)
+            emb = self.embedding.forward_device(batch, seg)
+            maps, _ = self.clustering.step_batch(seg, emb)
+            return seg, emb, maps
+        seg_net, emb_net = native
+        B, S = batch.shape
+        F, K = seg_net.dims(S)
+        _, D = emb_net.dims(S)
+        if self._fused is None:
+            h = C.c_void_p()
+            _lib.check(_lib.lib().dg_pipeline_create(seg_net.handle, emb_net.handle, self.clustering._handle(D),
+                                                     float(self.config.gamma), float(self.config.beta),
+                                                     int(self.config.normalize_embedding_weights), C.byref(h)))
+            self._fused = h
+        seg = torch.empty((B, F, K), device=device)
+        emb = torch.empty((B, K, D), device=device)
+        maps = torch.empty((B, K), device=device, dtype=torch.int32)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().dg_pipeline_step(self._fused, batch.data_ptr(), B, S, seg.data_ptr(),
+                                                   emb.data_ptr(), maps.data_ptr(), None, _lib.stream_ptr(device)))
+        return seg, emb, maps
+
+    def host_step(self, batch: np.ndarray):
+        """batch (B,S) float32 host array -> (segmentation, embeddings, map) numpy arrays; H2D/D2H inside."""
+        device = self.segmentation.device
+        B, S = batch.shape
+        if self._pinned is None or self._pinned.shape != (B, S):
+            self._pinned = torch.empty((B, S), dtype=torch.float32).pin_memory()
+        self._pinned.copy_(torch.from_numpy(batch))
+        dev = self._pinned.to(device, non_blocking=True)
+        seg, emb, maps = self.device_step(dev)
+        return seg.cpu().numpy(), emb.cpu().numpy(), maps.cpu().numpy()
+
+    # ------------------------------------------------------------------ the pipeline call
+    def __call__(self, waveforms: Sequence[SlidingWindowFeature]) -> Sequence[Tuple[Annotation, SlidingWindowFeature]]:
+        batch_size = len(waveforms)
+        assert batch_size >= 1, "Pipeline expected at least 1 input"
+        batch = np.stack([np.asarray(w.data, dtype=np.float32) for w in waveforms])   # (batch, samples, channels)
+        expected = int(np.rint(self.config.duration * self.config.sample_rate))
+        assert batch.shape[1] == expected, f"Expected {expected} samples per chunk, but got {batch.shape[1]}"
+        assert batch.shape[2] == 1, "expected mono audio"
+        seg, _, maps = self.host_step(np.ascontiguousarray(batch[:, :, 0]))
+        num_frames = seg.shape[1]
+        seg_resolution = waveforms[0].extent.duration / num_frames
+        outputs = []
+        for wav, s, amap in zip(waveforms, seg, maps):
+            sw = SlidingWindow(start=wav.extent.start, duration=seg_resolution, step=seg_resolution)
+            permuted = np.zeros((num_frames, self.config.max_speakers))          # SpeakerMap.apply
+            for k, g in enumerate(amap):
+                if g >= 0:
+                    permuted[:, g] = s[:, k]
+            self.chunk_buffer.append(wav)
+            self.pred_buffer.append(SlidingWindowFeature(permuted, sw))
+            agg_waveform = self.audio_aggregation(self.chunk_buffer)
+            agg_prediction = self.binarize(self.pred_aggregation(self.pred_buffer))
+            if self.timestamp_shift != 0:
+                shifted = Annotation(agg_prediction.uri)
+                for segment, track, speaker in agg_prediction.itertracks(yield_label=True):
+                    shifted[Segment(segment.start + self.timestamp_shift,
+                                    segment.end + self.timestamp_shift), track] = speaker
+                agg_prediction = shifted
+            outputs.append((agg_prediction, agg_waveform))
+            if len(self.chunk_buffer) == self.pred_aggregation.num_overlapping_windows:
+                self.chunk_buffer = self.chunk_buffer[1:]
+                self.pred_buffer = self.pred_buffer[1:]
+        return outputs

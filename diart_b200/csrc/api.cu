@@ -1,0 +1,777 @@
+// C ABI of libdiartb200.so (include/diart_b200.h): handles, weight preparation, workspaces and the
+// launch sequences of the two networks, the clustering step and the fused pipeline step.
+#include <math.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <vector>
+
+#include "../../include/diart_b200.h"
+#include "dg_common.cuh"
+
+namespace dg {
+
+static thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+void set_error(const std::string& msg) { g_err = msg; }
+
+int launch_stats_pool_ex(const float* x, int stride, int T, int C, const float* w, int F, int K, int layout,
+                         int n_groups, const int* grp_item, const int* grp_q0, const int* grp_nq, const int* idx0,
+                         const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st);
+
+// ------------------------------------------------------------------------------ small utilities
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int ensure(size_t n) {
+    if (n <= bytes) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+    DG_CUDA(cudaMalloc(&p, n));
+    DG_CUDA(cudaMemset(p, 0, n));
+    bytes = n;
+    return 0;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+  ~DevBuf() {
+    if (p) cudaFree(p);
+  }
+};
+
+struct Tensors {
+  std::map<std::string, std::pair<const float*, int64_t>> m;
+  Tensors(const dg_tensor* t, int n) {
+    for (int i = 0; i < n; i++)
+      if (t[i].name) m[t[i].name] = {t[i].data, t[i].numel};
+  }
+  const float* get(const std::string& name, int64_t numel) const {
+    auto it = m.find(name);
+    if (it == m.end()) {
+      set_error("missing tensor '" + name + "' in state dict");
+      return nullptr;
+    }
+    if (it->second.second != numel || !it->second.first) {
+      set_error("tensor '" + name + "' has " + std::to_string(it->second.second) + " elements, expected " +
+                std::to_string(numel));
+      return nullptr;
+    }
+    return it->second.first;
+  }
+  int64_t numel(const std::string& name) const {
+    auto it = m.find(name);
+    return it == m.end() ? -1 : it->second.second;
+  }
+};
+
+static int upload(DevBuf& b, const std::vector<float>& h) {
+  if (b.ensure(h.size() * sizeof(float))) return -2;
+  DG_CUDA(cudaMemcpy(b.p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------ SincNet front end
+struct SincWeights {
+  float wn_gamma = 1.f, wn_beta = 0.f;
+  DevBuf filt, g0, b0, w1, bias1, g1, b1, w2, bias2, g2, b2;
+};
+
+// ParamSincFB.filters() in float32, as asteroid-filterbanks computes it with torch
+static void sinc_filters(const float* low_hz_, const float* band_hz_, std::vector<float>& filt /*[251][80]*/) {
+  filt.assign(251 * 80, 0.f);
+  float n_[125], win[125];
+  for (int i = 0; i < 125; i++) {
+    const float t = (float)(i - 125) / 16000.0f;
+    n_[i] = 6.283185307179586f * t;
+    win[i] = (float)(0.54 - 0.46 * cos(2.0 * M_PI * i / 250.0));
+  }
+  for (int f = 0; f < 40; f++) {
+    const float low = 50.f + fabsf(low_hz_[f]);
+    float high = low + 50.f + fabsf(band_hz_[f]);
+    high = fminf(fmaxf(high, 50.f), 8000.f);
+    const float band = high - low, two_band = 2.f * band;
+    for (int i = 0; i < 125; i++) {
+      const float ft_low = low * n_[i], ft_high = high * n_[i], half_n = n_[i] / 2.f;
+      const float lc = ((sinf(ft_high) - sinf(ft_low)) / half_n) * win[i];
+      const float ls = ((cosf(ft_low) - cosf(ft_high)) / half_n) * win[i];
+      filt[i * 80 + f] = lc / two_band;
+      filt[(250 - i) * 80 + f] = lc / two_band;
+      filt[i * 80 + 40 + f] = ls / two_band;
+      filt[(250 - i) * 80 + 40 + f] = (-ls) / two_band;
+    }
+    filt[125 * 80 + f] = two_band / two_band;
+    filt[125 * 80 + 40 + f] = 0.f / two_band;
+  }
+}
+
+static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w) {
+  const float *g, *b;
+  if (!(g = t.get(pre + "wav_norm1d.weight", 1)) || !(b = t.get(pre + "wav_norm1d.bias", 1))) return DG_EWEIGHT;
+  w.wn_gamma = g[0];
+  w.wn_beta = b[0];
+  const float* lo = t.get(pre + "conv1d.0.filterbank.low_hz_", 40);
+  const float* bd = t.get(pre + "conv1d.0.filterbank.band_hz_", 40);
+  if (!lo || !bd) return DG_EWEIGHT;
+  std::vector<float> h;
+  sinc_filters(lo, bd, h);
+  if (upload(w.filt, h)) return DG_ECUDA;
+  auto pad_vec = [&](const std::string& name, int n, int npad, DevBuf& dst) -> int {
+    const float* s = t.get(name, n);
+    if (!s) return DG_EWEIGHT;
+    std::vector<float> v(npad, 0.f);
+    memcpy(v.data(), s, n * sizeof(float));
+    return upload(dst, v) ? DG_ECUDA : 0;
+  };
+  int rc;
+  if ((rc = pad_vec(pre + "norm1d.0.weight", 80, 80, w.g0)) || (rc = pad_vec(pre + "norm1d.0.bias", 80, 80, w.b0)) ||
+      (rc = pad_vec(pre + "norm1d.1.weight", 60, 64, w.g1)) || (rc = pad_vec(pre + "norm1d.1.bias", 60, 64, w.b1)) ||
+      (rc = pad_vec(pre + "norm1d.2.weight", 60, 64, w.g2)) || (rc = pad_vec(pre + "norm1d.2.bias", 60, 64, w.b2)) ||
+      (rc = pad_vec(pre + "conv1d.1.bias", 60, 64, w.bias1)) || (rc = pad_vec(pre + "conv1d.2.bias", 60, 64, w.bias2)))
+    return rc;
+  // Conv1d weights [out][in][k] -> shifted-window GEMM layout [(tap*Cin_pad + c)][out_pad]
+  auto conv_w = [&](const std::string& name, int out, int in, int k, int in_pad, int out_pad, DevBuf& dst) -> int {
+    const float* s = t.get(name, (int64_t)out * in * k);
+    if (!s) return DG_EWEIGHT;
+    std::vector<float> v((size_t)k * in_pad * out_pad, 0.f);
+    for (int o = 0; o < out; o++)
+      for (int c = 0; c < in; c++)
+        for (int j = 0; j < k; j++) v[((size_t)j * in_pad + c) * out_pad + o] = s[((size_t)o * in + c) * k + j];
+    return upload(dst, v) ? DG_ECUDA : 0;
+  };
+  if ((rc = conv_w(pre + "conv1d.1.weight", 60, 80, 5, 80, 64, w.w1)) ||
+      (rc = conv_w(pre + "conv1d.2.weight", 60, 60, 5, 64, 64, w.w2)))
+    return rc;
+  return 0;
+}
+
+struct SincWork {
+  DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
+  int ensure(int B, const Geom& g) {
+    const size_t tail = 64;  // spare rows so shifted windows of the last tile stay in bounds
+    if (wmean.ensure(B * 4) || wrstd.ensure(B * 4) || p0.ensure(((size_t)B * g.S0 + tail) * 80 * 4) ||
+        sc0.ensure((size_t)B * 80 * 4) || sh0.ensure((size_t)B * 80 * 4) ||
+        p1.ensure(((size_t)B * g.S1 + tail) * 64 * 4) || sc1.ensure((size_t)B * 64 * 4) ||
+        sh1.ensure((size_t)B * 64 * 4) || p2.ensure(((size_t)B * g.S2 + tail) * 64 * 4) ||
+        sc2.ensure((size_t)B * 64 * 4) || sh2.ensure((size_t)B * 64 * 4))
+      return DG_ECUDA;
+    return 0;
+  }
+};
+
+// waveform [B,S] -> p2 [B*S2, 64] (pre-norm conv2 output) + its InstanceNorm scale/shift
+static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int B, const Geom& g, cudaStream_t st) {
+  int rc;
+  if ((rc = k.ensure(B, g))) return rc;
+  if ((rc = launch_wave_stats(wav, B, g.S, k.wmean.as<float>(), k.wrstd.as<float>(), st))) return rc;
+  if ((rc = launch_sinc0(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt.as<float>(), B,
+                         g, k.p0.as<float>(), st)))
+    return rc;
+  if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),
+                                  k.sc0.as<float>(), k.sh0.as<float>(), st)))
+    return rc;
+  GemmArgs a{};
+  a.A = k.p0.as<float>(); a.lda = 80; a.Cin = 80; a.KW = 5; a.dil = 1;
+  a.Mtot = (long long)B * g.S0; a.M = (long long)B * g.S0;
+  a.W = w.w1.as<float>(); a.ldw = 64; a.N = 64; a.bias = w.bias1.as<float>();
+  a.in_sc = k.sc0.as<float>(); a.in_sh = k.sh0.as<float>(); a.item_rows = g.S0;
+  a.C = k.p1.as<float>(); a.ldc = 64; a.epi = EPI_BIAS_POOL3;
+  if ((rc = launch_gemm(a, st))) return rc;
+  if ((rc = launch_instnorm_stats(k.p1.as<float>(), B, g.S1, g.T1, 64, 64, w.g1.as<float>(), w.b1.as<float>(),
+                                  k.sc1.as<float>(), k.sh1.as<float>(), st)))
+    return rc;
+  a.A = k.p1.as<float>(); a.lda = 64; a.Cin = 64;
+  a.Mtot = (long long)B * g.S1; a.M = (long long)B * g.S1;
+  a.W = w.w2.as<float>(); a.bias = w.bias2.as<float>();
+  a.in_sc = k.sc1.as<float>(); a.in_sh = k.sh1.as<float>(); a.item_rows = g.S1;
+  a.C = k.p2.as<float>();
+  if ((rc = launch_gemm(a, st))) return rc;
+  return launch_instnorm_stats(k.p2.as<float>(), B, g.S2, g.T2, 64, 64, w.g2.as<float>(), w.b2.as<float>(),
+                               k.sc2.as<float>(), k.sh2.as<float>(), st);
+}
+
+}  // namespace dg
+
+using namespace dg;
+
+// ================================================================================== segmentation
+struct dg_seg {
+  int device = 0, K = 3;
+  SincWeights sw;
+  DevBuf wih[4], bih[4], whh[4];   // input projections [in_pad][1024], bias [1024], packed W_hh
+  DevBuf l1w, l1b, l2w, l2b, cw, cb;
+  SincWork work;
+  DevBuf gx, hA, hB, y1, y2;
+};
+
+static int seg_prepare(dg_seg* h, const Tensors& t) {
+  int rc;
+  if ((rc = prep_sincnet(t, "sincnet.", h->sw))) return rc;
+  for (int L = 0; L < 4; L++) {
+    const int in = L == 0 ? 60 : 256, in_pad = L == 0 ? 64 : 256;
+    std::vector<float> w((size_t)in_pad * 1024, 0.f), b(1024, 0.f), packed(lstm_whh_packed_floats());
+    const float* hh[2];
+    for (int d = 0; d < 2; d++) {
+      const std::string sfx = "_l" + std::to_string(L) + (d ? "_reverse" : "");
+      const float* wi = t.get("lstm.weight_ih" + sfx, (int64_t)512 * in);
+      const float* bi = t.get("lstm.bias_ih" + sfx, 512);
+      const float* bh = t.get("lstm.bias_hh" + sfx, 512);
+      hh[d] = t.get("lstm.weight_hh" + sfx, 512 * 128);
+      if (!wi || !bi || !bh || !hh[d]) return DG_EWEIGHT;
+      for (int r = 0; r < 512; r++) {
+        for (int c = 0; c < in; c++) w[(size_t)c * 1024 + d * 512 + r] = wi[(size_t)r * in + c];
+        b[d * 512 + r] = bi[r] + bh[r];
+      }
+    }
+    lstm_pack_whh(hh[0], hh[1], packed.data());
+    if (upload(h->wih[L], w) || upload(h->bih[L], b) || upload(h->whh[L], packed)) return DG_ECUDA;
+  }
+  auto linear_t = [&](const std::string& name, int out, int in, DevBuf& dw, DevBuf& db) -> int {
+    const float* w = t.get(name + ".weight", (int64_t)out * in);
+    const float* b = t.get(name + ".bias", out);
+    if (!w || !b) return DG_EWEIGHT;
+    std::vector<float> wt((size_t)in * out), bv(b, b + out);
+    for (int o = 0; o < out; o++)
+      for (int c = 0; c < in; c++) wt[(size_t)c * out + o] = w[(size_t)o * in + c];
+    return (upload(dw, wt) || upload(db, bv)) ? DG_ECUDA : 0;
+  };
+  if ((rc = linear_t("linear.0", 128, 256, h->l1w, h->l1b)) || (rc = linear_t("linear.1", 128, 128, h->l2w, h->l2b)))
+    return rc;
+  const int64_t cn = t.numel("classifier.bias");
+  if (cn < 1 || cn > 8) {
+    set_error("classifier.bias missing or more than 8 local speakers");
+    return DG_EWEIGHT;
+  }
+  h->K = (int)cn;
+  const float* cw = t.get("classifier.weight", cn * 128);
+  const float* cb = t.get("classifier.bias", cn);
+  if (!cw || !cb) return DG_EWEIGHT;
+  if (upload(h->cw, std::vector<float>(cw, cw + cn * 128)) || upload(h->cb, std::vector<float>(cb, cb + cn)))
+    return DG_ECUDA;
+  return 0;
+}
+
+extern "C" const char* dg_last_error(void) { return g_err.c_str(); }
+extern "C" int dg_version(void) { return 100; }
+extern "C" int64_t dg_launch_count(void) { return (int64_t)g_launches.load(); }
+
+extern "C" int dg_seg_create(const dg_tensor* tensors, int n, int device, dg_seg** out) {
+  if (!tensors || !out) {
+    set_error("dg_seg_create: null argument");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(device));
+  std::unique_ptr<dg_seg> h(new dg_seg());
+  h->device = device;
+  Tensors t(tensors, n);
+  int rc = seg_prepare(h.get(), t);
+  if (rc) return rc;
+  *out = h.release();
+  return DG_OK;
+}
+
+extern "C" int dg_seg_dims(const dg_seg* h, int num_samples, int* frames, int* speakers) {
+  if (!h || num_samples < 3000) {
+    set_error("dg_seg_dims: bad arguments");
+    return DG_EINVAL;
+  }
+  Geom g = make_geom(num_samples);
+  if (frames) *frames = g.T2;
+  if (speakers) *speakers = h->K;
+  return DG_OK;
+}
+
+extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* seg, void* stream) {
+  if (!h || !wav || !seg || B < 1 || S < 3000) {
+    set_error("dg_seg_forward: bad arguments (need B >= 1, S >= 3000)");
+    return DG_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaSetDevice(h->device));
+  const Geom g = make_geom(S);
+  int rc;
+  if ((rc = run_sincnet(h->sw, h->work, wav, B, g, st))) return rc;
+  const size_t rows = (size_t)B * g.S2 + 64;
+  if (h->gx.ensure(rows * 1024 * 4) || h->hA.ensure(rows * 256 * 4) || h->hB.ensure(rows * 256 * 4) ||
+      h->y1.ensure(rows * 128 * 4) || h->y2.ensure(rows * 128 * 4))
+    return DG_ECUDA;
+  const long long M = (long long)B * g.S2;
+  float* hin = nullptr;
+  float* hbuf[2] = {h->hA.as<float>(), h->hB.as<float>()};
+  for (int L = 0; L < 4; L++) {
+    GemmArgs a{};
+    if (L == 0) {
+      a.A = h->work.p2.as<float>(); a.lda = 64; a.Cin = 64;
+      a.in_sc = h->work.sc2.as<float>(); a.in_sh = h->work.sh2.as<float>(); a.item_rows = g.S2;
+    } else {
+      a.A = hin; a.lda = 256; a.Cin = 256;
+    }
+    a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;
+    a.W = h->wih[L].as<float>(); a.ldw = 1024; a.N = 1024; a.bias = h->bih[L].as<float>();
+    a.C = h->gx.as<float>(); a.ldc = 1024; a.epi = EPI_BIAS;
+    if ((rc = launch_gemm(a, st))) return rc;
+    float* hout = hbuf[L & 1];
+    if ((rc = launch_lstm_layer(h->gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st))) return rc;
+    hin = hout;
+  }
+  GemmArgs a{};
+  a.A = hin; a.lda = 256; a.Cin = 256; a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;
+  a.W = h->l1w.as<float>(); a.ldw = 128; a.N = 128; a.bias = h->l1b.as<float>();
+  a.C = h->y1.as<float>(); a.ldc = 128; a.epi = EPI_BIAS_LEAKY;
+  if ((rc = launch_gemm(a, st))) return rc;
+  a.A = h->y1.as<float>(); a.lda = 128; a.Cin = 128;
+  a.W = h->l2w.as<float>(); a.bias = h->l2b.as<float>(); a.C = h->y2.as<float>();
+  if ((rc = launch_gemm(a, st))) return rc;
+  return launch_seg_final(h->y2.as<float>(), h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
+}
+
+extern "C" int dg_seg_destroy(dg_seg* h) {
+  delete h;
+  return DG_OK;
+}
+
+// ===================================================================================== embedding
+struct dg_emb {
+  int device = 0, pool_mode = 31, D = 512;
+  SincWeights sw;
+  DevBuf tw[5], tb[5], bns[5], bnh[5];
+  DevBuf ew, eb;
+  SincWork work;
+  DevBuf tA, tB, t5, pooled, eraw;
+  DevBuf idx0, idx1, lam1;
+  int tab_F = -1, tab_T = -1;
+  DevBuf flags, uniq, grp, gathered;   // compatibility path
+};
+
+static const int TD_OUT[5] = {512, 512, 512, 512, 1500};
+static const int TD_K[5] = {5, 3, 3, 1, 1};
+static const int TD_DIL[5] = {1, 2, 3, 1, 1};
+
+static int emb_prepare(dg_emb* h, const Tensors& t) {
+  int rc;
+  if ((rc = prep_sincnet(t, "sincnet.", h->sw))) return rc;
+  int in = 60, in_pad = 64;
+  for (int L = 0; L < 5; L++) {
+    const int out = TD_OUT[L], k = TD_K[L];
+    const std::string cv = "tdnns." + std::to_string(3 * L), bn = "tdnns." + std::to_string(3 * L + 2);
+    const float* w = t.get(cv + ".weight", (int64_t)out * in * k);
+    const float* b = t.get(cv + ".bias", out);
+    const float* gm = t.get(bn + ".weight", out);
+    const float* bt = t.get(bn + ".bias", out);
+    const float* rm = t.get(bn + ".running_mean", out);
+    const float* rv = t.get(bn + ".running_var", out);
+    if (!w || !b || !gm || !bt || !rm || !rv) return DG_EWEIGHT;
+    std::vector<float> wt((size_t)k * in_pad * out, 0.f), bv(b, b + out), sc(out), sf(out);
+    for (int o = 0; o < out; o++) {
+      for (int c = 0; c < in; c++)
+        for (int j = 0; j < k; j++) wt[((size_t)j * in_pad + c) * out + o] = w[((size_t)o * in + c) * k + j];
+      // BatchNorm1d(eval): (x - mean) / sqrt(var + 1e-5) * gamma + beta  ==  x * sc + sf
+      sc[o] = gm[o] / sqrtf(rv[o] + 1e-5f);
+      sf[o] = bt[o] - rm[o] * sc[o];
+    }
+    if (upload(h->tw[L], wt) || upload(h->tb[L], bv) || upload(h->bns[L], sc) || upload(h->bnh[L], sf)) return DG_ECUDA;
+    in = out;
+    in_pad = out;
+  }
+  const int64_t dn = t.numel("embedding.bias");
+  if (dn < 4 || dn % 4) {
+    set_error("embedding.bias missing or dimension not a multiple of 4");
+    return DG_EWEIGHT;
+  }
+  h->D = (int)dn;
+  const float* ew = t.get("embedding.weight", dn * 3000);
+  const float* eb = t.get("embedding.bias", dn);
+  if (!ew || !eb) return DG_EWEIGHT;
+  std::vector<float> wt((size_t)3000 * dn);
+  for (int o = 0; o < dn; o++)
+    for (int c = 0; c < 3000; c++) wt[(size_t)c * dn + o] = ew[(size_t)o * 3000 + c];
+  if (upload(h->ew, wt) || upload(h->eb, std::vector<float>(eb, eb + dn))) return DG_ECUDA;
+  return 0;
+}
+
+extern "C" int dg_emb_create(const dg_tensor* tensors, int n, int pool_mode, int device, dg_emb** out) {
+  if (!tensors || !out || (pool_mode != 31 && pool_mode != 21)) {
+    set_error("dg_emb_create: bad arguments (pool_mode must be 31 or 21)");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(device));
+  std::unique_ptr<dg_emb> h(new dg_emb());
+  h->device = device;
+  h->pool_mode = pool_mode;
+  Tensors t(tensors, n);
+  int rc = emb_prepare(h.get(), t);
+  if (rc) return rc;
+  *out = h.release();
+  return DG_OK;
+}
+
+extern "C" int dg_emb_dims(const dg_emb* h, int num_samples, int* frames, int* dimension) {
+  if (!h || num_samples < 3000) {
+    set_error("dg_emb_dims: bad arguments");
+    return DG_EINVAL;
+  }
+  Geom g = make_geom(num_samples);
+  if (frames) *frames = g.T2 - 14;
+  if (dimension) *dimension = h->D;
+  return DG_OK;
+}
+
+// F.interpolate index tables, computed in float32 exactly like ATen's upsample kernels
+static int build_tables(dg_emb* h, int F, int T, cudaStream_t st) {
+  if (h->tab_F == F && h->tab_T == T) return 0;
+  std::vector<int> i0(T), i1(T);
+  std::vector<float> l1(T);
+  const float scale = (float)F / (float)T;
+  for (int t = 0; t < T; t++) {
+    if (F == T) {
+      i0[t] = i1[t] = t;
+      l1[t] = 0.f;
+    } else if (h->pool_mode == 31) {   // mode="nearest": min(floor(dst * scale), F - 1)
+      int s = (int)floorf((float)t * scale);
+      if (s > F - 1) s = F - 1;
+      i0[t] = i1[t] = s;
+      l1[t] = 0.f;
+    } else {                           // mode="linear", align_corners=False
+      float src = scale * ((float)t + 0.5f) - 0.5f;
+      if (src < 0.f) src = 0.f;
+      int a = (int)src;
+      if (a > F - 1) a = F - 1;
+      i0[t] = a;
+      i1[t] = a + (a < F - 1 ? 1 : 0);
+      l1[t] = src - (float)a;
+    }
+  }
+  if (h->idx0.ensure(T * 4) || h->idx1.ensure(T * 4) || h->lam1.ensure(T * 4)) return DG_ECUDA;
+  DG_CUDA(cudaStreamSynchronize(st));
+  DG_CUDA(cudaMemcpy(h->idx0.p, i0.data(), T * 4, cudaMemcpyHostToDevice));
+  DG_CUDA(cudaMemcpy(h->idx1.p, i1.data(), T * 4, cudaMemcpyHostToDevice));
+  DG_CUDA(cudaMemcpy(h->lam1.p, l1.data(), T * 4, cudaMemcpyHostToDevice));
+  h->tab_F = F;
+  h->tab_T = T;
+  return 0;
+}
+
+// waveform [U,S] -> t5 [U*S2, 1500]; returns the number of valid frames
+static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStream_t st, int* T_out) {
+  int rc;
+  if ((rc = run_sincnet(h->sw, h->work, wav, U, g, st))) return rc;
+  const size_t rows = (size_t)U * g.S2 + 64;
+  if (h->tA.ensure(rows * 512 * 4) || h->tB.ensure(rows * 512 * 4) || h->t5.ensure(rows * 1500 * 4)) return DG_ECUDA;
+  const long long M = (long long)U * g.S2;
+  const float* in = h->work.p2.as<float>();
+  int cin = 64, T = g.T2;
+  float* bufs[2] = {h->tA.as<float>(), h->tB.as<float>()};
+  for (int L = 0; L < 5; L++) {
+    GemmArgs a{};
+    a.A = in; a.lda = cin; a.Cin = cin; a.KW = TD_K[L]; a.dil = TD_DIL[L];
+    a.Mtot = M; a.M = M;
+    a.W = h->tw[L].as<float>(); a.ldw = TD_OUT[L]; a.N = TD_OUT[L]; a.bias = h->tb[L].as<float>();
+    a.bn_scale = h->bns[L].as<float>(); a.bn_shift = h->bnh[L].as<float>();
+    if (L == 0) {
+      a.in_sc = h->work.sc2.as<float>(); a.in_sh = h->work.sh2.as<float>(); a.item_rows = g.S2;
+    }
+    float* out = L == 4 ? h->t5.as<float>() : bufs[L & 1];
+    a.C = out; a.ldc = TD_OUT[L]; a.epi = EPI_BIAS_LEAKY_BN;
+    if ((rc = launch_gemm(a, st))) return rc;
+    in = out;
+    cin = TD_OUT[L];
+    T -= (TD_K[L] - 1) * TD_DIL[L];
+  }
+  *T_out = T;
+  return 0;
+}
+
+static int emb_project(dg_emb* h, int rows, int normalize, float norm, float* out, cudaStream_t st) {
+  GemmArgs a{};
+  a.A = h->pooled.as<float>(); a.lda = 3000; a.Cin = 3000; a.KW = 1; a.dil = 1; a.Mtot = rows; a.M = rows;
+  a.W = h->ew.as<float>(); a.ldw = h->D; a.N = h->D; a.bias = h->eb.as<float>();
+  a.ldc = h->D; a.epi = EPI_BIAS;
+  if (!normalize) {
+    a.C = out;
+    return launch_gemm(a, st);
+  }
+  if (h->eraw.ensure((size_t)rows * h->D * 4)) return DG_ECUDA;
+  a.C = h->eraw.as<float>();
+  int rc;
+  if ((rc = launch_gemm(a, st))) return rc;
+  return launch_l2norm(h->eraw.as<float>(), rows, h->D, norm, out, st);
+}
+
+extern "C" int dg_emb_forward(dg_emb* h, const float* wav, const float* weights, int B, int S, int F, int K,
+                              int normalize, float norm, float* out, void* stream) {
+  if (!h || !wav || !out || B < 1 || S < 3000 || K < 1 || (!weights && K != 1) || (weights && F < 1)) {
+    set_error("dg_emb_forward: bad arguments");
+    return DG_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaSetDevice(h->device));
+  const Geom g = make_geom(S);
+  int rc, T = 0;
+  if ((rc = emb_trunk(h, wav, B, g, st, &T))) return rc;
+  if (weights && (rc = build_tables(h, F, T, st))) return rc;
+  if (h->pooled.ensure((size_t)B * K * 3000 * 4)) return DG_ECUDA;
+  const float eps = h->pool_mode == 31 ? 1e-8f : 0.f;
+  if ((rc = launch_stats_pool(h->t5.as<float>(), B, g.S2, T, 1500, weights, F, K, h->idx0.as<int>(),
+                              h->idx1.as<int>(), h->lam1.as<float>(), weights ? eps : 0.f,
+                              h->pooled.as<float>(), st)))
+    return rc;
+  return emb_project(h, B * K, normalize, norm, out, st);
+}
+
+extern "C" int dg_emb_forward_rows(dg_emb* h, const float* wav, const float* weights, int N, int S, int F, float* out,
+                                   void* stream) {
+  if (!h || !wav || !out || N < 1 || S < 3000 || (weights && F < 1)) {
+    set_error("dg_emb_forward_rows: bad arguments");
+    return DG_EINVAL;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaSetDevice(h->device));
+  const Geom g = make_geom(S);
+  int rc, T = 0;
+  // consecutive identical rows (the reference repeats each waveform once per local speaker,
+  // src/diart/blocks/embedding.py:57-59) share one trunk pass
+  if (h->flags.ensure((size_t)N * 4)) return DG_ECUDA;
+  if ((rc = launch_row_equal_flags(wav, N, S, h->flags.as<int>(), st))) return rc;
+  std::vector<int> flags(N);
+  DG_CUDA(cudaMemcpyAsync(flags.data(), h->flags.p, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+  DG_CUDA(cudaStreamSynchronize(st));
+  std::vector<int> uniq, gi, gq0, gnq;
+  for (int n = 0; n < N; n++) {
+    if (!flags[n]) uniq.push_back(n);
+    const int item = (int)uniq.size() - 1;
+    if (!flags[n] || gnq.back() == 4) {
+      gi.push_back(item);
+      gq0.push_back(n);
+      gnq.push_back(1);
+    } else {
+      gnq.back()++;
+    }
+  }
+  const int U = (int)uniq.size(), G = (int)gi.size();
+  const float* trunk_in = wav;
+  if (U != N) {
+    if (h->uniq.ensure((size_t)U * 4) || h->gathered.ensure((size_t)U * S * 4)) return DG_ECUDA;
+    DG_CUDA(cudaMemcpyAsync(h->uniq.p, uniq.data(), (size_t)U * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_gather_rows(wav, h->uniq.as<int>(), U, S, h->gathered.as<float>(), st))) return rc;
+    trunk_in = h->gathered.as<float>();
+  }
+  if (h->grp.ensure((size_t)3 * G * 4)) return DG_ECUDA;
+  std::vector<int> packed(3 * G);
+  memcpy(packed.data(), gi.data(), G * 4);
+  memcpy(packed.data() + G, gq0.data(), G * 4);
+  memcpy(packed.data() + 2 * G, gnq.data(), G * 4);
+  DG_CUDA(cudaMemcpyAsync(h->grp.p, packed.data(), (size_t)3 * G * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = emb_trunk(h, trunk_in, U, g, st, &T))) return rc;
+  if (weights && (rc = build_tables(h, F, T, st))) return rc;
+  if (h->pooled.ensure((size_t)N * 3000 * 4)) return DG_ECUDA;
+  const float eps = (weights && h->pool_mode == 31) ? 1e-8f : 0.f;
+  const int* gp = h->grp.as<int>();
+  if ((rc = launch_stats_pool_ex(h->t5.as<float>(), g.S2, T, 1500, weights, F, 1, 1, G, gp, gp + G, gp + 2 * G,
+                                 h->idx0.as<int>(), h->idx1.as<int>(), h->lam1.as<float>(), eps,
+                                 h->pooled.as<float>(), st)))
+    return rc;
+  rc = emb_project(h, N, 0, 1.f, out, st);
+  DG_CUDA(cudaStreamSynchronize(st));   // host staging vectors above must outlive the async copies
+  return rc;
+}
+
+extern "C" int dg_emb_destroy(dg_emb* h) {
+  delete h;
+  return DG_OK;
+}
+
+// =========================================================================== element-wise blocks
+extern "C" int dg_osp(const float* seg, int B, int F, int K, float gamma, float beta, int normalize, float* out,
+                      void* stream) {
+  if (!seg || !out || B < 1 || F < 1 || K < 1) {
+    set_error("dg_osp: bad arguments");
+    return DG_EINVAL;
+  }
+  return launch_osp(seg, B, F, K, gamma, beta, normalize, out, (cudaStream_t)stream);
+}
+
+extern "C" int dg_normalize_embeddings(const float* emb, int rows, int D, float norm, float* out, void* stream) {
+  if (!emb || !out || rows < 1 || D < 1) {
+    set_error("dg_normalize_embeddings: bad arguments");
+    return DG_EINVAL;
+  }
+  return launch_l2norm(emb, rows, D, norm, out, (cudaStream_t)stream);
+}
+
+// ==================================================================================== clustering
+struct dg_cluster {
+  int device = 0;
+  ClusterParams p;
+  DevBuf centers, active, init, prep, prep_d, record;
+};
+
+extern "C" int dg_cluster_create(int max_speakers, int dim, double tau, double rho, double delta, int device,
+                                 dg_cluster** out) {
+  if (!out || max_speakers < 1 || max_speakers > 32 || dim < 1) {
+    set_error("dg_cluster_create: need 1 <= max_speakers <= 32 and dim >= 1");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(device));
+  std::unique_ptr<dg_cluster> h(new dg_cluster());
+  h->device = device;
+  h->p.M = max_speakers;
+  h->p.D = dim;
+  // numpy compares a float32 array with a Python float in float32 (weak scalar promotion)
+  h->p.tau_f = (float)tau;
+  h->p.rho_f = (float)rho;
+  h->p.delta = delta;
+  if (h->centers.ensure((size_t)max_speakers * dim * 8) || h->active.ensure(32 * 4) || h->init.ensure(2 * 4))
+    return DG_ECUDA;
+  *out = h.release();
+  return DG_OK;
+}
+
+extern "C" int dg_cluster_step(dg_cluster* h, const float* seg, const float* emb, int B, int F, int K, int32_t* map,
+                               float* permuted, void* stream) {
+  if (!h || !seg || !emb || !map || B < 0 || F < 1 || K < 1) {
+    set_error("dg_cluster_step: bad arguments");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  if (h->prep.ensure(cluster_prep_floats(B, K) * 4 + 16) || h->prep_d.ensure(cluster_prep_doubles(B, K) * 8 + 16))
+    return DG_ECUDA;
+  return launch_cluster_step(h->p, seg, emb, B, F, K, h->centers.as<double>(), h->active.as<int>(),
+                             h->init.as<int>(), h->prep.as<float>(), h->prep_d.as<double>(), map, permuted,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int dg_cluster_reset(dg_cluster* h) {
+  if (!h) return DG_EINVAL;
+  DG_CUDA(cudaSetDevice(h->device));
+  DG_CUDA(cudaDeviceSynchronize());
+  DG_CUDA(cudaMemset(h->centers.p, 0, h->centers.bytes));
+  DG_CUDA(cudaMemset(h->active.p, 0, h->active.bytes));
+  DG_CUDA(cudaMemset(h->init.p, 0, h->init.bytes));
+  return DG_OK;
+}
+
+extern "C" int dg_cluster_get_state(dg_cluster* h, double* centers, int32_t* active, int* initialized) {
+  if (!h) return DG_EINVAL;
+  DG_CUDA(cudaSetDevice(h->device));
+  DG_CUDA(cudaDeviceSynchronize());
+  int init[2] = {0, 0};
+  DG_CUDA(cudaMemcpy(init, h->init.p, 8, cudaMemcpyDeviceToHost));
+  if (init[1]) {
+    set_error("Cannot update unknown centers");   // reference clustering.py:98 (AssertionError)
+    return DG_EINVAL;
+  }
+  if (centers) DG_CUDA(cudaMemcpy(centers, h->centers.p, (size_t)h->p.M * h->p.D * 8, cudaMemcpyDeviceToHost));
+  if (active) DG_CUDA(cudaMemcpy(active, h->active.p, (size_t)h->p.M * 4, cudaMemcpyDeviceToHost));
+  if (initialized) *initialized = init[0];
+  return DG_OK;
+}
+
+extern "C" int dg_cluster_set_state(dg_cluster* h, const double* centers, const int32_t* active, int initialized) {
+  if (!h || !centers || !active) return DG_EINVAL;
+  DG_CUDA(cudaSetDevice(h->device));
+  DG_CUDA(cudaDeviceSynchronize());
+  int init[2] = {initialized ? 1 : 0, 0};
+  DG_CUDA(cudaMemcpy(h->centers.p, centers, (size_t)h->p.M * h->p.D * 8, cudaMemcpyHostToDevice));
+  DG_CUDA(cudaMemcpy(h->active.p, active, (size_t)h->p.M * 4, cudaMemcpyHostToDevice));
+  DG_CUDA(cudaMemcpy(h->init.p, init, 8, cudaMemcpyHostToDevice));
+  return DG_OK;
+}
+
+extern "C" int dg_cluster_destroy(dg_cluster* h) {
+  delete h;
+  return DG_OK;
+}
+
+// shared-identity extension: not wired in this round (multi-GPU)
+extern "C" int dg_cluster_record_len(const dg_cluster* h) { return h ? h->p.M * h->p.D + 2 * h->p.M + 2 : 0; }
+extern "C" int dg_cluster_export_delta(dg_cluster*, double*, void*) {
+  set_error("dg_cluster_export_delta: shared-identity mode is not implemented yet");
+  return DG_EINVAL;
+}
+extern "C" int dg_cluster_merge(dg_cluster*, const double*, int, void*) {
+  set_error("dg_cluster_merge: shared-identity mode is not implemented yet");
+  return DG_EINVAL;
+}
+
+// ================================================================================ fused pipeline
+struct dg_pipeline {
+  dg_seg* seg;
+  dg_emb* emb;
+  dg_cluster* clu;
+  float gamma, beta;
+  int normalize_weights;
+  DevBuf osp, wav, segd, embd, mapd, permd;
+  cudaStream_t st = nullptr;
+};
+
+extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
+                                  int normalize_weights, dg_pipeline** out) {
+  if (!seg || !emb || !clu || !out) {
+    set_error("dg_pipeline_create: null handle");
+    return DG_EINVAL;
+  }
+  if (seg->device != emb->device || seg->device != clu->device) {
+    set_error("dg_pipeline_create: handles live on different devices");
+    return DG_EINVAL;
+  }
+  if (clu->p.D != emb->D) {
+    set_error("dg_pipeline_create: clustering dimension != embedding dimension");
+    return DG_EINVAL;
+  }
+  std::unique_ptr<dg_pipeline> h(new dg_pipeline());
+  h->seg = seg; h->emb = emb; h->clu = clu;
+  h->gamma = gamma; h->beta = beta; h->normalize_weights = normalize_weights;
+  DG_CUDA(cudaSetDevice(seg->device));
+  DG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  *out = h.release();
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_step(dg_pipeline* h, const float* wav, int B, int S, float* seg, float* emb, int32_t* map,
+                                float* permuted, void* stream) {
+  if (!h || !wav || !seg || !emb || !map || B < 1) {
+    set_error("dg_pipeline_step: bad arguments");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  if ((rc = dg_seg_forward(h->seg, wav, B, S, seg, stream))) return rc;
+  if (h->osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
+  if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, h->osp.as<float>(), stream))) return rc;
+  if ((rc = dg_emb_forward(h->emb, wav, h->osp.as<float>(), B, S, F, K, 1, 1.f, emb, stream))) return rc;
+  return dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, stream);
+}
+
+extern "C" int dg_pipeline_step_host(dg_pipeline* h, const float* wav_host, int B, int S, float* seg_host,
+                                     float* emb_host, int32_t* map_host, float* permuted_host) {
+  if (!h || !wav_host || B < 1) {
+    set_error("dg_pipeline_step_host: bad arguments");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  const int D = h->emb->D, M = h->clu->p.M;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  if (h->wav.ensure((size_t)B * S * 4) || h->segd.ensure((size_t)B * F * K * 4) ||
+      h->embd.ensure((size_t)B * K * D * 4) || h->mapd.ensure((size_t)B * K * 4) ||
+      (permuted_host && h->permd.ensure((size_t)B * F * M * 4)))
+    return DG_ECUDA;
+  DG_CUDA(cudaMemcpyAsync(h->wav.p, wav_host, (size_t)B * S * 4, cudaMemcpyHostToDevice, h->st));
+  if ((rc = dg_pipeline_step(h, h->wav.as<float>(), B, S, h->segd.as<float>(), h->embd.as<float>(),
+                             h->mapd.as<int32_t>(), permuted_host ? h->permd.as<float>() : nullptr, h->st)))
+    return rc;
+  if (seg_host) DG_CUDA(cudaMemcpyAsync(seg_host, h->segd.p, (size_t)B * F * K * 4, cudaMemcpyDeviceToHost, h->st));
+  if (emb_host) DG_CUDA(cudaMemcpyAsync(emb_host, h->embd.p, (size_t)B * K * D * 4, cudaMemcpyDeviceToHost, h->st));
+  if (map_host) DG_CUDA(cudaMemcpyAsync(map_host, h->mapd.p, (size_t)B * K * 4, cudaMemcpyDeviceToHost, h->st));
+  if (permuted_host)
+    DG_CUDA(cudaMemcpyAsync(permuted_host, h->permd.p, (size_t)B * F * M * 4, cudaMemcpyDeviceToHost, h->st));
+  DG_CUDA(cudaStreamSynchronize(h->st));
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
+  if (h && h->st) cudaStreamDestroy(h->st);
+  delete h;
+  return DG_OK;
+}

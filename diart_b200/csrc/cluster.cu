@@ -1,0 +1,410 @@
+// OnlineSpeakerClustering on the device (float64 + int, bit-exact decision logic).
+//
+// Restates reference src/diart/blocks/clustering.py:119-218 (identify / __call__) and the SpeakerMap
+// operations it reaches in src/diart/mapping.py:179-360: every mutation (unmap_speakers,
+// unmap_threshold, set_source_speaker) yields a NEW cost matrix whose Hungarian assignment is
+// re-solved lazily; here a "map" is a (K x M) float64 matrix held one column per lane of warp 0, and
+// `solve()` is scipy.optimize.linear_sum_assignment's algorithm (Crouse 2016 shortest augmenting
+// path, the published algorithm behind scipy's rectangular LSAP) executed column-parallel with
+// scipy's tie-breaking order reproduced exactly (oracle/lsap_ref.py is the same restatement in
+// Python, fuzzed against scipy).
+//
+// Two kernels per batch:
+//   cluster_prep  (parallel over chunks)  per-speaker max / mean of the segmentation, NaN flags and
+//                                         float64 norms of the embeddings.
+//   cluster_seq   (one CTA per stream)    walks the B chunks in order: float64 cosine distances to
+//                                         the active centroids (8 warps), the assignment logic
+//                                         (warp 0), then centroid update + SpeakerMap.apply scatter
+//                                         (all threads).
+#include "dg_common.cuh"
+
+namespace dg {
+
+constexpr int CK = 8;          // max local speakers
+constexpr int CM = 32;         // max global speakers (one per lane)
+constexpr double INVALID = 1e10;
+constexpr unsigned FULL = 0xffffffffu;
+
+size_t cluster_prep_floats(int B, int K) { return (size_t)B * K * 3; }     // max, mean, nan flag
+size_t cluster_prep_doubles(int B, int K) { return (size_t)B * K; }        // ||e||
+
+// numpy semantics: np.max / np.mean over axis 0 of a float32 (F,K) array.  The mean is a float32
+// running sum in frame order followed by one float32 division (clustering.py:137-142).
+__global__ void __launch_bounds__(128) cluster_prep_kernel(const float* __restrict__ seg, const float* __restrict__ emb,
+                                                           int F, int K, int D, float* __restrict__ prep,
+                                                           double* __restrict__ prep_d) {
+  const int i = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* s = seg + (size_t)i * F * K;
+  if (threadIdx.x < K) {
+    float mx = -INFINITY, sum = 0.f;
+    for (int f = 0; f < F; f++) {
+      const float v = s[f * K + threadIdx.x];
+      mx = fmaxf(mx, v);
+      sum = __fadd_rn(sum, v);
+      if (isnan(v)) mx = v;   // np.max propagates NaN
+    }
+    prep[((size_t)i * K + threadIdx.x) * 3 + 0] = mx;
+    prep[((size_t)i * K + threadIdx.x) * 3 + 1] = __fdiv_rn(sum, (float)F);
+  }
+  for (int k = warp; k < K; k += 4) {
+    const float* e = emb + ((size_t)i * K + k) * D;
+    double ss = 0.0;
+    int nan = 0;
+    for (int d = lane; d < D; d += 32) {
+      const float v = e[d];
+      nan |= isnan(v);
+      ss = fma((double)v, (double)v, ss);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      ss += __shfl_xor_sync(FULL, ss, o);
+      nan |= __shfl_xor_sync(FULL, nan, o);
+    }
+    if (lane == 0) {
+      prep[((size_t)i * K + k) * 3 + 2] = nan ? 1.f : 0.f;
+      prep_d[(size_t)i * K + k] = sqrt(ss);
+    }
+  }
+}
+
+__device__ __forceinline__ double warp_min_d(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
+  return v;
+}
+__device__ __forceinline__ double sel(const double (&c)[CK], int i) {
+  double r = c[0];
+#pragma unroll
+  for (int q = 1; q < CK; q++) r = (i == q) ? c[q] : r;
+  return r;
+}
+__device__ __forceinline__ void put(double (&c)[CK], int i, double v) {
+#pragma unroll
+  for (int q = 0; q < CK; q++) c[q] = (i == q) ? v : c[q];
+}
+
+struct LsapScratch {
+  double u[CK];
+  int col4row[CK];
+  int sr[CK];
+};
+
+// Column-parallel rectangular LSAP (nr <= nc <= 32), warp-collective.  cost[i] is C[i][lane].
+// Result: s.col4row[i].  Arithmetic and tie-breaking follow scipy's implementation of Crouse's
+// algorithm: r = ((minVal + c) - u) - v; among equal shortest-path costs prefer an unassigned column,
+// scanning the `remaining` list (initialised in reverse, swap-removed) in order.
+__device__ void lsap_warp(const double (&cost)[CK], int nr, int nc, int lane, LsapScratch& s) {
+  double v = 0.0;
+  int row4col = -1;
+  if (lane < CK) {
+    s.u[lane] = 0.0;
+    s.col4row[lane] = -1;
+  }
+  __syncwarp();
+  for (int cur = 0; cur < nr; cur++) {
+    double minVal = 0.0, spc = INFINITY;
+    int i = cur, pos = nc - 1 - lane, path = -1, num = nc, sink = -1;
+    bool rem = lane < nc, sc = false;
+    if (lane < CK) s.sr[lane] = 0;
+    __syncwarp();
+    while (sink < 0) {
+      if (lane == 0) s.sr[i] = 1;
+      const double ui = s.u[i];
+      if (rem) {
+        const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, sel(cost, i)), ui), v);
+        if (r < spc) {
+          path = i;
+          spc = r;
+        }
+      }
+      const double lowest = warp_min_d(rem ? spc : INFINITY);
+      const bool is_c = rem && spc == lowest;
+      const unsigned cand = __ballot_sync(FULL, is_c);
+      const unsigned candfree = __ballot_sync(FULL, is_c && row4col < 0);
+      if (cand == 0) return;  // infeasible (never: all costs are finite)
+      // candfree: the candidate with the largest list position; else the smallest
+      int key = candfree ? ((is_c && row4col < 0) ? pos : -1) : (is_c ? -pos : -1000);
+      int best = key;
+      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+      const int j = __ffs(__ballot_sync(FULL, key == best && (candfree ? (is_c && row4col < 0) : is_c))) - 1;
+      minVal = lowest;
+      const int r4c = __shfl_sync(FULL, row4col, j);
+      const int idx = __shfl_sync(FULL, pos, j);
+      if (r4c < 0) sink = j;
+      else i = r4c;
+      if (lane == j) {
+        sc = true;
+        rem = false;
+      } else if (rem && pos == num - 1) {
+        pos = idx;
+      }
+      num--;
+      __syncwarp();
+    }
+    // dual updates
+    for (int q = 0; q < nr; q++) {
+      const int visited = s.sr[q], c4r = s.col4row[q];
+      if (visited && q != cur) {
+        const double sp = __shfl_sync(FULL, spc, c4r);
+        if (lane == 0) s.u[q] = __dadd_rn(s.u[q], __dsub_rn(minVal, sp));
+      }
+    }
+    if (lane == 0) s.u[cur] = __dadd_rn(s.u[cur], minVal);
+    if (sc) v = __dsub_rn(v, __dsub_rn(minVal, spc));
+    __syncwarp();
+    // augment along the path
+    int j = sink;
+    while (true) {
+      const int pi = __shfl_sync(FULL, path, j);
+      if (lane == j) row4col = pi;
+      const int prev = s.col4row[pi];
+      __syncwarp();
+      if (lane == 0) s.col4row[pi] = j;
+      __syncwarp();
+      j = prev;
+      if (pi == cur) break;
+    }
+  }
+}
+
+struct SeqShared {
+  double dist[CK][CM];
+  double cnorm[CM];
+  LsapScratch ls;
+  int map[CK];
+  int upd_k[CK], upd_g[CK], n_upd;   // centers[g] += emb[k]
+  int new_k[CK], new_g[CK], n_new;   // centers[g]  = emb[k]
+  int active[CM];
+  int initialized;
+  int error;
+};
+
+// mapped rows of a cost matrix held one column per lane: bit k set iff min_j C[k][j] != 1e10
+__device__ __forceinline__ unsigned mapped_rows(const double (&c)[CK], int K, int M, int lane) {
+  unsigned m = 0;
+#pragma unroll
+  for (int k = 0; k < CK; k++) {
+    if (k < K) {
+      const bool any = __any_sync(FULL, lane < M && c[k] != INVALID);
+      if (any) m |= 1u << k;
+    }
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(256)
+cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* __restrict__ emb, int B, int F, int K,
+                   double* __restrict__ centers, int* __restrict__ g_active, int* __restrict__ g_init,
+                   const float* __restrict__ prep, const double* __restrict__ prep_d, int32_t* __restrict__ map_out,
+                   float* __restrict__ permuted) {
+  __shared__ SeqShared sh;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int M = p.M, D = p.D;
+  if (tid < CM) sh.active[tid] = tid < M ? g_active[tid] : 0;
+  if (tid == 0) {
+    sh.initialized = *g_init;
+    sh.error = 0;
+  }
+  __syncthreads();
+
+  for (int ci = 0; ci < B; ci++) {
+    const float* e_chunk = emb + (size_t)ci * K * D;
+    const float* pr = prep + (size_t)ci * K * 3;
+    const bool init = sh.initialized != 0;
+    // ---------------- phase A: float64 cosine distances (scipy cdist 'cosine':
+    //                  1 - u.v / (|u| |v|), clipped to [-1, 1] before the subtraction)
+    if (init) {
+      for (int g = warp; g < M; g += 8) {
+        if (!sh.active[g]) continue;
+        const double* c = centers + (size_t)g * D;
+        double ss = 0.0;
+        for (int d = lane; d < D; d += 32) ss = fma(c[d], c[d], ss);
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
+        if (lane == 0) sh.cnorm[g] = sqrt(ss);
+      }
+      __syncthreads();
+      for (int item = warp; item < K * M; item += 8) {
+        const int k = item / M, g = item - k * M;
+        if (!sh.active[g]) continue;
+        const double* c = centers + (size_t)g * D;
+        const float* e = e_chunk + (size_t)k * D;
+        double dot = 0.0;
+        for (int d = lane; d < D; d += 32) dot = fma((double)e[d], c[d], dot);
+        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
+        if (lane == 0) {
+          double cosv = dot / (prep_d[(size_t)ci * K + k] * sh.cnorm[g]);
+          if (fabs(cosv) > 1.0) cosv = copysign(1.0, cosv);
+          sh.dist[k][g] = 1.0 - cosv;
+        }
+      }
+    }
+    __syncthreads();
+    // ---------------- phase B: assignment logic, warp 0, one global speaker per lane
+    if (warp == 0) {
+      unsigned active_spk = 0, long_spk = 0;
+      for (int k = 0; k < K; k++) {
+        // np.max(seg) >= tau, np.mean(seg) >= rho: float32 array vs Python float -> float32 compare
+        if (pr[k * 3 + 0] >= p.tau_f && pr[k * 3 + 2] == 0.f) active_spk |= 1u << k;   // clustering.py:137-145
+        if (pr[k * 3 + 1] >= p.rho_f) long_spk |= 1u << k;
+      }
+      int n_upd = 0, n_new = 0;
+      if (!init) {                                                                      // clustering.py:149-158
+        int next = 0;
+        for (int k = 0; k < K; k++) {
+          int g = -1;
+          if ((active_spk >> k) & 1u) {
+            g = next++;
+            if (lane == 0) {
+              sh.new_k[n_new] = k;
+              sh.new_g[n_new] = g;
+            }
+            n_new++;
+            if (lane == g) sh.active[g] = 1;
+          }
+          if (lane == 0) sh.map[k] = g;
+        }
+        if (lane == 0) sh.initialized = 1;
+      } else {
+        const bool act_c = lane < M && sh.active[lane];
+        const int n_active = __popc(__ballot_sync(FULL, act_c));
+        double dmap[CK], valid[CK];
+#pragma unroll
+        for (int k = 0; k < CK; k++) {                                                  // clustering.py:161-166
+          const bool live = k < K && ((active_spk >> k) & 1u) && act_c;
+          dmap[k] = live ? sh.dist[k < K ? k : 0][lane] : INVALID;
+          valid[k] = dmap[k];
+        }
+        // unmap_threshold (mapping.py:260-273)
+        lsap_warp(dmap, K, M, lane, sh.ls);
+        unsigned mapped = mapped_rows(dmap, K, M, lane);
+        bool dirty = false;
+        for (int k = 0; k < K; k++) {
+          if (!((mapped >> k) & 1u)) continue;
+          const int c = sh.ls.col4row[k];
+          const double cost = __shfl_sync(FULL, sel(dmap, k), c);
+          if (cost >= p.delta) {
+            put(valid, k, INVALID);
+            dirty = true;
+          }
+        }
+        unsigned vmapped = mapped_rows(valid, K, M, lane);
+        const unsigned missed = active_spk & ~vmapped;                                  // clustering.py:171-173
+        const int n_free = M - n_active;   // blocked_centers is always empty (clustering.py:46)
+        unsigned new_mask = 0;
+        for (int k = 0; k < K; k++) {                                                   // clustering.py:176-194
+          if (!((missed >> k) & 1u)) continue;
+          if (n_new < n_free && ((long_spk >> k) & 1u)) {
+            if (lane == 0) sh.new_k[n_new] = k;
+            n_new++;
+            new_mask |= 1u << k;
+          } else {
+            if (dirty) {
+              lsap_warp(valid, K, M, lane, sh.ls);
+              dirty = false;
+            }
+            vmapped = mapped_rows(valid, K, M, lane);
+            unsigned taken = 0;
+            for (int q = 0; q < K; q++)
+              if ((vmapped >> q) & 1u) taken |= 1u << sh.ls.col4row[q];
+            // closest active centre that is not already a target
+            const bool ok = act_c && !((taken >> lane) & 1u);
+            const double dk = ok ? sel(dmap, k) : INFINITY;
+            const double best = warp_min_d(dk);
+            const unsigned who = __ballot_sync(FULL, ok && dk == best);
+            if (who) {
+              const int g = __ffs(who) - 1;
+              if (lane == g) put(valid, k, 0.0);                                        // mapping.py:245-251
+              dirty = true;
+            }
+            __syncwarp();
+          }
+        }
+        if (dirty) {
+          lsap_warp(valid, K, M, lane, sh.ls);
+          dirty = false;
+        }
+        vmapped = mapped_rows(valid, K, M, lane);
+        for (int k = 0; k < K; k++) {                                                   // clustering.py:197-202
+          if (!((vmapped >> k) & 1u) || ((missed >> k) & 1u) || !((long_spk >> k) & 1u)) continue;
+          const int g = sh.ls.col4row[k];
+          if (!sh.active[g]) {
+            if (lane == 0) sh.error = 1;   // reference: AssertionError("Cannot update unknown centers")
+            continue;
+          }
+          if (lane == 0) {
+            sh.upd_k[n_upd] = k;
+            sh.upd_g[n_upd] = g;
+          }
+          n_upd++;
+        }
+        __syncwarp();
+        // new centres at the lowest free index (clustering.py:205-208, 68-71)
+        for (int q = 0; q < n_new; q++) {
+          const int k = sh.new_k[q];
+          const unsigned freeb = __ballot_sync(FULL, lane < M && !sh.active[lane]);
+          const int g = __ffs(freeb) - 1;
+          if (lane == g) {
+            sh.active[g] = 1;
+            put(valid, k, 0.0);
+          }
+          if (lane == 0) sh.new_g[q] = g;
+          dirty = true;
+          __syncwarp();
+        }
+        if (dirty) lsap_warp(valid, K, M, lane, sh.ls);
+        vmapped = mapped_rows(valid, K, M, lane);
+        if (lane < K) sh.map[lane] = ((vmapped >> lane) & 1u) ? sh.ls.col4row[lane] : -1;
+      }
+      if (lane == 0) {
+        sh.n_upd = n_upd;
+        sh.n_new = n_new;
+      }
+    }
+    __syncthreads();
+    // ---------------- phase C: centroid update / creation, outputs
+    for (int q = 0; q < sh.n_upd; q++) {
+      double* c = centers + (size_t)sh.upd_g[q] * D;
+      const float* e = e_chunk + (size_t)sh.upd_k[q] * D;
+      for (int d = tid; d < D; d += blockDim.x) c[d] += (double)e[d];
+    }
+    for (int q = 0; q < sh.n_new; q++) {
+      double* c = centers + (size_t)sh.new_g[q] * D;
+      const float* e = e_chunk + (size_t)sh.new_k[q] * D;
+      for (int d = tid; d < D; d += blockDim.x) c[d] = (double)e[d];
+    }
+    if (tid < K) map_out[(size_t)ci * K + tid] = sh.map[tid];
+    if (permuted) {                                                                     // mapping.py:341-360
+      float* o = permuted + (size_t)ci * F * M;
+      const float* s = seg + (size_t)ci * F * K;
+      for (int idx = tid; idx < F * M; idx += blockDim.x) o[idx] = 0.f;
+      __syncthreads();
+      for (int k = 0; k < K; k++) {
+        const int g = sh.map[k];
+        if (g < 0) continue;
+        for (int f = tid; f < F; f += blockDim.x) o[(size_t)f * M + g] = s[f * K + k];
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < M) g_active[tid] = sh.active[tid];
+  if (tid == 0) {
+    *g_init = sh.initialized;
+    if (sh.error) g_init[1] = 1;
+  }
+}
+
+int launch_cluster_step(const ClusterParams& p, const float* seg, const float* emb, int B, int F, int K,
+                        double* centers, int* active, int* initialized, float* prep, double* prep_d, int32_t* map,
+                        float* permuted, cudaStream_t st) {
+  if (K > CK || p.M > CM || K > p.M) {
+    set_error("cluster_step: need local speakers <= 8, max_speakers <= 32 and local <= max");
+    return -1;
+  }
+  if (B <= 0) return 0;
+  cluster_prep_kernel<<<B, 128, 0, st>>>(seg, emb, F, K, p.D, prep, prep_d);
+  DG_LAUNCHED();
+  cluster_seq_kernel<<<1, 256, 0, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map,
+                                        permuted);
+  DG_LAUNCHED();
+  return 0;
+}
+
+}  // namespace dg

@@ -1,0 +1,125 @@
+// Shared declarations for the diart_b200 CUDA translation units (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+namespace dg {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const std::string& msg);
+extern std::atomic<long long> g_launches;
+
+#define DG_CUDA(expr)                                                                   \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      dg::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+// every kernel launch goes through this so bench.py can report `gpu_launches`
+#define DG_LAUNCHED()                                                                   \
+  do {                                                                                  \
+    dg::g_launches.fetch_add(1, std::memory_order_relaxed);                             \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess) {                                                            \
+      dg::set_error(std::string("kernel launch failed at ") + __FILE__ + ":" +          \
+                    std::to_string(__LINE__) + ": " + cudaGetErrorString(_e));          \
+      return -2;                                                                        \
+    }                                                                                   \
+  } while (0)
+
+// ------------------------------------------------------------------ geometry of the path
+// 80000 samples -> sinc(k251,s10) 7975 -> pool3 2658 -> k5 2654 -> pool3 884 -> k5 880 -> pool3 293.
+// Activations are stored time-major / channels-last, [item][row][channel], with a fixed row
+// stride per item that is divisible by 9 so that the two pool-by-3 stages keep rows aligned:
+// a conv layer is then a pure shifted-window GEMM over the flattened [B*stride, C] matrix and
+// rows past an item's valid length are harmless finite garbage that no consumer reads.
+struct Geom {
+  int S;        // samples per chunk
+  int T0c;      // sinc conv outputs              (7975)
+  int T0;       // after pool                      (2658)
+  int T1;       // conv1+pool valid                (884)
+  int T2;       // conv2+pool valid = frames       (293)
+  int S0, S1, S2;  // row strides per item         (2664, 888, 296)
+};
+inline Geom make_geom(int S) {
+  Geom g;
+  g.S = S;
+  g.T0c = (S - 251) / 10 + 1;
+  g.T0 = g.T0c / 3;
+  g.T1 = (g.T0 - 4) / 3;
+  g.T2 = (g.T1 - 4) / 3;
+  g.S2 = g.T2 + 3;                      // >= T2, room for pool alignment
+  while ((g.S2 * 9) < g.T0 + 0 || (g.S2 * 3) < g.T1) g.S2++;
+  g.S1 = g.S2 * 3;
+  g.S0 = g.S1 * 3;
+  return g;
+}
+
+__device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x; }
+
+// ------------------------------------------------------------------ launchers (defined per .cu)
+// sincnet.cu
+int launch_wave_stats(const float* wav, int B, int S, float* mean, float* rstd, cudaStream_t st);
+int launch_sinc0(const float* wav, const float* mean, const float* rstd, float wn_gamma, float wn_beta,
+                 const float* filt /*[251][80]*/, int B, const Geom& g, float* p0 /*[B,S0,80]*/, cudaStream_t st);
+int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
+                          const float* beta, float* sc, float* sh, cudaStream_t st);
+// gemm.cu
+enum Epi { EPI_BIAS = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_LEAKY_BN = 2, EPI_BIAS_POOL3 = 3 };
+struct GemmArgs {
+  const float* A;      // [Mrows_in, lda]
+  int lda;             // channel stride of A (>= Cin)
+  int Cin;             // channels consumed per tap (multiple of 4)
+  int KW, dil;         // taps, dilation (rows)
+  long long Mtot;      // rows of A that exist (reads past it return 0)
+  long long M;         // output rows to produce (before pooling)
+  const float* W;      // [KW*Cin, ldw]
+  int ldw;             // column stride of W (>= N, multiple of 4)
+  int N;               // valid output channels
+  const float* bias;   // [N] or null
+  const float* bn_scale;  // [N] (EPI_BIAS_LEAKY_BN)
+  const float* bn_shift;
+  const float* in_sc;  // per-(item, channel) instance-norm scale/shift applied (+leaky) on load, or null
+  const float* in_sh;
+  int item_rows;       // rows per item (for in_sc indexing)
+  float* C;            // [M or M/3, ldc]
+  int ldc;
+  int epi;
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t st);
+// lstm.cu
+int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_packed, int B, int T, int stride,
+                      float* hout /*[B*stride,256]*/, cudaStream_t st);
+size_t lstm_whh_packed_floats();
+void lstm_pack_whh(const float* whh_fwd /*[512][128]*/, const float* whh_bwd, float* packed);
+// heads.cu
+int launch_seg_final(const float* y /*[B*stride,128]*/, const float* wc /*[K][128]*/, const float* bc, int B, int T,
+                     int stride, int K, float* seg /*[B,T,K]*/, cudaStream_t st);
+int launch_osp(const float* seg, int B, int F, int K, float gamma, float beta, int normalize, float* out,
+               cudaStream_t st);
+int launch_stats_pool(const float* x /*[B*stride,C]*/, int B, int stride, int T, int C, const float* w /*[B,F,K]*/,
+                      int F, int K, const int* idx0, const int* idx1, const float* lam1, float eps,
+                      float* pooled /*[B*K, 2C]*/, cudaStream_t st);
+int launch_l2norm(const float* in, int rows, int D, float norm, float* out, cudaStream_t st);
+int launch_row_equal_flags(const float* wav, int N, int S, int* flags, cudaStream_t st);
+int launch_gather_rows(const float* src, const int* index, int rows, int cols, float* dst, cudaStream_t st);
+// cluster.cu
+struct ClusterParams {
+  int M, D;
+  float tau_f, rho_f;   // thresholds as numpy compares them (float32, see cluster.cu)
+  double delta;
+};
+int launch_cluster_step(const ClusterParams& p, const float* seg, const float* emb, int B, int F, int K,
+                        double* centers, int* active, int* initialized, float* prep /*scratch*/,
+                        double* prep_d /*scratch*/, int32_t* map, float* permuted, cudaStream_t st);
+size_t cluster_prep_floats(int B, int K);
+size_t cluster_prep_doubles(int B, int K);
+
+}  // namespace dg

@@ -1,0 +1,133 @@
+/*
+ * diart_b200 -- C ABI of the B200-native diart hot path (libdiartb200.so, sm_100a).
+ *
+ * This is the drop-in boundary.  The reference is pure Python and has
+ * no FFI of its own; each entry point below names the reference interface it replaces and is
+ * what a ctypes/cffi binding of that interface would call.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative DG_E* code on failure; the message is
+ *     available from dg_last_error() (thread-local).
+ *   - pointers documented "dev" are device pointers on the handle's device; "host" are host
+ *     pointers.  Device entry points are stream-ordered on `stream` (a cudaStream_t passed as
+ *     void*, NULL = legacy default stream) and never synchronise, except where noted.
+ *   - a handle is not thread-safe; distinct handles are independent.  This matches the
+ *     reference, where a pipeline instance is only ever driven by one thread
+ *     (reference src/diart/inference.py:230).
+ *   - tensors are dense, row-major, float32 unless stated otherwise.
+ */
+#ifndef DIART_B200_H
+#define DIART_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DG_OK 0
+#define DG_EINVAL (-1)   /* bad argument / shape (the reference raises AssertionError / ValueError) */
+#define DG_ECUDA (-2)    /* CUDA runtime error */
+#define DG_EWEIGHT (-3)  /* missing / mis-shaped tensor in the state dict */
+#define DG_ENCCL (-4)
+
+/* One named float32 tensor of a pyannote state_dict (host memory), e.g.
+ * {"sincnet.conv1d.1.weight", ptr, 24000}.  Key names follow pyannote.audio's PyanNet /
+ * XVectorSincNet modules -- what reference src/diart/models.py:50 loads. */
+typedef struct dg_tensor {
+  const char* name;
+  const float* data;
+  int64_t numel;
+} dg_tensor;
+
+typedef struct dg_seg dg_seg;
+typedef struct dg_emb dg_emb;
+typedef struct dg_cluster dg_cluster;
+typedef struct dg_pipeline dg_pipeline;
+
+const char* dg_last_error(void);
+int dg_version(void);
+
+/* ---- segmentation model: replaces the callable behind SegmentationModel.__call__
+ *      (reference src/diart/models.py:188-198; call site src/diart/blocks/segmentation.py:47):
+ *      waveform (B,1,S) -> (B,F,K) sigmoid scores. ---- */
+int dg_seg_create(const dg_tensor* tensors, int n_tensors, int device, dg_seg** out);
+/* frames / local speakers produced for `num_samples`-sample chunks (293 / 3 for 80000) */
+int dg_seg_dims(const dg_seg* h, int num_samples, int* frames, int* speakers);
+int dg_seg_forward(dg_seg* h, const float* wav_dev /*[B,S]*/, int B, int S,
+                   float* seg_dev /*[B,F,K]*/, void* stream);
+int dg_seg_destroy(dg_seg* h);
+
+/* ---- embedding model: replaces the callable behind EmbeddingModel.__call__
+ *      (reference src/diart/models.py:248-265; call site src/diart/blocks/embedding.py:60-67).
+ *      pool_mode: 31 = pyannote.audio 3.1 StatsPool (nearest resize, +1e-8), 21 = 2.1 (linear). ---- */
+int dg_emb_create(const dg_tensor* tensors, int n_tensors, int pool_mode, int device, dg_emb** out);
+int dg_emb_dims(const dg_emb* h, int num_samples, int* frames, int* dimension);
+/* Fused form: one trunk pass per waveform, K weighted poolings.
+ * weights_dev [B,F,K] (the layout OverlappedSpeechPenalty returns) or NULL (unweighted, K must be 1).
+ * If normalize != 0 rows are L2-normalised to `norm` (EmbeddingNormalization,
+ * reference src/diart/blocks/embedding.py:110-120).  out_dev [B,K,D]. */
+int dg_emb_forward(dg_emb* h, const float* wav_dev /*[B,S]*/, const float* weights_dev, int B, int S,
+                   int F, int K, int normalize, float norm, float* out_dev, void* stream);
+/* Compatibility form, exactly the arguments the reference block passes
+ * (src/diart/blocks/embedding.py:57-65): waveform rows already repeated K times, weights (N,F).
+ * Consecutive identical waveform rows are detected on the device and share one trunk pass.
+ * Performs one small D2H read (row-group flags), i.e. synchronises `stream`. */
+int dg_emb_forward_rows(dg_emb* h, const float* wav_dev /*[N,S]*/, const float* weights_dev /*[N,F] or NULL*/,
+                        int N, int S, int F, float* out_dev /*[N,D]*/, void* stream);
+int dg_emb_destroy(dg_emb* h);
+
+/* ---- element-wise blocks ---- */
+/* OverlappedSpeechPenalty (reference src/diart/blocks/embedding.py:98-107, functional.py:6-13) */
+int dg_osp(const float* seg_dev /*[B,F,K]*/, int B, int F, int K, float gamma, float beta,
+           int normalize, float* out_dev, void* stream);
+/* EmbeddingNormalization (reference src/diart/functional.py:16-27): out = norm * e / ||e||_2 */
+int dg_normalize_embeddings(const float* emb_dev /*[rows,D]*/, int rows, int D, float norm,
+                            float* out_dev, void* stream);
+
+/* ---- OnlineSpeakerClustering (reference src/diart/blocks/clustering.py:31-218 and the
+ *      SpeakerMap logic of src/diart/mapping.py:179-360).  State (centroids, float64) lives on
+ *      the device. ---- */
+int dg_cluster_create(int max_speakers, int dim, double tau_active, double rho_update,
+                      double delta_new, int device, dg_cluster** out);
+/* Processes the B chunks in order (the reference's sequential loop, diarization.py:193-203).
+ * map_dev  int32 [B,K]: global speaker of each local speaker, -1 if unmapped.
+ * permuted_dev float32 [B,F,M] or NULL: SpeakerMap.apply output (values are float32-exact). */
+int dg_cluster_step(dg_cluster* h, const float* seg_dev /*[B,F,K]*/, const float* emb_dev /*[B,K,D]*/,
+                    int B, int F, int K, int32_t* map_dev, float* permuted_dev, void* stream);
+int dg_cluster_reset(dg_cluster* h);
+/* synchronous host copies of the state: centers [M,D] float64, active [M] int32 (0/1);
+ * *initialized = 0 until the first chunk was seen (reference `centers is None`). */
+int dg_cluster_get_state(dg_cluster* h, double* centers_host, int32_t* active_host, int* initialized);
+int dg_cluster_set_state(dg_cluster* h, const double* centers_host, const int32_t* active_host, int initialized);
+int dg_cluster_destroy(dg_cluster* h);
+
+/* ---- fused pipeline step: SpeakerDiarization.__call__ lines 177-203
+ *      (reference src/diart/blocks/diarization.py): segmentation -> OSP -> embedding ->
+ *      normalisation -> clustering, no host round trips.  The pipeline borrows the three handles. ---- */
+int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
+                       int normalize_weights, dg_pipeline** out);
+int dg_pipeline_step(dg_pipeline* h, const float* wav_dev /*[B,S]*/, int B, int S,
+                     float* seg_dev /*[B,F,K]*/, float* emb_dev /*[B,K,D]*/,
+                     int32_t* map_dev /*[B,K]*/, float* permuted_dev /*[B,F,M] or NULL*/, void* stream);
+/* Same with HOST buffers: H2D of the waveforms and D2H of the results inside the call
+ * (pinned staging owned by the handle); synchronous. */
+int dg_pipeline_step_host(dg_pipeline* h, const float* wav_host, int B, int S, float* seg_host,
+                          float* emb_host, int32_t* map_host, float* permuted_host /*nullable*/);
+int dg_pipeline_destroy(dg_pipeline* h);
+
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+int64_t dg_launch_count(void);
+
+/* ---- shared-identity mode (extension): merge per-rank centroid deltas that were
+ *      all-gathered by the host (NCCL) -- see dg_cluster_export_delta / dg_cluster_merge in
+ *      INTEGRATION.md. ---- */
+int dg_cluster_export_delta(dg_cluster* h, double* delta_dev /*[M*D + 2*M + 2] f64 record*/, void* stream);
+int dg_cluster_merge(dg_cluster* h, const double* records_dev /*[world, record]*/, int world, void* stream);
+int dg_cluster_record_len(const dg_cluster* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIART_B200_H */

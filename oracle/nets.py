@@ -217,90 +217,44 @@ class XVectorSincNet(nn.Module):
 
 
 # --------------------------------------------------------------------------------------
-# Seeded synthetic weights: no checkpoints exist offline.
+# Seeded synthetic weights / audio: generated by diart_b200.synth so
+# that the oracle and the CUDA side are fed the very same state dicts.
 # --------------------------------------------------------------------------------------
 
 def n_params(module: nn.Module) -> int:
     return sum(p.numel() for p in module.parameters())
 
 
-def make_segmentation(seed: int = 4321, num_speakers: int = 3) -> PyanNet:
-    """PyTorch-default init under ``seed``; classifier rescaled so the sigmoid outputs
-    straddle tau_active instead of idling at 0.5 (otherwise clustering branches never fire)."""
-    g = torch.Generator().manual_seed(seed)
-    torch.manual_seed(seed)
-    net = PyanNet(num_speakers=num_speakers)
-    with torch.no_grad():
-        for p in net.sincnet.norm1d.parameters():
-            p.add_(0.1 * torch.randn(p.shape, generator=g))
-        net.sincnet.wav_norm1d.weight.fill_(1.25)
-        net.sincnet.wav_norm1d.bias.fill_(0.05)
-        net.classifier.weight.mul_(60.0)
-        net.classifier.bias.copy_(torch.tensor([0.3, -0.2, 0.1, -0.4][:num_speakers]))
+def _load(net: nn.Module, state) -> nn.Module:
+    own = net.state_dict()
+    merged = {k: state.get(k, v) for k, v in own.items()}   # buffers (window_, n_) keep their own values
+    net.load_state_dict(merged)
     return net.eval()
 
 
-def make_embedding(seed: int = 8765, pool_mode: str = "3.1") -> XVectorSincNet:
-    g = torch.Generator().manual_seed(seed)
-    torch.manual_seed(seed)
-    net = XVectorSincNet(pool_mode=pool_mode)
-    with torch.no_grad():
-        for p in net.sincnet.norm1d.parameters():
-            p.add_(0.1 * torch.randn(p.shape, generator=g))
-        net.sincnet.wav_norm1d.weight.fill_(0.8)
-        net.sincnet.wav_norm1d.bias.fill_(-0.02)
-        for m in net.tdnns:
-            if isinstance(m, nn.BatchNorm1d):
-                m.running_mean.copy_(0.1 * torch.randn(m.running_mean.shape, generator=g))
-                m.running_var.copy_(0.5 + torch.rand(m.running_var.shape, generator=g))
-                m.weight.copy_(1.0 + 0.2 * torch.randn(m.weight.shape, generator=g))
-                m.bias.copy_(0.1 * torch.randn(m.bias.shape, generator=g))
-    return net.eval()
+def make_segmentation(seed: int = 4321, num_speakers: int = 3, calibrated: bool = True) -> PyanNet:
+    from diart_b200 import synth
+    return _load(PyanNet(num_speakers=num_speakers), synth.segmentation_state(seed, num_speakers, calibrated))
 
 
-def synth_audio(num_samples: int, seed: int = 1234, sample_rate: int = 16000, num_speakers: int = 4) -> np.ndarray:
-    """Mono float32 stream in [-1,1]: harmonic 'speakers' with formant-like envelopes gated by a
-    seeded two-state turn-taking chain with some overlap, plus -40 dB white noise."""
-    rng = np.random.default_rng(seed)
-    t = np.arange(num_samples, dtype=np.float64) / sample_rate
-    out = np.zeros(num_samples, dtype=np.float64)
-    seg_len = int(0.25 * sample_rate)
-    n_seg = num_samples // seg_len + 1
-    for s in range(num_speakers):
-        f0 = rng.uniform(90, 250)
-        formants = rng.uniform([300, 900, 2200], [800, 2200, 3400])
-        vib = 1.0 + 0.02 * np.sin(2 * np.pi * rng.uniform(3, 6) * t + rng.uniform(0, 6.28))
-        phase = 2 * np.pi * np.cumsum(f0 * vib) / sample_rate
-        voice = np.zeros(num_samples)
-        for h in range(1, 30):
-            fh = f0 * h
-            if fh > 3800:
-                break
-            amp = sum(np.exp(-0.5 * ((fh - fc) / 180.0) ** 2) for fc in formants) + 0.02
-            voice += amp / h ** 0.5 * np.sin(h * phase + rng.uniform(0, 6.28))
-        voice /= np.max(np.abs(voice)) + 1e-9
-        state, gate = rng.random() < 0.4, np.zeros(n_seg)
-        for i in range(n_seg):
-            if rng.random() < (0.25 if state else 0.12):
-                state = not state
-            gate[i] = 1.0 if state else 0.0
-        g = np.repeat(gate, seg_len)[:num_samples]
-        k = np.hanning(int(0.05 * sample_rate))
-        g = np.convolve(g, k / k.sum(), mode="same")
-        out += rng.uniform(0.25, 0.5) * g * voice
-    out += 10 ** (-40 / 20) * rng.standard_normal(num_samples)
-    out = np.clip(out, -1, 1)
-    return out.astype(np.float32)
+def make_embedding(seed: int = 8765, pool_mode: str = "3.1", calibrated: bool = True) -> XVectorSincNet:
+    from diart_b200 import synth
+    return _load(XVectorSincNet(pool_mode=pool_mode), synth.embedding_state(seed, 512, calibrated))
 
 
-def windows(stream: np.ndarray, n_chunks: int, chunk: int = 80000, step: int = 8000) -> np.ndarray:
-    """Chunk i = samples [step*i, step*i + chunk), exactly as ``rearrange_audio_stream``
-    (reference ``src/diart/operators.py:44-100``) emits them."""
-    idx = np.arange(chunk)[None, :] + step * np.arange(n_chunks)[:, None]
-    return stream[idx]
+def synth_audio(*args, **kwargs):
+    from diart_b200 import synth
+    return synth.synth_audio(*args, **kwargs)
+
+
+def windows(*args, **kwargs):
+    from diart_b200 import synth
+    return synth.windows(*args, **kwargs)
 
 
 if __name__ == "__main__":
+    import os, sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     seg, emb = make_segmentation(), make_embedding()
     print("PyanNet params", n_params(seg), "XVectorSincNet params", n_params(emb))
     x = torch.from_numpy(windows(synth_audio(80000 + 8000 * 3), 4))[:, None, :]
