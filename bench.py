@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of diart's per-chunk hot path on B200 ("Measurement").
+
+    python bench.py --gpus 1 --steps 10 --warmup 3                      # this repo's CUDA path
+    python bench.py --impl reference --gpus 1 --steps 3 --warmup 1      # the CPU path (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+           --master-port P bench.py --gpus N --steps K --warmup W       # N independent streams, 1/GPU
+
+Metric (BASELINE.json): stream audio-seconds per second = chunks/s x 0.5 s, 5 s windows @ 16 kHz,
+0.5 s step, batch 256.  A step is one pass of the fused pipeline (segmentation -> OSP -> embedding ->
+normalisation -> clustering, reference blocks/diarization.py:177-203) over one batch of 256 windows.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CHUNK, STEP, SR = 80000, 8000, 16000
+STEP_SECONDS = STEP / SR
+METRIC = "audio-seconds/sec (real-time factor) at 5s/0.5s step, batch 256"
+UNIT = "stream audio-seconds per second"
+WORKLOAD = ("configs[2]: full SpeakerDiarization hot path incl. OnlineSpeakerClustering, batch=256 windows of "
+            "5 s @ 16 kHz (0.5 s step) of one synthetic stream per GPU, max_speakers=20, pyannote/segmentation + "
+            "pyannote/embedding architectures with seeded random-init weights")
+
+# algorithmic FLOPs per chunk of every dense kernel; a launch processes B chunks
+FLOPS_PER_CHUNK = {
+    "sinc0": 2 * 251 * 80 * 7975,
+    "sinc_conv1": 2 * 400 * 60 * 2654,
+    "sinc_conv2": 2 * 300 * 60 * 880,
+    "lstm_inproj": 2 * 1024 * 293 * (60 + 3 * 256) / 4,      # mean over the 4 layers (one launch each)
+    "lstm_rec": 2 * 128 * 512 * 2 * 293,
+    "seg_linear": 2 * 293 * (256 * 128 + 128 * 128) / 2,
+    "tdnn1": 2 * 300 * 512 * 289,
+    "tdnn2": 2 * 1536 * 512 * 285,
+    "tdnn3": 2 * 1536 * 512 * 279,
+    "tdnn4": 2 * 512 * 512 * 279,
+    "tdnn5": 2 * 512 * 1500 * 279,
+    "emb_linear": 2 * 3000 * 512 * 3,
+}
+# compulsory HBM bytes per chunk of the whole step: waveform in, seg + emb out
+BYTES_PER_CHUNK = 80000 * 4 + 293 * 3 * 4 + 3 * 512 * 4
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_stream_batches(rank: int, n_batches: int, batch: int) -> np.ndarray:
+    from diart_b200 import synth
+
+    n_chunks = n_batches * batch
+    stream = synth.synth_audio(CHUNK + STEP * (n_chunks - 1), seed=1234 + rank)
+    return np.stack([synth.windows(stream, batch, first=j * batch) for j in range(n_batches)])
+
+
+# ------------------------------------------------------------------------------------ reference arm
+def run_reference(args):
+    """The reference's CPU path (oracle port: reference diart block logic restated in oracle/, torch-CPU
+    restatement of the pyannote networks), all host threads, same workload in bounded samples."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import nets
+    from oracle.pipeline import OraclePipeline
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pipe = OraclePipeline(nets.make_segmentation(), nets.make_embedding(), as_reference=True)
+    rb = args.ref_batch
+    data = torch.from_numpy(make_stream_batches(0, 1, max(rb, 64))[0])
+    nb = data.shape[0] // rb
+    for i in range(args.warmup):
+        pipe(data[(i % nb) * rb:(i % nb + 1) * rb])
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        pipe(data[(i % nb) * rb:(i % nb + 1) * rb])
+    dt = time.perf_counter() - t0
+    value = args.steps * rb * STEP_SECONDS / dt
+    sample = f"{args.steps} steps x {rb} consecutive windows (of the batch-256 workload), K-fold repeated trunk as the reference runs it"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample_batch": rb},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(budget_s: float = 12.0, rb: int = 64):
+    from oracle import nets
+    from oracle.pipeline import OraclePipeline
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    pipe = OraclePipeline(nets.make_segmentation(), nets.make_embedding(), as_reference=True)
+    data = torch.from_numpy(make_stream_batches(0, 1, 2 * rb)[0])
+    pipe(data[:rb])                                  # warm-up
+    n, t0 = 0, time.perf_counter()
+    while n < 2 or time.perf_counter() - t0 < budget_s:
+        pipe(data[(n % 2) * rb:(n % 2 + 1) * rb])
+        n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * rb * STEP_SECONDS / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} batches x {rb} consecutive windows of the same stream, oracle pipeline (K-fold repeated "
+                      f"trunk as the reference runs it), torch CPU float32, {dt:.1f} s"}
+
+
+# ------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    from diart_b200 import _lib, blocks, models, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the diart_b200 path has no CPU fallback")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+    lib = _lib.lib()
+    B = args.batch
+    config = blocks.SpeakerDiarizationConfig(
+        segmentation=models.SegmentationModel(models.B200SegmentationLoader(synth.segmentation_state())),
+        embedding=models.EmbeddingModel(models.B200EmbeddingLoader(synth.embedding_state())),
+        device=device)
+    pipe = blocks.SpeakerDiarization(config)
+    NB = 4                                                  # 4 x 82 MB of distinct inputs > 126 MB L2
+    host = make_stream_batches(rank, NB, B)
+    dev = [torch.from_numpy(host[j]).to(device) for j in range(NB)]
+    pinned = [torch.from_numpy(host[j]).pin_memory() for j in range(NB)]
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+
+    # ---------------- device-resident throughput (`value`) with per-kernel CUDA-event timing
+    for i in range(args.warmup):
+        pipe.device_step(dev[i % NB])
+    barrier()
+    lib.dg_profile_enable(1)
+    launches0 = lib.dg_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record()
+        for i in range(args.steps):
+            pipe.device_step(dev[i % NB])
+        ev1.record()
+        torch.cuda.synchronize(device)
+    ms = ev0.elapsed_time(ev1)
+    launches = lib.dg_launch_count() - launches0
+    buf = C.create_string_buffer(1 << 16)
+    lib.dg_profile_report(buf, len(buf))
+    lib.dg_profile_enable(0)
+    kernels = json.loads(buf.value.decode())
+    t = torch.tensor([ms], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * B * STEP_SECONDS / (ms_max / 1e3)
+
+    # ---------------- end to end through the C ABI with HOST buffers (H2D + D2H inside the call)
+    F, K = pipe.segmentation.model.model.dims(CHUNK)
+    _, D = pipe.embedding.embedding.native.dims(CHUNK)
+    seg_h = torch.empty((B, F, K)).pin_memory()
+    emb_h = torch.empty((B, K, D)).pin_memory()
+    map_h = torch.empty((B, K), dtype=torch.int32).pin_memory()
+    fused = pipe._fused
+
+    def host_step(i):
+        _lib.check(lib.dg_pipeline_step_host(fused, pinned[i % NB].data_ptr(), B, CHUNK, seg_h.data_ptr(),
+                                             emb_h.data_ptr(), map_h.data_ptr(), None))
+
+    for i in range(max(1, args.warmup)):
+        host_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        host_step(i)
+    torch.cuda.synchronize(device)
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * args.steps * B * STEP_SECONDS / float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    # ---------------- roofline of the dominant kernel
+    pk = peaks()
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])
+    per_launch_ms = kernels[dom]["ms"] / kernels[dom]["count"]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(dom)
+    if dom in FLOPS_PER_CHUNK:
+        achieved = FLOPS_PER_CHUNK[dom] * B / (per_launch_ms * 1e-3) / 1e12
+        roofline = {"kernel": dom, "bound": "tensor", "achieved": achieved, "peak": pk["tf"], "unit": "TFLOP/s",
+                    "frac": achieved / pk["tf"], "traffic": traffic, "peak_source": pk["src"] + " (bf16 sustained)",
+                    "ms_per_launch": per_launch_ms}
+    else:
+        achieved = BYTES_PER_CHUNK * B / (per_launch_ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                    "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["src"],
+                    "ms_per_launch": per_launch_ms}
+    step_flops = sum(FLOPS_PER_CHUNK[k] * (4 if k == "lstm_inproj" or k == "lstm_rec" else 2 if k in
+                     ("sinc0", "sinc_conv1", "sinc_conv2", "seg_linear") else 1) for k in FLOPS_PER_CHUNK) * B
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "batch": B, "streams": world, "parallelism": f"{world} independent streams, "
+                   "1 per GPU, no collectives", "l2": "inputs rotate over 4 distinct 82 MB batches (> 126 MB L2)"},
+        "chunks_per_s": value / STEP_SECONDS,
+        "step_tflops": step_flops / (ms_max / args.steps * 1e-3) / 1e12,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CHUNK * 4,
+                "d2h_bytes_per_step": B * F * K * 4 + B * K * D * 4 + B * K * 4,
+                "api": "dg_pipeline_step_host (C ABI, pinned host buffers)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roofline,
+        "kernels_ms_per_step": {k: round(v["ms"] / args.steps, 4) for k, v in sorted(kernels.items(),
+                                                                                     key=lambda kv: -kv[1]["ms"])},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline()
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--ref-batch", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -28,6 +28,8 @@ SIGNATURES = {
     "dg_last_error": (C.c_char_p, []),
     "dg_version": (C.c_int, []),
     "dg_launch_count": (C.c_int64, []),
+    "dg_profile_enable": (C.c_int, [C.c_int]),
+    "dg_profile_report": (C.c_int, [C.c_char_p, C.c_int]),
     "dg_seg_create": (C.c_int, [C.POINTER(DgTensor), C.c_int, C.c_int, C.POINTER(_P)]),
     "dg_seg_dims": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dg_seg_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

@@ -5,6 +5,7 @@
 
 #include <map>
 #include <memory>
+#include <sstream>
 #include <vector>
 
 #include "../../include/diart_b200.h"
@@ -15,6 +16,24 @@ namespace dg {
 static thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
 void set_error(const std::string& msg) { g_err = msg; }
+
+struct ProfRec {
+  std::string name;
+  cudaEvent_t a, b;
+};
+static bool g_prof = false;
+static std::vector<ProfRec> g_recs;
+ProfScope::ProfScope(const char* name_, cudaStream_t st_) : on(g_prof), st(st_), a(nullptr), b(nullptr), name(name_) {
+  if (!on) return;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  cudaEventRecord(a, st);
+}
+ProfScope::~ProfScope() {
+  if (!on) return;
+  cudaEventRecord(b, st);
+  g_recs.push_back({name, a, b});
+}
 
 int launch_stats_pool_ex(const float* x, int stride, int T, int C, const float* w, int F, int K, int layout,
                          int n_groups, const int* grp_item, const int* grp_q0, const int* grp_nq, const int* idx0,
@@ -176,7 +195,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
   a.Mtot = (long long)B * g.S0; a.M = (long long)B * g.S0;
   a.W = w.w1.as<float>(); a.ldw = 64; a.N = 64; a.bias = w.bias1.as<float>();
   a.in_sc = k.sc0.as<float>(); a.in_sh = k.sh0.as<float>(); a.item_rows = g.S0;
-  a.C = k.p1.as<float>(); a.ldc = 64; a.epi = EPI_BIAS_POOL3;
+  a.C = k.p1.as<float>(); a.ldc = 64; a.epi = EPI_BIAS_POOL3; a.tag = "sinc_conv1";
   if ((rc = launch_gemm(a, st))) return rc;
   if ((rc = launch_instnorm_stats(k.p1.as<float>(), B, g.S1, g.T1, 64, 64, w.g1.as<float>(), w.b1.as<float>(),
                                   k.sc1.as<float>(), k.sh1.as<float>(), st)))
@@ -185,7 +204,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
   a.Mtot = (long long)B * g.S1; a.M = (long long)B * g.S1;
   a.W = w.w2.as<float>(); a.bias = w.bias2.as<float>();
   a.in_sc = k.sc1.as<float>(); a.in_sh = k.sh1.as<float>(); a.item_rows = g.S1;
-  a.C = k.p2.as<float>();
+  a.C = k.p2.as<float>(); a.tag = "sinc_conv2";
   if ((rc = launch_gemm(a, st))) return rc;
   return launch_instnorm_stats(k.p2.as<float>(), B, g.S2, g.T2, 64, 64, w.g2.as<float>(), w.b2.as<float>(),
                                k.sc2.as<float>(), k.sh2.as<float>(), st);
@@ -256,6 +275,44 @@ extern "C" const char* dg_last_error(void) { return g_err.c_str(); }
 extern "C" int dg_version(void) { return 100; }
 extern "C" int64_t dg_launch_count(void) { return (int64_t)g_launches.load(); }
 
+extern "C" int dg_profile_enable(int enable) {
+  g_prof = enable != 0;
+  return DG_OK;
+}
+
+// JSON {"name": {"count": n, "ms": total}, ...} of everything recorded since the last report.
+// Synchronises the device.  Returns the number of bytes written (excluding the terminator).
+extern "C" int dg_profile_report(char* buf, int cap) {
+  cudaDeviceSynchronize();
+  std::map<std::string, std::pair<int, double>> agg;
+  for (auto& r : g_recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    auto& e = agg[r.name];
+    e.first++;
+    e.second += ms;
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_recs.clear();
+  std::ostringstream os;
+  os << "{";
+  bool first = true;
+  for (auto& kv : agg) {
+    if (!first) os << ", ";
+    first = false;
+    os << "\"" << kv.first << "\": {\"count\": " << kv.second.first << ", \"ms\": " << kv.second.second << "}";
+  }
+  os << "}";
+  const std::string s = os.str();
+  if (!buf || cap <= (int)s.size()) {
+    set_error("dg_profile_report: buffer too small");
+    return DG_EINVAL;
+  }
+  memcpy(buf, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
 extern "C" int dg_seg_create(const dg_tensor* tensors, int n, int device, dg_seg** out) {
   if (!tensors || !out) {
     set_error("dg_seg_create: null argument");
@@ -309,7 +366,7 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
     }
     a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;
     a.W = h->wih[L].as<float>(); a.ldw = 1024; a.N = 1024; a.bias = h->bih[L].as<float>();
-    a.C = h->gx.as<float>(); a.ldc = 1024; a.epi = EPI_BIAS;
+    a.C = h->gx.as<float>(); a.ldc = 1024; a.epi = EPI_BIAS; a.tag = "lstm_inproj";
     if ((rc = launch_gemm(a, st))) return rc;
     float* hout = hbuf[L & 1];
     if ((rc = launch_lstm_layer(h->gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st))) return rc;
@@ -318,7 +375,7 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
   GemmArgs a{};
   a.A = hin; a.lda = 256; a.Cin = 256; a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;
   a.W = h->l1w.as<float>(); a.ldw = 128; a.N = 128; a.bias = h->l1b.as<float>();
-  a.C = h->y1.as<float>(); a.ldc = 128; a.epi = EPI_BIAS_LEAKY;
+  a.C = h->y1.as<float>(); a.ldc = 128; a.epi = EPI_BIAS_LEAKY; a.tag = "seg_linear";
   if ((rc = launch_gemm(a, st))) return rc;
   a.A = h->y1.as<float>(); a.lda = 128; a.Cin = 128;
   a.W = h->l2w.as<float>(); a.bias = h->l2b.as<float>(); a.C = h->y2.as<float>();
@@ -473,6 +530,8 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
     }
     float* out = L == 4 ? h->t5.as<float>() : bufs[L & 1];
     a.C = out; a.ldc = TD_OUT[L]; a.epi = EPI_BIAS_LEAKY_BN;
+    static const char* kTags[5] = {"tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5"};
+    a.tag = kTags[L];
     if ((rc = launch_gemm(a, st))) return rc;
     in = out;
     cin = TD_OUT[L];
@@ -486,7 +545,7 @@ static int emb_project(dg_emb* h, int rows, int normalize, float norm, float* ou
   GemmArgs a{};
   a.A = h->pooled.as<float>(); a.lda = 3000; a.Cin = 3000; a.KW = 1; a.dil = 1; a.Mtot = rows; a.M = rows;
   a.W = h->ew.as<float>(); a.ldw = h->D; a.N = h->D; a.bias = h->eb.as<float>();
-  a.ldc = h->D; a.epi = EPI_BIAS;
+  a.ldc = h->D; a.epi = EPI_BIAS; a.tag = "emb_linear";
   if (!normalize) {
     a.C = out;
     return launch_gemm(a, st);

@@ -394,6 +394,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
 int launch_cluster_step(const ClusterParams& p, const float* seg, const float* emb, int B, int F, int K,
                         double* centers, int* active, int* initialized, float* prep, double* prep_d, int32_t* map,
                         float* permuted, cudaStream_t st) {
+  ProfScope _ps("cluster_step", st);
   if (K > CK || p.M > CM || K > p.M) {
     set_error("cluster_step: need local speakers <= 8, max_speakers <= 32 and local <= max");
     return -1;

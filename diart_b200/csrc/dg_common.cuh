@@ -34,6 +34,17 @@ extern std::atomic<long long> g_launches;
     }                                                                                   \
   } while (0)
 
+// per-kernel CUDA-event timing (bench.py's roofline leg): when enabled through dg_profile_enable(),
+// every launcher brackets its launch with two events on the launching stream.
+struct ProfScope {
+  bool on;
+  cudaStream_t st;
+  cudaEvent_t a, b;
+  const char* name;
+  ProfScope(const char* name, cudaStream_t st);
+  ~ProfScope();
+};
+
 // ------------------------------------------------------------------ geometry of the path
 // 80000 samples -> sinc(k251,s10) 7975 -> pool3 2658 -> k5 2654 -> pool3 884 -> k5 880 -> pool3 293.
 // Activations are stored time-major / channels-last, [item][row][channel], with a fixed row
@@ -92,6 +103,7 @@ struct GemmArgs {
   float* C;            // [M or M/3, ldc]
   int ldc;
   int epi;
+  const char* tag;   // kernel label for profiling (layer name)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 // lstm.cu

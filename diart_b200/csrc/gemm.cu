@@ -173,6 +173,7 @@ __global__ void __launch_bounds__(G_THREADS) gemm_kernel(GemmArgs a) {
 }
 
 int launch_gemm(const GemmArgs& a, cudaStream_t st) {
+  ProfScope _ps(a.tag ? a.tag : "gemm", st);
   if (a.Cin % 4 || a.lda % 4 || a.ldw % 4 || a.ldc % 4 || a.N % 4) {
     set_error("gemm: channel counts must be multiples of 4");
     return -1;

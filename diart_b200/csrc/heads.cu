@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(256) seg_final_kernel(const float* __restrict_
 
 int launch_seg_final(const float* y, const float* wc, const float* bc, int B, int T, int stride, int K, float* seg,
                      cudaStream_t st) {
+  ProfScope _ps("seg_final", st);
   if (K > 8) {
     set_error("seg_final: at most 8 local speakers");
     return -1;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(256) osp_kernel(const float* __restrict__ seg,
 
 int launch_osp(const float* seg, int B, int F, int K, float gamma, float beta, int normalize, float* out,
                cudaStream_t st) {
+  ProfScope _ps("osp", st);
   const size_t smem = ((size_t)F * K + 2 * K) * sizeof(float);
   if (smem > 48 * 1024) {
     set_error("osp: frames*speakers too large");
@@ -225,6 +227,7 @@ stats_pool_kernel(const float* __restrict__ x, int stride, int T, int C, const f
 int launch_stats_pool_ex(const float* x, int stride, int T, int C, const float* w, int F, int K, int layout,
                          int n_groups, const int* grp_item, const int* grp_q0, const int* grp_nq, const int* idx0,
                          const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st) {
+  ProfScope _ps("stats_pool", st);
   const size_t smem = ((size_t)T * PK + 4 * 64 * PK) * sizeof(float);
   dim3 grid((C + 63) / 64, n_groups);
   stats_pool_kernel<<<grid, 256, smem, st>>>(x, stride, T, C, w, F, K, layout, grp_item, grp_q0, grp_nq, idx0, idx1,
@@ -254,6 +257,7 @@ __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ i
 }
 
 int launch_l2norm(const float* in, int rows, int D, float norm, float* out, cudaStream_t st) {
+  ProfScope _ps("l2norm", st);
   l2norm_kernel<<<(rows + 7) / 8, 256, 0, st>>>(in, rows, D, norm, out);
   DG_LAUNCHED();
   return 0;

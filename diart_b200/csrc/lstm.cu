@@ -145,6 +145,7 @@ static int launch_R(const float* gx, const float* whh, int B, int T, int stride,
 
 int launch_lstm_layer(const float* gx, const float* whh_packed, int B, int T, int stride, float* hout,
                       cudaStream_t st) {
+  ProfScope _ps("lstm_rec", st);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -42,6 +42,7 @@ __global__ void __launch_bounds__(512) wave_stats_kernel(const float* __restrict
 }
 
 int launch_wave_stats(const float* wav, int B, int S, float* mean, float* rstd, cudaStream_t st) {
+  ProfScope _ps("wave_stats", st);
   wave_stats_kernel<<<B, 512, 0, st>>>(wav, S, mean, rstd);
   DG_LAUNCHED();
   return 0;
@@ -114,6 +115,7 @@ sinc0_kernel(const float* __restrict__ wav, const float* __restrict__ mean, cons
 
 int launch_sinc0(const float* wav, const float* mean, const float* rstd, float wn_gamma, float wn_beta,
                  const float* filt, int B, const Geom& g, float* p0, cudaStream_t st) {
+  ProfScope _ps("sinc0", st);
   static bool attr_done = false;
   const size_t smem = (size_t)(SINC_K * SINC_F + ((SINC_XSEG + 3) & ~3)) * sizeof(float);
   if (!attr_done) {
@@ -175,6 +177,7 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __rest
 
 int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
                           const float* beta, float* sc, float* sh, cudaStream_t st) {
+  ProfScope _ps("instnorm_stats", st);
   dim3 grid((C + 31) / 32, B);
   instnorm_stats_kernel<<<grid, 256, 0, st>>>(x, stride_rows, T, C, ldc, gamma, beta, sc, sh);
   DG_LAUNCHED();

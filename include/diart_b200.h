@@ -119,6 +119,11 @@ int dg_pipeline_destroy(dg_pipeline* h);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t dg_launch_count(void);
+/* per-kernel CUDA-event timing on the launching stream (bench.py's roofline leg).  While enabled,
+ * every kernel launch is bracketed by two events; dg_profile_report() synchronises the device and
+ * writes {"kernel": {"count": n, "ms": total}, ...} into buf. */
+int dg_profile_enable(int enable);
+int dg_profile_report(char* buf, int cap);
 
 /* ---- shared-identity mode (extension): merge per-rank centroid deltas that were
  *      all-gathered by the host (NCCL) -- see dg_cluster_export_delta / dg_cluster_merge in
