@@ -167,7 +167,6 @@ __device__ void lsap_warp(const double (&cost)[CK], int nr, int nc, int lane, Ls
 
 struct SeqShared {
   double dist[CK][CM];
-  double cnorm[CM];
   LsapScratch ls;
   int map[CK];
   int upd_k[CK], upd_g[CK], n_upd;   // centers[g] += emb[k]
@@ -196,8 +195,12 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
                    const float* __restrict__ prep, const double* __restrict__ prep_d, int32_t* __restrict__ map_out,
                    float* __restrict__ permuted) {
   __shared__ SeqShared sh;
+  extern __shared__ __align__(16) unsigned char dyn[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, D = p.D;
+  double* cs = reinterpret_cast<double*>(dyn);                 // centroids [M][D], resident for the whole batch
+  float* es = reinterpret_cast<float*>(cs + (size_t)M * D);    // this chunk's embeddings [K][D]
+  for (int i = tid; i < M * D; i += blockDim.x) cs[i] = centers[i];
   if (tid < CM) sh.active[tid] = tid < M ? g_active[tid] : 0;
   if (tid == 0) {
     sh.initialized = *g_init;
@@ -209,31 +212,37 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     const float* e_chunk = emb + (size_t)ci * K * D;
     const float* pr = prep + (size_t)ci * K * 3;
     const bool init = sh.initialized != 0;
+    for (int i = tid; i < K * D; i += blockDim.x) es[i] = e_chunk[i];
+    __syncthreads();
     // ---------------- phase A: float64 cosine distances (scipy cdist 'cosine':
-    //                  1 - u.v / (|u| |v|), clipped to [-1, 1] before the subtraction)
+    //                  1 - u.v / (|u| |v|), clipped to [-1, 1] before the subtraction).
+    //                  One warp per active centroid: its norm and its K dot products in one pass.
     if (init) {
       for (int g = warp; g < M; g += 8) {
         if (!sh.active[g]) continue;
-        const double* c = centers + (size_t)g * D;
-        double ss = 0.0;
-        for (int d = lane; d < D; d += 32) ss = fma(c[d], c[d], ss);
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(FULL, ss, o);
-        if (lane == 0) sh.cnorm[g] = sqrt(ss);
-      }
-      __syncthreads();
-      for (int item = warp; item < K * M; item += 8) {
-        const int k = item / M, g = item - k * M;
-        if (!sh.active[g]) continue;
-        const double* c = centers + (size_t)g * D;
-        const float* e = e_chunk + (size_t)k * D;
-        double dot = 0.0;
-        for (int d = lane; d < D; d += 32) dot = fma((double)e[d], c[d], dot);
-        for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(FULL, dot, o);
-        if (lane == 0) {
-          double cosv = dot / (prep_d[(size_t)ci * K + k] * sh.cnorm[g]);
-          if (fabs(cosv) > 1.0) cosv = copysign(1.0, cosv);
-          sh.dist[k][g] = 1.0 - cosv;
+        const double* c = cs + (size_t)g * D;
+        double acc[CK + 1];
+#pragma unroll
+        for (int k = 0; k <= CK; k++) acc[k] = 0.0;
+        for (int d = lane; d < D; d += 32) {
+          const double cv = c[d];
+          acc[CK] = fma(cv, cv, acc[CK]);
+#pragma unroll
+          for (int k = 0; k < CK; k++)
+            if (k < K) acc[k] = fma((double)es[k * D + d], cv, acc[k]);
         }
+#pragma unroll
+        for (int k = 0; k <= CK; k++)
+          if (k < K || k == CK)
+            for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(FULL, acc[k], o);
+        const double cn = sqrt(acc[CK]);
+#pragma unroll
+        for (int k = 0; k < CK; k++)
+          if (k < K && lane == k) {
+            double cosv = acc[k] / (prep_d[(size_t)ci * K + k] * cn);
+            if (fabs(cosv) > 1.0) cosv = copysign(1.0, cosv);
+            sh.dist[k][g] = 1.0 - cosv;
+          }
       }
     }
     __syncthreads();
@@ -361,13 +370,13 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     __syncthreads();
     // ---------------- phase C: centroid update / creation, outputs
     for (int q = 0; q < sh.n_upd; q++) {
-      double* c = centers + (size_t)sh.upd_g[q] * D;
-      const float* e = e_chunk + (size_t)sh.upd_k[q] * D;
+      double* c = cs + (size_t)sh.upd_g[q] * D;
+      const float* e = es + (size_t)sh.upd_k[q] * D;
       for (int d = tid; d < D; d += blockDim.x) c[d] += (double)e[d];
     }
     for (int q = 0; q < sh.n_new; q++) {
-      double* c = centers + (size_t)sh.new_g[q] * D;
-      const float* e = e_chunk + (size_t)sh.new_k[q] * D;
+      double* c = cs + (size_t)sh.new_g[q] * D;
+      const float* e = es + (size_t)sh.new_k[q] * D;
       for (int d = tid; d < D; d += blockDim.x) c[d] = (double)e[d];
     }
     if (tid < K) map_out[(size_t)ci * K + tid] = sh.map[tid];
@@ -384,6 +393,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     }
     __syncthreads();
   }
+  for (int i = tid; i < M * D; i += blockDim.x) centers[i] = cs[i];
   if (tid < M) g_active[tid] = sh.active[tid];
   if (tid == 0) {
     *g_init = sh.initialized;
@@ -402,8 +412,18 @@ int launch_cluster_step(const ClusterParams& p, const float* seg, const float* e
   if (B <= 0) return 0;
   cluster_prep_kernel<<<B, 128, 0, st>>>(seg, emb, F, K, p.D, prep, prep_d);
   DG_LAUNCHED();
-  cluster_seq_kernel<<<1, 256, 0, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map,
-                                        permuted);
+  const size_t dyn = (size_t)p.M * p.D * sizeof(double) + (size_t)K * p.D * sizeof(float);
+  if (dyn > 200 * 1024) {
+    set_error("cluster_step: max_speakers * dim too large for the resident centroid table (limit 200 KB)");
+    return -1;
+  }
+  static size_t dyn_set = 0;
+  if (dyn > dyn_set) {
+    DG_CUDA(cudaFuncSetAttribute(cluster_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    dyn_set = dyn;
+  }
+  cluster_seq_kernel<<<1, 256, dyn, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map,
+                                          permuted);
   DG_LAUNCHED();
   return 0;
 }

@@ -16,6 +16,10 @@ namespace cg = cooperative_groups;
 namespace dg {
 
 constexpr int H = 128, LSTM_THREADS = 512;
+// h rows are stored with 4 floats of padding after every 32 (k-slice s starts at 36*s): the four
+// k-slices read by the lanes of a warp then fall into different banks (no 4-way conflict)
+constexpr int HP = 144;
+__host__ __device__ constexpr int hidx(int u) { return u + 4 * (u >> 5); }
 
 // packed layout: [dir][cta][thread][64]
 size_t lstm_whh_packed_floats() { return (size_t)2 * 2 * LSTM_THREADS * 64; }
@@ -50,7 +54,7 @@ lstm_rec_kernel(const float* __restrict__ gx, const float* __restrict__ whh_pack
   const int b0 = (cl - dir * clusters_per_dir) * R;
   const int tid = threadIdx.x, pr = tid >> 2, ks = tid & 3;
 
-  __shared__ __align__(16) float hbuf[2][R][H];     // h_{t-1} of all 128 units, double buffered
+  __shared__ __align__(16) float hbuf[2][R][HP];     // h_{t-1} of all 128 units, double buffered
   __shared__ float gates[R][256];                   // this CTA's 256 gate pre-activations
   float* peer_h = cluster.map_shared_rank(&hbuf[0][0][0], crank ^ 1);
 
@@ -65,7 +69,7 @@ lstm_rec_kernel(const float* __restrict__ gx, const float* __restrict__ whh_pack
         w[j][4 * i + 0] = v.x; w[j][4 * i + 1] = v.y; w[j][4 * i + 2] = v.z; w[j][4 * i + 3] = v.w;
       }
   }
-  for (int i = tid; i < 2 * R * H; i += LSTM_THREADS) (&hbuf[0][0][0])[i] = 0.f;
+  for (int i = tid; i < 2 * R * HP; i += LSTM_THREADS) (&hbuf[0][0][0])[i] = 0.f;
   // activation-phase role: thread a < 64*R handles (row ar, local unit au)
   const int ar = tid >> 6, au = tid & 63;
   const bool act = tid < 64 * R && (b0 + ar) < B;
@@ -93,17 +97,19 @@ lstm_rec_kernel(const float* __restrict__ gx, const float* __restrict__ whh_pack
     for (int r = 0; r < R; r++) acc[0][r] = acc[1][r] = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
+      float4 hv[R];
+#pragma unroll
+      for (int r = 0; r < R; r++) hv[r] = *reinterpret_cast<const float4*>(&hbuf[cur][r][36 * ks + 4 * i]);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        const float4 hv = *reinterpret_cast<const float4*>(&hbuf[cur][r][32 * ks + 4 * i]);
-        acc[0][r] = fmaf(w[0][4 * i + 0], hv.x, acc[0][r]);
-        acc[0][r] = fmaf(w[0][4 * i + 1], hv.y, acc[0][r]);
-        acc[0][r] = fmaf(w[0][4 * i + 2], hv.z, acc[0][r]);
-        acc[0][r] = fmaf(w[0][4 * i + 3], hv.w, acc[0][r]);
-        acc[1][r] = fmaf(w[1][4 * i + 0], hv.x, acc[1][r]);
-        acc[1][r] = fmaf(w[1][4 * i + 1], hv.y, acc[1][r]);
-        acc[1][r] = fmaf(w[1][4 * i + 2], hv.z, acc[1][r]);
-        acc[1][r] = fmaf(w[1][4 * i + 3], hv.w, acc[1][r]);
+        acc[0][r] = fmaf(w[0][4 * i + 0], hv[r].x, acc[0][r]);
+        acc[1][r] = fmaf(w[1][4 * i + 0], hv[r].x, acc[1][r]);
+        acc[0][r] = fmaf(w[0][4 * i + 1], hv[r].y, acc[0][r]);
+        acc[1][r] = fmaf(w[1][4 * i + 1], hv[r].y, acc[1][r]);
+        acc[0][r] = fmaf(w[0][4 * i + 2], hv[r].z, acc[0][r]);
+        acc[1][r] = fmaf(w[1][4 * i + 2], hv[r].z, acc[1][r]);
+        acc[0][r] = fmaf(w[0][4 * i + 3], hv[r].w, acc[0][r]);
+        acc[1][r] = fmaf(w[1][4 * i + 3], hv[r].w, acc[1][r]);
       }
     }
 #pragma unroll
@@ -127,8 +133,8 @@ lstm_rec_kernel(const float* __restrict__ gx, const float* __restrict__ whh_pack
       cstate = fmaf(f_, cstate, i_ * g_);
       const float h = o_ * tanhf(cstate);
       const int u = 64 * crank + au;
-      hbuf[nxt][ar][u] = h;
-      peer_h[(nxt * R + ar) * H + u] = h;
+      hbuf[nxt][ar][hidx(u)] = h;
+      peer_h[(nxt * R + ar) * HP + hidx(u)] = h;
       hout[((size_t)(b0 + ar) * stride + t) * 256 + dir * H + u] = h;
     }
     cluster.sync();
