@@ -27,7 +27,7 @@ def oracle_nets():
 
     from oracle import nets
 
-    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    torch.set_num_threads(min(16, os.cpu_count() or 1))
     return nets.make_segmentation(), nets.make_embedding()
 
 
