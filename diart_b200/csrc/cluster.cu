@@ -66,9 +66,18 @@ __global__ void __launch_bounds__(128) cluster_prep_kernel(const float* __restri
   }
 }
 
+// warp-wide minimum of a double through two 32-bit redux.sync steps on an order-preserving integer
+// key (10 dependent shuffles otherwise; the assignment logic is a chain of such reductions)
 __device__ __forceinline__ double warp_min_d(double v) {
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(FULL, v, o));
-  return v;
+  v += 0.0;   // -0.0 -> +0.0 so that key order == numeric order for equal values
+  const long long b = __double_as_longlong(v);
+  const unsigned long long key = (unsigned long long)(b ^ ((b >> 63) | (long long)0x8000000000000000ull));
+  const unsigned hi = (unsigned)(key >> 32);
+  const unsigned mh = __reduce_min_sync(FULL, hi);
+  const unsigned ml = __reduce_min_sync(FULL, hi == mh ? (unsigned)key : 0xffffffffu);
+  const unsigned long long mk = ((unsigned long long)mh << 32) | ml;
+  const long long mb = (long long)(mk ^ (((long long)mk >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull));
+  return __longlong_as_double(mb);
 }
 __device__ __forceinline__ double sel(const double (&c)[CK], int i) {
   double r = c[0];
@@ -122,8 +131,7 @@ __device__ void lsap_warp(const double (&cost)[CK], int nr, int nc, int lane, Ls
       if (cand == 0) return;  // infeasible (never: all costs are finite)
       // candfree: the candidate with the largest list position; else the smallest
       int key = candfree ? ((is_c && row4col < 0) ? pos : -1) : (is_c ? -pos : -1000);
-      int best = key;
-      for (int o = 16; o > 0; o >>= 1) best = max(best, __shfl_xor_sync(FULL, best, o));
+      const int best = __reduce_max_sync(FULL, key);
       const int j = __ffs(__ballot_sync(FULL, key == best && (candfree ? (is_c && row4col < 0) : is_c))) - 1;
       minVal = lowest;
       const int r4c = __shfl_sync(FULL, row4col, j);
