@@ -132,6 +132,7 @@ class OnlineSpeakerClustering:
         segmentation (B,F,K), embeddings (B,K,D): float32 tensors (moved to the device if needed).
         Returns ``(maps int32 (B,K) on device, permuted float32 (B,F,M) on device or None)``.
         """
+        _lib.require_cuda(self.device)
         seg = segmentation.to(self.device, torch.float32).contiguous()
         emb = embeddings.to(self.device, torch.float32).contiguous()
         B, F, K = seg.shape

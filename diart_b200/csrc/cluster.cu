@@ -90,33 +90,23 @@ __device__ __forceinline__ void put(double (&c)[CK], int i, double v) {
   for (int q = 0; q < CK; q++) c[q] = (i == q) ? v : c[q];
 }
 
-struct LsapScratch {
-  double u[CK];
-  int col4row[CK];
-  int sr[CK];
-};
-
-// Column-parallel rectangular LSAP (nr <= nc <= 32), warp-collective.  cost[i] is C[i][lane].
-// Result: s.col4row[i].  Arithmetic and tie-breaking follow scipy's implementation of Crouse's
-// algorithm: r = ((minVal + c) - u) - v; among equal shortest-path costs prefer an unassigned column,
-// scanning the `remaining` list (initialised in reverse, swap-removed) in order.
-__device__ void lsap_warp(const double (&cost)[CK], int nr, int nc, int lane, LsapScratch& s) {
-  double v = 0.0;
-  int row4col = -1;
-  if (lane < CK) {
-    s.u[lane] = 0.0;
-    s.col4row[lane] = -1;
-  }
-  __syncwarp();
+// Column-parallel rectangular LSAP (nr <= nc <= 32), warp-collective, all state in registers:
+// lane j holds column j's dual v, shortest-path cost, predecessor and position in scipy's `remaining`
+// list; lane i (i < nr) also holds row i's dual u and its column.  cost[i] is C[i][lane].
+// Returns, in lane i < nr, the column assigned to row i.  Arithmetic and tie-breaking follow scipy's
+// implementation of Crouse's algorithm: r = ((minVal + c) - u) - v; among equal shortest-path costs
+// prefer an unassigned column, scanning `remaining` (initialised in reverse, swap-removed) in order.
+__device__ int lsap_warp(const double (&cost)[CK], int nr, int nc, int lane) {
+  double v = 0.0, u = 0.0;
+  int row4col = -1, c4r = -1;
   for (int cur = 0; cur < nr; cur++) {
     double minVal = 0.0, spc = INFINITY;
     int i = cur, pos = nc - 1 - lane, path = -1, num = nc, sink = -1;
     bool rem = lane < nc, sc = false;
-    if (lane < CK) s.sr[lane] = 0;
-    __syncwarp();
+    unsigned visited = 0;
     while (sink < 0) {
-      if (lane == 0) s.sr[i] = 1;
-      const double ui = s.u[i];
+      visited |= 1u << i;
+      const double ui = __shfl_sync(FULL, u, i);
       if (rem) {
         const double r = __dsub_rn(__dsub_rn(__dadd_rn(minVal, sel(cost, i)), ui), v);
         if (r < spc) {
@@ -128,11 +118,12 @@ __device__ void lsap_warp(const double (&cost)[CK], int nr, int nc, int lane, Ls
       const bool is_c = rem && spc == lowest;
       const unsigned cand = __ballot_sync(FULL, is_c);
       const unsigned candfree = __ballot_sync(FULL, is_c && row4col < 0);
-      if (cand == 0) return;  // infeasible (never: all costs are finite)
+      if (cand == 0) return c4r;  // infeasible (never: all costs are finite)
       // candfree: the candidate with the largest list position; else the smallest
-      int key = candfree ? ((is_c && row4col < 0) ? pos : -1) : (is_c ? -pos : -1000);
+      const bool mine = candfree ? (is_c && row4col < 0) : is_c;
+      const int key = mine ? (candfree ? pos : 64 - pos) : -1;
       const int best = __reduce_max_sync(FULL, key);
-      const int j = __ffs(__ballot_sync(FULL, key == best && (candfree ? (is_c && row4col < 0) : is_c))) - 1;
+      const int j = __ffs(__ballot_sync(FULL, mine && key == best)) - 1;
       minVal = lowest;
       const int r4c = __shfl_sync(FULL, row4col, j);
       const int idx = __shfl_sync(FULL, pos, j);
@@ -145,37 +136,28 @@ __device__ void lsap_warp(const double (&cost)[CK], int nr, int nc, int lane, Ls
         pos = idx;
       }
       num--;
-      __syncwarp();
     }
-    // dual updates
-    for (int q = 0; q < nr; q++) {
-      const int visited = s.sr[q], c4r = s.col4row[q];
-      if (visited && q != cur) {
-        const double sp = __shfl_sync(FULL, spc, c4r);
-        if (lane == 0) s.u[q] = __dadd_rn(s.u[q], __dsub_rn(minVal, sp));
-      }
-    }
-    if (lane == 0) s.u[cur] = __dadd_rn(s.u[cur], minVal);
+    // dual updates (rows: one per lane; uses the pre-augmentation col4row)
+    const double sp = __shfl_sync(FULL, spc, c4r >= 0 ? c4r : 0);
+    if (lane == cur) u = __dadd_rn(u, minVal);
+    else if (lane < nr && ((visited >> lane) & 1u)) u = __dadd_rn(u, __dsub_rn(minVal, sp));
     if (sc) v = __dsub_rn(v, __dsub_rn(minVal, spc));
-    __syncwarp();
     // augment along the path
     int j = sink;
     while (true) {
       const int pi = __shfl_sync(FULL, path, j);
       if (lane == j) row4col = pi;
-      const int prev = s.col4row[pi];
-      __syncwarp();
-      if (lane == 0) s.col4row[pi] = j;
-      __syncwarp();
+      const int prev = __shfl_sync(FULL, c4r, pi);
+      if (lane == pi) c4r = j;
       j = prev;
       if (pi == cur) break;
     }
   }
+  return c4r;
 }
 
 struct SeqShared {
   double dist[CK][CM];
-  LsapScratch ls;
   int map[CK];
   int upd_k[CK], upd_g[CK], n_upd;   // centers[g] += emb[k]
   int new_k[CK], new_g[CK], n_new;   // centers[g]  = emb[k]
@@ -197,36 +179,56 @@ __device__ __forceinline__ unsigned mapped_rows(const double (&c)[CK], int K, in
   return m;
 }
 
-__global__ void __launch_bounds__(256)
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(s), "l"(gmem));
+}
+
+constexpr int SEQ_THREADS = 512;
+
+__global__ void __launch_bounds__(SEQ_THREADS)
 cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* __restrict__ emb, int B, int F, int K,
                    double* __restrict__ centers, int* __restrict__ g_active, int* __restrict__ g_init,
                    const float* __restrict__ prep, const double* __restrict__ prep_d, int32_t* __restrict__ map_out,
                    float* __restrict__ permuted) {
   __shared__ SeqShared sh;
+  __shared__ float prs[2][CK * 3];      // per-chunk max / mean / nan flag, double buffered
+  __shared__ double ens[2][CK];         // per-chunk embedding norms
   extern __shared__ __align__(16) unsigned char dyn[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int M = p.M, D = p.D;
+  constexpr int NW = SEQ_THREADS / 32;
   double* cs = reinterpret_cast<double*>(dyn);                 // centroids [M][D], resident for the whole batch
-  float* es = reinterpret_cast<float*>(cs + (size_t)M * D);    // this chunk's embeddings [K][D]
-  for (int i = tid; i < M * D; i += blockDim.x) cs[i] = centers[i];
+  float* es = reinterpret_cast<float*>(cs + (size_t)M * D);    // embeddings [2][K][D], double buffered
+  auto prefetch = [&](int ci, int buf) {
+    const float* e = emb + (size_t)ci * K * D;
+    for (int i = tid; i < K * D; i += SEQ_THREADS) cp_async4(es + (size_t)buf * K * D + i, e + i);
+    if (tid < K * 3) cp_async4(&prs[buf][tid], prep + (size_t)ci * K * 3 + tid);
+    if (tid < K * 2) cp_async4(reinterpret_cast<float*>(&ens[buf][0]) + tid,
+                               reinterpret_cast<const float*>(prep_d + (size_t)ci * K) + tid);
+    asm volatile("cp.async.commit_group;");
+  };
+  prefetch(0, 0);
+  for (int i = tid; i < M * D; i += SEQ_THREADS) cs[i] = centers[i];
   if (tid < CM) sh.active[tid] = tid < M ? g_active[tid] : 0;
   if (tid == 0) {
     sh.initialized = *g_init;
     sh.error = 0;
   }
+  asm volatile("cp.async.wait_group 0;");
   __syncthreads();
 
   for (int ci = 0; ci < B; ci++) {
-    const float* e_chunk = emb + (size_t)ci * K * D;
-    const float* pr = prep + (size_t)ci * K * 3;
+    const int cur = ci & 1;
+    const float* ecur = es + (size_t)cur * K * D;
+    const float* pr = prs[cur];
     const bool init = sh.initialized != 0;
-    for (int i = tid; i < K * D; i += blockDim.x) es[i] = e_chunk[i];
-    __syncthreads();
+    if (ci + 1 < B) prefetch(ci + 1, cur ^ 1);
     // ---------------- phase A: float64 cosine distances (scipy cdist 'cosine':
     //                  1 - u.v / (|u| |v|), clipped to [-1, 1] before the subtraction).
     //                  One warp per active centroid: its norm and its K dot products in one pass.
     if (init) {
-      for (int g = warp; g < M; g += 8) {
+      for (int g = warp; g < M; g += NW) {
         if (!sh.active[g]) continue;
         const double* c = cs + (size_t)g * D;
         double acc[CK + 1];
@@ -237,7 +239,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
           acc[CK] = fma(cv, cv, acc[CK]);
 #pragma unroll
           for (int k = 0; k < CK; k++)
-            if (k < K) acc[k] = fma((double)es[k * D + d], cv, acc[k]);
+            if (k < K) acc[k] = fma((double)ecur[k * D + d], cv, acc[k]);
         }
 #pragma unroll
         for (int k = 0; k <= CK; k++)
@@ -247,7 +249,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
 #pragma unroll
         for (int k = 0; k < CK; k++)
           if (k < K && lane == k) {
-            double cosv = acc[k] / (prep_d[(size_t)ci * K + k] * cn);
+            double cosv = acc[k] / (ens[cur][k] * cn);
             if (fabs(cosv) > 1.0) cosv = copysign(1.0, cosv);
             sh.dist[k][g] = 1.0 - cosv;
           }
@@ -286,16 +288,16 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
 #pragma unroll
         for (int k = 0; k < CK; k++) {                                                  // clustering.py:161-166
           const bool live = k < K && ((active_spk >> k) & 1u) && act_c;
-          dmap[k] = live ? sh.dist[k < K ? k : 0][lane] : INVALID;
+          dmap[k] = live ? sh.dist[k][lane] : INVALID;
           valid[k] = dmap[k];
         }
         // unmap_threshold (mapping.py:260-273)
-        lsap_warp(dmap, K, M, lane, sh.ls);
+        int c4r = lsap_warp(dmap, K, M, lane);
         unsigned mapped = mapped_rows(dmap, K, M, lane);
         bool dirty = false;
         for (int k = 0; k < K; k++) {
           if (!((mapped >> k) & 1u)) continue;
-          const int c = sh.ls.col4row[k];
+          const int c = __shfl_sync(FULL, c4r, k);
           const double cost = __shfl_sync(FULL, sel(dmap, k), c);
           if (cost >= p.delta) {
             put(valid, k, INVALID);
@@ -309,20 +311,21 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
         for (int k = 0; k < K; k++) {                                                   // clustering.py:176-194
           if (!((missed >> k) & 1u)) continue;
           if (n_new < n_free && ((long_spk >> k) & 1u)) {
-            if (lane == 0) sh.new_k[n_new] = k;
             n_new++;
             new_mask |= 1u << k;
           } else {
             if (dirty) {
-              lsap_warp(valid, K, M, lane, sh.ls);
+              c4r = lsap_warp(valid, K, M, lane);
               dirty = false;
             }
             vmapped = mapped_rows(valid, K, M, lane);
-            unsigned taken = 0;
-            for (int q = 0; q < K; q++)
-              if ((vmapped >> q) & 1u) taken |= 1u << sh.ls.col4row[q];
+            unsigned tk = 0;
+            for (int q = 0; q < K; q++) {
+              const int cq = __shfl_sync(FULL, c4r, q);
+              if ((vmapped >> q) & 1u) tk |= 1u << cq;
+            }
             // closest active centre that is not already a target
-            const bool ok = act_c && !((taken >> lane) & 1u);
+            const bool ok = act_c && !((tk >> lane) & 1u);
             const double dk = ok ? sel(dmap, k) : INFINITY;
             const double best = warp_min_d(dk);
             const unsigned who = __ballot_sync(FULL, ok && dk == best);
@@ -331,17 +334,16 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
               if (lane == g) put(valid, k, 0.0);                                        // mapping.py:245-251
               dirty = true;
             }
-            __syncwarp();
           }
         }
         if (dirty) {
-          lsap_warp(valid, K, M, lane, sh.ls);
+          c4r = lsap_warp(valid, K, M, lane);
           dirty = false;
         }
         vmapped = mapped_rows(valid, K, M, lane);
         for (int k = 0; k < K; k++) {                                                   // clustering.py:197-202
           if (!((vmapped >> k) & 1u) || ((missed >> k) & 1u) || !((long_spk >> k) & 1u)) continue;
-          const int g = sh.ls.col4row[k];
+          const int g = __shfl_sync(FULL, c4r, k);
           if (!sh.active[g]) {
             if (lane == 0) sh.error = 1;   // reference: AssertionError("Cannot update unknown centers")
             continue;
@@ -352,23 +354,27 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
           }
           n_upd++;
         }
-        __syncwarp();
         // new centres at the lowest free index (clustering.py:205-208, 68-71)
-        for (int q = 0; q < n_new; q++) {
-          const int k = sh.new_k[q];
+        int q = 0;
+        for (int k = 0; k < K; k++) {
+          if (!((new_mask >> k) & 1u)) continue;
           const unsigned freeb = __ballot_sync(FULL, lane < M && !sh.active[lane]);
           const int g = __ffs(freeb) - 1;
           if (lane == g) {
             sh.active[g] = 1;
             put(valid, k, 0.0);
           }
-          if (lane == 0) sh.new_g[q] = g;
+          if (lane == 0) {
+            sh.new_k[q] = k;
+            sh.new_g[q] = g;
+          }
+          q++;
           dirty = true;
           __syncwarp();
         }
-        if (dirty) lsap_warp(valid, K, M, lane, sh.ls);
+        if (dirty) c4r = lsap_warp(valid, K, M, lane);
         vmapped = mapped_rows(valid, K, M, lane);
-        if (lane < K) sh.map[lane] = ((vmapped >> lane) & 1u) ? sh.ls.col4row[lane] : -1;
+        if (lane < K) sh.map[lane] = ((vmapped >> lane) & 1u) ? c4r : -1;
       }
       if (lane == 0) {
         sh.n_upd = n_upd;
@@ -379,29 +385,30 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     // ---------------- phase C: centroid update / creation, outputs
     for (int q = 0; q < sh.n_upd; q++) {
       double* c = cs + (size_t)sh.upd_g[q] * D;
-      const float* e = es + (size_t)sh.upd_k[q] * D;
-      for (int d = tid; d < D; d += blockDim.x) c[d] += (double)e[d];
+      const float* e = ecur + (size_t)sh.upd_k[q] * D;
+      for (int d = tid; d < D; d += SEQ_THREADS) c[d] += (double)e[d];
     }
     for (int q = 0; q < sh.n_new; q++) {
       double* c = cs + (size_t)sh.new_g[q] * D;
-      const float* e = es + (size_t)sh.new_k[q] * D;
-      for (int d = tid; d < D; d += blockDim.x) c[d] = (double)e[d];
+      const float* e = ecur + (size_t)sh.new_k[q] * D;
+      for (int d = tid; d < D; d += SEQ_THREADS) c[d] = (double)e[d];
     }
     if (tid < K) map_out[(size_t)ci * K + tid] = sh.map[tid];
     if (permuted) {                                                                     // mapping.py:341-360
       float* o = permuted + (size_t)ci * F * M;
       const float* s = seg + (size_t)ci * F * K;
-      for (int idx = tid; idx < F * M; idx += blockDim.x) o[idx] = 0.f;
+      for (int idx = tid; idx < F * M; idx += SEQ_THREADS) o[idx] = 0.f;
       __syncthreads();
       for (int k = 0; k < K; k++) {
         const int g = sh.map[k];
         if (g < 0) continue;
-        for (int f = tid; f < F; f += blockDim.x) o[(size_t)f * M + g] = s[f * K + k];
+        for (int f = tid; f < F; f += SEQ_THREADS) o[(size_t)f * M + g] = s[f * K + k];
       }
     }
+    asm volatile("cp.async.wait_group 0;");
     __syncthreads();
   }
-  for (int i = tid; i < M * D; i += blockDim.x) centers[i] = cs[i];
+  for (int i = tid; i < M * D; i += SEQ_THREADS) centers[i] = cs[i];
   if (tid < M) g_active[tid] = sh.active[tid];
   if (tid == 0) {
     *g_init = sh.initialized;
@@ -420,7 +427,7 @@ int launch_cluster_step(const ClusterParams& p, const float* seg, const float* e
   if (B <= 0) return 0;
   cluster_prep_kernel<<<B, 128, 0, st>>>(seg, emb, F, K, p.D, prep, prep_d);
   DG_LAUNCHED();
-  const size_t dyn = (size_t)p.M * p.D * sizeof(double) + (size_t)K * p.D * sizeof(float);
+  const size_t dyn = (size_t)p.M * p.D * sizeof(double) + (size_t)2 * K * p.D * sizeof(float);
   if (dyn > 200 * 1024) {
     set_error("cluster_step: max_speakers * dim too large for the resident centroid table (limit 200 KB)");
     return -1;
@@ -430,7 +437,7 @@ int launch_cluster_step(const ClusterParams& p, const float* seg, const float* e
     DG_CUDA(cudaFuncSetAttribute(cluster_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     dyn_set = dyn;
   }
-  cluster_seq_kernel<<<1, 256, dyn, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map,
+  cluster_seq_kernel<<<1, SEQ_THREADS, dyn, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map,
                                           permuted);
   DG_LAUNCHED();
   return 0;

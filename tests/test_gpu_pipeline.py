@@ -1,0 +1,108 @@
+"""End-to-end parity of the fused pipeline step (dg_pipeline_step) and of the SpeakerDiarization drop-in
+against the oracle pipeline (reference diarization.py:177-203 restated in oracle/pipeline.py).
+
+Bars: segmentation scores within 2e-4, unit-norm embeddings within 5e-4 (float32 re-association only),
+speaker maps IDENTICAL to what the oracle clustering produces from the same scores/embeddings, and
+identical to the oracle's own end-to-end maps unless the oracle's decision margin at the first differing
+chunk is below the float tolerance (reported, never silently skipped)."""
+import numpy as np
+import pytest
+import torch
+
+from diart_b200 import blocks, models, synth
+from diart_b200.core import SlidingWindow, SlidingWindowFeature
+from oracle.clustering import OracleClustering
+from oracle.pipeline import OraclePipeline
+
+pytestmark = pytest.mark.gpu
+N_CHUNKS, BATCH = 48, 16
+
+
+@pytest.fixture(scope="module")
+def stream():
+    return synth.synth_audio(80000 + 8000 * (N_CHUNKS - 1), seed=4242, num_speakers=4)
+
+
+def make_pipeline(oracle_nets, device, **kw):
+    seg_o, emb_o = oracle_nets
+    config = blocks.SpeakerDiarizationConfig(
+        segmentation=models.SegmentationModel(models.B200SegmentationLoader(seg_o.state_dict())),
+        embedding=models.EmbeddingModel(models.B200EmbeddingLoader(emb_o.state_dict())), device=device, **kw)
+    return blocks.SpeakerDiarization(config)
+
+
+@pytest.mark.parametrize("params", [dict(), dict(tau_active=0.5, rho_update=0.2, delta_new=0.8, max_speakers=4)])
+def test_fused_step_matches_oracle(params, oracle_nets, stream, cuda_device):
+    pipe = make_pipeline(oracle_nets, cuda_device, **params)
+    cfg = pipe.config
+    oracle = OraclePipeline(*oracle_nets, tau_active=cfg.tau_active, rho_update=cfg.rho_update,
+                            delta_new=cfg.delta_new, max_speakers=cfg.max_speakers, as_reference=False)
+    replay = OracleClustering(cfg.tau_active, cfg.rho_update, cfg.delta_new, "cosine", cfg.max_speakers)
+    seg_err = emb_err = 0.0
+    first_diff = None
+    for b in range(N_CHUNKS // BATCH):
+        x = torch.from_numpy(synth.windows(stream, BATCH, first=b * BATCH))
+        seg, emb, maps = pipe.device_step(x.to(cuda_device))
+        seg, emb, maps = seg.cpu().numpy(), emb.cpu().numpy(), maps.cpu().numpy()
+        o_seg, o_emb, o_maps, margins = oracle(x)
+        seg_err = max(seg_err, np.abs(seg - o_seg).max())
+        emb_err = max(emb_err, np.abs(emb - o_emb).max())
+        # (1) integer logic: oracle clustering replayed on the CUDA path's own scores / embeddings
+        r_maps = np.stack([replay(s, e)[0] for s, e in zip(seg, emb)])
+        assert np.array_equal(maps, r_maps), f"batch {b}: clustering kernel differs from the oracle on identical inputs"
+        # (2) end to end
+        if first_diff is None and not np.array_equal(maps, o_maps):
+            i = int(np.where((maps != o_maps).any(axis=1))[0][0])
+            first_diff = (b * BATCH + i, float(margins[i]))
+    print(f"seg max abs err {seg_err:.2e}, emb max abs err {emb_err:.2e}, first end-to-end difference {first_diff}")
+    assert seg_err < 2e-4 and emb_err < 5e-4
+    if first_diff is not None:
+        assert first_diff[1] < 1e-3, f"maps diverge at chunk {first_diff[0]} although the decision margin is {first_diff[1]}"
+    assert np.array_equal(pipe.clustering.centers, replay.centers)
+
+
+def test_speaker_diarization_drop_in(oracle_nets, stream, cuda_device):
+    """SpeakerDiarization.__call__(Sequence[SlidingWindowFeature]) -> Sequence[(Annotation, SlidingWindowFeature)],
+    the contract StreamingInference relies on (reference inference.py:137-141)."""
+    pipe = make_pipeline(oracle_nets, cuda_device)
+    host = make_pipeline(oracle_nets, cuda_device)          # same pipeline, fed through the per-block API
+    sr, step, n = 16000, 0.5, 12
+    chunks = [SlidingWindowFeature(stream[8000 * i:8000 * i + 80000, None],
+                                   SlidingWindow(start=step * i, duration=1 / sr, step=1 / sr)) for i in range(n)]
+    out = pipe(chunks[:5]) + pipe(chunks[5:])
+    assert len(out) == n
+    x = torch.from_numpy(synth.windows(stream, n))
+    seg = host.segmentation(x[:, :, None])
+    emb = host.embedding(x[:, :, None], seg)
+    res = 5 / seg.shape[1]
+    rttm_ref = []
+    pred_buffer = []
+    for i in range(n):
+        swf = SlidingWindowFeature(seg[i].numpy(), SlidingWindow(start=step * i, duration=res, step=res))
+        pred_buffer = [host.clustering(swf, emb[i])]
+        rttm_ref.append(host.binarize(host.pred_aggregation(pred_buffer)).to_rttm())
+    for i, (annotation, audio) in enumerate(out):
+        assert annotation.to_rttm() == rttm_ref[i], f"chunk {i}"
+        assert audio.data.shape[1] == 1 and 7999 <= audio.data.shape[0] <= 80000
+    assert abs(out[0][1].extent.start) < 1e-9 and abs(out[3][1].extent.start - (3 * step + 4.5)) < 1e-3
+    with pytest.raises(AssertionError):
+        pipe([SlidingWindowFeature(stream[:1000, None], SlidingWindow(start=0, duration=1 / sr, step=1 / sr))])
+    pipe.reset()
+    assert pipe.clustering.centers is None
+
+
+def test_foreign_models_behind_loader_api(oracle_nets, stream, cuda_device):
+    """any Callable behind SegmentationModel / EmbeddingModel still works (block-by-block path);
+    here: the oracle torch modules moved to the GPU"""
+    import copy
+
+    seg_o, emb_o = (copy.deepcopy(m) for m in oracle_nets)
+    config = blocks.SpeakerDiarizationConfig(segmentation=models.SegmentationModel(lambda: seg_o),
+                                             embedding=models.EmbeddingModel(lambda: emb_o), device=cuda_device)
+    pipe = blocks.SpeakerDiarization(config)
+    native = make_pipeline(oracle_nets, cuda_device)
+    x = torch.from_numpy(synth.windows(stream, 4)).to(cuda_device)
+    s1, e1, m1 = pipe.device_step(x)
+    s2, e2, m2 = native.device_step(x)
+    assert (s1 - s2).abs().max().item() < 2e-4 and (e1 - e2).abs().max().item() < 5e-4
+    assert torch.equal(m1, m2)

@@ -1,0 +1,98 @@
+"""Host-side mirror of the reference interface: type plumbing, result objects, post-path blocks, and the
+'no silent CPU fallback' rule."""
+import numpy as np
+import pytest
+import torch
+
+from diart_b200 import _lib, blocks, models
+from diart_b200.core import Annotation, Segment, SlidingWindow, SlidingWindowFeature
+from diart_b200.features import TemporalFeatureFormatter
+from diart_b200.mapping import SpeakerMap
+
+
+def test_formatter_round_trips_like_the_reference():
+    f = TemporalFeatureFormatter()
+    x = np.random.rand(10, 2)
+    t = f.cast(x)
+    assert t.shape == (1, 10, 2) and t.dtype == torch.float32
+    assert isinstance(f.restore_type(t), np.ndarray)
+    swf = SlidingWindowFeature(np.random.rand(10, 2), SlidingWindow(start=2.0, duration=0.5, step=0.5))
+    t = f.cast(swf)
+    back = f.restore_type(torch.zeros(1, 20, 3))
+    assert isinstance(back, SlidingWindowFeature) and back.sliding_window.start == 2.0
+    assert abs(back.sliding_window.step - 0.25) < 1e-12              # 5 s / 20 frames
+    assert f.restore_type(f.cast(torch.zeros(4, 10, 2))).shape == (4, 10, 2)
+    with pytest.raises(ValueError):
+        f.cast([1, 2, 3])
+    with pytest.raises(AssertionError):
+        f.cast(np.zeros(5))
+
+
+def test_speaker_map_result_object():
+    m = SpeakerMap(np.array([2, -1, 0]), 5)
+    assert m.valid_assignments() == ([0, 2], [2, 0]) and m.to_dict() == {0: 2, 2: 0}
+    assert m.is_source_speaker_mapped(0) and not m.is_source_speaker_mapped(1)
+    scores = np.arange(12, dtype=np.float32).reshape(4, 3)
+    out = m.apply(scores)
+    assert out.dtype == np.float64 and out.shape == (4, 5)
+    assert np.array_equal(out[:, 2], scores[:, 0]) and np.array_equal(out[:, 0], scores[:, 2]) and not out[:, 1].any()
+    assert m.mapping_matrix[1].min() == 1e10 and m.mapping_matrix[0, 2] == 0
+
+
+def test_binarize_turns_at_frame_middles():
+    res = 0.1
+    data = np.zeros((10, 3))
+    data[0:3, 0] = 0.9            # active from the very first frame
+    data[4:6, 1] = 0.9
+    data[8:10, 1] = 0.9           # still active at the last frame
+    swf = SlidingWindowFeature(data, SlidingWindow(start=5.0, duration=res, step=res))
+    ann = blocks.Binarize(0.5)(swf)
+    got = sorted((round(s.start, 6), round(s.end, 6), lab) for s, _, lab in ann.itertracks(yield_label=True))
+    assert got == [(5.05, 5.35, "speaker0"), (5.45, 5.65, "speaker1"), (5.85, 6.05, "speaker1")]
+    assert "SPEAKER <NA> 1 5.050 0.300 <NA> <NA> speaker0 <NA> <NA>" in ann.to_rttm()
+
+
+def test_delayed_aggregation_latency_equals_step():
+    agg = blocks.DelayedAggregation(step=0.5, latency=0.5, strategy="hamming", cropping_mode="loose")
+    assert agg.num_overlapping_windows == 1
+    res = 5 / 293
+    first = SlidingWindowFeature(np.random.rand(293, 4), SlidingWindow(start=0, duration=res, step=res))
+    out = agg([first])
+    assert out.data.shape[1] == 4 and abs(out.extent.start) < 1e-9 and abs(out.extent.end - 5.0) < 1e-6
+    later = SlidingWindowFeature(np.random.rand(293, 4), SlidingWindow(start=3.0, duration=res, step=res))
+    out = agg([later])
+    assert 29 <= out.data.shape[0] <= 31 and abs(out.extent.start - 7.5) < 1e-6
+
+
+def test_no_cpu_fallback():
+    net = models.B200PyanNet({})
+    with pytest.raises(_lib.DiartB200Error):
+        net.to(torch.device("cpu"))
+    with pytest.raises(_lib.DiartB200Error):
+        net(torch.zeros(1, 1, 80000))             # not on a CUDA device yet
+    if not torch.cuda.is_available():
+        with pytest.raises(_lib.DiartB200Error):
+            net.to(torch.device("cuda"))
+        with pytest.raises(_lib.DiartB200Error):
+            blocks.OnlineSpeakerClustering(0.6, 0.3, 1.0).step_batch(torch.zeros(1, 293, 3), torch.zeros(1, 3, 512))
+
+
+def test_loader_plugin_contract():
+    """SegmentationModel / EmbeddingModel keep the reference's lazy-loading interface (models.py:112-139)"""
+    calls = []
+
+    class Fake:
+        def to(self, device):
+            calls.append(("to", str(device)))
+            return self
+
+        def __call__(self, *args):
+            return torch.zeros(1)
+
+    m = models.SegmentationModel(lambda: calls.append("load") or Fake())
+    assert not m.is_in_memory()
+    m.eval()
+    m.to(torch.device("cpu"))
+    assert calls == ["load", ("to", "cpu")] and m.is_in_memory()
+    e = models.EmbeddingModel(lambda: (lambda w, x=None: np.zeros((2, 4), dtype=np.float32)))
+    assert isinstance(e(torch.zeros(2, 1, 10)), torch.Tensor)      # ndarray results become tensors (models.py:262-264)

@@ -1,0 +1,86 @@
+"""The oracle (oracle/) against the committed golden vectors, which were produced by the REFERENCE'S
+OWN code in the authoring container (oracle/make_golden.py).  Runs without a GPU and without
+/root/reference."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from diart_b200 import synth
+from oracle import nets
+from oracle.clustering import OracleClustering
+from oracle.pipeline import OraclePipeline, normalize_embeddings, osp_block, overlapped_speech_penalty
+from oracle.synth_cluster import make_stream
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_parameter_and_frame_counts(oracle_nets):
+    seg, emb = oracle_nets
+    assert nets.n_params(seg) == 1_472_749      # pyannote/segmentation
+    assert nets.n_params(emb) == 4_346_366      # pyannote/embedding
+    x = torch.zeros(1, 1, 80000)
+    with torch.no_grad():
+        assert seg(x).shape == (1, 293, 3)
+        assert emb.trunk(x).shape == (1, 1500, 279)
+
+
+def test_clustering_traces_match_reference():
+    g = np.load(os.path.join(GOLD, "cluster_traces.npz"))
+    branches = set()
+    for cfg in g["configs"]:
+        seed, M, sigma, delta, tau, rho, K, n = cfg
+        seed, M, K, n = int(seed), int(M), int(K), int(n)
+        seg, emb = make_stream(n, seed, K=K, sigma=sigma)
+        o = OracleClustering(tau, rho, delta, "cosine", M)
+        maps = np.stack([o(s, e)[0] for s, e in zip(seg, emb)])
+        assert np.array_equal(maps, g[f"maps_{seed}"].astype(np.int32)), f"config {seed}"
+        assert hashlib.sha256(o.centers.tobytes()).hexdigest() == str(g[f"centers_sha_{seed}"])
+        assert sorted(o.active_centers) == list(g[f"active_{seed}"])
+        if len(o.active_centers) == M:
+            branches.add("full")
+        if (maps == -1).any():
+            branches.add("unmapped")
+    assert branches == {"full", "unmapped"}
+
+
+def test_functional_known_answers():
+    g = np.load(os.path.join(GOLD, "functional_kats.npz"))
+    seg, emb = torch.from_numpy(g["seg"]), torch.from_numpy(g["emb"])
+    for name, (gamma, beta) in {"osp_3_10": (3, 10), "osp_2_5": (2, 5), "osp_2p5_7": (2.5, 7)}.items():
+        np.testing.assert_allclose(overlapped_speech_penalty(seg.clone(), gamma, beta).numpy(), g[name], rtol=1e-6)
+    np.testing.assert_allclose(osp_block(seg.clone(), 3, 10, True).numpy(), g["osp_norm"], rtol=1e-6)
+    assert (g["osp_norm"][1, :, 1] == np.float32(1e-8)).all()       # min == max column -> nan_to_num(1e-8)
+    assert g["osp_3_10"].min() == np.float32(1e-8)                   # clamp branch
+    np.testing.assert_allclose(normalize_embeddings(emb, 1).numpy(), g["normalize_1"], rtol=1e-6)
+    np.testing.assert_allclose(normalize_embeddings(emb, 2.5).numpy(), g["normalize_2p5"], rtol=1e-6)
+
+
+def test_pipeline_nets_match_reference_blocks(oracle_nets):
+    """oracle/pipeline.py (restating diarization.py:177-188, embedding.py:51-68) == the reference's own
+    SpeakerSegmentation + OverlapAwareSpeakerEmbedding blocks run over the same networks"""
+    g = np.load(os.path.join(GOLD, "nets.npz"))
+    seg_net, emb_net = oracle_nets
+    stream = synth.synth_audio(80000 + 8000 * 7, seed=1234)
+    x = torch.from_numpy(synth.windows(stream, 8)[:2])
+    pipe = OraclePipeline(seg_net, emb_net, as_reference=True)
+    seg, emb = pipe.nets(x)
+    # same code, possibly another CPU / thread count: float32 re-association noise only
+    assert np.abs(seg.numpy() - g["seg"]).max() < 2e-5
+    assert np.abs(emb.numpy() - g["emb"]).max() < 1e-4
+    dedup = OraclePipeline(seg_net, emb_net, as_reference=False).nets(x)[1]
+    assert np.abs(dedup.numpy() - g["emb"]).max() < 1e-4   # trunk-once == K-fold repeat
+
+
+def test_numpy_reduction_semantics():
+    """the clustering kernel mirrors np.max / np.mean over axis 0 of a float32 (F,K) array:
+    the mean is a float32 running sum in frame order followed by one float32 division"""
+    rng = np.random.default_rng(0)
+    seg = rng.random((293, 3)).astype(np.float32)
+    run = np.zeros(3, dtype=np.float32)
+    for f in range(293):
+        run = (run + seg[f]).astype(np.float32)
+    assert np.array_equal(np.mean(seg, axis=0), run / np.float32(293))
+    assert (np.float32(0.6) >= 0.6) and not (np.float32(0.59999996) >= 0.6)   # float32 comparison (weak scalar)
