@@ -30,6 +30,8 @@ SIGNATURES = {
     "dg_launch_count": (C.c_int64, []),
     "dg_profile_enable": (C.c_int, [C.c_int]),
     "dg_profile_report": (C.c_int, [C.c_char_p, C.c_int]),
+    "dg_selftest_gemm_tc": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                      C.POINTER(C.c_float)]),
     "dg_seg_create": (C.c_int, [C.POINTER(DgTensor), C.c_int, C.c_int, C.POINTER(_P)]),
     "dg_seg_dims": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dg_seg_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

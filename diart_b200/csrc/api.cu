@@ -1,6 +1,7 @@
 // C ABI of libdiartb200.so (include/diart_b200.h): handles, weight preparation, workspaces and the
 // launch sequences of the two networks, the clustering step and the fused pipeline step.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -84,6 +85,29 @@ struct Tensors {
     return it == m.end() ? -1 : it->second.second;
   }
 };
+
+// DG_SIMT=1 forces the float32 SIMT GEMMs everywhere (A/B switch for the parity tests and bench)
+static bool use_tensor_cores() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("DG_SIMT");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v == 1;
+}
+
+static int upload_u16(DevBuf& b, const std::vector<uint16_t>& h) {
+  if (b.ensure(h.size() * 2)) return -2;
+  DG_CUDA(cudaMemcpy(b.p, h.data(), h.size() * 2, cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// float32 [N][K] host weights -> zero-padded bf16 hi/lo device planes [Npad][K]
+static int upload_split(DevBuf& hi, DevBuf& lo, const std::vector<float>& w_nk, int N, int Npad, int K) {
+  std::vector<uint16_t> h((size_t)Npad * K), l((size_t)Npad * K);
+  split_weights_host(w_nk.data(), N, Npad, K, h.data(), l.data());
+  return (upload_u16(hi, h) || upload_u16(lo, l)) ? DG_ECUDA : 0;
+}
 
 static int upload(DevBuf& b, const std::vector<float>& h) {
   if (b.ensure(h.size() * sizeof(float))) return -2;
@@ -219,6 +243,8 @@ struct dg_seg {
   int device = 0, K = 3;
   SincWeights sw;
   DevBuf wih[4], bih[4], whh[4];   // input projections [in_pad][1024], bias [1024], packed W_hh
+  DevBuf wih_hi[4], wih_lo[4];     // the same as bf16 hi/lo planes [1024][in_pad] for the tcgen05 path
+  DevBuf xh, xl;                   // bf16 hi/lo planes of the current in-projection input
   DevBuf l1w, l1b, l2w, l2b, cw, cb;
   SincWork work;
   DevBuf gx, hA, hB, y1, y2;
@@ -245,6 +271,10 @@ static int seg_prepare(dg_seg* h, const Tensors& t) {
     }
     lstm_pack_whh(hh[0], hh[1], packed.data());
     if (upload(h->wih[L], w) || upload(h->bih[L], b) || upload(h->whh[L], packed)) return DG_ECUDA;
+    std::vector<float> w_nk((size_t)1024 * in_pad, 0.f);
+    for (int n = 0; n < 1024; n++)
+      for (int c = 0; c < in; c++) w_nk[(size_t)n * in_pad + c] = w[(size_t)c * 1024 + n];
+    if (upload_split(h->wih_hi[L], h->wih_lo[L], w_nk, 1024, 1024, in_pad)) return DG_ECUDA;
   }
   auto linear_t = [&](const std::string& name, int out, int in, DevBuf& dw, DevBuf& db) -> int {
     const float* w = t.get(name + ".weight", (int64_t)out * in);
@@ -356,7 +386,27 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
   const long long M = (long long)B * g.S2;
   float* hin = nullptr;
   float* hbuf[2] = {h->hA.as<float>(), h->hB.as<float>()};
+  const bool tc = use_tensor_cores();
+  if (tc && (h->xh.ensure(rows * 256 * 2) || h->xl.ensure(rows * 256 * 2))) return DG_ECUDA;
   for (int L = 0; L < 4; L++) {
+    if (tc) {
+      const int cin = L == 0 ? 64 : 256;
+      if (L == 0)
+        rc = launch_split(h->work.p2.as<float>(), M, 64, g.S2, h->work.sc2.as<float>(), h->work.sh2.as<float>(),
+                          h->xh.p, h->xl.p, st);
+      else
+        rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, h->xh.p, h->xl.p, st);
+      if (rc) return rc;
+      TcGemm t{};
+      t.A_hi = h->xh.p; t.A_lo = h->xl.p; t.lda = cin; t.Cin = cin; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
+      t.W_hi = h->wih_hi[L].p; t.W_lo = h->wih_lo[L].p; t.Npad = 1024; t.N = 1024; t.bias = h->bih[L].as<float>();
+      t.out_f32 = h->gx.as<float>(); t.ldc = 1024; t.epi = 0; t.tag = "lstm_inproj";
+      if ((rc = launch_gemm_tc(t, st))) return rc;
+      float* hout = hbuf[L & 1];
+      if ((rc = launch_lstm_layer(h->gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st))) return rc;
+      hin = hout;
+      continue;
+    }
     GemmArgs a{};
     if (L == 0) {
       a.A = h->work.p2.as<float>(); a.lda = 64; a.Cin = 64;
@@ -393,6 +443,8 @@ struct dg_emb {
   int device = 0, pool_mode = 31, D = 512;
   SincWeights sw;
   DevBuf tw[5], tb[5], bns[5], bnh[5];
+  DevBuf tw_hi[5], tw_lo[5];             // bf16 hi/lo planes [Npad][K] for the tcgen05 path
+  DevBuf xh, xl, aH, aL, bH, bL;         // bf16 hi/lo activation planes
   DevBuf ew, eb;
   SincWork work;
   DevBuf tA, tB, t5, pooled, eraw;
@@ -428,6 +480,14 @@ static int emb_prepare(dg_emb* h, const Tensors& t) {
       sf[o] = bt[o] - rm[o] * sc[o];
     }
     if (upload(h->tw[L], wt) || upload(h->tb[L], bv) || upload(h->bns[L], sc) || upload(h->bnh[L], sf)) return DG_ECUDA;
+    {
+      const int K = k * in_pad, npad = (out + 255) / 256 * 256;
+      std::vector<float> w_nk((size_t)out * K, 0.f);
+      for (int o = 0; o < out; o++)
+        for (int c = 0; c < in; c++)
+          for (int j = 0; j < k; j++) w_nk[(size_t)o * K + j * in_pad + c] = w[((size_t)o * in + c) * k + j];
+      if (upload_split(h->tw_hi[L], h->tw_lo[L], w_nk, out, npad, K)) return DG_ECUDA;
+    }
     in = out;
     in_pad = out;
   }
@@ -516,6 +576,37 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
   const size_t rows = (size_t)U * g.S2 + 64;
   if (h->tA.ensure(rows * 512 * 4) || h->tB.ensure(rows * 512 * 4) || h->t5.ensure(rows * 1500 * 4)) return DG_ECUDA;
   const long long M = (long long)U * g.S2;
+  if (use_tensor_cores()) {
+    if (h->xh.ensure(rows * 64 * 2) || h->xl.ensure(rows * 64 * 2) || h->aH.ensure(rows * 512 * 2) ||
+        h->aL.ensure(rows * 512 * 2) || h->bH.ensure(rows * 512 * 2) || h->bL.ensure(rows * 512 * 2))
+      return DG_ECUDA;
+    if ((rc = launch_split(h->work.p2.as<float>(), M, 64, g.S2, h->work.sc2.as<float>(), h->work.sh2.as<float>(),
+                           h->xh.p, h->xl.p, st)))
+      return rc;
+    const void *ih = h->xh.p, *il = h->xl.p;
+    int cin = 64, T = g.T2;
+    void* oh[2] = {h->aH.p, h->bH.p};
+    void* ol[2] = {h->aL.p, h->bL.p};
+    static const char* kTags[5] = {"tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5"};
+    for (int L = 0; L < 5; L++) {
+      TcGemm t{};
+      t.A_hi = ih; t.A_lo = il; t.lda = cin; t.Cin = cin; t.KW = TD_K[L]; t.dil = TD_DIL[L]; t.Mtot = M; t.M = M;
+      t.W_hi = h->tw_hi[L].p; t.W_lo = h->tw_lo[L].p; t.Npad = (TD_OUT[L] + 255) / 256 * 256; t.N = TD_OUT[L];
+      t.bias = h->tb[L].as<float>(); t.bn_scale = h->bns[L].as<float>(); t.bn_shift = h->bnh[L].as<float>();
+      t.tag = kTags[L];
+      if (L == 4) {
+        t.out_f32 = h->t5.as<float>(); t.ldc = 1500; t.epi = 2;
+      } else {
+        t.out_hi = oh[L & 1]; t.out_lo = ol[L & 1]; t.ldc = 512; t.epi = 1;
+      }
+      if ((rc = launch_gemm_tc(t, st))) return rc;
+      ih = oh[L & 1]; il = ol[L & 1];
+      cin = TD_OUT[L];
+      T -= (TD_K[L] - 1) * TD_DIL[L];
+    }
+    *T_out = T;
+    return 0;
+  }
   const float* in = h->work.p2.as<float>();
   int cin = 64, T = g.T2;
   float* bufs[2] = {h->tA.as<float>(), h->tB.as<float>()};
@@ -751,6 +842,84 @@ extern "C" int dg_cluster_export_delta(dg_cluster*, double*, void*) {
 extern "C" int dg_cluster_merge(dg_cluster*, const double*, int, void*) {
   set_error("dg_cluster_merge: shared-identity mode is not implemented yet");
   return DG_EINVAL;
+}
+
+// ================================================================================== self test
+// Runs the same shifted-window GEMM through the float32 SIMT kernel and through the tcgen05 bf16x3
+// kernel on seeded random data and reports the largest absolute difference and the output scale.
+extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int epi, float* max_abs_diff,
+                                   float* out_rms) {
+  if (M < 1 || Cin % 64 || KW < 1 || N % 4 || !max_abs_diff || !out_rms) {
+    set_error("dg_selftest_gemm_tc: bad arguments");
+    return DG_EINVAL;
+  }
+  const int K = KW * Cin, npad = (N + 255) / 256 * 256;
+  const long long Mtot = M;
+  std::vector<float> A((size_t)Mtot * Cin), Wkn((size_t)K * N), Wnk((size_t)N * K), bias(N), bsc(N), bsh(N);
+  uint32_t seed = 12345u;
+  auto rnd = [&]() {
+    seed = seed * 1664525u + 1013904223u;
+    return ((seed >> 8) & 0xFFFF) / 65536.f - 0.5f;
+  };
+  for (auto& v : A) v = 2.f * rnd();
+  for (int k = 0; k < K; k++)
+    for (int n = 0; n < N; n++) {
+      const float w = rnd() * 0.25f;
+      Wkn[(size_t)k * N + n] = w;
+      Wnk[(size_t)n * K + k] = w;
+    }
+  for (int n = 0; n < N; n++) {
+    bias[n] = rnd();
+    bsc[n] = 1.f + rnd();
+    bsh[n] = rnd();
+  }
+  DevBuf dA, dWkn, dWh, dWl, dB, dS, dH, dAh, dAl, dC0, dC1, dOh, dOl;
+  if (upload(dA, A) || upload(dWkn, Wkn) || upload(dB, bias) || upload(dS, bsc) || upload(dH, bsh) ||
+      upload_split(dWh, dWl, Wnk, N, npad, K))
+    return DG_ECUDA;
+  if (dAh.ensure((size_t)Mtot * Cin * 2) || dAl.ensure((size_t)Mtot * Cin * 2) || dC0.ensure((size_t)M * N * 4) ||
+      dC1.ensure((size_t)M * N * 4) || dOh.ensure((size_t)M * N * 2) || dOl.ensure((size_t)M * N * 2))
+    return DG_ECUDA;
+  int rc;
+  GemmArgs g{};
+  g.A = dA.as<float>(); g.lda = Cin; g.Cin = Cin; g.KW = KW; g.dil = dil; g.Mtot = Mtot; g.M = M;
+  g.W = dWkn.as<float>(); g.ldw = N; g.N = N; g.bias = dB.as<float>(); g.bn_scale = dS.as<float>();
+  g.bn_shift = dH.as<float>(); g.C = dC0.as<float>(); g.ldc = N; g.epi = epi == 0 ? EPI_BIAS : EPI_BIAS_LEAKY_BN;
+  g.tag = "selftest_simt";
+  if ((rc = launch_gemm(g, nullptr))) return rc;
+  if ((rc = launch_split(dA.as<float>(), Mtot, Cin, 1, nullptr, nullptr, dAh.p, dAl.p, nullptr))) return rc;
+  TcGemm t{};
+  t.A_hi = dAh.p; t.A_lo = dAl.p; t.lda = Cin; t.Cin = Cin; t.KW = KW; t.dil = dil; t.Mtot = Mtot; t.M = M;
+  t.W_hi = dWh.p; t.W_lo = dWl.p; t.Npad = npad; t.N = N; t.bias = dB.as<float>(); t.bn_scale = dS.as<float>();
+  t.bn_shift = dH.as<float>(); t.out_f32 = dC1.as<float>(); t.out_hi = dOh.p; t.out_lo = dOl.p; t.ldc = N;
+  t.epi = epi; t.tag = "selftest_tc";
+  if ((rc = launch_gemm_tc(t, nullptr))) return rc;
+  DG_CUDA(cudaDeviceSynchronize());
+  std::vector<float> c0((size_t)M * N), c1((size_t)M * N);
+  DG_CUDA(cudaMemcpy(c0.data(), dC0.p, c0.size() * 4, cudaMemcpyDeviceToHost));
+  if (epi == 1) {
+    std::vector<uint16_t> oh((size_t)M * N), ol((size_t)M * N);
+    DG_CUDA(cudaMemcpy(oh.data(), dOh.p, oh.size() * 2, cudaMemcpyDeviceToHost));
+    DG_CUDA(cudaMemcpy(ol.data(), dOl.p, ol.size() * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < c1.size(); i++) {
+      uint32_t a = (uint32_t)oh[i] << 16, b = (uint32_t)ol[i] << 16;
+      float fa, fb;
+      memcpy(&fa, &a, 4);
+      memcpy(&fb, &b, 4);
+      c1[i] = fa + fb;
+    }
+  } else {
+    DG_CUDA(cudaMemcpy(c1.data(), dC1.p, c1.size() * 4, cudaMemcpyDeviceToHost));
+  }
+  double md = 0, ss = 0;
+  for (size_t i = 0; i < c0.size(); i++) {
+    const double d = fabs((double)c0[i] - (double)c1[i]);
+    if (!(d <= md)) md = d;     // NaN-propagating max
+    ss += (double)c0[i] * c0[i];
+  }
+  *max_abs_diff = (float)md;
+  *out_rms = (float)sqrt(ss / c0.size());
+  return DG_OK;
 }
 
 // ================================================================================ fused pipeline

@@ -106,6 +106,29 @@ struct GemmArgs {
   const char* tag;   // kernel label for profiling (layer name)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
+// gemm_tc.cu -- tcgen05 / TMEM / TMA path (bf16x3 split precision)
+struct TcGemm {
+  const void* A_hi;    // bf16 [Mtot, lda]
+  const void* A_lo;
+  int lda, Cin, KW, dil;
+  long long Mtot, M;
+  const void* W_hi;    // bf16 [Npad, KW*Cin]  (n-major: row n holds its K weights, tap-major)
+  const void* W_lo;
+  int Npad, N;
+  const float* bias;
+  const float* bn_scale;
+  const float* bn_shift;
+  float* out_f32;      // [M, ldc] (float32 epilogues)
+  void* out_hi;        // bf16 [M, ldc] (split epilogue)
+  void* out_lo;
+  int ldc;
+  int epi;             // 0 bias -> f32, 1 bias+leaky+bn -> hi/lo planes, 2 bias+leaky+bn -> f32
+  const char* tag;
+};
+int launch_gemm_tc(const TcGemm& g, cudaStream_t st);
+int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
+                 void* lo, cudaStream_t st);
+void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo);
 // lstm.cu
 int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_packed, int B, int T, int stride,
                       float* hout /*[B*stride,256]*/, cudaStream_t st);

@@ -1,0 +1,471 @@
+// Shifted-window GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), "bf16x3" precision.
+//
+//     C[m, n] = epi( sum_{j<KW} sum_{c<Cin} A[m + j*dil, c] * W[n, j*Cin + c] + bias[n] )
+//
+// The dense contractions of the path -- the five TDNN layers of XVectorSincNet (dilated Conv1d ->
+// LeakyReLU -> BatchNorm1d(eval)) and the LSTM input projections of PyanNet (SURVEY.md Appendix
+// A.3/A.4; reached from the reference through src/diart/models.py:131-133) -- must stay at float32-level
+// accuracy because their outputs feed hard thresholds (tau_active, rho_update, delta_new).  Each float32
+// operand x is therefore carried as two bf16 planes, hi = bf16(x) and lo = bf16(x - hi) (16 significand
+// bits), and every k-step issues three tcgen05.mma (hi*hi + lo*hi + hi*lo) into the same float32 TMEM
+// accumulator.  Measured against float32 this costs < 1e-5 relative error per layer (oracle test).
+//
+// Because activations are stored time-major ([item][row][channel]) a Conv1d tap is just a TMA box whose
+// row coordinate is shifted by j*dil: no im2col is ever materialised.
+//
+// CTA = 192 threads, persistent over (m_tile, n_tile):
+//   warp 0      TMA producer: per k-block four boxes (A_hi, A_lo: 128 rows x 64 ch; W_hi, W_lo: BN x 64)
+//               into a 128B-swizzled, NSTAGE-deep shared-memory ring, completion on full[] mbarriers
+//   warp 1      MMA issuer (one elected lane): 12 tcgen05.mma per k-block into one of two TMEM
+//               accumulators (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem slot
+//   warps 2-5   epilogue: tcgen05.ld the finished accumulator (one TMEM lane quadrant per warp), bias,
+//               LeakyReLU, BatchNorm affine, then either float32 rows or the next layer's hi/lo bf16
+//               planes; overlaps the next tile's MMAs through the second accumulator.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <string.h>
+
+#include "dg_common.cuh"
+
+namespace dg {
+
+constexpr int TC_BM = 128, TC_BK = 64, TC_THREADS = 192;
+
+struct TcArgs {
+  long long M;          // output rows
+  int N;                // valid output channels
+  int m_tiles, n_tiles;
+  int KW, dil, cin_blocks;
+  const float* bias;
+  const float* bn_scale;
+  const float* bn_shift;
+  float* out_f32;       // EPI_F32*: [M, ldc]
+  __nv_bfloat16* out_hi;   // EPI_*_SPLIT: [M, ldc] each
+  __nv_bfloat16* out_lo;
+  int ldc;
+};
+
+enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2 };
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must surface as a trapped kernel, never as a hung GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset
+  d |= (uint64_t)1 << 46;                        // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+      ::"r"(tmem_c), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------ the kernel
+template <int BN>
+struct TcSmem {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB per plane
+  static constexpr int W_BYTES = BN * TC_BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int NSTAGE = BN == 256 ? 2 : 3;
+  static constexpr int PARAM_BYTES = 3 * BN * 4;
+  static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
+};
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+               const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcArgs a) {
+  using S = TcSmem<BN>;
+  constexpr int NSTAGE = S::NSTAGE;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* params = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES);          // bias | bn_scale | bn_shift
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES);
+  uint64_t* full = bars;                 // [NSTAGE] TMA -> MMA
+  uint64_t* empty = bars + NSTAGE;       // [NSTAGE] MMA -> TMA
+  uint64_t* acc_full = bars + 2 * NSTAGE;      // [2] MMA -> epilogue
+  uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = a.m_tiles * a.n_tiles;
+  const int kblocks = a.KW * a.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);     // one arrive per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM: two accumulators of BN fp32 columns
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        const int m0 = mt * TC_BM, n0 = nt * BN;
+        for (int j = 0; j < a.KW; j++) {
+          for (int cb = 0; cb < a.cin_blocks; cb++) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* st = smem + stage * S::STAGE_BYTES;
+            mbar_expect_tx(&full[stage], S::STAGE_BYTES);
+            const int kcol = (j * a.cin_blocks + cb) * TC_BK;
+            tma_load_2d(st, &tmA_hi, cb * TC_BK, m0 + j * a.dil, &full[stage]);
+            tma_load_2d(st + S::A_BYTES, &tmA_lo, cb * TC_BK, m0 + j * a.dil, &full[stage]);
+            tma_load_2d(st + 2 * S::A_BYTES, &tmW_hi, kcol, n0, &full[stage]);
+            tma_load_2d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, kcol, n0, &full[stage]);
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; kb++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + S::A_BYTES);
+          const uint64_t w_hi = umma_desc(sa + 2 * S::A_BYTES), w_lo = umma_desc(sa + 2 * S::A_BYTES + S::W_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 16; ks++) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 bytes per 16-element k-step
+            umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, (kb | ks) != 0);
+            umma_bf16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
+            umma_bf16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
+          }
+          umma_commit(&empty[stage]);           // smem slot reusable once these MMAs have read it
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&acc_full[acc]);            // accumulator complete -> epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int et = threadIdx.x - 64;            // 0..127
+    int acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int n0 = nt * BN;
+      const long long m = (long long)mt * TC_BM + quad * 32 + lane;
+      // stage the per-column parameters of this tile (named barrier 1: the 128 epilogue threads only)
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < BN; i += 128) {
+        const int n = n0 + i;
+        const bool ok = n < a.N;
+        params[i] = (ok && a.bias) ? a.bias[n] : 0.f;
+        params[BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_scale[n] : 1.f;
+        params[2 * BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_shift[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c, r);
+        if (n0 + c >= a.N) continue;
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) {
+          float x = __uint_as_float(r[i]) + params[c + i];
+          if (EPI != TC_BIAS_F32) {
+            x = leaky(x);
+            x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
+          }
+          v[i] = x;
+        }
+        if (m < a.M) {
+          if (EPI == TC_LEAKY_BN_SPLIT) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+              hi[i] = pack_bf16x2(h0, h1);
+              lo[i] = pack_bf16x2(l0, l1);
+            }
+            uint4* ph = reinterpret_cast<uint4*>(a.out_hi + m * a.ldc + n0 + c);
+            uint4* pl = reinterpret_cast<uint4*>(a.out_lo + m * a.ldc + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          } else {
+            float* po = a.out_f32 + m * a.ldc + n0 + c;
+            if (n0 + c + 32 <= a.N) {
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                reinterpret_cast<float4*>(po)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; i++)
+                if (n0 + c + i < a.N) po[i] = v[i];
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// bf16 matrix [rows, cols] row-major (cols contiguous, row pitch `ld` elements); box = 64 cols x box_rows
+static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, int ld, int box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return -2;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return -2;
+  }
+  return 0;
+}
+
+template <int BN, int EPI>
+static int launch_tc(const TcGemm& g, cudaStream_t st) {
+  using S = TcSmem<BN>;
+  CUtensorMap ta_hi, ta_lo, tw_hi, tw_lo;
+  const int Ktot = g.KW * g.Cin;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  if (make_map(&ta_hi, g.A_hi, g.Mtot, g.Cin, g.lda, TC_BM) || make_map(&ta_lo, g.A_lo, g.Mtot, g.Cin, g.lda, TC_BM) ||
+      make_map(&tw_hi, g.W_hi, g.Npad, Ktot, Ktot, BN) || make_map(&tw_lo, g.W_lo, g.Npad, Ktot, Ktot, BN))
+    return -2;
+  TcArgs a{};
+  a.M = g.M; a.N = g.N; a.m_tiles = (int)((g.M + TC_BM - 1) / TC_BM); a.n_tiles = n_tiles;
+  a.KW = g.KW; a.dil = g.dil; a.cin_blocks = g.Cin / TC_BK;
+  a.bias = g.bias; a.bn_scale = g.bn_scale; a.bn_shift = g.bn_shift;
+  a.out_f32 = g.out_f32; a.out_hi = reinterpret_cast<__nv_bfloat16*>(g.out_hi);
+  a.out_lo = reinterpret_cast<__nv_bfloat16*>(g.out_lo); a.ldc = g.ldc;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int tiles = a.m_tiles * a.n_tiles;
+  const int grid = tiles < sms ? tiles : sms;
+  gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
+  DG_LAUNCHED();
+  return 0;
+}
+
+int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
+  ProfScope _ps(g.tag ? g.tag : "gemm_tc", st);
+  if (g.Cin % TC_BK || g.lda % 8 || g.ldc % 8 || g.Npad % 128) {
+    set_error("gemm_tc: Cin must be a multiple of 64, pitches multiples of 8, padded N a multiple of 128");
+    return -1;
+  }
+  const bool wide = g.Npad % 256 == 0;
+  switch (g.epi) {
+    case TC_BIAS_F32:
+      return wide ? launch_tc<256, TC_BIAS_F32>(g, st) : launch_tc<128, TC_BIAS_F32>(g, st);
+    case TC_LEAKY_BN_SPLIT:
+      return wide ? launch_tc<256, TC_LEAKY_BN_SPLIT>(g, st) : launch_tc<128, TC_LEAKY_BN_SPLIT>(g, st);
+    default:
+      return wide ? launch_tc<256, TC_LEAKY_BN_F32>(g, st) : launch_tc<128, TC_LEAKY_BN_F32>(g, st);
+  }
+}
+
+// ------------------------------------------------------------------------------------ bf16 hi/lo split
+// x [rows, C] float32 (optionally through the previous InstanceNorm1d + LeakyReLU) -> hi/lo bf16 planes
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, long long n4, int C, int item_rows,
+                                                    const float* __restrict__ sc, const float* __restrict__ sh,
+                                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[i];
+    if (sc) {
+      const long long e = i * 4, row = e / C;
+      const int c = (int)(e - row * C);
+      const long long item = row / item_rows;
+      const float4 s = *reinterpret_cast<const float4*>(sc + item * C + c);
+      const float4 h = *reinterpret_cast<const float4*>(sh + item * C + c);
+      v.x = leaky(fmaf(v.x, s.x, h.x)); v.y = leaky(fmaf(v.y, s.y, h.y));
+      v.z = leaky(fmaf(v.z, s.z, h.z)); v.w = leaky(fmaf(v.w, s.w, h.w));
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
+                        h3 = __float2bfloat16_rn(v.w);
+    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
+                        l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+  }
+}
+
+int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
+                 void* lo, cudaStream_t st) {
+  ProfScope _ps("split_bf16", st);
+  const long long n4 = rows * C / 4;
+  const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  split_kernel<<<grid, 256, 0, st>>>(x, n4, C, item_rows, sc, sh, reinterpret_cast<__nv_bfloat16*>(hi),
+                                     reinterpret_cast<__nv_bfloat16*>(lo));
+  DG_LAUNCHED();
+  return 0;
+}
+
+// host: float32 [N][K] -> zero-padded bf16 hi/lo planes [Npad][K]
+void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo) {
+  auto to_bf16 = [](float f) -> uint16_t {   // round to nearest even
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(r >> 16);
+  };
+  auto from_bf16 = [](uint16_t h) -> float {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  for (size_t i = 0; i < (size_t)Npad * K; i++) hi[i] = lo[i] = 0;
+  for (int n = 0; n < N; n++)
+    for (int k = 0; k < K; k++) {
+      const float f = w[(size_t)n * K + k];
+      const uint16_t h = to_bf16(f);
+      hi[(size_t)n * K + k] = h;
+      lo[(size_t)n * K + k] = to_bf16(f - from_bf16(h));
+    }
+}
+
+}  // namespace dg

@@ -123,6 +123,9 @@ int64_t dg_launch_count(void);
  * every kernel launch is bracketed by two events; dg_profile_report() synchronises the device and
  * writes {"kernel": {"count": n, "ms": total}, ...} into buf. */
 int dg_profile_enable(int enable);
+/* test hook: the same random shifted-window GEMM through the float32 SIMT kernel and the tcgen05 (bf16x3)
+ * kernel; epi 0 = bias -> f32, 1 = bias+leaky+bn -> bf16 hi/lo planes, 2 = bias+leaky+bn -> f32. */
+int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int epi, float* max_abs_diff, float* out_rms);
 int dg_profile_report(char* buf, int cap);
 
 /* ---- shared-identity mode (extension): merge per-rank centroid deltas that were
