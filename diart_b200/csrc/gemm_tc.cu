@@ -393,8 +393,9 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
 
 int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
   ProfScope _ps(g.tag ? g.tag : "gemm_tc", st);
-  if (g.Cin % TC_BK || g.lda % 8 || g.ldc % 8 || g.Npad % 128) {
-    set_error("gemm_tc: Cin must be a multiple of 64, pitches multiples of 8, padded N a multiple of 128");
+  if (g.Cin % TC_BK || g.lda % 8 || g.ldc % (g.epi == TC_LEAKY_BN_SPLIT ? 8 : 4) || g.Npad % 128) {
+    set_error("gemm_tc: Cin must be a multiple of 64, A pitch a multiple of 8, output pitch a multiple of 4 "
+              "(8 for bf16 planes), padded N a multiple of 128");
     return -1;
   }
   const bool wide = g.Npad % 256 == 0;
