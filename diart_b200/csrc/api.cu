@@ -119,6 +119,7 @@ static int upload(DevBuf& b, const std::vector<float>& h) {
 struct SincWeights {
   float wn_gamma = 1.f, wn_beta = 0.f;
   DevBuf filt, g0, b0, w1, bias1, g1, b1, w2, bias2, g2, b2;
+  DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: bf16 hi/lo planes [128][5*128] and [128][5*64]
 };
 
 // ParamSincFB.filters() in float32, as asteroid-filterbanks computes it with torch
@@ -186,11 +187,34 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
   if ((rc = conv_w(pre + "conv1d.1.weight", 60, 80, 5, 80, 64, w.w1)) ||
       (rc = conv_w(pre + "conv1d.2.weight", 60, 60, 5, 64, 64, w.w2)))
     return rc;
+  auto conv_w_tc = [&](const std::string& name, int out, int in, int k, int in_pad, DevBuf& hi, DevBuf& lo) -> int {
+    const float* s = t.get(name, (int64_t)out * in * k);
+    if (!s) return DG_EWEIGHT;
+    std::vector<float> w_nk((size_t)out * k * in_pad, 0.f);
+    for (int o = 0; o < out; o++)
+      for (int c = 0; c < in; c++)
+        for (int j = 0; j < k; j++) w_nk[(size_t)o * k * in_pad + j * in_pad + c] = s[((size_t)o * in + c) * k + j];
+    return upload_split(hi, lo, w_nk, out, 128, k * in_pad);
+  };
+  if ((rc = conv_w_tc(pre + "conv1d.1.weight", 60, 80, 5, 128, w.w1_hi, w.w1_lo)) ||
+      (rc = conv_w_tc(pre + "conv1d.2.weight", 60, 60, 5, 64, w.w2_hi, w.w2_lo)))
+    return rc;
   return 0;
 }
 
 struct SincWork {
   DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
+  DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: bf16 planes of the conv inputs, un-pooled conv outputs
+  const float* out = nullptr;          // conv2 output that the next layer normalises on load ...
+  int out_pool = 0;                    // ... 1: still un-pooled (rows = 3x), MaxPool1d(3) is applied on load
+  int ensure_tc(int B, const Geom& g) {
+    const size_t tail = 64;
+    if (a0h.ensure(((size_t)B * g.S0 + tail) * 128 * 2) || a0l.ensure(((size_t)B * g.S0 + tail) * 128 * 2) ||
+        c1.ensure(((size_t)B * g.S0 + tail) * 64 * 4) || a1h.ensure(((size_t)B * g.S1 + tail) * 64 * 2) ||
+        a1l.ensure(((size_t)B * g.S1 + tail) * 64 * 2) || c2.ensure(((size_t)B * g.S1 + tail) * 64 * 4))
+      return DG_ECUDA;
+    return 0;
+  }
   int ensure(int B, const Geom& g) {
     const size_t tail = 64;  // spare rows so shifted windows of the last tile stay in bounds
     if (wmean.ensure(B * 4) || wrstd.ensure(B * 4) || p0.ensure(((size_t)B * g.S0 + tail) * 80 * 4) ||
@@ -203,10 +227,48 @@ struct SincWork {
   }
 };
 
-// waveform [B,S] -> p2 [B*S2, 64] (pre-norm conv2 output) + its InstanceNorm scale/shift
+// waveform [B,S] -> k.out (pre-norm conv2 output, pooled [B*S2,64] or un-pooled [B*S1,64]) + its
+// InstanceNorm scale/shift (k.sc2, k.sh2)
 static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int B, const Geom& g, cudaStream_t st) {
   int rc;
   if ((rc = k.ensure(B, g))) return rc;
+  if (use_tensor_cores()) {
+    if ((rc = k.ensure_tc(B, g))) return rc;
+    if ((rc = launch_wave_stats(wav, B, g.S, k.wmean.as<float>(), k.wrstd.as<float>(), st))) return rc;
+    if ((rc = launch_sinc0(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt.as<float>(),
+                           B, g, k.p0.as<float>(), st)))
+      return rc;
+    if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),
+                                    k.sc0.as<float>(), k.sh0.as<float>(), st)))
+      return rc;
+    // Conv1d(80,60,5): normalised input as bf16 planes (80 -> 128 channels), un-pooled float32 output
+    const long long M0 = (long long)B * g.S0, M1 = (long long)B * g.S1;
+    if ((rc = launch_split_ex(k.p0.as<float>(), M0, 80, 80, 128, 0, g.S0, k.sc0.as<float>(), k.sh0.as<float>(),
+                              k.a0h.p, k.a0l.p, st)))
+      return rc;
+    TcGemm t{};
+    t.A_hi = k.a0h.p; t.A_lo = k.a0l.p; t.lda = 128; t.Cin = 128; t.KW = 5; t.dil = 1; t.Mtot = M0; t.M = M0;
+    t.W_hi = w.w1_hi.p; t.W_lo = w.w1_lo.p; t.Npad = 128; t.N = 64; t.bias = w.bias1.as<float>();
+    t.out_f32 = k.c1.as<float>(); t.ldc = 64; t.epi = 0; t.tag = "sinc_conv1";
+    if ((rc = launch_gemm_tc(t, st))) return rc;
+    if ((rc = launch_instnorm_stats(k.c1.as<float>(), B, g.S0, g.T1, 64, 64, w.g1.as<float>(), w.b1.as<float>(),
+                                    k.sc1.as<float>(), k.sh1.as<float>(), st, 1)))
+      return rc;
+    // Conv1d(60,60,5) on MaxPool(conv1) -> norm -> leaky, again un-pooled output
+    if ((rc = launch_split_ex(k.c1.as<float>(), M1, 64, 64, 64, 1, g.S1, k.sc1.as<float>(), k.sh1.as<float>(),
+                              k.a1h.p, k.a1l.p, st)))
+      return rc;
+    t.A_hi = k.a1h.p; t.A_lo = k.a1l.p; t.lda = 64; t.Cin = 64; t.Mtot = M1; t.M = M1;
+    t.W_hi = w.w2_hi.p; t.W_lo = w.w2_lo.p; t.bias = w.bias2.as<float>();
+    t.out_f32 = k.c2.as<float>(); t.tag = "sinc_conv2";
+    if ((rc = launch_gemm_tc(t, st))) return rc;
+    k.out = k.c2.as<float>();
+    k.out_pool = 1;
+    return launch_instnorm_stats(k.c2.as<float>(), B, g.S1, g.T2, 64, 64, w.g2.as<float>(), w.b2.as<float>(),
+                                 k.sc2.as<float>(), k.sh2.as<float>(), st, 1);
+  }
+  k.out = k.p2.as<float>();
+  k.out_pool = 0;
   if ((rc = launch_wave_stats(wav, B, g.S, k.wmean.as<float>(), k.wrstd.as<float>(), st))) return rc;
   if ((rc = launch_sinc0(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt.as<float>(), B,
                          g, k.p0.as<float>(), st)))
@@ -392,8 +454,8 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
     if (tc) {
       const int cin = L == 0 ? 64 : 256;
       if (L == 0)
-        rc = launch_split(h->work.p2.as<float>(), M, 64, g.S2, h->work.sc2.as<float>(), h->work.sh2.as<float>(),
-                          h->xh.p, h->xl.p, st);
+        rc = launch_split_ex(h->work.out, M, 64, 64, 64, h->work.out_pool, g.S2, h->work.sc2.as<float>(),
+                             h->work.sh2.as<float>(), h->xh.p, h->xl.p, st);
       else
         rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, h->xh.p, h->xl.p, st);
       if (rc) return rc;
@@ -444,6 +506,7 @@ struct dg_emb {
   SincWeights sw;
   DevBuf tw[5], tb[5], bns[5], bnh[5];
   DevBuf tw_hi[5], tw_lo[5];             // bf16 hi/lo planes [Npad][K] for the tcgen05 path
+  DevBuf ew_hi, ew_lo, ph, pl;           // Linear(3000, D): weights [Dpad][3008], pooled statistics planes
   DevBuf xh, xl, aH, aL, bH, bL;         // bf16 hi/lo activation planes
   DevBuf ew, eb;
   SincWork work;
@@ -504,6 +567,11 @@ static int emb_prepare(dg_emb* h, const Tensors& t) {
   for (int o = 0; o < dn; o++)
     for (int c = 0; c < 3000; c++) wt[(size_t)c * dn + o] = ew[(size_t)o * 3000 + c];
   if (upload(h->ew, wt) || upload(h->eb, std::vector<float>(eb, eb + dn))) return DG_ECUDA;
+  {
+    std::vector<float> w_nk((size_t)dn * 3008, 0.f);
+    for (int o = 0; o < dn; o++) memcpy(&w_nk[(size_t)o * 3008], ew + (size_t)o * 3000, 3000 * sizeof(float));
+    if (upload_split(h->ew_hi, h->ew_lo, w_nk, (int)dn, ((int)dn + 255) / 256 * 256, 3008)) return DG_ECUDA;
+  }
   return 0;
 }
 
@@ -580,8 +648,8 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
     if (h->xh.ensure(rows * 64 * 2) || h->xl.ensure(rows * 64 * 2) || h->aH.ensure(rows * 512 * 2) ||
         h->aL.ensure(rows * 512 * 2) || h->bH.ensure(rows * 512 * 2) || h->bL.ensure(rows * 512 * 2))
       return DG_ECUDA;
-    if ((rc = launch_split(h->work.p2.as<float>(), M, 64, g.S2, h->work.sc2.as<float>(), h->work.sh2.as<float>(),
-                           h->xh.p, h->xl.p, st)))
+    if ((rc = launch_split_ex(h->work.out, M, 64, 64, 64, h->work.out_pool, g.S2, h->work.sc2.as<float>(),
+                              h->work.sh2.as<float>(), h->xh.p, h->xl.p, st)))
       return rc;
     const void *ih = h->xh.p, *il = h->xl.p;
     int cin = 64, T = g.T2;
@@ -633,6 +701,24 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
 }
 
 static int emb_project(dg_emb* h, int rows, int normalize, float norm, float* out, cudaStream_t st) {
+  if (use_tensor_cores()) {
+    int rc;
+    if (h->ph.ensure(((size_t)rows + 128) * 3008 * 2) || h->pl.ensure(((size_t)rows + 128) * 3008 * 2)) return DG_ECUDA;
+    if ((rc = launch_split_ex(h->pooled.as<float>(), rows, 3000, 3000, 3008, 0, 1, nullptr, nullptr, h->ph.p, h->pl.p,
+                              st)))
+      return rc;
+    float* dst = out;
+    if (normalize) {
+      if (h->eraw.ensure((size_t)rows * h->D * 4)) return DG_ECUDA;
+      dst = h->eraw.as<float>();
+    }
+    TcGemm t{};
+    t.A_hi = h->ph.p; t.A_lo = h->pl.p; t.lda = 3008; t.Cin = 3008; t.KW = 1; t.dil = 1; t.Mtot = rows; t.M = rows;
+    t.W_hi = h->ew_hi.p; t.W_lo = h->ew_lo.p; t.Npad = (h->D + 255) / 256 * 256; t.N = h->D;
+    t.bias = h->eb.as<float>(); t.out_f32 = dst; t.ldc = h->D; t.epi = 0; t.tag = "emb_linear";
+    if ((rc = launch_gemm_tc(t, st))) return rc;
+    return normalize ? launch_l2norm(dst, rows, h->D, norm, out, st) : 0;
+  }
   GemmArgs a{};
   a.A = h->pooled.as<float>(); a.lda = 3000; a.Cin = 3000; a.KW = 1; a.dil = 1; a.Mtot = rows; a.M = rows;
   a.W = h->ew.as<float>(); a.ldw = h->D; a.N = h->D; a.bias = h->eb.as<float>();

@@ -81,7 +81,7 @@ int launch_wave_stats(const float* wav, int B, int S, float* mean, float* rstd, 
 int launch_sinc0(const float* wav, const float* mean, const float* rstd, float wn_gamma, float wn_beta,
                  const float* filt /*[251][80]*/, int B, const Geom& g, float* p0 /*[B,S0,80]*/, cudaStream_t st);
 int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
-                          const float* beta, float* sc, float* sh, cudaStream_t st);
+                          const float* beta, float* sc, float* sh, cudaStream_t st, int pool = 0);
 // gemm.cu
 enum Epi { EPI_BIAS = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_LEAKY_BN = 2, EPI_BIAS_POOL3 = 3 };
 struct GemmArgs {
@@ -128,6 +128,8 @@ struct TcGemm {
 int launch_gemm_tc(const TcGemm& g, cudaStream_t st);
 int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
                  void* lo, cudaStream_t st);
+int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld_out, int pool, int item_rows,
+                    const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st);
 void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo);
 // lstm.cu
 int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_packed, int B, int T, int stride,

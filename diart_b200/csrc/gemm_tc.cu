@@ -410,20 +410,36 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------ bf16 hi/lo split
-// x [rows, C] float32 (optionally through the previous InstanceNorm1d + LeakyReLU) -> hi/lo bf16 planes
-__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, long long n4, int C, int item_rows,
-                                                    const float* __restrict__ sc, const float* __restrict__ sh,
-                                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+// x [rows_in, ld_in] float32 -> hi/lo bf16 planes [rows_out, ld_out]; optionally MaxPool1d(3) over rows
+// (out row r <- max of in rows 3r..3r+2) and the previous InstanceNorm1d + LeakyReLU (scale/shift per
+// (item, channel), item = out row / item_rows); channels [C, ld_out) are written as zeros.
+__global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, long long rows_out, int C, int ld_in,
+                                                    int ld_out, int pool, int item_rows, const float* __restrict__ sc,
+                                                    const float* __restrict__ sh, __nv_bfloat16* __restrict__ hi,
+                                                    __nv_bfloat16* __restrict__ lo) {
+  const int q_per_row = ld_out >> 2;
+  const long long n4 = rows_out * q_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-    float4 v = reinterpret_cast<const float4*>(x)[i];
-    if (sc) {
-      const long long e = i * 4, row = e / C;
-      const int c = (int)(e - row * C);
-      const long long item = row / item_rows;
-      const float4 s = *reinterpret_cast<const float4*>(sc + item * C + c);
-      const float4 h = *reinterpret_cast<const float4*>(sh + item * C + c);
-      v.x = leaky(fmaf(v.x, s.x, h.x)); v.y = leaky(fmaf(v.y, s.y, h.y));
-      v.z = leaky(fmaf(v.z, s.z, h.z)); v.w = leaky(fmaf(v.w, s.w, h.w));
+    const long long row = i / q_per_row;
+    const int c = (int)(i - row * q_per_row) << 2;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c < C) {
+      if (pool) {
+        const float* p = x + (row * 3) * ld_in + c;
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + ld_in),
+                     d = *reinterpret_cast<const float4*>(p + 2 * ld_in);
+        v = make_float4(fmaxf(fmaxf(a.x, b.x), d.x), fmaxf(fmaxf(a.y, b.y), d.y), fmaxf(fmaxf(a.z, b.z), d.z),
+                        fmaxf(fmaxf(a.w, b.w), d.w));
+      } else {
+        v = *reinterpret_cast<const float4*>(x + row * ld_in + c);
+      }
+      if (sc) {
+        const long long item = row / item_rows;
+        const float4 s = *reinterpret_cast<const float4*>(sc + item * ld_in + c);
+        const float4 h = *reinterpret_cast<const float4*>(sh + item * ld_in + c);
+        v.x = leaky(fmaf(v.x, s.x, h.x)); v.y = leaky(fmaf(v.y, s.y, h.y));
+        v.z = leaky(fmaf(v.z, s.z, h.z)); v.w = leaky(fmaf(v.w, s.w, h.w));
+      }
     }
     const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
                         h3 = __float2bfloat16_rn(v.w);
@@ -434,15 +450,25 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
   }
 }
 
-int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
-                 void* lo, cudaStream_t st) {
+int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld_out, int pool, int item_rows,
+                    const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st) {
   ProfScope _ps("split_bf16", st);
-  const long long n4 = rows * C / 4;
-  const int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
-  split_kernel<<<grid, 256, 0, st>>>(x, n4, C, item_rows, sc, sh, reinterpret_cast<__nv_bfloat16*>(hi),
-                                     reinterpret_cast<__nv_bfloat16*>(lo));
+  if (C % 4 || ld_in % 4 || ld_out % 4) {
+    set_error("split: channel counts must be multiples of 4");
+    return -1;
+  }
+  const long long n4 = rows_out * (ld_out / 4);
+  const long long want = (n4 + 255) / 256;
+  const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
+  split_kernel<<<grid, 256, 0, st>>>(x, rows_out, C, ld_in, ld_out, pool, item_rows, sc, sh,
+                                     reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
   DG_LAUNCHED();
   return 0;
+}
+
+int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
+                 void* lo, cudaStream_t st) {
+  return launch_split_ex(x, rows, C, C, C, 0, item_rows, sc, sh, hi, lo, st);
 }
 
 // host: float32 [N][K] -> zero-padded bf16 hi/lo planes [Npad][K]

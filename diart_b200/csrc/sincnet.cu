@@ -140,19 +140,26 @@ int launch_sinc0(const float* wav, const float* mean, const float* rstd, float w
 // leaky(x * sc + sh) on load.  CTA = (item, 32-channel group); 8 warps stride over rows; sums are
 // taken around the first row's value (pivot) to avoid E[x^2]-E[x]^2 cancellation, combined in double.
 // ---------------------------------------------------------------------------------------------
+// pool != 0: x holds the un-pooled conv output (stride_rows rows per item) and the statistics are taken over
+// MaxPool1d(3) of it, i.e. value(t) = max(x[3t], x[3t+1], x[3t+2]) for t < T.
 __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x, int stride_rows, int T, int C,
                                                              int ldc, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ sc,
-                                                             float* __restrict__ sh) {
+                                                             float* __restrict__ sh, int pool) {
   __shared__ double s1[8][32], s2[8][32];
   const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
   const bool ok = c < C;
   const float* xb = x + (size_t)b * stride_rows * ldc;
-  const float pivot = ok ? xb[c] : 0.f;
+  auto val = [&](int t) -> float {
+    if (!pool) return xb[(size_t)t * ldc + c];
+    const float* p = xb + (size_t)(3 * t) * ldc + c;
+    return fmaxf(fmaxf(p[0], p[ldc]), p[2 * ldc]);
+  };
+  const float pivot = ok ? val(0) : 0.f;
   float a1 = 0.f, a2 = 0.f;
   if (ok)
     for (int t = w; t < T; t += 8) {
-      float d = xb[(size_t)t * ldc + c] - pivot;
+      float d = val(t) - pivot;
       a1 += d;
       a2 = fmaf(d, d, a2);
     }
@@ -176,10 +183,10 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __rest
 }
 
 int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
-                          const float* beta, float* sc, float* sh, cudaStream_t st) {
+                          const float* beta, float* sc, float* sh, cudaStream_t st, int pool) {
   ProfScope _ps("instnorm_stats", st);
   dim3 grid((C + 31) / 32, B);
-  instnorm_stats_kernel<<<grid, 256, 0, st>>>(x, stride_rows, T, C, ldc, gamma, beta, sc, sh);
+  instnorm_stats_kernel<<<grid, 256, 0, st>>>(x, stride_rows, T, C, ldc, gamma, beta, sc, sh, pool);
   DG_LAUNCHED();
   return 0;
 }

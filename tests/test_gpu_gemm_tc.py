@@ -17,6 +17,8 @@ SHAPES = [  # (M, Cin, KW, dil, N, epi)
     (1184, 512, 1, 1, 1500, 2),      # tdnn5: N not a multiple of the tile
     (4096, 256, 1, 1, 1024, 0),      # LSTM input projection
     (300, 128, 2, 7, 128, 0),        # BN=128 variant, odd dilation
+    (5328, 128, 5, 1, 64, 0),        # SincNet conv1 (80 -> 128 padded channels, N = 64 of a 128 tile)
+    (768, 3008, 1, 1, 512, 0),       # Linear(3000, 512) with K padded to 47 k-blocks
 ]
 
 

@@ -96,6 +96,9 @@ def test_foreign_models_behind_loader_api(oracle_nets, stream, cuda_device):
     here: the oracle torch modules moved to the GPU"""
     import copy
 
+    # torch's own GPU kernels default to TF32 convolutions (1e-3 error): compare against true float32
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     seg_o, emb_o = (copy.deepcopy(m) for m in oracle_nets)
     config = blocks.SpeakerDiarizationConfig(segmentation=models.SegmentationModel(lambda: seg_o),
                                              embedding=models.EmbeddingModel(lambda: emb_o), device=cuda_device)
