@@ -120,6 +120,7 @@ struct SincWeights {
   float wn_gamma = 1.f, wn_beta = 0.f;
   DevBuf filt, g0, b0, w1, bias1, g1, b1, w2, bias2, g2, b2;
   DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: bf16 hi/lo planes [128][5*128] and [128][5*64]
+  DevBuf filt_hi, filt_lo;             // sinc filter bank as bf16 hi/lo planes [80][256]
 };
 
 // ParamSincFB.filters() in float32, as asteroid-filterbanks computes it with torch
@@ -161,6 +162,11 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
   std::vector<float> h;
   sinc_filters(lo, bd, h);
   if (upload(w.filt, h)) return DG_ECUDA;
+  {
+    std::vector<uint16_t> fh(80 * 256), fl(80 * 256);
+    sinc_tc_pack_filters(h.data(), fh.data(), fl.data());
+    if (upload_u16(w.filt_hi, fh) || upload_u16(w.filt_lo, fl)) return DG_ECUDA;
+  }
   auto pad_vec = [&](const std::string& name, int n, int npad, DevBuf& dst) -> int {
     const float* s = t.get(name, n);
     if (!s) return DG_EWEIGHT;
@@ -205,6 +211,7 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
 struct SincWork {
   DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
   DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: bf16 planes of the conv inputs, un-pooled conv outputs
+  DevBuf wh, wl;                       // four shifted copies of the normalised waveform, bf16 hi / lo
   const float* out = nullptr;          // conv2 output that the next layer normalises on load ...
   int out_pool = 0;                    // ... 1: still un-pooled (rows = 3x), MaxPool1d(3) is applied on load
   int ensure_tc(int B, const Geom& g) {
@@ -235,9 +242,17 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
   if (use_tensor_cores()) {
     if ((rc = k.ensure_tc(B, g))) return rc;
     if ((rc = launch_wave_stats(wav, B, g.S, k.wmean.as<float>(), k.wrstd.as<float>(), st))) return rc;
-    if ((rc = launch_sinc0(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt.as<float>(),
-                           B, g, k.p0.as<float>(), st)))
-      return rc;
+    static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
+    if (sinc_simt) {
+      rc = launch_sinc0(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt.as<float>(), B,
+                        g, k.p0.as<float>(), st);
+    } else {
+      const size_t bytes = 4 * sinc_tc_plane_elems(B, g) * 2;
+      if (k.wh.ensure(bytes) || k.wl.ensure(bytes)) return DG_ECUDA;
+      rc = launch_sinc0_tc(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt_hi.p,
+                           w.filt_lo.p, B, g, k.wh.p, k.wl.p, k.p0.as<float>(), st);
+    }
+    if (rc) return rc;
     if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),
                                     k.sc0.as<float>(), k.sh0.as<float>(), st)))
       return rc;

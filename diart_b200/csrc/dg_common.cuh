@@ -131,6 +131,13 @@ int launch_split(const float* x, long long rows, int C, int item_rows, const flo
 int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld_out, int pool, int item_rows,
                     const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st);
 void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo);
+// sinc_tc.cu -- SincNet stage 0 on tcgen05 (overlapping-row TMA view of the waveform)
+int sinc_tc_rows_per_item(const Geom& g);
+size_t sinc_tc_plane_elems(int B, const Geom& g);
+void sinc_tc_pack_filters(const float* filt, uint16_t* hi, uint16_t* lo);
+int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, float gamma, float beta,
+                    const void* w_hi, const void* w_lo, int B, const Geom& g, void* planes_hi, void* planes_lo,
+                    float* p0, cudaStream_t st);
 // lstm.cu
 int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_packed, int B, int T, int stride,
                       float* hout /*[B*stride,256]*/, cudaStream_t st);

@@ -1,0 +1,288 @@
+// SincNet stage 0 on the tensor cores:  InstanceNorm1d(1) -> ParamSincFB (80 x k251, stride 10) -> |.| ->
+// MaxPool1d(3)   (pyannote SincNet; reached through reference models.py:131-133)
+//
+// As a GEMM the layer is out[t, f] = sum_k x[10 t + k] h[f, k]: M = 7975 conv positions per chunk, N = 80,
+// K = 251 (padded to 256), and its A operand is a Toeplitz view of the waveform whose rows OVERLAP (row t
+// starts 10 samples = 20 bytes after row t-1).  Instead of materialising a 2 GB im2col matrix per batch, the
+// rows are read in place by TMA through tensor maps whose row pitch (240 B) is smaller than the row length:
+//
+//   * conv positions are split into 12 classes s = t mod 12 (12 = lcm(4, 3)): inside a class consecutive rows
+//     are 120 samples = 240 B apart, a legal (16 B multiple) TMA stride;
+//   * row (t'', s) starts at sample 120 t'' + 10 s, i.e. at byte offset 20 s mod 16 in {0, 4, 8, 12}: the
+//     normalised waveform is stored as four copies shifted by 0/2/4/6 samples so that class s reads copy
+//     s mod 4 at an 8-sample-aligned inner coordinate e_s = 10 s - 2 (s mod 4);
+//   * the three classes 3q, 3q+1, 3q+2 of a MaxPool group are three accumulators of ONE CTA tile, so the
+//     pooled value is an element-wise max over accumulators in the epilogue: pooled row p = 4 t'' + q.
+//   * items are laid out back to back with 667 rows each, so 128-row tiles run across item boundaries
+//     (rows 665/666 of an item are padding that the epilogue drops).
+//
+// bf16x3 split precision as in gemm_tc.cu.  CTA = 192 threads: warp 0 TMA producer (A tiles, 4-stage ring;
+// the 80 KB filter bank hi/lo is loaded once and stays resident), warp 1 MMA issuer, warps 2-5 epilogue
+// (TMEM double buffered: 2 x 3 x 80 columns).
+#include <string.h>
+
+#include "dg_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dg {
+
+constexpr int ST_ROWS = 128, ST_N = 80, ST_KB = 4, ST_NSTAGE = 4;
+constexpr int ST_A_BYTES = ST_ROWS * 64 * 2;           // 16 KB per plane per k-block
+constexpr int ST_STAGE = 2 * ST_A_BYTES;               // hi + lo
+constexpr int ST_W_BYTES = ST_N * 64 * 2;              // 10 KB per plane per k-block
+constexpr int ST_W_TOTAL = ST_KB * 2 * ST_W_BYTES;     // 80 KB
+constexpr int ST_SMEM = ST_W_TOTAL + ST_NSTAGE * ST_STAGE + 256 + 1024;
+
+struct SincTcMaps {
+  CUtensorMap a_hi[4], a_lo[4];   // shifted copies of the normalised waveform, hi / lo planes
+  CUtensorMap w_hi, w_lo;         // filter bank [80][256]
+};
+
+__global__ void __launch_bounds__(192, 1)
+sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows_total, int rows_per_item, int T0,
+                int S0, float* __restrict__ p0) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* wsm = smem;                       // [kb][plane][80 x 128 B]
+  unsigned char* asm_ = smem + ST_W_TOTAL;         // [stage][plane][128 x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ST_W_TOTAL + ST_NSTAGE * ST_STAGE);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + ST_NSTAGE;
+  uint64_t* acc_full = bars + 2 * ST_NSTAGE;
+  uint64_t* acc_empty = bars + 2 * ST_NSTAGE + 2;
+  uint64_t* w_full = bars + 2 * ST_NSTAGE + 4;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST_NSTAGE + 5);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_tiles = row_tiles * 4;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ST_NSTAGE; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);
+    }
+    mbar_init(w_full, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, ST_W_TOTAL);
+      for (int kb = 0; kb < ST_KB; kb++) {
+        tma_load_2d(wsm + (kb * 2 + 0) * ST_W_BYTES, &maps.w_hi, kb * 64, 0, w_full);
+        tma_load_2d(wsm + (kb * 2 + 1) * ST_W_BYTES, &maps.w_lo, kb * 64, 0, w_full);
+      }
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int rt = tile >> 2, q = tile & 3;
+        for (int kb = 0; kb < ST_KB; kb++)
+          for (int s3 = 0; s3 < 3; s3++) {
+            const int s = 3 * q + s3, c = s & 3, e = 10 * s - 2 * c;
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* st = asm_ + stage * ST_STAGE;
+            mbar_expect_tx(&full[stage], ST_STAGE);
+            tma_load_2d(st, &maps.a_hi[c], e + kb * 64, rt * ST_ROWS, &full[stage]);
+            tma_load_2d(st + ST_A_BYTES, &maps.a_lo[c], e + kb * 64, rt * ST_ROWS, &full[stage]);
+            if (++stage == ST_NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ST_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      mbar_wait(w_full, 0);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        for (int kb = 0; kb < ST_KB; kb++) {
+          const uint32_t wa = smem_u32(wsm + kb * 2 * ST_W_BYTES);
+          const uint64_t w_hi = umma_desc(wa), w_lo = umma_desc(wa + ST_W_BYTES);
+          for (int s3 = 0; s3 < 3; s3++) {
+            mbar_wait(&full[stage], phase);
+            tc_fence_after();
+            const uint32_t sa = smem_u32(asm_ + stage * ST_STAGE);
+            const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + ST_A_BYTES);
+            const uint32_t tmem_c = tmem_base + acc * 256 + s3 * ST_N;
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++) {
+              const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, (kb | ks) != 0);
+              umma_bf16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
+              umma_bf16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
+            }
+            umma_commit(&empty[stage]);
+            if (++stage == ST_NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+        umma_commit(&acc_full[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    int acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int rt = tile >> 2, q = tile & 3;
+      const int R = rt * ST_ROWS + quad * 32 + lane;           // flattened (item, t'') row
+      const int b = R / rows_per_item, tpp = R - b * rows_per_item;
+      const int p = 4 * tpp + q;                               // pooled output row
+      const bool ok = R < rows_total && p < T0;
+      float* o = p0 + ((size_t)b * S0 + (ok ? p : 0)) * ST_N;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
+#pragma unroll 1
+      for (int c = 0; c < ST_N; c += 16) {
+        uint32_t r0[16], r1[16], r2[16];
+        tmem_ld16(taddr + c, r0);
+        tmem_ld16(taddr + ST_N + c, r1);
+        tmem_ld16(taddr + 2 * ST_N + c, r2);
+        tmem_ld_wait();
+        if (ok) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++)
+            v[i] = fmaxf(fmaxf(fabsf(__uint_as_float(r0[i])), fabsf(__uint_as_float(r1[i]))),
+                         fabsf(__uint_as_float(r2[i])));
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            reinterpret_cast<float4*>(o + c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+// normalised waveform -> four shifted copies, bf16 hi / lo planes:  plane[c][b*Lp + i] = split(xn[b][i + 2c])
+__global__ void __launch_bounds__(256) sinc_prep_kernel(const float* __restrict__ wav, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, float gamma, float beta,
+                                                        int S, int Lp, size_t plane_elems,
+                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int b = blockIdx.y;
+  const float mu = mean[b], sc = rstd[b] * gamma;
+  const float* x = wav + (size_t)b * S;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Lp + 8; i += gridDim.x * blockDim.x) {
+    const float v = i < S ? (x[i] - mu) * sc + beta : 0.f;     // InstanceNorm1d(1, affine), as the SIMT kernel
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int j = i - 2 * c;                                 // copy c holds xn[j + 2c] at position j
+      if (j >= 0 && j < Lp) {
+        hi[(size_t)c * plane_elems + (size_t)b * Lp + j] = h;
+        lo[(size_t)c * plane_elems + (size_t)b * Lp + j] = l;
+      }
+    }
+  }
+}
+
+static int make_map2(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch_bytes,
+                     uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return -2;
+  }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (overlapping-row waveform view) failed with code " + std::to_string((int)r));
+    return -2;
+  }
+  return 0;
+}
+
+int sinc_tc_rows_per_item(const Geom& g) {
+  const int by_rows = (g.T0c + 11) / 12, by_len = (g.S + 8 + 119) / 120;
+  return by_rows > by_len ? by_rows : by_len;
+}
+size_t sinc_tc_plane_elems(int B, const Geom& g) { return (size_t)B * sinc_tc_rows_per_item(g) * 120 + 1024; }
+
+// filt [251][80] float32 (k-major) -> bf16 hi/lo planes [80][256] (n-major, K padded with zeros)
+void sinc_tc_pack_filters(const float* filt, uint16_t* hi, uint16_t* lo) {
+  float w[80 * 256];
+  memset(w, 0, sizeof(w));
+  for (int k = 0; k < 251; k++)
+    for (int f = 0; f < 80; f++) w[f * 256 + k] = filt[k * 80 + f];
+  split_weights_host(w, 80, 80, 256, hi, lo);
+}
+
+int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, float gamma, float beta,
+                    const void* w_hi, const void* w_lo, int B, const Geom& g, void* planes_hi, void* planes_lo,
+                    float* p0, cudaStream_t st) {
+  const int rpi = sinc_tc_rows_per_item(g), Lp = rpi * 120;
+  const size_t plane = sinc_tc_plane_elems(B, g);
+  {
+    ProfScope _ps("sinc0_prep", st);
+    dim3 grid((Lp + 8 + 255) / 256, B);
+    sinc_prep_kernel<<<grid, 256, 0, st>>>(wav, mean, rstd, gamma, beta, g.S, Lp, plane,
+                                           reinterpret_cast<__nv_bfloat16*>(planes_hi),
+                                           reinterpret_cast<__nv_bfloat16*>(planes_lo));
+    DG_LAUNCHED();
+  }
+  ProfScope _ps("sinc0", st);
+  SincTcMaps maps;
+  const uint64_t rows = (uint64_t)B * rpi;
+  for (int c = 0; c < 4; c++) {
+    const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(planes_hi) + (size_t)c * plane;
+    const __nv_bfloat16* bl = reinterpret_cast<const __nv_bfloat16*>(planes_lo) + (size_t)c * plane;
+    if (make_map2(&maps.a_hi[c], bh, 384, rows, 240, ST_ROWS) || make_map2(&maps.a_lo[c], bl, 384, rows, 240, ST_ROWS))
+      return -2;
+  }
+  if (make_map2(&maps.w_hi, w_hi, 256, 80, 512, ST_N) || make_map2(&maps.w_lo, w_lo, 256, 80, 512, ST_N)) return -2;
+  static bool attr_done = false;
+  if (!attr_done) {
+    DG_CUDA(cudaFuncSetAttribute(sinc0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int row_tiles = (int)((rows + ST_ROWS - 1) / ST_ROWS);
+  const int tiles = row_tiles * 4;
+  sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0);
+  DG_LAUNCHED();
+  return 0;
+}
+
+}  // namespace dg
