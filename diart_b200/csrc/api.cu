@@ -120,7 +120,7 @@ struct SincWeights {
   float wn_gamma = 1.f, wn_beta = 0.f;
   DevBuf filt, g0, b0, w1, bias1, g1, b1, w2, bias2, g2, b2;
   DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: bf16 hi/lo planes [128][5*128] and [128][5*64]
-  DevBuf filt_hi, filt_lo;             // sinc filter bank as bf16 hi/lo planes [80][256]
+  DevBuf filt_planes;                  // sinc filter bank as three bf16 planes [3][80][256] (hi, lo, lo2)
 };
 
 // ParamSincFB.filters() in float32, as asteroid-filterbanks computes it with torch
@@ -163,9 +163,9 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
   sinc_filters(lo, bd, h);
   if (upload(w.filt, h)) return DG_ECUDA;
   {
-    std::vector<uint16_t> fh(80 * 256), fl(80 * 256);
-    sinc_tc_pack_filters(h.data(), fh.data(), fl.data());
-    if (upload_u16(w.filt_hi, fh) || upload_u16(w.filt_lo, fl)) return DG_ECUDA;
+    std::vector<uint16_t> fp(3 * 80 * 256);
+    sinc_tc_pack_filters(h.data(), fp.data());
+    if (upload_u16(w.filt_planes, fp)) return DG_ECUDA;
   }
   auto pad_vec = [&](const std::string& name, int n, int npad, DevBuf& dst) -> int {
     const float* s = t.get(name, n);
@@ -249,8 +249,8 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
     } else {
       const size_t bytes = 4 * sinc_tc_plane_elems(B, g) * 2;
       if (k.wh.ensure(bytes) || k.wl.ensure(bytes)) return DG_ECUDA;
-      rc = launch_sinc0_tc(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt_hi.p,
-                           w.filt_lo.p, B, g, k.wh.p, k.wl.p, k.p0.as<float>(), st);
+      rc = launch_sinc0_tc(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt_planes.p, B,
+                           g, k.wh.p, k.wl.p, k.p0.as<float>(), st);
     }
     if (rc) return rc;
     if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),

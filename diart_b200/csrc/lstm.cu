@@ -127,6 +127,7 @@ lstm_rec_kernel(const float* __restrict__ gx, const float* __restrict__ whh_pack
       }
     }
     __syncthreads();
+    float hval = 0.f;
     if (act) {
       const float gi = gates[ar][au], gf = gates[ar][64 + au], gg = gates[ar][128 + au], go = gates[ar][192 + au];
       const float i_ = sigmoidf_(gi), f_ = sigmoidf_(gf), g_ = tanhf(gg), o_ = sigmoidf_(go);
@@ -135,9 +136,13 @@ lstm_rec_kernel(const float* __restrict__ gx, const float* __restrict__ whh_pack
       const int u = 64 * crank + au;
       hbuf[nxt][ar][hidx(u)] = h;
       peer_h[(nxt * R + ar) * HP + hidx(u)] = h;
-      hout[((size_t)(b0 + ar) * stride + t) * 256 + dir * H + u] = h;
+      hval = h;
     }
-    cluster.sync();
+    // split barrier: the release only has to cover the (distributed) shared-memory writes of h; the global
+    // store of this step's output is issued between arrive and wait so that its latency is off the chain
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    if (act) hout[((size_t)(b0 + ar) * stride + t) * 256 + dir * H + 64 * crank + au] = hval;
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
   }
 }
 

@@ -26,16 +26,16 @@
 
 namespace dg {
 
-constexpr int ST_ROWS = 128, ST_N = 80, ST_KB = 4, ST_NSTAGE = 4;
+constexpr int ST_ROWS = 128, ST_N = 80, ST_KB = 4, ST_NSTAGE = 3, ST_WP = 3;   // 3 filter planes: hi, lo, lo2
 constexpr int ST_A_BYTES = ST_ROWS * 64 * 2;           // 16 KB per plane per k-block
 constexpr int ST_STAGE = 2 * ST_A_BYTES;               // hi + lo
 constexpr int ST_W_BYTES = ST_N * 64 * 2;              // 10 KB per plane per k-block
-constexpr int ST_W_TOTAL = ST_KB * 2 * ST_W_BYTES;     // 80 KB
+constexpr int ST_W_TOTAL = ST_KB * ST_WP * ST_W_BYTES; // 120 KB
 constexpr int ST_SMEM = ST_W_TOTAL + ST_NSTAGE * ST_STAGE + 256 + 1024;
 
 struct SincTcMaps {
   CUtensorMap a_hi[4], a_lo[4];   // shifted copies of the normalised waveform, hi / lo planes
-  CUtensorMap w_hi, w_lo;         // filter bank [80][256]
+  CUtensorMap w[3];               // filter bank [80][256]: bf16 hi, lo and second-order lo2 planes
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -81,8 +81,8 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
     if (lane == 0) {
       mbar_expect_tx(w_full, ST_W_TOTAL);
       for (int kb = 0; kb < ST_KB; kb++) {
-        tma_load_2d(wsm + (kb * 2 + 0) * ST_W_BYTES, &maps.w_hi, kb * 64, 0, w_full);
-        tma_load_2d(wsm + (kb * 2 + 1) * ST_W_BYTES, &maps.w_lo, kb * 64, 0, w_full);
+        for (int pl = 0; pl < ST_WP; pl++)
+          tma_load_2d(wsm + (kb * ST_WP + pl) * ST_W_BYTES, &maps.w[pl], kb * 64, 0, w_full);
       }
       int stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -111,8 +111,8 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
         for (int kb = 0; kb < ST_KB; kb++) {
-          const uint32_t wa = smem_u32(wsm + kb * 2 * ST_W_BYTES);
-          const uint64_t w_hi = umma_desc(wa), w_lo = umma_desc(wa + ST_W_BYTES);
+          const uint32_t wa = smem_u32(wsm + kb * ST_WP * ST_W_BYTES);
+          const uint64_t w_hi = umma_desc(wa), w_lo = umma_desc(wa + ST_W_BYTES), w_l2 = umma_desc(wa + 2 * ST_W_BYTES);
           for (int s3 = 0; s3 < 3; s3++) {
             mbar_wait(&full[stage], phase);
             tc_fence_after();
@@ -122,7 +122,11 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
 #pragma unroll
             for (int ks = 0; ks < 4; ks++) {
               const uint64_t adv = (uint64_t)((ks * 32) >> 4);
-              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, (kb | ks) != 0);
+              // five of the nine hi/lo/lo2 products: everything down to 2^-24 of the leading term.  This
+              // layer's error is amplified by every later layer, so the filters carry 24 significand bits.
+              umma_bf16(tmem_c, a_lo + adv, w_lo + adv, idesc, (kb | ks) != 0);
+              umma_bf16(tmem_c, a_hi + adv, w_l2 + adv, idesc, 1);
+              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, 1);
               umma_bf16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
               umma_bf16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
             }
@@ -238,18 +242,28 @@ int sinc_tc_rows_per_item(const Geom& g) {
 }
 size_t sinc_tc_plane_elems(int B, const Geom& g) { return (size_t)B * sinc_tc_rows_per_item(g) * 120 + 1024; }
 
-// filt [251][80] float32 (k-major) -> bf16 hi/lo planes [80][256] (n-major, K padded with zeros)
-void sinc_tc_pack_filters(const float* filt, uint16_t* hi, uint16_t* lo) {
-  float w[80 * 256];
+// filt [251][80] float32 (k-major) -> three bf16 planes [3][80][256] (n-major, K padded with zeros):
+// hi = bf16(w), lo = bf16(w - hi), lo2 = bf16(w - hi - lo)
+void sinc_tc_pack_filters(const float* filt, uint16_t* planes) {
+  static float w[80 * 256], r[80 * 256];
+  static uint16_t dummy[80 * 256];
   memset(w, 0, sizeof(w));
   for (int k = 0; k < 251; k++)
     for (int f = 0; f < 80; f++) w[f * 256 + k] = filt[k * 80 + f];
-  split_weights_host(w, 80, 80, 256, hi, lo);
+  split_weights_host(w, 80, 80, 256, planes, planes + 80 * 256);
+  auto from_bf16 = [](uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  for (int i = 0; i < 80 * 256; i++) r[i] = (w[i] - from_bf16(planes[i])) - from_bf16(planes[80 * 256 + i]);
+  split_weights_host(r, 80, 80, 256, planes + 2 * 80 * 256, dummy);
 }
 
 int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, float gamma, float beta,
-                    const void* w_hi, const void* w_lo, int B, const Geom& g, void* planes_hi, void* planes_lo,
-                    float* p0, cudaStream_t st) {
+                    const void* w_planes, int B, const Geom& g, void* planes_hi, void* planes_lo, float* p0,
+                    cudaStream_t st) {
   const int rpi = sinc_tc_rows_per_item(g), Lp = rpi * 120;
   const size_t plane = sinc_tc_plane_elems(B, g);
   {
@@ -269,7 +283,9 @@ int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, floa
     if (make_map2(&maps.a_hi[c], bh, 384, rows, 240, ST_ROWS) || make_map2(&maps.a_lo[c], bl, 384, rows, 240, ST_ROWS))
       return -2;
   }
-  if (make_map2(&maps.w_hi, w_hi, 256, 80, 512, ST_N) || make_map2(&maps.w_lo, w_lo, 256, 80, 512, ST_N)) return -2;
+  for (int pl = 0; pl < ST_WP; pl++)
+    if (make_map2(&maps.w[pl], reinterpret_cast<const uint16_t*>(w_planes) + (size_t)pl * 80 * 256, 256, 80, 512, ST_N))
+      return -2;
   static bool attr_done = false;
   if (!attr_done) {
     DG_CUDA(cudaFuncSetAttribute(sinc0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
