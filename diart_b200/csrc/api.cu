@@ -321,6 +321,7 @@ struct dg_seg {
   SincWeights sw;
   DevBuf wih[4], bih[4], whh[4];   // input projections [in_pad][1024], bias [1024], packed W_hh
   DevBuf wih_hi[4], wih_lo[4];     // the same as bf16 hi/lo planes [1024][in_pad] for the tcgen05 path
+  DevBuf whh_hi[4], whh_lo[4];     // W_hh as bf16 hi/lo planes [2][512][128] for the tcgen05 recurrence
   DevBuf xh, xl;                   // bf16 hi/lo planes of the current in-projection input
   DevBuf l1w, l1b, l2w, l2b, cw, cb;
   SincWork work;
@@ -352,6 +353,11 @@ static int seg_prepare(dg_seg* h, const Tensors& t) {
     for (int n = 0; n < 1024; n++)
       for (int c = 0; c < in; c++) w_nk[(size_t)n * in_pad + c] = w[(size_t)c * 1024 + n];
     if (upload_split(h->wih_hi[L], h->wih_lo[L], w_nk, 1024, 1024, in_pad)) return DG_ECUDA;
+    {
+      std::vector<uint16_t> rh(lstm_tc_plane_elems()), rl(lstm_tc_plane_elems());
+      lstm_tc_pack_whh(hh[0], hh[1], rh.data(), rl.data());
+      if (upload_u16(h->whh_hi[L], rh) || upload_u16(h->whh_lo[L], rl)) return DG_ECUDA;
+    }
   }
   auto linear_t = [&](const std::string& name, int out, int in, DevBuf& dw, DevBuf& db) -> int {
     const float* w = t.get(name + ".weight", (int64_t)out * in);
@@ -480,7 +486,12 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
       t.out_f32 = h->gx.as<float>(); t.ldc = 1024; t.epi = 0; t.tag = "lstm_inproj";
       if ((rc = launch_gemm_tc(t, st))) return rc;
       float* hout = hbuf[L & 1];
-      if ((rc = launch_lstm_layer(h->gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st))) return rc;
+      static const bool lstm_simt = getenv("DG_LSTM_SIMT") && getenv("DG_LSTM_SIMT")[0] == '1';
+      if (lstm_simt)
+        rc = launch_lstm_layer(h->gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st);
+      else
+        rc = launch_lstm_layer_tc(h->gx.as<float>(), h->whh_hi[L].p, h->whh_lo[L].p, B, g.T2, g.S2, hout, st);
+      if (rc) return rc;
       hin = hout;
       continue;
     }

@@ -143,6 +143,11 @@ int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_pack
                       float* hout /*[B*stride,256]*/, cudaStream_t st);
 size_t lstm_whh_packed_floats();
 void lstm_pack_whh(const float* whh_fwd /*[512][128]*/, const float* whh_bwd, float* packed);
+// lstm_tc.cu -- recurrence on tcgen05 (W_hh hi plane in shared memory, lo plane in tensor memory)
+size_t lstm_tc_plane_elems();
+void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo);
+int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, int B, int T, int stride, float* hout,
+                         cudaStream_t st);
 // heads.cu
 int launch_seg_final(const float* y /*[B*stride,128]*/, const float* wc /*[K][128]*/, const float* bc, int B, int T,
                      int stride, int K, float* seg /*[B,T,K]*/, cudaStream_t st);

@@ -1,0 +1,252 @@
+// Bidirectional LSTM recurrence of PyanNet on the tensor cores (tcgen05), bf16x3 split precision.
+// (nn.LSTM(60,128,num_layers=4,bidirectional); reached from the reference through
+// src/diart/models.py:131-133.)  The input projections are hoisted into gemm_tc.cu; this kernel runs the 293
+// dependent steps of one layer.
+//
+// One CTA owns 16 batch rows of one direction and ALL 4 x 128 gate rows, so a step is
+//     gates^T[512, 16] = W_hh[512, 128] . h_{t-1}^T[128, 16]          (M = gate rows, N = batch rows)
+// i.e. four M=128 tiles, one per gate: TMEM lane u of the four accumulators holds i, f, g, o of hidden unit u,
+// and the thread that owns that lane updates c and h of the unit with no cross-thread exchange.
+// W_hh must be resident for the whole sequence: its bf16 hi plane (128 KB) lives in shared memory
+// (A operand from a descriptor), its lo plane (another 128 KB) in TENSOR MEMORY (A operand from TMEM, 256 of
+// the 512 columns) -- the only place left on the SM.  h_{t-1} is re-written every step by the epilogue threads
+// as the B operand (hi/lo planes, 128B-swizzled K-major rows).  Products per k-step: Whi.hlo, Wlo.hhi, Whi.hhi.
+//
+// 288 threads: warps 0-7 epilogue (TMEM lane quadrant = warp % 4, batch columns 8*(warp/4) ..), warp 8 issues
+// the TMA load of W_hi once and the 96 tcgen05.mma of every step.
+#include <string.h>
+
+#include "dg_common.cuh"
+#include "tc_ptx.cuh"
+
+namespace dg {
+
+constexpr int LT_NB = 16, LT_THREADS = 288;
+constexpr int LT_W_BYTES = 4 * 2 * 128 * 128;          // W_hi: 4 gates x 2 k-blocks x (128 rows x 128 B)
+constexpr int LT_H_TILE = LT_NB * 128;                 // one k-block of h^T: 16 rows x 128 B
+constexpr int LT_H_BYTES = 2 * 2 * 2 * LT_H_TILE;      // [buffer][plane][k-block]
+constexpr int LT_SMEM = LT_W_BYTES + LT_H_BYTES + 256 + 1024;
+constexpr uint32_t LT_COL_D = 0, LT_COL_WLO = 64;      // TMEM columns: 4 x 16 accumulators, 4 x 64 W_lo
+
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
+      ::"r"(tmem_c), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+}
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(LT_THREADS, 1)
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __restrict__ w_lo /*[2][512][128] bf16*/,
+               const float* __restrict__ gx, int B, int T, int stride, int groups_per_dir, float* __restrict__ hout) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* wsm = smem;                         // [gate][k-block][128 x 128 B]
+  unsigned char* hsm = smem + LT_W_BYTES;            // [buffer][plane][k-block][16 x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + LT_W_BYTES + LT_H_BYTES);
+  uint64_t* w_full = bars;
+  uint64_t* mma_done = bars + 1;
+  uint64_t* h_ready = bars + 2;                      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dir = blockIdx.x / groups_per_dir;
+  const int b0 = (blockIdx.x - dir * groups_per_dir) * LT_NB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(&h_ready[0], 8);
+    mbar_init(&h_ready[1], 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < LT_H_BYTES / 4; i += LT_THREADS) reinterpret_cast<uint32_t*>(hsm)[i] = 0u;   // h_0 = 0
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 8) {
+    // ================================================================ TMA (once) + MMA issuer
+    if (lane == 0) {
+      mbar_expect_tx(w_full, LT_W_BYTES);
+      for (int g = 0; g < 4; g++)
+        for (int kb = 0; kb < 2; kb++)
+          tma_load_2d(wsm + (g * 2 + kb) * 16384, &tm_whi, kb * 64, dir * 512 + g * 128, w_full);
+      mbar_wait(w_full, 0);
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // ================================================================ W_lo -> tensor memory (A operand)
+    // lane r of gate tile g holds W_lo[g*128 + r][0..127] as 64 packed bf16 pairs (low half = even k)
+    const int r = warp * 32 + lane;
+    for (int g = 0; g < 4; g++) {
+      const uint4* src = reinterpret_cast<const uint4*>(w_lo + ((size_t)dir * 512 + g * 128 + r) * 128);
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        uint32_t v[32];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const uint4 q = src[half * 8 + i];
+          v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+        }
+        tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + LT_COL_WLO + g * 64 + half * 32, v);
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zeroed h buffers -> visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      for (int step = 0; step < T; step++) {
+        const int buf = step & 1;
+        if (step > 0) {
+          mbar_wait(&h_ready[buf], ((step - 1) >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t hb = smem_u32(hsm + buf * (LT_H_BYTES / 2));
+#pragma unroll 1
+        for (int g = 0; g < 4; g++) {
+          const uint32_t d = tmem_base + LT_COL_D + g * LT_NB;
+#pragma unroll
+          for (int ks = 0; ks < 8; ks++) {
+            const int kb = ks >> 2, kk = ks & 3;
+            const uint64_t adv = (uint64_t)((kk * 32) >> 4);
+            const uint64_t a_hi = umma_desc(smem_u32(wsm + (g * 2 + kb) * 16384)) + adv;
+            const uint64_t b_hi = umma_desc(hb + kb * LT_H_TILE) + adv;
+            const uint64_t b_lo = umma_desc(hb + 2 * LT_H_TILE + kb * LT_H_TILE) + adv;
+            const uint32_t a_lo = tmem_base + LT_COL_WLO + g * 64 + ks * 8;
+            umma_bf16(d, a_hi, b_lo, idesc, ks != 0);
+            umma_bf16_ts(d, a_lo, b_hi, idesc, 1);
+            umma_bf16(d, a_hi, b_hi, idesc, 1);
+          }
+        }
+        umma_commit(mma_done);
+      }
+    }
+  } else {
+    // ================================================================ gate math / state update (warps 0..7)
+    const int quad = warp & 3, ch = warp >> 2;
+    const int u = quad * 32 + lane;                 // hidden unit == TMEM lane
+    float c[8];
+#pragma unroll
+    for (int n = 0; n < 8; n++) c[n] = 0.f;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + LT_COL_D + ch * 8;
+    const int kb_u = u >> 6, kq = u & 63, chunk = kq >> 3, e2 = (kq & 7) * 2;
+    for (int step = 0; step < T; step++) {
+      const int t = dir == 0 ? step : T - 1 - step;
+      const int nxt = (step + 1) & 1;
+      float xg[4][8];
+#pragma unroll
+      for (int n = 0; n < 8; n++) {
+        const int b = b0 + ch * 8 + n;
+        const float* p = gx + ((size_t)(b < B ? b : 0) * stride + t) * 1024 + dir * 512 + u;
+#pragma unroll
+        for (int g = 0; g < 4; g++) xg[g][n] = b < B ? p[g * 128] : 0.f;
+      }
+      mbar_wait(mma_done, step & 1);
+      tc_fence_after();
+      uint32_t ri[8], rf[8], rg[8], ro[8];
+      tmem_ld8(tlane + 0 * LT_NB, ri);
+      tmem_ld8(tlane + 1 * LT_NB, rf);
+      tmem_ld8(tlane + 2 * LT_NB, rg);
+      tmem_ld8(tlane + 3 * LT_NB, ro);
+      tmem_ld_wait();
+      unsigned char* hdst = hsm + nxt * (LT_H_BYTES / 2) + kb_u * LT_H_TILE;
+#pragma unroll
+      for (int n = 0; n < 8; n++) {
+        const float i_ = sigmoid_acc(__uint_as_float(ri[n]) + xg[0][n]);
+        const float f_ = sigmoid_acc(__uint_as_float(rf[n]) + xg[1][n]);
+        const float g_ = tanhf(__uint_as_float(rg[n]) + xg[2][n]);
+        const float o_ = sigmoid_acc(__uint_as_float(ro[n]) + xg[3][n]);
+        c[n] = fmaf(f_, c[n], i_ * g_);
+        const float h = o_ * tanhf(c[n]);
+        const int row = ch * 8 + n, b = b0 + row;
+        if (b < B) hout[((size_t)b * stride + t) * 256 + dir * 128 + u] = h;
+        const __nv_bfloat16 hh = __float2bfloat16_rn(h);
+        const __nv_bfloat16 hl = __float2bfloat16_rn(h - __bfloat162float(hh));
+        const int off = row * 128 + ((chunk ^ (row & 7)) << 4) + e2;       // 128B swizzle of the K-major row
+        *reinterpret_cast<__nv_bfloat16*>(hdst + off) = hh;
+        *reinterpret_cast<__nv_bfloat16*>(hdst + 2 * LT_H_TILE + off) = hl;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_ready[nxt]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+size_t lstm_tc_plane_elems() { return (size_t)2 * 512 * 128; }
+
+// torch weight_hh_l{L}[_reverse] ([512][128], gate order i,f,g,o) -> bf16 hi / lo planes [2][512][128]
+void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo) {
+  split_weights_host(whh_fwd, 512, 512, 128, hi, lo);
+  split_weights_host(whh_bwd, 512, 512, 128, hi + 512 * 128, lo + 512 * 128);
+}
+
+int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, int B, int T, int stride, float* hout,
+                         cudaStream_t st) {
+  ProfScope _ps("lstm_rec", st);
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return -2;
+  }
+  CUtensorMap tm;
+  cuuint64_t dims[2] = {128, 1024};
+  cuuint64_t strides[1] = {256};
+  cuuint32_t box[2] = {64, 128};
+  cuuint32_t estr[2] = {1, 1};
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(whh_hi), dims, strides, box, estr,
+         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed for W_hh");
+    return -2;
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+    attr_done = true;
+  }
+  const int gpd = (B + LT_NB - 1) / LT_NB;
+  lstm_tc_kernel<<<2 * gpd, LT_THREADS, LT_SMEM, st>>>(tm, reinterpret_cast<const uint16_t*>(whh_lo), gx, B, T, stride,
+                                                        gpd, hout);
+  DG_LAUNCHED();
+  return 0;
+}
+
+}  // namespace dg
