@@ -16,6 +16,7 @@ namespace dg {
 
 static thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
+int g_sm_limit = 0;
 void set_error(const std::string& msg) { g_err = msg; }
 
 struct ProfRec {
@@ -1043,6 +1044,10 @@ struct dg_pipeline {
   int normalize_weights;
   DevBuf osp, wav, segd, embd, mapd, permd;
   cudaStream_t st = nullptr;
+  // two-stream overlap inside a step: the segmentation chain (critical path, high priority) and the
+  // embedding trunk (independent of it until the pooling weights exist) run concurrently
+  cudaStream_t s_seg = nullptr, s_emb = nullptr;
+  cudaEvent_t e_start = nullptr, e_osp = nullptr, e_emb = nullptr, e_done = nullptr;
 };
 
 extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
@@ -1064,6 +1069,14 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
   h->gamma = gamma; h->beta = beta; h->normalize_weights = normalize_weights;
   DG_CUDA(cudaSetDevice(seg->device));
   DG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  int lo = 0, hi = 0;
+  DG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+  DG_CUDA(cudaStreamCreateWithPriority(&h->s_seg, cudaStreamNonBlocking, hi));
+  DG_CUDA(cudaStreamCreateWithPriority(&h->s_emb, cudaStreamNonBlocking, lo));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_start, cudaEventDisableTiming));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_osp, cudaEventDisableTiming));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_emb, cudaEventDisableTiming));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_done, cudaEventDisableTiming));
   *out = h.release();
   return DG_OK;
 }
@@ -1076,11 +1089,48 @@ extern "C" int dg_pipeline_step(dg_pipeline* h, const float* wav, int B, int S, 
   }
   int rc, F = 0, K = 0;
   if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
-  if ((rc = dg_seg_forward(h->seg, wav, B, S, seg, stream))) return rc;
   if (h->osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
-  if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, h->osp.as<float>(), stream))) return rc;
-  if ((rc = dg_emb_forward(h->emb, wav, h->osp.as<float>(), B, S, F, K, 1, 1.f, emb, stream))) return rc;
-  return dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, stream);
+  static const bool serial = getenv("DG_NO_OVERLAP") && getenv("DG_NO_OVERLAP")[0] == '1';
+  if (serial || !use_tensor_cores()) {
+    if ((rc = dg_seg_forward(h->seg, wav, B, S, seg, stream))) return rc;
+    if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, h->osp.as<float>(), stream))) return rc;
+    if ((rc = dg_emb_forward(h->emb, wav, h->osp.as<float>(), B, S, F, K, 1, 1.f, emb, stream))) return rc;
+    return dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, stream);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  const Geom g = make_geom(S);
+  DG_CUDA(cudaEventRecord(h->e_start, st));
+  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_start, 0));
+  DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_start, 0));
+  // embedding trunk first in host order (low-priority stream, grid capped to the SMs the LSTM leaves free)
+  int T = 0;
+  {
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->seg->device);
+    const int lstm_ctas = 2 * ((B + 15) / 16);
+    g_sm_limit = sms - lstm_ctas > sms / 2 ? sms - lstm_ctas : 0;
+    rc = emb_trunk(h->emb, wav, B, g, h->s_emb, &T);
+    g_sm_limit = 0;
+    if (rc) return rc;
+  }
+  if ((rc = dg_seg_forward(h->seg, wav, B, S, seg, h->s_seg))) return rc;
+  if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, h->osp.as<float>(), h->s_seg))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_osp, h->s_seg));
+  DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_osp, 0));
+  if ((rc = build_tables(h->emb, F, T, h->s_emb))) return rc;
+  if (h->emb->pooled.ensure((size_t)B * K * 3000 * 4)) return DG_ECUDA;
+  if ((rc = launch_stats_pool(h->emb->t5.as<float>(), B, g.S2, T, 1500, h->osp.as<float>(), F, K,
+                              h->emb->idx0.as<int>(), h->emb->idx1.as<int>(), h->emb->lam1.as<float>(),
+                              h->emb->pool_mode == 31 ? 1e-8f : 0.f, h->emb->pooled.as<float>(), h->s_emb)))
+    return rc;
+  if ((rc = emb_project(h->emb, B * K, 1, 1.f, emb, h->s_emb))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));
+  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_emb, 0));
+  if ((rc = dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, h->s_seg))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_done, h->s_seg));
+  DG_CUDA(cudaStreamWaitEvent(st, h->e_done, 0));
+  return DG_OK;
 }
 
 extern "C" int dg_pipeline_step_host(dg_pipeline* h, const float* wav_host, int B, int S, float* seg_host,
@@ -1111,6 +1161,12 @@ extern "C" int dg_pipeline_step_host(dg_pipeline* h, const float* wav_host, int 
 }
 
 extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
+  if (h) {
+    if (h->s_seg) cudaStreamDestroy(h->s_seg);
+    if (h->s_emb) cudaStreamDestroy(h->s_emb);
+    for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done})
+      if (e) cudaEventDestroy(e);
+  }
   if (h && h->st) cudaStreamDestroy(h->st);
   delete h;
   return DG_OK;

@@ -12,6 +12,15 @@ namespace dg {
 // ------------------------------------------------------------------ error plumbing
 void set_error(const std::string& msg);
 extern std::atomic<long long> g_launches;
+// persistent kernels size their grid to the SM count; while two streams overlap (fused pipeline) the
+// kernels of the lower-priority stream are capped so that they never wait for SMs held by the other one
+extern int g_sm_limit;
+inline int usable_sms() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return (g_sm_limit > 0 && g_sm_limit < sms) ? g_sm_limit : sms;
+}
 
 #define DG_CUDA(expr)                                                                   \
   do {                                                                                  \

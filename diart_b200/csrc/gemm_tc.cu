@@ -290,9 +290,7 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
     DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = usable_sms();
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
   gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);

@@ -21,12 +21,14 @@
 
 namespace dg {
 
-constexpr int LT_NB = 16, LT_THREADS = 288;
+constexpr int LT_NB = 16, LT_THREADS = 384;   // 8 epilogue warps + 4 MMA-issuing warps (one per gate)
 constexpr int LT_W_BYTES = 4 * 2 * 128 * 128;          // W_hi: 4 gates x 2 k-blocks x (128 rows x 128 B)
 constexpr int LT_H_TILE = LT_NB * 128;                 // one k-block of h^T: 16 rows x 128 B
 constexpr int LT_H_BYTES = 2 * 2 * 2 * LT_H_TILE;      // [buffer][plane][k-block]
 constexpr int LT_SMEM = LT_W_BYTES + LT_H_BYTES + 256 + 1024;
-constexpr uint32_t LT_COL_D = 0, LT_COL_WLO = 64;      // TMEM columns: 4 x 16 accumulators, 4 x 64 W_lo
+// TMEM columns: 8 accumulators of 16 (gate x k-half: eight independent accumulation chains hide the
+// latency between dependent tcgen05.mma; the halves are summed in the epilogue), then 4 x 64 columns of W_lo
+constexpr uint32_t LT_COL_D = 0, LT_COL_WLO = 128;
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -75,7 +77,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __res
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
-    mbar_init(mma_done, 1);
+    mbar_init(mma_done, 4);
     mbar_init(&h_ready[0], 8);
     mbar_init(&h_ready[1], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -92,7 +94,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __res
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 8) {
-    // ================================================================ TMA (once) + MMA issuer
+    // ================================================================ TMA (once)
     if (lane == 0) {
       mbar_expect_tx(w_full, LT_W_BYTES);
       for (int g = 0; g < 4; g++)
@@ -125,7 +127,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __res
   __syncthreads();
   tc_fence_after();
 
-  if (warp == 8) {
+  if (warp >= 8) {
+    // issuing a tcgen05.mma costs the issuing thread ~50 cycles (descriptor moves into uniform registers);
+    // with N = 16 the math is only 8 cycles, so the four gates are issued by four warps in parallel
+    const int g = warp - 8;
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // all descriptors are affine in (gate, k-step): one base each, compile-time offsets in 16-byte units
@@ -140,23 +145,29 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __res
         }
         const uint64_t b0d = buf ? bb1 : bb0;
 #pragma unroll
-        for (int g = 0; g < 4; g++) {
+        for (int kk = 0; kk < 4; kk++) {
 #pragma unroll
-          for (int ks = 0; ks < 8; ks++) {
-            constexpr int kTile = 16384 >> 4, kHTile = LT_H_TILE >> 4;
-            const int kb = ks >> 2, kk = ks & 3;
-            const uint64_t a_hi = a0 + (uint64_t)((g * 2 + kb) * kTile + kk * 2);
-            const uint64_t b_hi = b0d + (uint64_t)(kb * kHTile + kk * 2);
-            const uint64_t b_lo = b0d + (uint64_t)(2 * kHTile + kb * kHTile + kk * 2);
-            umma_bf16(d0 + g * LT_NB, a_hi, b_lo, idesc, ks != 0);
-            umma_bf16_ts(d0 + g * LT_NB, alo0 + g * 64 + ks * 8, b_hi, idesc, 1);
-            umma_bf16(d0 + g * LT_NB, a_hi, b_hi, idesc, 1);
+          for (int prod = 0; prod < 3; prod++) {
+#pragma unroll
+            for (int kb = 0; kb < 2; kb++) {
+              {
+                constexpr int kTile = 16384 >> 4, kHTile = LT_H_TILE >> 4;
+                const int ks = kb * 4 + kk;
+                const uint64_t a_hi = a0 + (uint64_t)((g * 2 + kb) * kTile + kk * 2);
+                const uint64_t b_hi = b0d + (uint64_t)(kb * kHTile + kk * 2);
+                const uint64_t b_lo = b0d + (uint64_t)(2 * kHTile + kb * kHTile + kk * 2);
+                const uint32_t d = d0 + (g * 2 + kb) * LT_NB;
+                if (prod == 0) umma_bf16(d, a_hi, b_lo, idesc, kk != 0);
+                else if (prod == 1) umma_bf16_ts(d, alo0 + g * 64 + ks * 8, b_hi, idesc, 1);
+                else umma_bf16(d, a_hi, b_hi, idesc, 1);
+              }
+            }
           }
         }
         umma_commit(mma_done);
       }
     }
-  } else {
+  } else if (warp < 8) {
     // ================================================================ gate math / state update (warps 0..7)
     const int quad = warp & 3, ch = warp >> 2;
     const int u = quad * 32 + lane;                 // hidden unit == TMEM lane
@@ -178,12 +189,23 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __res
       }
       mbar_wait(mma_done, step & 1);
       tc_fence_after();
-      uint32_t ri[8], rf[8], rg[8], ro[8];
+      uint32_t ri[8], rf[8], rg[8], ro[8], si[8], sf[8], sg[8], so[8];
       tmem_ld8(tlane + 0 * LT_NB, ri);
-      tmem_ld8(tlane + 1 * LT_NB, rf);
-      tmem_ld8(tlane + 2 * LT_NB, rg);
-      tmem_ld8(tlane + 3 * LT_NB, ro);
+      tmem_ld8(tlane + 1 * LT_NB, si);
+      tmem_ld8(tlane + 2 * LT_NB, rf);
+      tmem_ld8(tlane + 3 * LT_NB, sf);
+      tmem_ld8(tlane + 4 * LT_NB, rg);
+      tmem_ld8(tlane + 5 * LT_NB, sg);
+      tmem_ld8(tlane + 6 * LT_NB, ro);
+      tmem_ld8(tlane + 7 * LT_NB, so);
       tmem_ld_wait();
+#pragma unroll
+      for (int n = 0; n < 8; n++) {   // sum the two k-half accumulators
+        ri[n] = __float_as_uint(__uint_as_float(ri[n]) + __uint_as_float(si[n]));
+        rf[n] = __float_as_uint(__uint_as_float(rf[n]) + __uint_as_float(sf[n]));
+        rg[n] = __float_as_uint(__uint_as_float(rg[n]) + __uint_as_float(sg[n]));
+        ro[n] = __float_as_uint(__uint_as_float(ro[n]) + __uint_as_float(so[n]));
+      }
       unsigned char* hdst = hsm + nxt * (LT_H_BYTES / 2) + kb_u * LT_H_TILE;
 #pragma unroll
       for (int n = 0; n < 8; n++) {

@@ -293,9 +293,7 @@ int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, floa
     DG_CUDA(cudaFuncSetAttribute(sinc0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
     attr_done = true;
   }
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = usable_sms();
   const int row_tiles = (int)((rows + ST_ROWS - 1) / ST_ROWS);
   const int tiles = row_tiles * 4;
   sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0,
