@@ -146,7 +146,7 @@ def run_reference(args):
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    _RESULT_LINES.append(json.dumps(line))
 
 
 def pick_threads(pipe, data) -> int:
@@ -219,16 +219,30 @@ def run_ours(args):
             dist.barrier()
 
     # ---------------- device-resident throughput (`value`) with per-kernel CUDA-event timing
-    for i in range(args.warmup):
-        pipe.device_step(dev[i % NB])
+    fused, F, K, D = pipe._ensure_fused(CHUNK)
+    stream = _lib.stream_ptr(device)
+
+    def run_steps(n):
+        """n pipeline steps, depth-2 pipelined (dg_pipeline_submit / collect): clustering of step i overlaps the
+        networks of step i+1; every step's results are complete when the last collect is reached on the stream"""
+        if args.serial:
+            for i in range(n):
+                pipe.device_step(dev[i % NB])
+            return
+        for i in range(n):
+            _lib.check(lib.dg_pipeline_submit(fused, dev[i % NB].data_ptr(), B, CHUNK, stream))
+            if i > 0:
+                _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
+        _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
+
+    run_steps(args.warmup)
     barrier()
     lib.dg_profile_enable(1)
     launches0 = lib.dg_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
         ev0.record()
-        for i in range(args.steps):
-            pipe.device_step(dev[i % NB])
+        run_steps(args.steps)
         ev1.record()
         torch.cuda.synchronize(device)
     ms = ev0.elapsed_time(ev1)
@@ -244,23 +258,30 @@ def run_ours(args):
     value = world * args.steps * B * STEP_SECONDS / (ms_max / 1e3)
 
     # ---------------- end to end through the C ABI with HOST buffers (H2D + D2H inside the call)
-    F, K = pipe.segmentation.model.model.dims(CHUNK)
-    _, D = pipe.embedding.embedding.native.dims(CHUNK)
-    seg_h = torch.empty((B, F, K)).pin_memory()
-    emb_h = torch.empty((B, K, D)).pin_memory()
-    map_h = torch.empty((B, K), dtype=torch.int32).pin_memory()
-    fused = pipe._fused
+    seg_h = [torch.empty((B, F, K)).pin_memory() for _ in range(2)]
+    emb_h = [torch.empty((B, K, D)).pin_memory() for _ in range(2)]
+    map_h = [torch.empty((B, K), dtype=torch.int32).pin_memory() for _ in range(2)]
 
-    def host_step(i):
-        _lib.check(lib.dg_pipeline_step_host(fused, pinned[i % NB].data_ptr(), B, CHUNK, seg_h.data_ptr(),
-                                             emb_h.data_ptr(), map_h.data_ptr(), None))
+    def host_steps(n):
+        """host buffers in, host buffers out, every step: pinned waveforms are uploaded inside submit_host, the
+        step's scores / embeddings / speaker map are downloaded inside collect_host (blocking)"""
+        if args.serial:
+            for i in range(n):
+                _lib.check(lib.dg_pipeline_step_host(fused, pinned[i % NB].data_ptr(), B, CHUNK, seg_h[0].data_ptr(),
+                                                     emb_h[0].data_ptr(), map_h[0].data_ptr(), None))
+            return
+        for i in range(n):
+            _lib.check(lib.dg_pipeline_submit_host(fused, pinned[i % NB].data_ptr(), B, CHUNK))
+            if i > 0:
+                j = (i - 1) & 1
+                _lib.check(lib.dg_pipeline_collect_host(fused, seg_h[j].data_ptr(), emb_h[j].data_ptr(), map_h[j].data_ptr()))
+        j = (n - 1) & 1
+        _lib.check(lib.dg_pipeline_collect_host(fused, seg_h[j].data_ptr(), emb_h[j].data_ptr(), map_h[j].data_ptr()))
 
-    for i in range(max(1, args.warmup)):
-        host_step(i)
+    host_steps(max(2, args.warmup))
     barrier()
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        host_step(i)
+    host_steps(args.steps)
     torch.cuda.synchronize(device)
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
@@ -314,7 +335,8 @@ def run_ours(args):
         "step_tflops": step_flops / (ms_max / args.steps * 1e-3) / 1e12,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CHUNK * 4,
                 "d2h_bytes_per_step": B * F * K * 4 + B * K * D * 4 + B * K * 4,
-                "api": "dg_pipeline_step_host (C ABI, pinned host buffers)"},
+                "api": ("dg_pipeline_step_host" if args.serial else "dg_pipeline_submit_host / collect_host, depth 2") +
+                       " (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roofline,
@@ -323,12 +345,31 @@ def run_ours(args):
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline()
-    print(json.dumps(line))
+    _RESULT_LINES.append(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 
 
 def main():
+    # the driver parses ONE JSON line from stdout: anything libraries print (e.g. NCCL's version banner) goes to
+    # stderr instead; the real stdout is restored only for the result line
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        _main()
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for line in _RESULT_LINES:
+        print(line, flush=True)
+
+
+_RESULT_LINES = []
+
+
+def _main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -337,6 +378,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ref-batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial", action="store_true", help="one step at a time (dg_pipeline_step) instead of depth-2 pipelining")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

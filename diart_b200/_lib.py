@@ -55,6 +55,11 @@ SIGNATURES = {
     "dg_pipeline_create": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int, C.POINTER(_P)]),
     "dg_pipeline_step": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "dg_pipeline_step_host": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P]),
+    "dg_pipeline_submit": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
+    "dg_pipeline_collect": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.POINTER(_P), _P]),
+    "dg_pipeline_collect_copy": (C.c_int, [_P, _P, _P, _P, _P]),
+    "dg_pipeline_submit_host": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "dg_pipeline_collect_host": (C.c_int, [_P, _P, _P, _P]),
     "dg_pipeline_destroy": (C.c_int, [_P]),
 }
 

@@ -132,6 +132,45 @@ class SpeakerDiarization(base.Pipeline):
             return seg, emb
         return None
 
+    def _ensure_fused(self, num_samples: int):
+        """creates the fused dg_pipeline handle (native models only); returns (handle, F, K, D)"""
+        native = self._native_models()
+        if native is None:
+            raise _lib.DiartB200Error("the fused / pipelined step needs the B200 segmentation and embedding models")
+        seg_net, emb_net = native
+        F, K = seg_net.dims(num_samples)
+        _, D = emb_net.dims(num_samples)
+        if self._fused is None:
+            h = C.c_void_p()
+            _lib.check(_lib.lib().dg_pipeline_create(seg_net.handle, emb_net.handle, self.clustering._handle(D),
+                                                     float(self.config.gamma), float(self.config.beta),
+                                                     int(self.config.normalize_embedding_weights), C.byref(h)))
+            self._fused = h
+        return self._fused, F, K, D
+
+    def submit(self, batch: torch.Tensor):
+        """Pipelined step (depth 2): enqueue a (B,S) device batch and return; clustering of this step overlaps the
+        networks of the next one.  ``batch`` must stay alive until the matching :meth:`collect`."""
+        device = self.segmentation.device
+        h, F, K, D = self._ensure_fused(batch.shape[1])
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().dg_pipeline_submit(h, batch.data_ptr(), batch.shape[0], batch.shape[1],
+                                                     _lib.stream_ptr(device)))
+        self._pending = getattr(self, "_pending", []) + [(batch.shape[0], F, K, D)]
+
+    def collect(self) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+        """Oldest submitted step -> (segmentation (B,F,K), embeddings (B,K,D), map (B,K) int32) device tensors
+        (copies of the handle's slot buffers, ordered on the current stream)."""
+        device = self.segmentation.device
+        B, F, K, D = self._pending.pop(0)
+        seg = torch.empty((B, F, K), device=device)
+        emb = torch.empty((B, K, D), device=device)
+        maps = torch.empty((B, K), device=device, dtype=torch.int32)
+        with torch.cuda.device(device):
+            _lib.check(_lib.lib().dg_pipeline_collect_copy(self._fused, seg.data_ptr(), emb.data_ptr(), maps.data_ptr(),
+                                                           _lib.stream_ptr(device)))
+        return seg, emb, maps
+
     def device_step(self, batch: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
         """batch (B,S) float32 on the device -> (segmentation (B,F,K), embeddings (B,K,D), map (B,K) int32),
         all on the device; clustering state advances by B chunks."""
@@ -142,16 +181,8 @@ class SpeakerDiarization(base.Pipeline):
             emb = self.embedding.forward_device(batch, seg)
             maps, _ = self.clustering.step_batch(seg, emb)
             return seg, emb, maps
-        seg_net, emb_net = native
         B, S = batch.shape
-        F, K = seg_net.dims(S)
-        _, D = emb_net.dims(S)
-        if self._fused is None:
-            h = C.c_void_p()
-            _lib.check(_lib.lib().dg_pipeline_create(seg_net.handle, emb_net.handle, self.clustering._handle(D),
-                                                     float(self.config.gamma), float(self.config.beta),
-                                                     int(self.config.normalize_embedding_weights), C.byref(h)))
-            self._fused = h
+        _, F, K, D = self._ensure_fused(S)
         seg = torch.empty((B, F, K), device=device)
         emb = torch.empty((B, K, D), device=device)
         maps = torch.empty((B, K), device=device, dtype=torch.int32)

@@ -1046,8 +1046,12 @@ struct dg_pipeline {
   cudaStream_t st = nullptr;
   // two-stream overlap inside a step: the segmentation chain (critical path, high priority) and the
   // embedding trunk (independent of it until the pooling weights exist) run concurrently
-  cudaStream_t s_seg = nullptr, s_emb = nullptr;
+  cudaStream_t s_seg = nullptr, s_emb = nullptr, s_clu = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   cudaEvent_t e_start = nullptr, e_osp = nullptr, e_emb = nullptr, e_done = nullptr;
+  // depth-2 pipelining (dg_pipeline_submit* / collect*)
+  DevBuf slot_wav[2], slot_seg[2], slot_emb[2], slot_map[2];
+  cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_slot_done[2] = {nullptr, nullptr};
+  int slot_B[2] = {0, 0}, slot_S[2] = {0, 0}, head = 0, outstanding = 0;
 };
 
 extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
@@ -1077,32 +1081,27 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
   DG_CUDA(cudaEventCreateWithFlags(&h->e_osp, cudaEventDisableTiming));
   DG_CUDA(cudaEventCreateWithFlags(&h->e_emb, cudaEventDisableTiming));
   DG_CUDA(cudaEventCreateWithFlags(&h->e_done, cudaEventDisableTiming));
+  DG_CUDA(cudaStreamCreateWithPriority(&h->s_clu, cudaStreamNonBlocking, hi));
+  DG_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
+  DG_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    DG_CUDA(cudaEventCreateWithFlags(&h->e_h2d[i], cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&h->e_slot_done[i], cudaEventDisableTiming));
+  }
+  DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));   // so that the first step's wait on it is well defined
   *out = h.release();
   return DG_OK;
 }
 
-extern "C" int dg_pipeline_step(dg_pipeline* h, const float* wav, int B, int S, float* seg, float* emb, int32_t* map,
-                                float* permuted, void* stream) {
-  if (!h || !wav || !seg || !emb || !map || B < 1) {
-    set_error("dg_pipeline_step: bad arguments");
-    return DG_EINVAL;
-  }
-  int rc, F = 0, K = 0;
-  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
-  if (h->osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
-  static const bool serial = getenv("DG_NO_OVERLAP") && getenv("DG_NO_OVERLAP")[0] == '1';
-  if (serial || !use_tensor_cores()) {
-    if ((rc = dg_seg_forward(h->seg, wav, B, S, seg, stream))) return rc;
-    if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, h->osp.as<float>(), stream))) return rc;
-    if ((rc = dg_emb_forward(h->emb, wav, h->osp.as<float>(), B, S, F, K, 1, 1.f, emb, stream))) return rc;
-    return dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, stream);
-  }
-  cudaStream_t st = (cudaStream_t)stream;
-  DG_CUDA(cudaSetDevice(h->seg->device));
+// segmentation chain on s_seg and embedding chain on s_emb, both starting after `start`; on return
+// e_emb (recorded on s_emb) marks seg, osp and emb complete
+static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, int K, float* seg, float* emb,
+                         cudaEvent_t start) {
+  int rc;
   const Geom g = make_geom(S);
-  DG_CUDA(cudaEventRecord(h->e_start, st));
-  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_start, 0));
-  DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_start, 0));
+  DG_CUDA(cudaStreamWaitEvent(h->s_seg, start, 0));
+  DG_CUDA(cudaStreamWaitEvent(h->s_emb, start, 0));
+  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_emb, 0));   // the previous step's pooling has consumed `osp`
   // embedding trunk first in host order (low-priority stream, grid capped to the SMs the LSTM leaves free)
   int T = 0;
   {
@@ -1126,10 +1125,161 @@ extern "C" int dg_pipeline_step(dg_pipeline* h, const float* wav, int B, int S, 
     return rc;
   if ((rc = emb_project(h->emb, B * K, 1, 1.f, emb, h->s_emb))) return rc;
   DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));
-  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_emb, 0));
-  if ((rc = dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, h->s_seg))) return rc;
-  DG_CUDA(cudaEventRecord(h->e_done, h->s_seg));
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_step(dg_pipeline* h, const float* wav, int B, int S, float* seg, float* emb, int32_t* map,
+                                float* permuted, void* stream) {
+  if (!h || !wav || !seg || !emb || !map || B < 1) {
+    set_error("dg_pipeline_step: bad arguments");
+    return DG_EINVAL;
+  }
+  if (h->outstanding) {
+    set_error("dg_pipeline_step: submitted steps are outstanding; collect them first");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  if (h->osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
+  static const bool serial = getenv("DG_NO_OVERLAP") && getenv("DG_NO_OVERLAP")[0] == '1';
+  if (serial || !use_tensor_cores()) {
+    if ((rc = dg_seg_forward(h->seg, wav, B, S, seg, stream))) return rc;
+    if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, h->osp.as<float>(), stream))) return rc;
+    if ((rc = dg_emb_forward(h->emb, wav, h->osp.as<float>(), B, S, F, K, 1, 1.f, emb, stream))) return rc;
+    return dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, stream);
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  DG_CUDA(cudaEventRecord(h->e_start, st));
+  if ((rc = pipeline_nets(h, wav, B, S, F, K, seg, emb, h->e_start))) return rc;
+  DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_emb, 0));
+  if ((rc = dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, h->s_clu))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_done, h->s_clu));
   DG_CUDA(cudaStreamWaitEvent(st, h->e_done, 0));
+  return DG_OK;
+}
+
+// ---- pipelined (depth 2) variants: the sequential clustering of step i and the host copies overlap the
+//      networks of step i+1.  Per stream the chunk order is preserved: clustering runs on one stream.
+static int pipeline_slot_prepare(dg_pipeline* h, int slot, int B, int S, int F, int K, bool host_in) {
+  const int D = h->emb->D;
+  if (h->osp.ensure((size_t)B * F * K * 4) || h->slot_seg[slot].ensure((size_t)B * F * K * 4) ||
+      h->slot_emb[slot].ensure((size_t)B * K * D * 4) || h->slot_map[slot].ensure((size_t)B * K * 4) ||
+      (host_in && h->slot_wav[slot].ensure((size_t)B * S * 4)))
+    return DG_ECUDA;
+  return DG_OK;
+}
+
+static int pipeline_submit_common(dg_pipeline* h, const float* wav_dev, int B, int S, int F, int K, int slot,
+                                  cudaEvent_t start) {
+  int rc;
+  // the slot's previous occupant (two submits ago) must be fully clustered before its buffers are rewritten
+  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_slot_done[slot], 0));
+  DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_slot_done[slot], 0));
+  if ((rc = pipeline_nets(h, wav_dev, B, S, F, K, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), start)))
+    return rc;
+  DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_emb, 0));
+  if ((rc = dg_cluster_step(h->clu, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), B, F, K,
+                            h->slot_map[slot].as<int32_t>(), nullptr, h->s_clu)))
+    return rc;
+  DG_CUDA(cudaEventRecord(h->e_slot_done[slot], h->s_clu));
+  h->slot_B[slot] = B;
+  h->slot_S[slot] = S;
+  h->head = (h->head + 1) & 1;
+  h->outstanding++;
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_submit(dg_pipeline* h, const float* wav_dev, int B, int S, void* stream) {
+  if (!h || !wav_dev || B < 1) {
+    set_error("dg_pipeline_submit: bad arguments");
+    return DG_EINVAL;
+  }
+  if (h->outstanding >= 2) {
+    set_error("dg_pipeline_submit: two steps are already outstanding; collect one first");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  const int slot = h->head;
+  if ((rc = pipeline_slot_prepare(h, slot, B, S, F, K, false))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_start, (cudaStream_t)stream));
+  return pipeline_submit_common(h, wav_dev, B, S, F, K, slot, h->e_start);
+}
+
+extern "C" int dg_pipeline_collect(dg_pipeline* h, const float** seg_dev, const float** emb_dev,
+                                   const int32_t** map_dev, void* stream) {
+  if (!h || h->outstanding < 1) {
+    set_error("dg_pipeline_collect: nothing outstanding");
+    return DG_EINVAL;
+  }
+  const int slot = (h->head - h->outstanding) & 1;
+  DG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->e_slot_done[slot], 0));
+  if (seg_dev) *seg_dev = h->slot_seg[slot].as<float>();
+  if (emb_dev) *emb_dev = h->slot_emb[slot].as<float>();
+  if (map_dev) *map_dev = h->slot_map[slot].as<int32_t>();
+  h->outstanding--;
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_collect_copy(dg_pipeline* h, float* seg_dev, float* emb_dev, int32_t* map_dev,
+                                        void* stream) {
+  if (!h || h->outstanding < 1) {
+    set_error("dg_pipeline_collect_copy: nothing outstanding");
+    return DG_EINVAL;
+  }
+  const int slot = (h->head - h->outstanding) & 1;
+  int F = 0, K = 0;
+  const int B = h->slot_B[slot], D = h->emb->D;
+  dg_seg_dims(h->seg, h->slot_S[slot], &F, &K);
+  cudaStream_t st = (cudaStream_t)stream;
+  DG_CUDA(cudaStreamWaitEvent(st, h->e_slot_done[slot], 0));
+  if (seg_dev) DG_CUDA(cudaMemcpyAsync(seg_dev, h->slot_seg[slot].p, (size_t)B * F * K * 4, cudaMemcpyDeviceToDevice, st));
+  if (emb_dev) DG_CUDA(cudaMemcpyAsync(emb_dev, h->slot_emb[slot].p, (size_t)B * K * D * 4, cudaMemcpyDeviceToDevice, st));
+  if (map_dev) DG_CUDA(cudaMemcpyAsync(map_dev, h->slot_map[slot].p, (size_t)B * K * 4, cudaMemcpyDeviceToDevice, st));
+  h->outstanding--;
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_submit_host(dg_pipeline* h, const float* wav_host, int B, int S) {
+  if (!h || !wav_host || B < 1) {
+    set_error("dg_pipeline_submit_host: bad arguments");
+    return DG_EINVAL;
+  }
+  if (h->outstanding >= 2) {
+    set_error("dg_pipeline_submit_host: two steps are already outstanding; collect one first");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  const int slot = h->head;
+  if ((rc = pipeline_slot_prepare(h, slot, B, S, F, K, true))) return rc;
+  DG_CUDA(cudaStreamWaitEvent(h->s_h2d, h->e_slot_done[slot], 0));
+  DG_CUDA(cudaMemcpyAsync(h->slot_wav[slot].p, wav_host, (size_t)B * S * 4, cudaMemcpyHostToDevice, h->s_h2d));
+  DG_CUDA(cudaEventRecord(h->e_h2d[slot], h->s_h2d));
+  return pipeline_submit_common(h, h->slot_wav[slot].as<float>(), B, S, F, K, slot, h->e_h2d[slot]);
+}
+
+extern "C" int dg_pipeline_collect_host(dg_pipeline* h, float* seg_host, float* emb_host, int32_t* map_host) {
+  if (!h || h->outstanding < 1) {
+    set_error("dg_pipeline_collect_host: nothing outstanding");
+    return DG_EINVAL;
+  }
+  const int slot = (h->head - h->outstanding) & 1;
+  int F = 0, K = 0;
+  const int B = h->slot_B[slot], D = h->emb->D;
+  dg_seg_dims(h->seg, h->slot_S[slot], &F, &K);
+  DG_CUDA(cudaStreamWaitEvent(h->s_d2h, h->e_slot_done[slot], 0));
+  if (seg_host)
+    DG_CUDA(cudaMemcpyAsync(seg_host, h->slot_seg[slot].p, (size_t)B * F * K * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+  if (emb_host)
+    DG_CUDA(cudaMemcpyAsync(emb_host, h->slot_emb[slot].p, (size_t)B * K * D * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+  if (map_host)
+    DG_CUDA(cudaMemcpyAsync(map_host, h->slot_map[slot].p, (size_t)B * K * 4, cudaMemcpyDeviceToHost, h->s_d2h));
+  DG_CUDA(cudaStreamSynchronize(h->s_d2h));
+  h->outstanding--;
   return DG_OK;
 }
 
@@ -1164,7 +1314,11 @@ extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
   if (h) {
     if (h->s_seg) cudaStreamDestroy(h->s_seg);
     if (h->s_emb) cudaStreamDestroy(h->s_emb);
-    for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done})
+    if (h->s_clu) cudaStreamDestroy(h->s_clu);
+    if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
+    if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
+    for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done, h->e_h2d[0], h->e_h2d[1], h->e_slot_done[0],
+                          h->e_slot_done[1]})
       if (e) cudaEventDestroy(e);
   }
   if (h && h->st) cudaStreamDestroy(h->st);

@@ -110,3 +110,31 @@ def test_foreign_models_behind_loader_api(oracle_nets, stream, cuda_device):
     # torch's cuDNN / cuBLAS float32 kernels re-associate differently from both the CPU oracle and this path
     assert (s1 - s2).abs().max().item() < 1e-3 and (e1 - e2).abs().max().item() < 2e-3
     assert m1.shape == m2.shape and m1.dtype == torch.int32
+
+
+def test_pipelined_submit_collect_equals_sequential_steps(oracle_nets, stream, cuda_device):
+    """dg_pipeline_submit / collect (clustering of step i overlapping the networks of step i+1) must give exactly
+    what one-step-at-a-time dg_pipeline_step gives: chunk order per stream is preserved"""
+    a = make_pipeline(oracle_nets, cuda_device)
+    b = make_pipeline(oracle_nets, cuda_device)
+    batches = [torch.from_numpy(synth.windows(stream, BATCH, first=i * BATCH)).to(cuda_device) for i in range(3)]
+    ref = [a.device_step(x) for x in batches]
+    got = []
+    b.submit(batches[0])
+    b.submit(batches[1])
+    got.append(b.collect())
+    b.submit(batches[2])
+    got.append(b.collect())
+    got.append(b.collect())
+    torch.cuda.synchronize()
+    for (s1, e1, m1), (s2, e2, m2) in zip(ref, got):
+        assert torch.equal(s1, s2) and torch.equal(e1, e2) and torch.equal(m1, m2)
+    assert np.array_equal(a.clustering.centers, b.clustering.centers)
+    with pytest.raises(ValueError):
+        b.collect() if False else _lib_collect_empty(b)
+
+
+def _lib_collect_empty(pipe):
+    from diart_b200 import _lib
+
+    _lib.check(_lib.lib().dg_pipeline_collect(pipe._fused, None, None, None, None))
