@@ -323,10 +323,15 @@ struct dg_seg {
   DevBuf wih[4], bih[4], whh[4];   // input projections [in_pad][1024], bias [1024], packed W_hh
   DevBuf wih_hi[4], wih_lo[4];     // the same as bf16 hi/lo planes [1024][in_pad] for the tcgen05 path
   DevBuf whh_hi[4], whh_lo[4];     // W_hh as bf16 hi/lo planes [2][512][128] for the tcgen05 recurrence
-  DevBuf xh, xl;                   // bf16 hi/lo planes of the current in-projection input
   DevBuf l1w, l1b, l2w, l2b, cw, cb;
-  SincWork work;
-  DevBuf gx, hA, hB, y1, y2;
+  // activations: two independent sets ("lanes") so that the fused pipeline can run the segmentation chains of
+  // two consecutive steps concurrently (the recurrence occupies only 32 SMs)
+  struct Scratch {
+    SincWork work;
+    DevBuf gx, hA, hB, y1, y2;
+    DevBuf xh, xl;                 // bf16 hi/lo planes of the current in-projection input
+  } scr[2];
+  int lane = 0;
 };
 
 static int seg_prepare(dg_seg* h, const Tensors& t) {
@@ -460,66 +465,67 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
   }
   cudaStream_t st = (cudaStream_t)stream;
   DG_CUDA(cudaSetDevice(h->device));
+  dg_seg::Scratch& w = h->scr[h->lane & 1];
   const Geom g = make_geom(S);
   int rc;
-  if ((rc = run_sincnet(h->sw, h->work, wav, B, g, st))) return rc;
+  if ((rc = run_sincnet(h->sw, w.work, wav, B, g, st))) return rc;
   const size_t rows = (size_t)B * g.S2 + 64;
-  if (h->gx.ensure(rows * 1024 * 4) || h->hA.ensure(rows * 256 * 4) || h->hB.ensure(rows * 256 * 4) ||
-      h->y1.ensure(rows * 128 * 4) || h->y2.ensure(rows * 128 * 4))
+  if (w.gx.ensure(rows * 1024 * 4) || w.hA.ensure(rows * 256 * 4) || w.hB.ensure(rows * 256 * 4) ||
+      w.y1.ensure(rows * 128 * 4) || w.y2.ensure(rows * 128 * 4))
     return DG_ECUDA;
   const long long M = (long long)B * g.S2;
   float* hin = nullptr;
-  float* hbuf[2] = {h->hA.as<float>(), h->hB.as<float>()};
+  float* hbuf[2] = {w.hA.as<float>(), w.hB.as<float>()};
   const bool tc = use_tensor_cores();
-  if (tc && (h->xh.ensure(rows * 256 * 2) || h->xl.ensure(rows * 256 * 2))) return DG_ECUDA;
+  if (tc && (w.xh.ensure(rows * 256 * 2) || w.xl.ensure(rows * 256 * 2))) return DG_ECUDA;
   for (int L = 0; L < 4; L++) {
     if (tc) {
       const int cin = L == 0 ? 64 : 256;
       if (L == 0)
-        rc = launch_split_ex(h->work.out, M, 64, 64, 64, h->work.out_pool, g.S2, h->work.sc2.as<float>(),
-                             h->work.sh2.as<float>(), h->xh.p, h->xl.p, st);
+        rc = launch_split_ex(w.work.out, M, 64, 64, 64, w.work.out_pool, g.S2, w.work.sc2.as<float>(),
+                             w.work.sh2.as<float>(), w.xh.p, w.xl.p, st);
       else
-        rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, h->xh.p, h->xl.p, st);
+        rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, w.xh.p, w.xl.p, st);
       if (rc) return rc;
       TcGemm t{};
-      t.A_hi = h->xh.p; t.A_lo = h->xl.p; t.lda = cin; t.Cin = cin; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
+      t.A_hi = w.xh.p; t.A_lo = w.xl.p; t.lda = cin; t.Cin = cin; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
       t.W_hi = h->wih_hi[L].p; t.W_lo = h->wih_lo[L].p; t.Npad = 1024; t.N = 1024; t.bias = h->bih[L].as<float>();
-      t.out_f32 = h->gx.as<float>(); t.ldc = 1024; t.epi = 0; t.tag = "lstm_inproj";
+      t.out_f32 = w.gx.as<float>(); t.ldc = 1024; t.epi = 0; t.tag = "lstm_inproj";
       if ((rc = launch_gemm_tc(t, st))) return rc;
       float* hout = hbuf[L & 1];
       static const bool lstm_simt = getenv("DG_LSTM_SIMT") && getenv("DG_LSTM_SIMT")[0] == '1';
       if (lstm_simt)
-        rc = launch_lstm_layer(h->gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st);
+        rc = launch_lstm_layer(w.gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st);
       else
-        rc = launch_lstm_layer_tc(h->gx.as<float>(), h->whh_hi[L].p, h->whh_lo[L].p, B, g.T2, g.S2, hout, st);
+        rc = launch_lstm_layer_tc(w.gx.as<float>(), h->whh_hi[L].p, h->whh_lo[L].p, B, g.T2, g.S2, hout, st);
       if (rc) return rc;
       hin = hout;
       continue;
     }
     GemmArgs a{};
     if (L == 0) {
-      a.A = h->work.p2.as<float>(); a.lda = 64; a.Cin = 64;
-      a.in_sc = h->work.sc2.as<float>(); a.in_sh = h->work.sh2.as<float>(); a.item_rows = g.S2;
+      a.A = w.work.p2.as<float>(); a.lda = 64; a.Cin = 64;
+      a.in_sc = w.work.sc2.as<float>(); a.in_sh = w.work.sh2.as<float>(); a.item_rows = g.S2;
     } else {
       a.A = hin; a.lda = 256; a.Cin = 256;
     }
     a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;
     a.W = h->wih[L].as<float>(); a.ldw = 1024; a.N = 1024; a.bias = h->bih[L].as<float>();
-    a.C = h->gx.as<float>(); a.ldc = 1024; a.epi = EPI_BIAS; a.tag = "lstm_inproj";
+    a.C = w.gx.as<float>(); a.ldc = 1024; a.epi = EPI_BIAS; a.tag = "lstm_inproj";
     if ((rc = launch_gemm(a, st))) return rc;
     float* hout = hbuf[L & 1];
-    if ((rc = launch_lstm_layer(h->gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st))) return rc;
+    if ((rc = launch_lstm_layer(w.gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st))) return rc;
     hin = hout;
   }
   GemmArgs a{};
   a.A = hin; a.lda = 256; a.Cin = 256; a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;
   a.W = h->l1w.as<float>(); a.ldw = 128; a.N = 128; a.bias = h->l1b.as<float>();
-  a.C = h->y1.as<float>(); a.ldc = 128; a.epi = EPI_BIAS_LEAKY; a.tag = "seg_linear";
+  a.C = w.y1.as<float>(); a.ldc = 128; a.epi = EPI_BIAS_LEAKY; a.tag = "seg_linear";
   if ((rc = launch_gemm(a, st))) return rc;
-  a.A = h->y1.as<float>(); a.lda = 128; a.Cin = 128;
-  a.W = h->l2w.as<float>(); a.bias = h->l2b.as<float>(); a.C = h->y2.as<float>();
+  a.A = w.y1.as<float>(); a.lda = 128; a.Cin = 128;
+  a.W = h->l2w.as<float>(); a.bias = h->l2b.as<float>(); a.C = w.y2.as<float>();
   if ((rc = launch_gemm(a, st))) return rc;
-  return launch_seg_final(h->y2.as<float>(), h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
+  return launch_seg_final(w.y2.as<float>(), h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
 }
 
 extern "C" int dg_seg_destroy(dg_seg* h) {
@@ -1046,7 +1052,9 @@ struct dg_pipeline {
   cudaStream_t st = nullptr;
   // two-stream overlap inside a step: the segmentation chain (critical path, high priority) and the
   // embedding trunk (independent of it until the pooling weights exist) run concurrently
-  cudaStream_t s_seg = nullptr, s_emb = nullptr, s_clu = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  cudaStream_t s_seg = nullptr, s_seg2 = nullptr, s_emb = nullptr, s_clu = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+  DevBuf osp2;
+  cudaEvent_t e_osp2 = nullptr;
   cudaEvent_t e_start = nullptr, e_osp = nullptr, e_emb = nullptr, e_done = nullptr;
   // depth-2 pipelining (dg_pipeline_submit* / collect*)
   DevBuf slot_wav[2], slot_seg[2], slot_emb[2], slot_map[2];
@@ -1082,6 +1090,8 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
   DG_CUDA(cudaEventCreateWithFlags(&h->e_emb, cudaEventDisableTiming));
   DG_CUDA(cudaEventCreateWithFlags(&h->e_done, cudaEventDisableTiming));
   DG_CUDA(cudaStreamCreateWithPriority(&h->s_clu, cudaStreamNonBlocking, hi));
+  DG_CUDA(cudaStreamCreateWithPriority(&h->s_seg2, cudaStreamNonBlocking, hi));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_osp2, cudaEventDisableTiming));
   DG_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
   DG_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) {
@@ -1096,12 +1106,17 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
 // segmentation chain on s_seg and embedding chain on s_emb, both starting after `start`; on return
 // e_emb (recorded on s_emb) marks seg, osp and emb complete
 static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, int K, float* seg, float* emb,
-                         cudaEvent_t start) {
+                         cudaEvent_t start, int lane = 0) {
   int rc;
   const Geom g = make_geom(S);
-  DG_CUDA(cudaStreamWaitEvent(h->s_seg, start, 0));
+  // lane 0 / 1: segmentation stream, scratch set, OSP buffer and event of this step (consecutive pipelined steps
+  // alternate, so step i+1's segmentation chain can start while step i's is still in its recurrence)
+  cudaStream_t s_seg = lane ? h->s_seg2 : h->s_seg;
+  DevBuf& osp = lane ? h->osp2 : h->osp;
+  cudaEvent_t e_osp = lane ? h->e_osp2 : h->e_osp;
+  if (osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
+  DG_CUDA(cudaStreamWaitEvent(s_seg, start, 0));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, start, 0));
-  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_emb, 0));   // the previous step's pooling has consumed `osp`
   // embedding trunk first in host order (low-priority stream, grid capped to the SMs the LSTM leaves free)
   int T = 0;
   {
@@ -1113,13 +1128,16 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     g_sm_limit = 0;
     if (rc) return rc;
   }
-  if ((rc = dg_seg_forward(h->seg, wav, B, S, seg, h->s_seg))) return rc;
-  if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, h->osp.as<float>(), h->s_seg))) return rc;
-  DG_CUDA(cudaEventRecord(h->e_osp, h->s_seg));
-  DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_osp, 0));
+  h->seg->lane = lane;
+  rc = dg_seg_forward(h->seg, wav, B, S, seg, s_seg);
+  h->seg->lane = 0;
+  if (rc) return rc;
+  if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, osp.as<float>(), s_seg))) return rc;
+  DG_CUDA(cudaEventRecord(e_osp, s_seg));
+  DG_CUDA(cudaStreamWaitEvent(h->s_emb, e_osp, 0));
   if ((rc = build_tables(h->emb, F, T, h->s_emb))) return rc;
   if (h->emb->pooled.ensure((size_t)B * K * 3000 * 4)) return DG_ECUDA;
-  if ((rc = launch_stats_pool(h->emb->t5.as<float>(), B, g.S2, T, 1500, h->osp.as<float>(), F, K,
+  if ((rc = launch_stats_pool(h->emb->t5.as<float>(), B, g.S2, T, 1500, osp.as<float>(), F, K,
                               h->emb->idx0.as<int>(), h->emb->idx1.as<int>(), h->emb->lam1.as<float>(),
                               h->emb->pool_mode == 31 ? 1e-8f : 0.f, h->emb->pooled.as<float>(), h->s_emb)))
     return rc;
@@ -1174,9 +1192,10 @@ static int pipeline_submit_common(dg_pipeline* h, const float* wav_dev, int B, i
                                   cudaEvent_t start) {
   int rc;
   // the slot's previous occupant (two submits ago) must be fully clustered before its buffers are rewritten
-  DG_CUDA(cudaStreamWaitEvent(h->s_seg, h->e_slot_done[slot], 0));
+  DG_CUDA(cudaStreamWaitEvent(slot ? h->s_seg2 : h->s_seg, h->e_slot_done[slot], 0));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_slot_done[slot], 0));
-  if ((rc = pipeline_nets(h, wav_dev, B, S, F, K, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), start)))
+  if ((rc = pipeline_nets(h, wav_dev, B, S, F, K, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), start,
+                          slot)))
     return rc;
   DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_emb, 0));
   if ((rc = dg_cluster_step(h->clu, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), B, F, K,
@@ -1315,6 +1334,8 @@ extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
     if (h->s_seg) cudaStreamDestroy(h->s_seg);
     if (h->s_emb) cudaStreamDestroy(h->s_emb);
     if (h->s_clu) cudaStreamDestroy(h->s_clu);
+    if (h->s_seg2) cudaStreamDestroy(h->s_seg2);
+    if (h->e_osp2) cudaEventDestroy(h->e_osp2);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done, h->e_h2d[0], h->e_h2d[1], h->e_slot_done[0],
