@@ -50,8 +50,12 @@ struct DevBuf {
     if (p) cudaFree(p);
     p = nullptr;
     bytes = 0;
+    // (re)allocation is rare (first step at a given batch size).  The handles drive several non-blocking
+    // streams, which do not order against the legacy stream this memset runs on: drain the device on both sides.
+    DG_CUDA(cudaDeviceSynchronize());
     DG_CUDA(cudaMalloc(&p, n));
     DG_CUDA(cudaMemset(p, 0, n));
+    DG_CUDA(cudaDeviceSynchronize());
     bytes = n;
     return 0;
   }
