@@ -877,6 +877,7 @@ struct dg_cluster {
   int device = 0;
   ClusterParams p;
   DevBuf centers, active, init, prep, prep_d, record;
+  DevBuf base, base_active, relabel;   // shared-identity mode: table at the last merge, relabel of created centres
 };
 
 extern "C" int dg_cluster_create(int max_speakers, int dim, double tau, double rho, double delta, int device,
@@ -894,7 +895,8 @@ extern "C" int dg_cluster_create(int max_speakers, int dim, double tau, double r
   h->p.tau_f = (float)tau;
   h->p.rho_f = (float)rho;
   h->p.delta = delta;
-  if (h->centers.ensure((size_t)max_speakers * dim * 8) || h->active.ensure(32 * 4) || h->init.ensure(2 * 4))
+  if (h->centers.ensure((size_t)max_speakers * dim * 8) || h->active.ensure(32 * 4) || h->init.ensure(2 * 4) ||
+      h->base.ensure((size_t)max_speakers * dim * 8) || h->base_active.ensure(32 * 4) || h->relabel.ensure(32 * 4))
     return DG_ECUDA;
   *out = h.release();
   return DG_OK;
@@ -921,6 +923,8 @@ extern "C" int dg_cluster_reset(dg_cluster* h) {
   DG_CUDA(cudaMemset(h->centers.p, 0, h->centers.bytes));
   DG_CUDA(cudaMemset(h->active.p, 0, h->active.bytes));
   DG_CUDA(cudaMemset(h->init.p, 0, h->init.bytes));
+  DG_CUDA(cudaMemset(h->base.p, 0, h->base.bytes));
+  DG_CUDA(cudaMemset(h->base_active.p, 0, h->base_active.bytes));
   return DG_OK;
 }
 
@@ -948,6 +952,8 @@ extern "C" int dg_cluster_set_state(dg_cluster* h, const double* centers, const 
   DG_CUDA(cudaMemcpy(h->centers.p, centers, (size_t)h->p.M * h->p.D * 8, cudaMemcpyHostToDevice));
   DG_CUDA(cudaMemcpy(h->active.p, active, (size_t)h->p.M * 4, cudaMemcpyHostToDevice));
   DG_CUDA(cudaMemcpy(h->init.p, init, 8, cudaMemcpyHostToDevice));
+  DG_CUDA(cudaMemcpy(h->base.p, centers, (size_t)h->p.M * h->p.D * 8, cudaMemcpyHostToDevice));
+  DG_CUDA(cudaMemcpy(h->base_active.p, active, (size_t)h->p.M * 4, cudaMemcpyHostToDevice));
   return DG_OK;
 }
 
@@ -956,15 +962,33 @@ extern "C" int dg_cluster_destroy(dg_cluster* h) {
   return DG_OK;
 }
 
-// shared-identity extension: not wired in this round (multi-GPU)
-extern "C" int dg_cluster_record_len(const dg_cluster* h) { return h ? h->p.M * h->p.D + 2 * h->p.M + 2 : 0; }
-extern "C" int dg_cluster_export_delta(dg_cluster*, double*, void*) {
-  set_error("dg_cluster_export_delta: shared-identity mode is not implemented yet");
-  return DG_EINVAL;
+// shared-identity extension (BASELINE config 5); kernels and rule in cluster.cu
+extern "C" int dg_cluster_record_len(const dg_cluster* h) { return h ? h->p.M * h->p.D + h->p.M + 2 : 0; }
+
+extern "C" int dg_cluster_export_delta(dg_cluster* h, double* record_dev, void* stream) {
+  if (!h || !record_dev) {
+    set_error("dg_cluster_export_delta: bad arguments");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  return launch_cluster_export(h->centers.as<double>(), h->active.as<int>(), h->base.as<double>(),
+                               h->base_active.as<int>(), h->p.M, h->p.D, record_dev, (cudaStream_t)stream);
 }
-extern "C" int dg_cluster_merge(dg_cluster*, const double*, int, void*) {
-  set_error("dg_cluster_merge: shared-identity mode is not implemented yet");
-  return DG_EINVAL;
+
+extern "C" int dg_cluster_merge(dg_cluster* h, const double* records_dev, int world, int rank, int32_t* maps_dev,
+                                int n_maps, void* stream) {
+  if (!h || !records_dev || world < 1 || rank < 0 || rank >= world) {
+    set_error("dg_cluster_merge: bad arguments");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  int rc;
+  if ((rc = launch_cluster_merge(records_dev, world, rank, h->p, dg_cluster_record_len(h), h->centers.as<double>(),
+                                 h->active.as<int>(), h->base.as<double>(), h->base_active.as<int>(),
+                                 h->init.as<int>(), h->relabel.as<int32_t>(), (cudaStream_t)stream)))
+    return rc;
+  if (maps_dev && n_maps > 0) return launch_relabel_maps(maps_dev, n_maps, h->relabel.as<int32_t>(), (cudaStream_t)stream);
+  return DG_OK;
 }
 
 // ================================================================================== self test

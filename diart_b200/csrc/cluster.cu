@@ -443,4 +443,168 @@ int launch_cluster_step(const ClusterParams& p, const float* seg, const float* e
   return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Shared-identity mode (extension beyond the reference, SURVEY.md 8(e) / BASELINE config 5): G ranks diarize
+// independent streams against ONE table of global speakers.  After every pipeline step each rank exports a
+// fixed-size record of what it changed since the last merge, the records are all-gathered (one NCCL collective of
+// M*(D+1)+2 doubles per rank) and every rank applies all of them in rank order with the same rule, so all ranks
+// hold bit-identical tables again.
+//   record = [M][D] payload, [M] kind, 2 reserved;  kind 0: untouched / inactive, 1: payload = centroid - base
+//   (centre existed at the last merge), 2: payload = a centre this rank CREATED during the step.
+// Merge: base += deltas (rank order); then every created centre, in (rank, index) order: a rank already judged its
+// creation new w.r.t. every centre it could see, so only centres created by EARLIER ranks in this merge are
+// candidates for being the same speaker (cosine distance < delta_new -> summed into it); otherwise it takes the
+// lowest free index; with a full table it joins the closest centre.  Creations of one rank stay distinct.
+// `relabel` tells the calling rank where each of its own created centres ended up (identity for the rest).
+__global__ void __launch_bounds__(128) cluster_export_kernel(const double* __restrict__ centers, const int* __restrict__ active,
+                                                             const double* __restrict__ base, const int* __restrict__ base_active,
+                                                             int M, int D, double* __restrict__ record) {
+  const int g = blockIdx.x;
+  const int kind = !active[g] ? 0 : (base_active[g] ? 1 : 2);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double c = centers[(size_t)g * D + d];
+    record[(size_t)g * D + d] = kind == 1 ? c - base[(size_t)g * D + d] : (kind == 2 ? c : 0.0);
+  }
+  if (threadIdx.x == 0) {
+    record[(size_t)M * D + g] = (double)kind;
+    if (g == 0) record[(size_t)M * D + M] = record[(size_t)M * D + M + 1] = 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(256) cluster_merge_kernel(const double* __restrict__ records, int world, int rank, int M, int D,
+                                                            int rec_len, double delta_new, double* __restrict__ centers,
+                                                            int* __restrict__ active, double* __restrict__ base,
+                                                            int* __restrict__ base_active, int* __restrict__ initialized,
+                                                            int32_t* __restrict__ relabel) {
+  __shared__ int s_active[CM], s_fresh[CM], s_used[CM];
+  __shared__ double s_dist[CM];
+  __shared__ int s_target;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid < CM) {
+    s_active[tid] = tid < M ? base_active[tid] : 0;
+    s_fresh[tid] = 0;
+  }
+  if (tid < M) relabel[tid] = tid;
+  for (int i = tid; i < M * D; i += blockDim.x) centers[i] = base[i];
+  __syncthreads();
+  // 1. updates of centres that existed at the last merge, rank order
+  for (int r = 0; r < world; r++) {
+    const double* rec = records + (size_t)r * rec_len;
+    for (int g = 0; g < M; g++) {
+      if (rec[(size_t)M * D + g] != 1.0) continue;
+      for (int d = tid; d < D; d += blockDim.x) centers[(size_t)g * D + d] += rec[(size_t)g * D + d];
+    }
+  }
+  __syncthreads();
+  // 2. centres created during the step, (rank, index) order
+  for (int r = 0; r < world; r++) {
+    const double* rec = records + (size_t)r * rec_len;
+    __syncthreads();
+    if (tid < CM) s_used[tid] = 0;
+    __syncthreads();
+    for (int g = 0; g < M; g++) {
+      if (rec[(size_t)M * D + g] != 2.0) continue;
+      const double* c = rec + (size_t)g * D;
+      for (int a = warp; a < M; a += 8) {     // cosine distance to every active centre (warp per centre)
+        double dot = 0.0, na = 0.0, nc = 0.0;
+        if (s_active[a])
+          for (int d = lane; d < D; d += 32) {
+            const double x = centers[(size_t)a * D + d], y = c[d];
+            dot = fma(x, y, dot);
+            na = fma(x, x, na);
+            nc = fma(y, y, nc);
+          }
+        for (int o = 16; o > 0; o >>= 1) {
+          dot += __shfl_xor_sync(FULL, dot, o);
+          na += __shfl_xor_sync(FULL, na, o);
+          nc += __shfl_xor_sync(FULL, nc, o);
+        }
+        if (lane == 0) {
+          double dist = INFINITY;
+          if (s_active[a]) {
+            double cosv = dot / (sqrt(nc) * sqrt(na));
+            if (fabs(cosv) > 1.0) cosv = copysign(1.0, cosv);
+            dist = 1.0 - cosv;
+          }
+          s_dist[a] = dist;
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        int best = -1, free_idx = -1;
+        double bd = INFINITY;
+        for (int a = 0; a < M; a++)
+          if (!s_active[a] && free_idx < 0) free_idx = a;
+        for (int a = 0; a < M; a++) {
+          const bool cand = s_active[a] && !s_used[a] && (free_idx < 0 || s_fresh[a]);
+          if (cand && s_dist[a] < bd) {
+            bd = s_dist[a];
+            best = a;
+          }
+        }
+        int target = -1;
+        if (best >= 0 && (bd < delta_new || free_idx < 0)) target = best;
+        else if (free_idx >= 0) target = free_idx;
+        s_target = target;
+      }
+      __syncthreads();
+      const int target = s_target;
+      if (target < 0) continue;            // full table and every centre already taken by this rank's creations
+      if (s_active[target]) {
+        for (int d = tid; d < D; d += blockDim.x) centers[(size_t)target * D + d] += c[d];
+      } else {
+        for (int d = tid; d < D; d += blockDim.x) centers[(size_t)target * D + d] = c[d];
+      }
+      __syncthreads();
+      if (tid == 0) {
+        if (!s_active[target]) s_fresh[target] = 1;
+        s_active[target] = 1;
+        s_used[target] = 1;
+        if (r == rank) relabel[g] = target;
+      }
+      __syncthreads();
+    }
+  }
+  for (int i = tid; i < M * D; i += blockDim.x) base[i] = centers[i];
+  if (tid < M) {
+    active[tid] = s_active[tid];
+    base_active[tid] = s_active[tid];
+  }
+  if (tid == 0) {
+    int any = 0;
+    for (int a = 0; a < M; a++) any |= s_active[a];
+    if (any) *initialized = 1;
+  }
+}
+
+__global__ void relabel_maps_kernel(int32_t* __restrict__ maps, int n, const int32_t* __restrict__ relabel) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && maps[i] >= 0) maps[i] = relabel[maps[i]];
+}
+
+int launch_cluster_export(const double* centers, const int* active, const double* base, const int* base_active, int M,
+                          int D, double* record, cudaStream_t st) {
+  ProfScope _ps("cluster_export", st);
+  cluster_export_kernel<<<M, 128, 0, st>>>(centers, active, base, base_active, M, D, record);
+  DG_LAUNCHED();
+  return 0;
+}
+
+int launch_cluster_merge(const double* records, int world, int rank, const ClusterParams& p, int rec_len, double* centers,
+                         int* active, double* base, int* base_active, int* initialized, int32_t* relabel,
+                         cudaStream_t st) {
+  ProfScope _ps("cluster_merge", st);
+  cluster_merge_kernel<<<1, 256, 0, st>>>(records, world, rank, p.M, p.D, rec_len, p.delta, centers, active, base,
+                                          base_active, initialized, relabel);
+  DG_LAUNCHED();
+  return 0;
+}
+
+int launch_relabel_maps(int32_t* maps, int n, const int32_t* relabel, cudaStream_t st) {
+  ProfScope _ps("relabel_maps", st);
+  relabel_maps_kernel<<<(n + 255) / 256, 256, 0, st>>>(maps, n, relabel);
+  DG_LAUNCHED();
+  return 0;
+}
+
 }  // namespace dg

@@ -177,6 +177,12 @@ struct ClusterParams {
 int launch_cluster_step(const ClusterParams& p, const float* seg, const float* emb, int B, int F, int K,
                         double* centers, int* active, int* initialized, float* prep /*scratch*/,
                         double* prep_d /*scratch*/, int32_t* map, float* permuted, cudaStream_t st);
+int launch_cluster_export(const double* centers, const int* active, const double* base, const int* base_active, int M,
+                          int D, double* record, cudaStream_t st);
+int launch_cluster_merge(const double* records, int world, int rank, const ClusterParams& p, int rec_len, double* centers,
+                         int* active, double* base, int* base_active, int* initialized, int32_t* relabel,
+                         cudaStream_t st);
+int launch_relabel_maps(int32_t* maps, int n, const int32_t* relabel, cudaStream_t st);
 size_t cluster_prep_floats(int B, int K);
 size_t cluster_prep_doubles(int B, int K);
 

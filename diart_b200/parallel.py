@@ -72,3 +72,43 @@ def gather_maps(local_maps: Sequence[torch.Tensor]) -> List[List[torch.Tensor]]:
     out: List[Optional[List[torch.Tensor]]] = [None] * dist.get_world_size()
     dist.all_gather_object(out, [m.cpu() for m in local_maps])
     return out  # type: ignore[return-value]
+
+
+class SharedIdentity:
+    """Shared global-speaker table across ranks (extension beyond the reference).
+
+    After every pipeline step call :meth:`sync` with the step's speaker maps: this rank's centroid changes are
+    exported, all ranks' records are exchanged with ONE all-gather (NCCL on GPUs; ~82 KB per rank), merged in rank
+    order by every rank with the same deterministic rule (``csrc/cluster.cu``), and the maps are rewritten where a
+    centre this rank created was merged into / moved to another global index.  All ranks hold bit-identical tables
+    afterwards.  ``world == 1`` degenerates to a local merge (no collective)."""
+
+    def __init__(self, clustering, group=None):
+        import ctypes as C
+
+        from . import _lib
+
+        self._C, self._lib = C, _lib
+        self.clustering, self.group = clustering, group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def sync(self, maps: torch.Tensor) -> torch.Tensor:
+        lib, clu = self._lib.lib(), self.clustering
+        if clu._h is None:
+            raise self._lib.DiartB200Error("SharedIdentity.sync before the first clustering step")
+        device = clu.device
+        n = lib.dg_cluster_record_len(clu._h)
+        rec = torch.empty(n, dtype=torch.float64, device=device)
+        stream = self._lib.stream_ptr(device)
+        with torch.cuda.device(device):
+            self._lib.check(lib.dg_cluster_export_delta(clu._h, rec.data_ptr(), stream))
+            if self.world > 1:
+                gathered = torch.empty(self.world * n, dtype=torch.float64, device=device)
+                dist.all_gather_into_tensor(gathered, rec, group=self.group)
+            else:
+                gathered = rec
+            assert maps.dtype == torch.int32 and maps.is_contiguous() and maps.device == device
+            self._lib.check(lib.dg_cluster_merge(clu._h, gathered.data_ptr(), self.world, self.rank, maps.data_ptr(),
+                                                 maps.numel(), stream))
+        return maps

@@ -141,12 +141,17 @@ int dg_profile_enable(int enable);
 int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int epi, float* max_abs_diff, float* out_rms);
 int dg_profile_report(char* buf, int cap);
 
-/* ---- shared-identity mode (extension): merge per-rank centroid deltas that were
- *      all-gathered by the host (NCCL) -- see dg_cluster_export_delta / dg_cluster_merge in
- *      INTEGRATION.md. ---- */
-int dg_cluster_export_delta(dg_cluster* h, double* delta_dev /*[M*D + 2*M + 2] f64 record*/, void* stream);
-int dg_cluster_merge(dg_cluster* h, const double* records_dev /*[world, record]*/, int world, void* stream);
+/* ---- shared-identity mode (extension beyond the reference; SURVEY.md 8(e), BASELINE config 5): G ranks diarize
+ *      independent streams against one table of global speakers.  Per pipeline step and rank:
+ *        dg_cluster_export_delta -> record [M*D payload | M kinds | 2 reserved] float64 (what changed since the
+ *        last merge); the host all-gathers the records (one NCCL all-gather, ~82 KB per rank);
+ *        dg_cluster_merge applies all records in rank order with one deterministic rule (cluster.cu) so that all
+ *        ranks hold bit-identical tables, and rewrites this rank's speaker maps of the step (maps_dev, n_maps
+ *        int32 values) where a centre it created was merged into / moved to another index. ---- */
 int dg_cluster_record_len(const dg_cluster* h);
+int dg_cluster_export_delta(dg_cluster* h, double* record_dev, void* stream);
+int dg_cluster_merge(dg_cluster* h, const double* records_dev /*[world, record_len]*/, int world, int rank,
+                     int32_t* maps_dev /*nullable*/, int n_maps, void* stream);
 
 #ifdef __cplusplus
 }
