@@ -222,9 +222,21 @@ def run_ours(args):
     fused, F, K, D = pipe._ensure_fused(CHUNK)
     stream = _lib.stream_ptr(device)
 
+    shared = None
+    if args.shared_identity:
+        from diart_b200.parallel import SharedIdentity
+
+        args.serial = True                               # the merge needs this step's maps before the next step
+        shared = SharedIdentity(pipe.clustering)        # the clustering handle exists: _ensure_fused created it
+
     def run_steps(n):
         """n pipeline steps, depth-2 pipelined (dg_pipeline_submit / collect): clustering of step i overlaps the
         networks of step i+1; every step's results are complete when the last collect is reached on the stream"""
+        if shared is not None:   # BASELINE config 5: one all-gather of centroid deltas per step (NCCL), then merge
+            for i in range(n):
+                _, _, maps = pipe.device_step(dev[i % NB])
+                shared.sync(maps)
+            return
         if args.serial:
             for i in range(n):
                 pipe.device_step(dev[i % NB])
@@ -329,8 +341,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": B, "streams": world, "parallelism": f"{world} independent streams, "
-                   "1 per GPU, no collectives", "l2": "inputs rotate over 4 distinct 82 MB batches (> 126 MB L2)"},
+        "config": {"workload": WORKLOAD, "batch": B, "streams": world, "parallelism": (f"{world} independent streams, "
+                   "1 per GPU, no collectives" if shared is None else f"{world} streams, 1 per GPU, shared speaker "
+                   "identity: one NCCL all-gather of centroid-delta records per step + deterministic merge"), "l2": "inputs rotate over 4 distinct 82 MB batches (> 126 MB L2)"},
         "chunks_per_s": value / STEP_SECONDS,
         "step_tflops": step_flops / (ms_max / args.steps * 1e-3) / 1e12,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CHUNK * 4,
@@ -378,6 +391,8 @@ def _main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ref-batch", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shared-identity", action="store_true",
+                    help="BASELINE config 5: share the global speaker table across ranks (one all-gather per step)")
     ap.add_argument("--serial", action="store_true", help="one step at a time (dg_pipeline_step) instead of depth-2 pipelining")
     args = ap.parse_args()
     if args.impl == "reference":
