@@ -205,7 +205,7 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
     for (int o = 0; o < out; o++)
       for (int c = 0; c < in; c++)
         for (int j = 0; j < k; j++) w_nk[(size_t)o * k * in_pad + j * in_pad + c] = s[((size_t)o * in + c) * k + j];
-    return upload_split(hi, lo, w_nk, out, 128, k * in_pad);
+    return upload_split(hi, lo, w_nk, out, 64, k * in_pad);
   };
   if ((rc = conv_w_tc(pre + "conv1d.1.weight", 60, 80, 5, 128, w.w1_hi, w.w1_lo)) ||
       (rc = conv_w_tc(pre + "conv1d.2.weight", 60, 60, 5, 64, w.w2_hi, w.w2_lo)))
@@ -268,7 +268,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
       return rc;
     TcGemm t{};
     t.A_hi = k.a0h.p; t.A_lo = k.a0l.p; t.lda = 128; t.Cin = 128; t.KW = 5; t.dil = 1; t.Mtot = M0; t.M = M0;
-    t.W_hi = w.w1_hi.p; t.W_lo = w.w1_lo.p; t.Npad = 128; t.N = 64; t.bias = w.bias1.as<float>();
+    t.W_hi = w.w1_hi.p; t.W_lo = w.w1_lo.p; t.Npad = 64; t.N = 64; t.bias = w.bias1.as<float>();
     t.out_f32 = k.c1.as<float>(); t.ldc = 64; t.epi = 0; t.tag = "sinc_conv1";
     if ((rc = launch_gemm_tc(t, st))) return rc;
     if ((rc = launch_instnorm_stats(k.c1.as<float>(), B, g.S0, g.T1, 64, 64, w.g1.as<float>(), w.b1.as<float>(),
@@ -1000,7 +1000,7 @@ extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int e
     set_error("dg_selftest_gemm_tc: bad arguments");
     return DG_EINVAL;
   }
-  const int K = KW * Cin, npad = (N + 255) / 256 * 256;
+  const int K = KW * Cin, npad = N == 64 ? 64 : (N + 255) / 256 * 256;
   const long long Mtot = M;
   std::vector<float> A((size_t)Mtot * Cin), Wkn((size_t)K * N), Wnk((size_t)N * K), bias(N), bsc(N), bsh(N);
   uint32_t seed = 12345u;

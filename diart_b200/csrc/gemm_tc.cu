@@ -54,7 +54,7 @@ struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB per plane
   static constexpr int W_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int NSTAGE = BN == 256 ? 2 : 3;
+  static constexpr int NSTAGE = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
   static constexpr int PARAM_BYTES = 3 * BN * 4;
   static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
@@ -92,7 +92,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   }
   if (warp == 1) {   // TMEM: two accumulators of BN fp32 columns
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(2 * BN)
+                 "r"(2 * BN < 32 ? 32 : 2 * BN)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -300,12 +300,13 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
 
 int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
   ProfScope _ps(g.tag ? g.tag : "gemm_tc", st);
-  if (g.Cin % TC_BK || g.lda % 8 || g.ldc % (g.epi == TC_LEAKY_BN_SPLIT ? 8 : 4) || g.Npad % 128) {
+  if (g.Cin % TC_BK || g.lda % 8 || g.ldc % (g.epi == TC_LEAKY_BN_SPLIT ? 8 : 4) || (g.Npad % 128 && g.Npad != 64)) {
     set_error("gemm_tc: Cin must be a multiple of 64, A pitch a multiple of 8, output pitch a multiple of 4 "
               "(8 for bf16 planes), padded N a multiple of 128");
     return -1;
   }
   const bool wide = g.Npad % 256 == 0;
+  if (g.Npad == 64 && g.epi == TC_BIAS_F32) return launch_tc<64, TC_BIAS_F32>(g, st);
   switch (g.epi) {
     case TC_BIAS_F32:
       return wide ? launch_tc<256, TC_BIAS_F32>(g, st) : launch_tc<128, TC_BIAS_F32>(g, st);
