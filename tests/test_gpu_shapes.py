@@ -1,0 +1,38 @@
+"""Edge shapes through the CUDA path vs the oracle: other chunk durations (the geometry is derived, not hard
+coded), batch sizes that are not multiples of any tile, a single chunk, and 4 local speakers."""
+import numpy as np
+import pytest
+import torch
+
+from diart_b200 import blocks, models, synth
+from oracle import nets
+from oracle.pipeline import OraclePipeline
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("num_samples,batch,num_speakers", [(48000, 5, 3), (80000, 1, 3), (32000, 3, 4), (80000, 7, 4)])
+def test_shapes_match_oracle(num_samples, batch, num_speakers, cuda_device):
+    seg_o = nets.make_segmentation(num_speakers=num_speakers, calibrated=num_speakers == 3)
+    if num_speakers != 3:   # uncalibrated classifier: give the logits some spread so OSP weights are not uniform
+        with torch.no_grad():
+            seg_o.classifier.weight.mul_(20.0)
+    emb_o = nets.make_embedding()
+    stream = synth.synth_audio(num_samples + 8000 * (batch - 1), seed=77)
+    x = torch.from_numpy(synth.windows(stream, batch, chunk=num_samples))
+    oracle = OraclePipeline(seg_o, emb_o, as_reference=False)
+    o_seg, o_emb, o_maps, margins = oracle(x)
+    config = blocks.SpeakerDiarizationConfig(
+        segmentation=models.SegmentationModel(models.B200SegmentationLoader(seg_o.state_dict())),
+        embedding=models.EmbeddingModel(models.B200EmbeddingLoader(emb_o.state_dict())),
+        duration=num_samples / 16000, device=cuda_device)
+    pipe = blocks.SpeakerDiarization(config)
+    seg, emb, maps = pipe.device_step(x.to(cuda_device))
+    seg, emb, maps = seg.cpu().numpy(), emb.cpu().numpy(), maps.cpu().numpy()
+    assert seg.shape == o_seg.shape and emb.shape == o_emb.shape and maps.shape == o_maps.shape
+    seg_err, emb_err = np.abs(seg - o_seg).max(), np.abs(emb - o_emb).max()
+    print(f"S={num_samples} B={batch} K={num_speakers}: frames {seg.shape[1]}, seg err {seg_err:.2e}, emb err {emb_err:.2e}")
+    assert seg_err < 3e-4 and emb_err < 1e-3
+    if not np.array_equal(maps, o_maps):
+        i = int(np.where((maps != o_maps).any(axis=1))[0][0])
+        assert margins[i] < 1e-3, f"maps differ at chunk {i} with margin {margins[i]}"
