@@ -59,7 +59,8 @@ __device__ __forceinline__ float sigmoid_acc(float x) { return __fdividef(1.f, 1
 __device__ __forceinline__ float tanh_acc(float x) { return 1.f - __fdividef(2.f, expf(2.f * x) + 1.f); }
 
 __global__ void __launch_bounds__(LT_THREADS, 1)
-lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __restrict__ w_lo /*[2][512][128] bf16*/,
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi /*smem-resident plane (W_lo)*/,
+               const uint16_t* __restrict__ w_lo /*TMEM-resident plane (W_hi), [2][512][128] bf16*/,
                const float* __restrict__ gx, int B, int T, int stride, int groups_per_dir, float* __restrict__ hout) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -157,9 +158,11 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi, const uint16_t* __res
                 const uint64_t b_hi = b0d + (uint64_t)(kb * kHTile + kk * 2);
                 const uint64_t b_lo = b0d + (uint64_t)(2 * kHTile + kb * kHTile + kk * 2);
                 const uint32_t d = d0 + (g * 2 + kb) * LT_NB;
-                if (prod == 0) umma_bf16(d, a_hi, b_lo, idesc, kk != 0);
-                else if (prod == 1) umma_bf16_ts(d, alo0 + g * 64 + ks * 8, b_hi, idesc, 1);
-                else umma_bf16(d, a_hi, b_hi, idesc, 1);
+                // the HI plane of W_hh is the one in tensor memory: two of the three products then read their A
+                // operand from TMEM and only one (W_lo . h_hi) pays the 4 KB shared-memory read of an SS MMA
+                if (prod == 0) umma_bf16_ts(d, alo0 + g * 64 + ks * 8, b_lo, idesc, kk != 0);
+                else if (prod == 1) umma_bf16(d, a_hi, b_hi, idesc, 1);
+                else umma_bf16_ts(d, alo0 + g * 64 + ks * 8, b_hi, idesc, 1);
               }
             }
           }
@@ -258,7 +261,8 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
   cuuint64_t strides[1] = {256};
   cuuint32_t box[2] = {64, 128};
   cuuint32_t estr[2] = {1, 1};
-  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(whh_hi), dims, strides, box, estr,
+  // smem-resident plane = lo, TMEM-resident plane = hi (see the MMA sequence in the kernel)
+  if (fn(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(whh_lo), dims, strides, box, estr,
          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed for W_hh");
@@ -270,7 +274,7 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     attr_done = true;
   }
   const int gpd = (B + LT_NB - 1) / LT_NB;
-  lstm_tc_kernel<<<2 * gpd, LT_THREADS, LT_SMEM, st>>>(tm, reinterpret_cast<const uint16_t*>(whh_lo), gx, B, T, stride,
+  lstm_tc_kernel<<<2 * gpd, LT_THREADS, LT_SMEM, st>>>(tm, reinterpret_cast<const uint16_t*>(whh_hi), gx, B, T, stride,
                                                         gpd, hout);
   DG_LAUNCHED();
   return 0;
