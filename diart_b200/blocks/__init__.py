@@ -6,3 +6,4 @@ from .embedding import (EmbeddingNormalization, OverlapAwareSpeakerEmbedding, Ov
                         SpeakerEmbedding)
 from .segmentation import SpeakerSegmentation
 from .utils import Binarize
+from .vad import VoiceActivityDetection, VoiceActivityDetectionConfig

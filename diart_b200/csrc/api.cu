@@ -328,12 +328,14 @@ struct dg_seg {
   DevBuf wih_hi[4], wih_lo[4];     // the same as bf16 hi/lo planes [1024][in_pad] for the tcgen05 path
   DevBuf whh_hi[4], whh_lo[4];     // W_hh as bf16 hi/lo planes [2][512][128] for the tcgen05 recurrence
   DevBuf l1w, l1b, l2w, l2b, cw, cb;
+  DevBuf l1_hi, l1_lo, l2_hi, l2_lo, ones128, zeros128;   // head Linears as bf16 planes [128][in] (tcgen05 path)
   // activations: two independent sets ("lanes") so that the fused pipeline can run the segmentation chains of
   // two consecutive steps concurrently (the recurrence occupies only 32 SMs)
   struct Scratch {
     SincWork work;
     DevBuf gx, hA, hB, y1, y2;
     DevBuf xh, xl;                 // bf16 hi/lo planes of the current in-projection input
+    DevBuf y1h, y1l;               // bf16 planes of the first head Linear's output
   } scr[2];
   int lane = 0;
 };
@@ -380,6 +382,15 @@ static int seg_prepare(dg_seg* h, const Tensors& t) {
   };
   if ((rc = linear_t("linear.0", 128, 256, h->l1w, h->l1b)) || (rc = linear_t("linear.1", 128, 128, h->l2w, h->l2b)))
     return rc;
+  {
+    const float* w0 = t.get("linear.0.weight", 128 * 256);
+    const float* w1 = t.get("linear.1.weight", 128 * 128);
+    if (!w0 || !w1) return DG_EWEIGHT;
+    if (upload_split(h->l1_hi, h->l1_lo, std::vector<float>(w0, w0 + 128 * 256), 128, 128, 256) ||
+        upload_split(h->l2_hi, h->l2_lo, std::vector<float>(w1, w1 + 128 * 128), 128, 128, 128) ||
+        upload(h->ones128, std::vector<float>(128, 1.f)) || upload(h->zeros128, std::vector<float>(128, 0.f)))
+      return DG_ECUDA;
+  }
   const int64_t cn = t.numel("classifier.bias");
   if (cn < 1 || cn > 8) {
     set_error("classifier.bias missing or more than 8 local speakers");
@@ -520,6 +531,22 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
     float* hout = hbuf[L & 1];
     if ((rc = launch_lstm_layer(w.gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st))) return rc;
     hin = hout;
+  }
+  if (tc) {
+    // Linear(256,128) -> leaky -> Linear(128,128) -> leaky on the tcgen05 GEMM (identity "BatchNorm")
+    if (w.y1h.ensure(rows * 128 * 2) || w.y1l.ensure(rows * 128 * 2)) return DG_ECUDA;
+    if ((rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, w.xh.p, w.xl.p, st))) return rc;
+    TcGemm t{};
+    t.A_hi = w.xh.p; t.A_lo = w.xl.p; t.lda = 256; t.Cin = 256; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
+    t.W_hi = h->l1_hi.p; t.W_lo = h->l1_lo.p; t.Npad = 128; t.N = 128; t.bias = h->l1b.as<float>();
+    t.bn_scale = h->ones128.as<float>(); t.bn_shift = h->zeros128.as<float>();
+    t.out_hi = w.y1h.p; t.out_lo = w.y1l.p; t.ldc = 128; t.epi = 1; t.tag = "seg_linear";
+    if ((rc = launch_gemm_tc(t, st))) return rc;
+    t.A_hi = w.y1h.p; t.A_lo = w.y1l.p; t.lda = 128; t.Cin = 128;
+    t.W_hi = h->l2_hi.p; t.W_lo = h->l2_lo.p; t.bias = h->l2b.as<float>();
+    t.out_hi = nullptr; t.out_lo = nullptr; t.out_f32 = w.y2.as<float>(); t.epi = 2;
+    if ((rc = launch_gemm_tc(t, st))) return rc;
+    return launch_seg_final(w.y2.as<float>(), h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
   }
   GemmArgs a{};
   a.A = hin; a.lda = 256; a.Cin = 256; a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;

@@ -138,3 +138,26 @@ def _lib_collect_empty(pipe):
     from diart_b200 import _lib
 
     _lib.check(_lib.lib().dg_pipeline_collect(pipe._fused, None, None, None, None))
+
+
+def test_voice_activity_detection_pipeline(oracle_nets, stream, cuda_device):
+    """VAD = max over local speakers of the same segmentation (reference blocks/vad.py:145-148)"""
+    seg_o, _ = oracle_nets
+    config = blocks.VoiceActivityDetectionConfig(
+        segmentation=models.SegmentationModel(models.B200SegmentationLoader(seg_o.state_dict())), device=cuda_device)
+    vad = blocks.VoiceActivityDetection(config)
+    sr, n = 16000, 4
+    chunks = [SlidingWindowFeature(stream[8000 * i:8000 * i + 80000, None],
+                                   SlidingWindow(start=0.5 * i, duration=1 / sr, step=1 / sr)) for i in range(n)]
+    out = vad(chunks)
+    assert len(out) == n
+    x = torch.from_numpy(synth.windows(stream, n))
+    with torch.no_grad():
+        ref = seg_o(x[:, None, :]).max(dim=-1, keepdim=True)[0].numpy()
+    res = 5 / ref.shape[1]
+    for i, (annotation, audio) in enumerate(out):
+        swf = SlidingWindowFeature(ref[i], SlidingWindow(start=0.5 * i, duration=res, step=res))
+        expect = vad.binarize(blocks.DelayedAggregation(0.5, 0.5, "hamming", "loose")([swf]))
+        got = sorted((round(s.start, 3), round(s.end, 3)) for s, _ in annotation.itertracks())
+        want = sorted((round(s.start, 3), round(s.end, 3)) for s, _ in expect.itertracks())
+        assert got == want and all(lab == "speech" for _, _, lab in annotation.itertracks(yield_label=True))
