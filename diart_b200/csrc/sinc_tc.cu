@@ -41,7 +41,7 @@ struct SincTcMaps {
 
 __global__ void __launch_bounds__(192, 1)
 sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows_total, int rows_per_item, int T0,
-                int S0, float* __restrict__ p0, int terms) {
+                int S0, float* __restrict__ p0) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                       // [kb][plane][80 x 128 B]
@@ -125,10 +125,9 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
               const uint64_t adv = (uint64_t)((ks * 32) >> 4);
               // five of the nine hi/lo/lo2 products: everything down to 2^-24 of the leading term.  This
               // layer's error is amplified by every later layer, so the filters carry 24 significand bits.
-              uint32_t accf = (kb | ks) != 0;
-              if (terms & 1) { umma_bf16(tmem_c, a_lo + adv, w_lo + adv, idesc, accf); accf = 1; }
-              if (terms & 2) { umma_bf16(tmem_c, a_hi + adv, w_l2 + adv, idesc, accf); accf = 1; }
-              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, accf);
+              umma_bf16(tmem_c, a_lo + adv, w_lo + adv, idesc, (kb | ks) != 0);
+              umma_bf16(tmem_c, a_hi + adv, w_l2 + adv, idesc, 1);
+              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, 1);
               umma_bf16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
               umma_bf16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
             }
@@ -296,8 +295,7 @@ int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, floa
   const int sms = usable_sms();
   const int row_tiles = (int)((rows + ST_ROWS - 1) / ST_ROWS);
   const int tiles = row_tiles * 4;
-  sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0,
-                                                                    getenv("DG_SINC_TERMS") ? atoi(getenv("DG_SINC_TERMS")) : 3);
+  sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0);
   DG_LAUNCHED();
   return 0;
 }
