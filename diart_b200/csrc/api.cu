@@ -126,6 +126,7 @@ struct SincWeights {
   DevBuf filt, g0, b0, w1, bias1, g1, b1, w2, bias2, g2, b2;
   DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: bf16 hi/lo planes [128][5*128] and [128][5*64]
   DevBuf filt_planes;                  // sinc filter bank as three bf16 planes [3][80][256] (hi, lo, lo2)
+  DevBuf cf;                           // folded wav-norm affine: beta * sum_k h[f][k]
 };
 
 // ParamSincFB.filters() in float32, as asteroid-filterbanks computes it with torch
@@ -171,6 +172,9 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
     std::vector<uint16_t> fp(3 * 80 * 256);
     sinc_tc_pack_filters(h.data(), fp.data());
     if (upload_u16(w.filt_planes, fp)) return DG_ECUDA;
+    std::vector<float> cf(80);
+    sinc_tc_affine_consts(h.data(), w.wn_beta, cf.data());
+    if (upload(w.cf, cf)) return DG_ECUDA;
   }
   auto pad_vec = [&](const std::string& name, int n, int npad, DevBuf& dst) -> int {
     const float* s = t.get(name, n);
@@ -213,10 +217,19 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
   return 0;
 }
 
+// waveform statistics and the standardised-waveform planes of a batch; both networks' SincNets read the same
+// ones, so the fused pipeline computes them once per step
+struct SincPrep {
+  DevBuf wmean, wrstd, wh, wl;
+  int ensure(int B, const Geom& g) {
+    const size_t bytes = 4 * sinc_tc_plane_elems(B, g) * 2;
+    return (wmean.ensure(B * 4) || wrstd.ensure(B * 4) || wh.ensure(bytes) || wl.ensure(bytes)) ? DG_ECUDA : 0;
+  }
+};
 struct SincWork {
   DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
   DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: bf16 planes of the conv inputs, un-pooled conv outputs
-  DevBuf wh, wl;                       // four shifted copies of the normalised waveform, bf16 hi / lo
+  SincPrep own_prep;                   // statistics + waveform planes when no shared ones are supplied
   const float* out = nullptr;          // conv2 output that the next layer normalises on load ...
   int out_pool = 0;                    // ... 1: still un-pooled (rows = 3x), MaxPool1d(3) is applied on load
   int ensure_tc(int B, const Geom& g) {
@@ -239,23 +252,34 @@ struct SincWork {
   }
 };
 
+static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cudaStream_t st) {
+  int rc;
+  if ((rc = p.ensure(B, g))) return rc;
+  if ((rc = launch_wave_stats(wav, B, g.S, p.wmean.as<float>(), p.wrstd.as<float>(), st))) return rc;
+  return launch_sinc_prep(wav, p.wmean.as<float>(), p.wrstd.as<float>(), B, g, p.wh.p, p.wl.p, st);
+}
+
 // waveform [B,S] -> k.out (pre-norm conv2 output, pooled [B*S2,64] or un-pooled [B*S1,64]) + its
 // InstanceNorm scale/shift (k.sc2, k.sh2)
-static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int B, const Geom& g, cudaStream_t st) {
+static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int B, const Geom& g, cudaStream_t st,
+                       const SincPrep* shared = nullptr) {
   int rc;
   if ((rc = k.ensure(B, g))) return rc;
   if (use_tensor_cores()) {
     if ((rc = k.ensure_tc(B, g))) return rc;
-    if ((rc = launch_wave_stats(wav, B, g.S, k.wmean.as<float>(), k.wrstd.as<float>(), st))) return rc;
     static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
     if (sinc_simt) {
+      if ((rc = launch_wave_stats(wav, B, g.S, k.wmean.as<float>(), k.wrstd.as<float>(), st))) return rc;
       rc = launch_sinc0(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt.as<float>(), B,
                         g, k.p0.as<float>(), st);
     } else {
-      const size_t bytes = 4 * sinc_tc_plane_elems(B, g) * 2;
-      if (k.wh.ensure(bytes) || k.wl.ensure(bytes)) return DG_ECUDA;
-      rc = launch_sinc0_tc(wav, k.wmean.as<float>(), k.wrstd.as<float>(), w.wn_gamma, w.wn_beta, w.filt_planes.p, B,
-                           g, k.wh.p, k.wl.p, k.p0.as<float>(), st);
+      const SincPrep* prep = shared;
+      if (!prep) {
+        if ((rc = run_sinc_prep(k.own_prep, wav, B, g, st))) return rc;
+        prep = &k.own_prep;
+      }
+      rc = launch_sinc0_tc(w.wn_gamma, w.cf.as<float>(), w.filt_planes.p, B, g, prep->wh.p, prep->wl.p,
+                           k.p0.as<float>(), st);
     }
     if (rc) return rc;
     if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),
@@ -338,6 +362,7 @@ struct dg_seg {
     DevBuf y1h, y1l;               // bf16 planes of the first head Linear's output
   } scr[2];
   int lane = 0;
+  const SincPrep* shared_prep = nullptr;   // set by the fused pipeline: statistics + planes computed once per step
 };
 
 static int seg_prepare(dg_seg* h, const Tensors& t) {
@@ -483,7 +508,7 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
   dg_seg::Scratch& w = h->scr[h->lane & 1];
   const Geom g = make_geom(S);
   int rc;
-  if ((rc = run_sincnet(h->sw, w.work, wav, B, g, st))) return rc;
+  if ((rc = run_sincnet(h->sw, w.work, wav, B, g, st, h->shared_prep))) return rc;
   const size_t rows = (size_t)B * g.S2 + 64;
   if (w.gx.ensure(rows * 1024 * 4) || w.hA.ensure(rows * 256 * 4) || w.hB.ensure(rows * 256 * 4) ||
       w.y1.ensure(rows * 128 * 4) || w.y2.ensure(rows * 128 * 4))
@@ -578,6 +603,7 @@ struct dg_emb {
   DevBuf idx0, idx1, lam1;
   int tab_F = -1, tab_T = -1;
   DevBuf flags, uniq, grp, gathered;   // compatibility path
+  const SincPrep* shared_prep = nullptr;
 };
 
 static const int TD_OUT[5] = {512, 512, 512, 512, 1500};
@@ -704,7 +730,7 @@ static int build_tables(dg_emb* h, int F, int T, cudaStream_t st) {
 // waveform [U,S] -> t5 [U*S2, 1500]; returns the number of valid frames
 static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStream_t st, int* T_out) {
   int rc;
-  if ((rc = run_sincnet(h->sw, h->work, wav, U, g, st))) return rc;
+  if ((rc = run_sincnet(h->sw, h->work, wav, U, g, st, h->shared_prep))) return rc;
   const size_t rows = (size_t)U * g.S2 + 64;
   if (h->tA.ensure(rows * 512 * 4) || h->tB.ensure(rows * 512 * 4) || h->t5.ensure(rows * 1500 * 4)) return DG_ECUDA;
   const long long M = (long long)U * g.S2;
@@ -1110,6 +1136,8 @@ struct dg_pipeline {
   cudaStream_t s_seg = nullptr, s_seg2 = nullptr, s_emb = nullptr, s_clu = nullptr, s_h2d = nullptr, s_d2h = nullptr;
   DevBuf osp2;
   cudaEvent_t e_osp2 = nullptr;
+  SincPrep prep[2];
+  cudaEvent_t e_prep[2] = {nullptr, nullptr};
   cudaEvent_t e_start = nullptr, e_osp = nullptr, e_emb = nullptr, e_done = nullptr;
   // depth-2 pipelining (dg_pipeline_submit* / collect*)
   DevBuf slot_wav[2], slot_seg[2], slot_emb[2], slot_map[2];
@@ -1147,6 +1175,8 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
   DG_CUDA(cudaStreamCreateWithPriority(&h->s_clu, cudaStreamNonBlocking, hi));
   DG_CUDA(cudaStreamCreateWithPriority(&h->s_seg2, cudaStreamNonBlocking, hi));
   DG_CUDA(cudaEventCreateWithFlags(&h->e_osp2, cudaEventDisableTiming));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_prep[0], cudaEventDisableTiming));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_prep[1], cudaEventDisableTiming));
   DG_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
   DG_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
   for (int i = 0; i < 2; i++) {
@@ -1172,6 +1202,15 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   if (osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
   DG_CUDA(cudaStreamWaitEvent(s_seg, start, 0));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, start, 0));
+  // waveform statistics + standardised bf16 planes once, for both networks' SincNets
+  static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
+  const SincPrep* shared = nullptr;
+  if (!sinc_simt) {
+    if ((rc = run_sinc_prep(h->prep[lane], wav, B, g, s_seg))) return rc;
+    DG_CUDA(cudaEventRecord(h->e_prep[lane], s_seg));
+    DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_prep[lane], 0));
+    shared = &h->prep[lane];
+  }
   // embedding trunk first in host order (low-priority stream, grid capped to the SMs the LSTM leaves free)
   int T = 0;
   {
@@ -1179,13 +1218,17 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->seg->device);
     const int lstm_ctas = 2 * ((B + 15) / 16);
     g_sm_limit = sms - lstm_ctas > sms / 2 ? sms - lstm_ctas : 0;
+    h->emb->shared_prep = shared;
     rc = emb_trunk(h->emb, wav, B, g, h->s_emb, &T);
+    h->emb->shared_prep = nullptr;
     g_sm_limit = 0;
     if (rc) return rc;
   }
   h->seg->lane = lane;
+  h->seg->shared_prep = shared;
   rc = dg_seg_forward(h->seg, wav, B, S, seg, s_seg);
   h->seg->lane = 0;
+  h->seg->shared_prep = nullptr;
   if (rc) return rc;
   if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, osp.as<float>(), s_seg))) return rc;
   DG_CUDA(cudaEventRecord(e_osp, s_seg));
@@ -1391,6 +1434,8 @@ extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
     if (h->s_clu) cudaStreamDestroy(h->s_clu);
     if (h->s_seg2) cudaStreamDestroy(h->s_seg2);
     if (h->e_osp2) cudaEventDestroy(h->e_osp2);
+    if (h->e_prep[0]) cudaEventDestroy(h->e_prep[0]);
+    if (h->e_prep[1]) cudaEventDestroy(h->e_prep[1]);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done, h->e_h2d[0], h->e_h2d[1], h->e_slot_done[0],

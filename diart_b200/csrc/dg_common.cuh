@@ -144,9 +144,11 @@ void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, ui
 int sinc_tc_rows_per_item(const Geom& g);
 size_t sinc_tc_plane_elems(int B, const Geom& g);
 void sinc_tc_pack_filters(const float* filt, uint16_t* planes /*[3][80][256]*/);
-int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, float gamma, float beta,
-                    const void* w_planes, int B, const Geom& g, void* planes_hi, void* planes_lo, float* p0,
-                    cudaStream_t st);
+void sinc_tc_affine_consts(const float* filt, float beta, float* cf);
+int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int B, const Geom& g, void* planes_hi,
+                     void* planes_lo, cudaStream_t st);
+int launch_sinc0_tc(float gamma, const float* cf_dev, const void* w_planes, int B, const Geom& g, const void* planes_hi,
+                    const void* planes_lo, float* p0, cudaStream_t st);
 // lstm.cu
 int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_packed, int B, int T, int stride,
                       float* hout /*[B*stride,256]*/, cudaStream_t st);

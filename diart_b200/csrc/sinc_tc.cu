@@ -41,7 +41,7 @@ struct SincTcMaps {
 
 __global__ void __launch_bounds__(192, 1)
 sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows_total, int rows_per_item, int T0,
-                int S0, float* __restrict__ p0) {
+                int S0, float* __restrict__ p0, float gamma, const float* __restrict__ cf) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                       // [kb][plane][80 x 128 B]
@@ -168,9 +168,13 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
         if (ok) {
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; i++)
-            v[i] = fmaxf(fmaxf(fabsf(__uint_as_float(r0[i])), fabsf(__uint_as_float(r1[i]))),
-                         fabsf(__uint_as_float(r2[i])));
+          for (int i = 0; i < 16; i++) {
+            // the planes hold the standardised waveform; InstanceNorm1d(1)'s affine enters here:
+            // conv(gamma * x + beta) = gamma * conv(x) + beta * sum_k h[k]
+            const float c0 = cf[c + i];
+            v[i] = fmaxf(fmaxf(fabsf(fmaf(gamma, __uint_as_float(r0[i]), c0)), fabsf(fmaf(gamma, __uint_as_float(r1[i]), c0))),
+                         fabsf(fmaf(gamma, __uint_as_float(r2[i]), c0)));
+          }
 #pragma unroll
           for (int i = 0; i < 4; i++)
             reinterpret_cast<float4*>(o + c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -195,14 +199,13 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
 
 // normalised waveform -> four shifted copies, bf16 hi / lo planes:  plane[c][b*Lp + i] = split(xn[b][i + 2c])
 __global__ void __launch_bounds__(256) sinc_prep_kernel(const float* __restrict__ wav, const float* __restrict__ mean,
-                                                        const float* __restrict__ rstd, float gamma, float beta,
-                                                        int S, int Lp, size_t plane_elems,
+                                                        const float* __restrict__ rstd, int S, int Lp, size_t plane_elems,
                                                         __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
   const int b = blockIdx.y;
-  const float mu = mean[b], sc = rstd[b] * gamma;
+  const float mu = mean[b], sc = rstd[b];
   const float* x = wav + (size_t)b * S;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Lp + 8; i += gridDim.x * blockDim.x) {
-    const float v = i < S ? (x[i] - mu) * sc + beta : 0.f;     // InstanceNorm1d(1, affine), as the SIMT kernel
+    const float v = i < S ? (x[i] - mu) * sc : 0.f;            // standardised waveform; the affine is applied in sinc0's epilogue
     const __nv_bfloat16 h = __float2bfloat16_rn(v);
     const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
 #pragma unroll
@@ -262,19 +265,32 @@ void sinc_tc_pack_filters(const float* filt, uint16_t* planes) {
   split_weights_host(r, 80, 80, 256, planes + 2 * 80 * 256, dummy);
 }
 
-int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, float gamma, float beta,
-                    const void* w_planes, int B, const Geom& g, void* planes_hi, void* planes_lo, float* p0,
-                    cudaStream_t st) {
+// per-filter constant of the folded InstanceNorm1d(1) affine: cf[f] = beta * sum_k h[f][k]
+void sinc_tc_affine_consts(const float* filt /*[251][80]*/, float beta, float* cf /*[80]*/) {
+  for (int f = 0; f < 80; f++) {
+    double s = 0;
+    for (int k = 0; k < 251; k++) s += filt[k * 80 + f];
+    cf[f] = (float)(beta * s);
+  }
+}
+
+// standardised waveform -> four shifted bf16 hi/lo copies (shared by every SincNet that reads this batch)
+int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int B, const Geom& g, void* planes_hi,
+                     void* planes_lo, cudaStream_t st) {
   const int rpi = sinc_tc_rows_per_item(g), Lp = rpi * 120;
   const size_t plane = sinc_tc_plane_elems(B, g);
-  {
-    ProfScope _ps("sinc0_prep", st);
-    dim3 grid((Lp + 8 + 255) / 256, B);
-    sinc_prep_kernel<<<grid, 256, 0, st>>>(wav, mean, rstd, gamma, beta, g.S, Lp, plane,
-                                           reinterpret_cast<__nv_bfloat16*>(planes_hi),
-                                           reinterpret_cast<__nv_bfloat16*>(planes_lo));
-    DG_LAUNCHED();
-  }
+  ProfScope _ps("sinc0_prep", st);
+  dim3 grid((Lp + 8 + 255) / 256, B);
+  sinc_prep_kernel<<<grid, 256, 0, st>>>(wav, mean, rstd, g.S, Lp, plane, reinterpret_cast<__nv_bfloat16*>(planes_hi),
+                                         reinterpret_cast<__nv_bfloat16*>(planes_lo));
+  DG_LAUNCHED();
+  return 0;
+}
+
+int launch_sinc0_tc(float gamma, const float* cf_dev, const void* w_planes, int B, const Geom& g, const void* planes_hi,
+                    const void* planes_lo, float* p0, cudaStream_t st) {
+  const int rpi = sinc_tc_rows_per_item(g);
+  const size_t plane = sinc_tc_plane_elems(B, g);
   ProfScope _ps("sinc0", st);
   SincTcMaps maps;
   const uint64_t rows = (uint64_t)B * rpi;
@@ -295,7 +311,8 @@ int launch_sinc0_tc(const float* wav, const float* mean, const float* rstd, floa
   const int sms = usable_sms();
   const int row_tiles = (int)((rows + ST_ROWS - 1) / ST_ROWS);
   const int tiles = row_tiles * 4;
-  sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0);
+  sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0,
+                                                                    gamma, cf_dev);
   DG_LAUNCHED();
   return 0;
 }
