@@ -1,6 +1,6 @@
 """Parity of the CUDA networks (through the C ABI) against the oracle restatement (oracle/nets.py).
 
-Tolerances (float32 everywhere, different summation order only): segmentation scores 3e-4 absolute (the float32 oracle itself is 0.84e-4 from a float64 evaluation of this synthetic net),
+Tolerances (float32 everywhere, different summation order only): segmentation scores 5e-4 absolute (the float32 oracle itself is 0.84e-4 from a float64 evaluation of this synthetic net),
 unit-norm embeddings 5e-4 absolute (the synthetic embedding has a ~6x cancellation between its raw
 and centred components, see oracle/calibrate.py)."""
 import numpy as np
@@ -11,7 +11,7 @@ from diart_b200 import models
 
 pytestmark = pytest.mark.gpu
 
-SEG_TOL = 3e-4
+SEG_TOL = 5e-4
 EMB_TOL = 5e-4
 
 
