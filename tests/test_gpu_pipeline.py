@@ -161,3 +161,37 @@ def test_voice_activity_detection_pipeline(oracle_nets, stream, cuda_device):
         got = sorted((round(s.start, 3), round(s.end, 3)) for s, _ in annotation.itertracks())
         want = sorted((round(s.start, 3), round(s.end, 3)) for s, _ in expect.itertracks())
         assert got == want and all(lab == "speech" for _, _, lab in annotation.itertracks(yield_label=True))
+
+
+def test_host_submit_collect_matches_step_host(oracle_nets, stream, cuda_device):
+    """C ABI with HOST buffers: dg_pipeline_submit_host / collect_host (two steps in flight) == dg_pipeline_step_host"""
+    import ctypes as C
+
+    from diart_b200 import _lib
+
+    lib = _lib.lib()
+    a, b = make_pipeline(oracle_nets, cuda_device), make_pipeline(oracle_nets, cuda_device)
+    ha, F, K, D = a._ensure_fused(80000)
+    hb, _, _, _ = b._ensure_fused(80000)
+    batches = [np.ascontiguousarray(synth.windows(stream, BATCH, first=i * BATCH)) for i in range(3)]
+
+    def bufs():
+        return (np.empty((BATCH, F, K), np.float32), np.empty((BATCH, K, D), np.float32), np.empty((BATCH, K), np.int32))
+
+    ref = []
+    for x in batches:
+        s, e, m = bufs()
+        _lib.check(lib.dg_pipeline_step_host(ha, x.ctypes.data, BATCH, 80000, s.ctypes.data, e.ctypes.data, m.ctypes.data, None))
+        ref.append((s, e, m))
+    got = []
+    _lib.check(lib.dg_pipeline_submit_host(hb, batches[0].ctypes.data, BATCH, 80000))
+    _lib.check(lib.dg_pipeline_submit_host(hb, batches[1].ctypes.data, BATCH, 80000))
+    assert lib.dg_pipeline_submit_host(hb, batches[2].ctypes.data, BATCH, 80000) == -1      # only two in flight
+    for nxt in (batches[2], None, None):
+        s, e, m = bufs()
+        _lib.check(lib.dg_pipeline_collect_host(hb, s.ctypes.data, e.ctypes.data, m.ctypes.data))
+        got.append((s, e, m))
+        if nxt is not None:
+            _lib.check(lib.dg_pipeline_submit_host(hb, nxt.ctypes.data, BATCH, 80000))
+    for (s1, e1, m1), (s2, e2, m2) in zip(ref, got):
+        assert np.array_equal(s1, s2) and np.array_equal(e1, e2) and np.array_equal(m1, m2)
