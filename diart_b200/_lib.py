@@ -32,6 +32,7 @@ SIGNATURES = {
     "dg_profile_report": (C.c_int, [C.c_char_p, C.c_int]),
     "dg_selftest_gemm_tc": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                       C.POINTER(C.c_float)]),
+    "dg_selftest_split_host": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P]),
     "dg_seg_create": (C.c_int, [C.POINTER(DgTensor), C.c_int, C.c_int, C.POINTER(_P)]),
     "dg_seg_dims": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "dg_seg_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),

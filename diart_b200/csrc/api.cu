@@ -110,7 +110,7 @@ static int upload_u16(DevBuf& b, const std::vector<uint16_t>& h) {
 // float32 [N][K] host weights -> zero-padded bf16 hi/lo device planes [Npad][K]
 static int upload_split(DevBuf& hi, DevBuf& lo, const std::vector<float>& w_nk, int N, int Npad, int K) {
   std::vector<uint16_t> h((size_t)Npad * K), l((size_t)Npad * K);
-  split_weights_host(w_nk.data(), N, Npad, K, h.data(), l.data());
+  split_weights_host(w_nk.data(), N, Npad, K, h.data(), l.data(), split_f16());
   return (upload_u16(hi, h) || upload_u16(lo, l)) ? DG_ECUDA : 0;
 }
 
@@ -170,7 +170,7 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
   if (upload(w.filt, h)) return DG_ECUDA;
   {
     std::vector<uint16_t> fp(3 * 80 * 256);
-    sinc_tc_pack_filters(h.data(), fp.data());
+    sinc_tc_pack_filters(h.data(), fp.data(), split_f16());
     if (upload_u16(w.filt_planes, fp)) return DG_ECUDA;
     std::vector<float> cf(80);
     sinc_tc_affine_consts(h.data(), w.wn_beta, cf.data());
@@ -392,7 +392,7 @@ static int seg_prepare(dg_seg* h, const Tensors& t) {
     if (upload_split(h->wih_hi[L], h->wih_lo[L], w_nk, 1024, 1024, in_pad)) return DG_ECUDA;
     {
       std::vector<uint16_t> rh(lstm_tc_plane_elems()), rl(lstm_tc_plane_elems());
-      lstm_tc_pack_whh(hh[0], hh[1], rh.data(), rl.data());
+      lstm_tc_pack_whh(hh[0], hh[1], rh.data(), rl.data(), split_f16());
       if (upload_u16(h->whh_hi[L], rh) || upload_u16(h->whh_lo[L], rl)) return DG_ECUDA;
     }
   }
@@ -1045,6 +1045,18 @@ extern "C" int dg_cluster_merge(dg_cluster* h, const double* records_dev, int wo
 }
 
 // ================================================================================== self test
+extern "C" int dg_selftest_split_host(const float* x, long long n, int f16, unsigned short* hi, unsigned short* lo) {
+  if (!x || !hi || !lo || n < 0) {
+    set_error("dg_selftest_split_host: null argument");
+    return DG_EINVAL;
+  }
+  for (long long i = 0; i < n; i++) {
+    hi[i] = host_f32_to_h16(x[i], f16);
+    lo[i] = host_f32_to_h16(x[i] - host_h16_to_f32(hi[i], f16), f16);
+  }
+  return DG_OK;
+}
+
 // Runs the same shifted-window GEMM through the float32 SIMT kernel and through the tcgen05 bf16x3
 // kernel on seeded random data and reports the largest absolute difference and the output scale.
 extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int epi, float* max_abs_diff,
@@ -1101,13 +1113,7 @@ extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int e
     std::vector<uint16_t> oh((size_t)M * N), ol((size_t)M * N);
     DG_CUDA(cudaMemcpy(oh.data(), dOh.p, oh.size() * 2, cudaMemcpyDeviceToHost));
     DG_CUDA(cudaMemcpy(ol.data(), dOl.p, ol.size() * 2, cudaMemcpyDeviceToHost));
-    for (size_t i = 0; i < c1.size(); i++) {
-      uint32_t a = (uint32_t)oh[i] << 16, b = (uint32_t)ol[i] << 16;
-      float fa, fb;
-      memcpy(&fa, &a, 4);
-      memcpy(&fb, &b, 4);
-      c1[i] = fa + fb;
-    }
+    for (size_t i = 0; i < c1.size(); i++) c1[i] = host_h16_to_f32(oh[i], split_f16()) + host_h16_to_f32(ol[i], split_f16());
   } else {
     DG_CUDA(cudaMemcpy(c1.data(), dC1.p, c1.size() * 4, cudaMemcpyDeviceToHost));
   }

@@ -139,11 +139,15 @@ int launch_split(const float* x, long long rows, int C, int item_rows, const flo
                  void* lo, cudaStream_t st);
 int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld_out, int pool, int item_rows,
                     const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st);
-void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo);
+// element type of the 16-bit operand planes: 1 = fp16 (default), 0 = bf16 (DG_SPLIT_BF16=1); fixed at first use
+int split_f16();
+void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo, int f16);
+uint16_t host_f32_to_h16(float f, int f16);
+float host_h16_to_f32(uint16_t h, int f16);
 // sinc_tc.cu -- SincNet stage 0 on tcgen05 (overlapping-row TMA view of the waveform)
 int sinc_tc_rows_per_item(const Geom& g);
 size_t sinc_tc_plane_elems(int B, const Geom& g);
-void sinc_tc_pack_filters(const float* filt, uint16_t* planes /*[3][80][256]*/);
+void sinc_tc_pack_filters(const float* filt, uint16_t* planes /*[3][80][256]*/, int f16);
 void sinc_tc_affine_consts(const float* filt, float beta, float* cf);
 int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int B, const Geom& g, void* planes_hi,
                      void* planes_lo, cudaStream_t st);
@@ -156,7 +160,7 @@ size_t lstm_whh_packed_floats();
 void lstm_pack_whh(const float* whh_fwd /*[512][128]*/, const float* whh_bwd, float* packed);
 // lstm_tc.cu -- recurrence on tcgen05 (W_hh hi plane in shared memory, lo plane in tensor memory)
 size_t lstm_tc_plane_elems();
-void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo);
+void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16);
 int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, int B, int T, int stride, float* hout,
                          cudaStream_t st);
 // heads.cu

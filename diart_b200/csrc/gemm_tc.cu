@@ -23,6 +23,7 @@
 //               planes; overlaps the next tile's MMAs through the second accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "dg_common.cuh"
@@ -44,6 +45,7 @@ struct TcArgs {
   __nv_bfloat16* out_hi;   // EPI_*_SPLIT: [M, ldc] each
   __nv_bfloat16* out_lo;
   int ldc;
+  int f16;              // operand planes are fp16 (1) or bf16 (0)
 };
 
 enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2 };
@@ -75,7 +77,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int num_tiles = a.m_tiles * a.n_tiles;
   const int kblocks = a.KW * a.cin_blocks;
 
@@ -99,7 +101,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -128,9 +130,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // (elect_one, not lane == 0: descriptors stay in uniform registers and the tcgen05.mma issue back to back)
+    if (elect_one()) {
       // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | idesc_ab_format(a.f16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
@@ -204,11 +207,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 16; i++) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]), h1 = __float2bfloat16_rn(v[2 * i + 1]);
-              const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-              const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-              hi[i] = pack_bf16x2(h0, h1);
-              lo[i] = pack_bf16x2(l0, l1);
+              uint16_t h0, l0, h1, l1;
+              split_h16(v[2 * i], a.f16, h0, l0);
+              split_h16(v[2 * i + 1], a.f16, h1, l1);
+              hi[i] = pack_u16x2(h0, h1);
+              lo[i] = pack_u16x2(l0, l1);
             }
             uint4* ph = reinterpret_cast<uint4*>(a.out_hi + m * a.ldc + n0 + c);
             uint4* pl = reinterpret_cast<uint4*>(a.out_lo + m * a.ldc + n0 + c);
@@ -285,6 +288,7 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
   a.bias = g.bias; a.bn_scale = g.bn_scale; a.bn_shift = g.bn_shift;
   a.out_f32 = g.out_f32; a.out_hi = reinterpret_cast<__nv_bfloat16*>(g.out_hi);
   a.out_lo = reinterpret_cast<__nv_bfloat16*>(g.out_lo); a.ldc = g.ldc;
+  a.f16 = split_f16();
   static bool attr_done = false;
   if (!attr_done) {
     DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
@@ -324,7 +328,7 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, long long rows_out, int C, int ld_in,
                                                     int ld_out, int pool, int item_rows, const float* __restrict__ sc,
                                                     const float* __restrict__ sh, __nv_bfloat16* __restrict__ hi,
-                                                    __nv_bfloat16* __restrict__ lo) {
+                                                    __nv_bfloat16* __restrict__ lo, int f16) {
   const int q_per_row = ld_out >> 2;
   const long long n4 = rows_out * q_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -349,12 +353,13 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
         v.z = leaky(fmaf(v.z, s.z, h.z)); v.w = leaky(fmaf(v.w, s.w, h.w));
       }
     }
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v.x), h1 = __float2bfloat16_rn(v.y), h2 = __float2bfloat16_rn(v.z),
-                        h3 = __float2bfloat16_rn(v.w);
-    const __nv_bfloat16 l0 = __float2bfloat16_rn(v.x - __bfloat162float(h0)), l1 = __float2bfloat16_rn(v.y - __bfloat162float(h1)),
-                        l2 = __float2bfloat16_rn(v.z - __bfloat162float(h2)), l3 = __float2bfloat16_rn(v.w - __bfloat162float(h3));
-    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_bf16x2(h0, h1), pack_bf16x2(h2, h3));
-    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_bf16x2(l0, l1), pack_bf16x2(l2, l3));
+    uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+    split_h16(v.x, f16, h0, l0);
+    split_h16(v.y, f16, h1, l1);
+    split_h16(v.z, f16, h2, l2);
+    split_h16(v.w, f16, h3, l3);
+    reinterpret_cast<uint2*>(hi)[i] = make_uint2(pack_u16x2(h0, h1), pack_u16x2(h2, h3));
+    reinterpret_cast<uint2*>(lo)[i] = make_uint2(pack_u16x2(l0, l1), pack_u16x2(l2, l3));
   }
 }
 
@@ -369,7 +374,7 @@ int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld
   const long long want = (n4 + 255) / 256;
   const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
   split_kernel<<<grid, 256, 0, st>>>(x, rows_out, C, ld_in, ld_out, pool, item_rows, sc, sh,
-                                     reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+                                     reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), split_f16());
   DG_LAUNCHED();
   return 0;
 }
@@ -379,27 +384,58 @@ int launch_split(const float* x, long long rows, int C, int item_rows, const flo
   return launch_split_ex(x, rows, C, C, C, 0, item_rows, sc, sh, hi, lo, st);
 }
 
-// host: float32 [N][K] -> zero-padded bf16 hi/lo planes [Npad][K]
-void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo) {
-  auto to_bf16 = [](float f) -> uint16_t {   // round to nearest even
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
-    return (uint16_t)(r >> 16);
-  };
-  auto from_bf16 = [](uint16_t h) -> float {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-  };
+int split_f16() {
+  static const int f16 = !(getenv("DG_SPLIT_BF16") && getenv("DG_SPLIT_BF16")[0] == '1');
+  return f16;
+}
+
+// host-side conversions, round to nearest even (fp16: subnormals kept, finite overflow saturates like cvt.satfinite)
+uint16_t host_f32_to_h16(float f, int f16) {
+  uint32_t u;
+  memcpy(&u, &f, 4);
+  if (!f16) return (uint16_t)((u + 0x7FFFu + ((u >> 16) & 1u)) >> 16);
+  const uint32_t sign = (u >> 16) & 0x8000u;
+  const uint32_t au = u & 0x7FFFFFFFu;
+  if (au > 0x7F800000u) return (uint16_t)(sign | 0x7FFFu);                  // NaN
+  if (au >= 0x477FF000u) return (uint16_t)(sign | 0x7BFFu);                 // >= 65520 (or inf): largest finite
+  if (au < 0x33000001u) return (uint16_t)sign;                              // <= 2^-25: rounds to zero
+  const int e = (int)(au >> 23) - 127;                                      // unbiased exponent
+  uint32_t mant = (au & 0x7FFFFFu) | 0x800000u;                             // 24-bit significand
+  int shift = e >= -14 ? 13 : 13 + (-14 - e);                               // bits dropped
+  uint32_t q = mant >> shift;
+  const uint32_t rem = mant & ((1u << shift) - 1u), half = 1u << (shift - 1);
+  if (rem > half || (rem == half && (q & 1u))) q++;
+  // normal: q has the implicit bit at position 10 -> exponent field e + 15 (a carry out of rounding propagates by itself)
+  const uint32_t bits = e >= -14 ? (uint32_t)((e + 14) << 10) + q : q;
+  return (uint16_t)(sign | bits);
+}
+float host_h16_to_f32(uint16_t h, int f16) {
+  uint32_t u;
+  if (!f16) {
+    u = (uint32_t)h << 16;
+  } else {
+    const uint32_t sign = ((uint32_t)h & 0x8000u) << 16, e = (h >> 10) & 31u, m = h & 0x3FFu;
+    if (e == 0) {
+      const float v = (float)m * 5.9604644775390625e-08f;                  // m * 2^-24
+      float r = sign ? -v : v;
+      return r;
+    }
+    u = e == 31 ? (sign | 0x7F800000u | (m << 13)) : (sign | ((e + 112u) << 23) | (m << 13));
+  }
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+// host: float32 [N][K] -> zero-padded 16-bit hi/lo planes [Npad][K]
+void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo, int f16) {
   for (size_t i = 0; i < (size_t)Npad * K; i++) hi[i] = lo[i] = 0;
   for (int n = 0; n < N; n++)
     for (int k = 0; k < K; k++) {
       const float f = w[(size_t)n * K + k];
-      const uint16_t h = to_bf16(f);
+      const uint16_t h = host_f32_to_h16(f, f16);
       hi[(size_t)n * K + k] = h;
-      lo[(size_t)n * K + k] = to_bf16(f - from_bf16(h));
+      lo[(size_t)n * K + k] = host_f32_to_h16(f - host_h16_to_f32(h, f16), f16);
     }
 }
 

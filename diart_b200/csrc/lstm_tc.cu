@@ -14,6 +14,7 @@
 //
 // 288 threads: warps 0-7 epilogue (TMEM lane quadrant = warp % 4, batch columns 8*(warp/4) ..), warp 8 issues
 // the TMA load of W_hi once and the 96 tcgen05.mma of every step.
+#include <stdlib.h>
 #include <string.h>
 
 #include "dg_common.cuh"
@@ -61,7 +62,8 @@ __device__ __forceinline__ float tanh_acc(float x) { return 1.f - __fdividef(2.f
 __global__ void __launch_bounds__(LT_THREADS, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi /*smem-resident plane (W_lo)*/,
                const uint16_t* __restrict__ w_lo /*TMEM-resident plane (W_hi), [2][512][128] bf16*/,
-               const float* __restrict__ gx, int B, int T, int stride, int groups_per_dir, float* __restrict__ hout) {
+               const float* __restrict__ gx, int B, int T, int stride, int groups_per_dir, float* __restrict__ hout,
+               int f16) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                         // [gate][k-block][128 x 128 B]
@@ -133,7 +135,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi /*smem-resident plane 
     // with N = 16 the math is only 8 cycles, so the four gates are issued by four warps in parallel
     const int g = warp - 8;
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(LT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | idesc_ab_format(f16) | ((uint32_t)(LT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       // all descriptors are affine in (gate, k-step): one base each, compile-time offsets in 16-byte units
       const uint64_t a0 = umma_desc(smem_u32(wsm));
       const uint64_t bb0 = umma_desc(smem_u32(hsm)), bb1 = umma_desc(smem_u32(hsm + LT_H_BYTES / 2));
@@ -220,12 +222,218 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi /*smem-resident plane 
         const float h = o_ * tanh_acc(c[n]);
         const int row = ch * 8 + n, b = b0 + row;
         if (b < B) hout[((size_t)b * stride + t) * 256 + dir * 128 + u] = h;
-        const __nv_bfloat16 hh = __float2bfloat16_rn(h);
-        const __nv_bfloat16 hl = __float2bfloat16_rn(h - __bfloat162float(hh));
+        uint16_t hh, hl;
+        split_h16(h, f16, hh, hl);
         const int off = row * 128 + ((chunk ^ (row & 7)) << 4) + e2;       // 128B swizzle of the K-major row
-        *reinterpret_cast<__nv_bfloat16*>(hdst + off) = hh;
-        *reinterpret_cast<__nv_bfloat16*>(hdst + 2 * LT_H_TILE + off) = hl;
+        *reinterpret_cast<uint16_t*>(hdst + off) = hh;
+        *reinterpret_cast<uint16_t*>(hdst + 2 * LT_H_TILE + off) = hl;
       }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&h_ready[nxt]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+  }
+}
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Version 3 of the recurrence (default).  Same decomposition (CTA = 16 batch rows x one direction x 512 gate rows,
+// TMEM lane u = hidden unit u), but
+//  * both planes of W_hh live in TENSOR MEMORY as far as they fit: hi plane of all four gates (256 columns) + lo plane of
+//    gates i, f, g (192 columns) + four 16-column accumulators = 512 columns; only the lo plane of gate o stays in
+//    shared memory, so 88 of the 96 tcgen05.mma of a step read their A operand from TMEM and only 8 pay the 4 KB
+//    shared-memory operand read of an SS MMA (32 in version 2 -- the MMA phase was bound by exactly those reads);
+//  * the MMAs are issued by ONE elected lane from warp-uniform descriptors (uniform registers, back-to-back UTCHMMA);
+//  * the cell update needs 7 MUFU operations instead of 10 (one reciprocal for f*c + i*g, one for o*tanh(c)) and
+//    ~50 instead of ~135 instructions per cell: with 2048 cells per step on one SM this phase is MUFU / issue bound;
+//  * rows past the batch are skipped (batch-1 latency).
+constexpr int L3_THREADS = 288;                        // 8 cell-update warps + 1 issuing warp
+constexpr int L3_WS_BYTES = 2 * 128 * 128;             // W_lo of gate o: 2 k-blocks x (128 rows x 128 B)
+constexpr int L3_SMEM = L3_WS_BYTES + LT_H_BYTES + 256 + 1024;
+constexpr uint32_t L3_COL_D = 0, L3_COL_WHI = 64, L3_COL_WLO = 320;
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__global__ void __launch_bounds__(L3_THREADS, 1)
+lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __restrict__ w_hi,
+                const uint16_t* __restrict__ w_lo /*both [2][512][128] bf16*/, const float* __restrict__ gx, int B, int T,
+                int stride, int groups_per_dir, float* __restrict__ hout, int f16) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* wsm = smem;                         // [k-block][128 x 128 B]   (W_lo, gate o)
+  unsigned char* hsm = smem + L3_WS_BYTES;           // [buffer][plane][k-block][16 x 128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L3_WS_BYTES + LT_H_BYTES);
+  uint64_t* w_full = bars;
+  uint64_t* mma_done = bars + 1;
+  uint64_t* h_ready = bars + 2;                      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int dir = blockIdx.x / groups_per_dir;
+  const int b0 = (blockIdx.x - dir * groups_per_dir) * LT_NB;
+
+  if (threadIdx.x == 0) {
+    mbar_init(w_full, 1);
+    mbar_init(mma_done, 1);
+    mbar_init(&h_ready[0], 8);
+    mbar_init(&h_ready[1], 8);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 8) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  for (int i = threadIdx.x; i < LT_H_BYTES / 4; i += L3_THREADS) reinterpret_cast<uint32_t*>(hsm)[i] = 0u;   // h_0 = 0
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 8) {
+    if (lane == 0) {
+      mbar_expect_tx(w_full, L3_WS_BYTES);
+      for (int kb = 0; kb < 2; kb++) tma_load_2d(wsm + kb * 16384, &tm_wlo, kb * 64, dir * 512 + 3 * 128, w_full);
+      mbar_wait(w_full, 0);
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    // lane r of gate tile g holds W[g*128 + r][0..127] as 64 packed bf16 pairs (low half = even k)
+    const int r = warp * 32 + lane;
+    for (int plane = 0; plane < 2; plane++) {
+      for (int g = 0; g < (plane ? 3 : 4); g++) {
+        const uint4* src = reinterpret_cast<const uint4*>((plane ? w_lo : w_hi) + ((size_t)dir * 512 + g * 128 + r) * 128);
+        const uint32_t col = (plane ? L3_COL_WLO : L3_COL_WHI) + g * 64;
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+          uint32_t v[32];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const uint4 q = src[half * 8 + i];
+            v[4 * i] = q.x; v[4 * i + 1] = q.y; v[4 * i + 2] = q.z; v[4 * i + 3] = q.w;
+          }
+          tmem_st32(tmem_base + ((uint32_t)(warp * 32) << 16) + col + half * 32, v);
+        }
+      }
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // zeroed h buffers -> visible to the tensor core
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+
+  if (warp == 8) {
+    if (elect_one()) {
+      const uint32_t idesc = (1u << 4) | idesc_ab_format(f16) | ((uint32_t)(LT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint64_t a_s = umma_desc(smem_u32(wsm));
+      const uint64_t bb0 = umma_desc(smem_u32(hsm)), bb1 = umma_desc(smem_u32(hsm + LT_H_BYTES / 2));
+      for (int step = 0; step < T; step++) {
+        const int buf = step & 1;
+        if (step > 0) {
+          mbar_wait(&h_ready[buf], ((step - 1) >> 1) & 1);
+          tc_fence_after();
+        }
+        const uint64_t b0d = buf ? bb1 : bb0;
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+          constexpr int kTile = 16384 >> 4, kHTile = LT_H_TILE >> 4;
+          const int kb = ks >> 2, kk = ks & 3;
+          const uint64_t b_hi = b0d + (uint64_t)(kb * kHTile + kk * 2);
+          const uint64_t b_lo = b0d + (uint64_t)(2 * kHTile + kb * kHTile + kk * 2);
+#pragma unroll
+          for (int g = 0; g < 4; g++) {
+            const uint32_t d = tmem_base + L3_COL_D + g * LT_NB;
+            const uint32_t a_hi = tmem_base + L3_COL_WHI + g * 64 + ks * 8;
+            umma_bf16_ts(d, a_hi, b_lo, idesc, ks != 0);                                     // W_hi . h_lo
+            if (g < 3) umma_bf16_ts(d, tmem_base + L3_COL_WLO + g * 64 + ks * 8, b_hi, idesc, 1);   // W_lo . h_hi
+            else umma_bf16(d, a_s + (uint64_t)(kb * kTile + kk * 2), b_hi, idesc, 1);
+            umma_bf16_ts(d, a_hi, b_hi, idesc, 1);                                           // W_hi . h_hi
+          }
+        }
+        umma_commit(mma_done);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================================================ cell update (warps 0..7)
+    const int quad = warp & 3, ch = warp >> 2;
+    const int u = quad * 32 + lane;                 // hidden unit == TMEM lane
+    const int rows = min(8, max(0, B - (b0 + ch * 8)));          // valid batch rows of this warp's 8 columns
+    float c[8];
+#pragma unroll
+    for (int n = 0; n < 8; n++) c[n] = 0.f;
+    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + L3_COL_D + ch * 8;
+    const int kb_u = u >> 6, kq = u & 63, chunk = kq >> 3, e2 = (kq & 7) * 2;
+    const size_t row_gx = (size_t)stride * 1024, row_h = (size_t)stride * 256;
+    const int t0 = dir == 0 ? 0 : T - 1;
+    const float* gp = gx + ((size_t)(b0 + ch * 8) * stride + t0) * 1024 + dir * 512 + u;
+    float* hp = hout + ((size_t)(b0 + ch * 8) * stride + t0) * 256 + dir * 128 + u;
+    const ptrdiff_t dgx = dir == 0 ? 1024 : -1024, dh = dir == 0 ? 256 : -256;
+    const float L2E = 1.4426950408889634f;
+    for (int step = 0; step < T; step++) {
+      const int nxt = (step + 1) & 1;
+      float xg[4][8];
+#pragma unroll
+      for (int n = 0; n < 8; n++) {
+        if (n < rows) {
+#pragma unroll
+          for (int g = 0; g < 4; g++) xg[g][n] = __ldg(gp + n * row_gx + g * 128);
+        } else {
+#pragma unroll
+          for (int g = 0; g < 4; g++) xg[g][n] = 0.f;
+        }
+      }
+      mbar_wait(mma_done, step & 1);
+      tc_fence_after();
+      uint32_t ri[8], rf[8], rg[8], ro[8];
+      tmem_ld8(tlane + 0 * LT_NB, ri);
+      tmem_ld8(tlane + 1 * LT_NB, rf);
+      tmem_ld8(tlane + 2 * LT_NB, rg);
+      tmem_ld8(tlane + 3 * LT_NB, ro);
+      tmem_ld_wait();
+      unsigned char* hdst = hsm + nxt * (LT_H_BYTES / 2) + kb_u * LT_H_TILE;
+#pragma unroll
+      for (int n = 0; n < 8; n++) {
+        if (n < rows) {
+          // e^-i, e^-f, e^2g (exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127)
+          const float ei = ex2_approx(fminf((__uint_as_float(ri[n]) + xg[0][n]) * -L2E, 40.f));
+          const float ef = ex2_approx(fminf((__uint_as_float(rf[n]) + xg[1][n]) * -L2E, 40.f));
+          const float eg = ex2_approx(fminf((__uint_as_float(rg[n]) + xg[2][n]) * (2.f * L2E), 40.f));
+          const float eo = ex2_approx(fminf((__uint_as_float(ro[n]) + xg[3][n]) * -L2E, 40.f));
+          // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(1 + eg))  over one common denominator
+          const float df = 1.f + ef, p = (1.f + ei) * (1.f + eg);
+          c[n] = fmaf(c[n], p, (eg - 1.f) * df) * rcp_approx(p * df);
+          // h = tanh(c') / (1 + eo)
+          const float ec = ex2_approx(fminf(c[n] * (2.f * L2E), 40.f));
+          const float h = (ec - 1.f) * rcp_approx((1.f + eo) * (ec + 1.f));
+          hp[n * row_h] = h;
+          uint16_t hh, hl;
+          split_h16(h, f16, hh, hl);
+          const int row = ch * 8 + n;
+          const int off = row * 128 + ((chunk ^ (row & 7)) << 4) + e2;       // 128B swizzle of the K-major row
+          *reinterpret_cast<uint16_t*>(hdst + off) = hh;
+          *reinterpret_cast<uint16_t*>(hdst + 2 * LT_H_TILE + off) = hl;
+        }
+      }
+      gp += dgx;
+      hp += dh;
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -243,9 +451,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi /*smem-resident plane 
 size_t lstm_tc_plane_elems() { return (size_t)2 * 512 * 128; }
 
 // torch weight_hh_l{L}[_reverse] ([512][128], gate order i,f,g,o) -> bf16 hi / lo planes [2][512][128]
-void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo) {
-  split_weights_host(whh_fwd, 512, 512, 128, hi, lo);
-  split_weights_host(whh_bwd, 512, 512, 128, hi + 512 * 128, lo + 512 * 128);
+void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16) {
+  split_weights_host(whh_fwd, 512, 512, 128, hi, lo, f16);
+  split_weights_host(whh_bwd, 512, 512, 128, hi + 512 * 128, lo + 512 * 128, f16);
 }
 
 int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, int B, int T, int stride, float* hout,
@@ -269,13 +477,24 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     return -2;
   }
   static bool attr_done = false;
+  static int version = 3;
   if (!attr_done) {
     DG_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    const char* e = getenv("DG_LSTM_V2");      // A/B switch: the version-2 kernel (W_lo wholly in shared memory)
+    if (e && e[0] == '1') version = 2;
     attr_done = true;
   }
   const int gpd = (B + LT_NB - 1) / LT_NB;
+  if (version == 3) {
+    lstm_tc3_kernel<<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, reinterpret_cast<const uint16_t*>(whh_hi),
+                                                         reinterpret_cast<const uint16_t*>(whh_lo), gx, B, T, stride, gpd, hout,
+                                                         split_f16());
+    DG_LAUNCHED();
+    return 0;
+  }
   lstm_tc_kernel<<<2 * gpd, LT_THREADS, LT_SMEM, st>>>(tm, reinterpret_cast<const uint16_t*>(whh_hi), gx, B, T, stride,
-                                                        gpd, hout);
+                                                        gpd, hout, split_f16());
   DG_LAUNCHED();
   return 0;
 }

@@ -41,7 +41,7 @@ struct SincTcMaps {
 
 __global__ void __launch_bounds__(192, 1)
 sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows_total, int rows_per_item, int T0,
-                int S0, float* __restrict__ p0, float gamma, const float* __restrict__ cf) {
+                int S0, float* __restrict__ p0, float gamma, const float* __restrict__ cf, int f16) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                       // [kb][plane][80 x 128 B]
@@ -53,7 +53,7 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
   uint64_t* acc_empty = bars + 2 * ST_NSTAGE + 2;
   uint64_t* w_full = bars + 2 * ST_NSTAGE + 4;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST_NSTAGE + 5);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int num_tiles = row_tiles * 4;
 
   if (threadIdx.x == 0) {
@@ -76,7 +76,7 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -104,8 +104,8 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(ST_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (elect_one()) {   // uniform-register descriptors, back-to-back tcgen05.mma
+      const uint32_t idesc = (1u << 4) | idesc_ab_format(f16) | ((uint32_t)(ST_N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       mbar_wait(w_full, 0);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -125,9 +125,12 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
               const uint64_t adv = (uint64_t)((ks * 32) >> 4);
               // five of the nine hi/lo/lo2 products: everything down to 2^-24 of the leading term.  This
               // layer's error is amplified by every later layer, so the filters carry 24 significand bits.
-              umma_bf16(tmem_c, a_lo + adv, w_lo + adv, idesc, (kb | ks) != 0);
-              umma_bf16(tmem_c, a_hi + adv, w_l2 + adv, idesc, 1);
-              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, 1);
+              // (fp16 planes: hi + lo already carry 22 bits of both operands, three products suffice)
+              if (!f16) {
+                umma_bf16(tmem_c, a_lo + adv, w_lo + adv, idesc, (kb | ks) != 0);
+                umma_bf16(tmem_c, a_hi + adv, w_l2 + adv, idesc, 1);
+              }
+              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, f16 ? (uint32_t)((kb | ks) != 0) : 1u);
               umma_bf16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
               umma_bf16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
             }
@@ -200,14 +203,14 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
 // normalised waveform -> four shifted copies, bf16 hi / lo planes:  plane[c][b*Lp + i] = split(xn[b][i + 2c])
 __global__ void __launch_bounds__(256) sinc_prep_kernel(const float* __restrict__ wav, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, int S, int Lp, size_t plane_elems,
-                                                        __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int f16) {
   const int b = blockIdx.y;
   const float mu = mean[b], sc = rstd[b];
   const float* x = wav + (size_t)b * S;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Lp + 8; i += gridDim.x * blockDim.x) {
     const float v = i < S ? (x[i] - mu) * sc : 0.f;            // standardised waveform; the affine is applied in sinc0's epilogue
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    const __nv_bfloat16 l = __float2bfloat16_rn(v - __bfloat162float(h));
+    uint16_t h, l;
+    split_h16(v, f16, h, l);
 #pragma unroll
     for (int c = 0; c < 4; c++) {
       const int j = i - 2 * c;                                 // copy c holds xn[j + 2c] at position j
@@ -248,21 +251,16 @@ size_t sinc_tc_plane_elems(int B, const Geom& g) { return (size_t)B * sinc_tc_ro
 
 // filt [251][80] float32 (k-major) -> three bf16 planes [3][80][256] (n-major, K padded with zeros):
 // hi = bf16(w), lo = bf16(w - hi), lo2 = bf16(w - hi - lo)
-void sinc_tc_pack_filters(const float* filt, uint16_t* planes) {
+void sinc_tc_pack_filters(const float* filt, uint16_t* planes, int f16) {
   static float w[80 * 256], r[80 * 256];
   static uint16_t dummy[80 * 256];
   memset(w, 0, sizeof(w));
   for (int k = 0; k < 251; k++)
     for (int f = 0; f < 80; f++) w[f * 256 + k] = filt[k * 80 + f];
-  split_weights_host(w, 80, 80, 256, planes, planes + 80 * 256);
-  auto from_bf16 = [](uint16_t h) {
-    uint32_t u = (uint32_t)h << 16;
-    float f;
-    memcpy(&f, &u, 4);
-    return f;
-  };
-  for (int i = 0; i < 80 * 256; i++) r[i] = (w[i] - from_bf16(planes[i])) - from_bf16(planes[80 * 256 + i]);
-  split_weights_host(r, 80, 80, 256, planes + 2 * 80 * 256, dummy);
+  split_weights_host(w, 80, 80, 256, planes, planes + 80 * 256, f16);
+  for (int i = 0; i < 80 * 256; i++)
+    r[i] = (w[i] - host_h16_to_f32(planes[i], f16)) - host_h16_to_f32(planes[80 * 256 + i], f16);
+  split_weights_host(r, 80, 80, 256, planes + 2 * 80 * 256, dummy, f16);      // third plane: used by the bf16 mode only
 }
 
 // per-filter constant of the folded InstanceNorm1d(1) affine: cf[f] = beta * sum_k h[f][k]
@@ -281,8 +279,8 @@ int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int
   const size_t plane = sinc_tc_plane_elems(B, g);
   ProfScope _ps("sinc0_prep", st);
   dim3 grid((Lp + 8 + 255) / 256, B);
-  sinc_prep_kernel<<<grid, 256, 0, st>>>(wav, mean, rstd, g.S, Lp, plane, reinterpret_cast<__nv_bfloat16*>(planes_hi),
-                                         reinterpret_cast<__nv_bfloat16*>(planes_lo));
+  sinc_prep_kernel<<<grid, 256, 0, st>>>(wav, mean, rstd, g.S, Lp, plane, reinterpret_cast<uint16_t*>(planes_hi),
+                                         reinterpret_cast<uint16_t*>(planes_lo), split_f16());
   DG_LAUNCHED();
   return 0;
 }
@@ -312,7 +310,7 @@ int launch_sinc0_tc(float gamma, const float* cf_dev, const void* w_planes, int 
   const int row_tiles = (int)((rows + ST_ROWS - 1) / ST_ROWS);
   const int tiles = row_tiles * 4;
   sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0,
-                                                                    gamma, cf_dev);
+                                                                    gamma, cf_dev, split_f16());
   DG_LAUNCHED();
   return 0;
 }

@@ -44,6 +44,36 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+// ---- 16-bit operand planes.  A float32 value travels as hi + lo; the element type is fp16 (default: |x| < 65504 and
+// 22 significand bits for the pair) or bf16 (16 bits for the pair, float32 range).  `f16` is warp-uniform.
+__device__ __forceinline__ uint16_t f32_to_h16(float x, int f16) {
+  uint16_t r;
+  if (f16) asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  else asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float h16_to_f32(uint16_t h, int f16) {
+  float f;
+  if (f16) asm("cvt.f32.f16 %0, %1;" : "=f"(f) : "h"(h));
+  else f = __uint_as_float((uint32_t)h << 16);
+  return f;
+}
+__device__ __forceinline__ void split_h16(float x, int f16, uint16_t& hi, uint16_t& lo) {
+  hi = f32_to_h16(x, f16);
+  lo = f32_to_h16(x - h16_to_f32(hi, f16), f16);
+}
+__device__ __forceinline__ uint32_t pack_u16x2(uint16_t a, uint16_t b) { return (uint32_t)a | ((uint32_t)b << 16); }
+// tcgen05 instruction-descriptor bits of the A / B element type (kind::f16): 0 = fp16, 1 = bf16
+__device__ __forceinline__ uint32_t idesc_ab_format(int f16) { return f16 ? 0u : ((1u << 7) | (1u << 10)); }
+
+// one lane of a converged warp; unlike `lane == 0` the compiler keeps everything computed from warp-uniform values in
+// UNIFORM registers inside the branch, so tcgen05.mma issues back to back (a divergent `lane == 0` branch costs an
+// ELECT / R2UR.BROADCAST loop of ~50 cycles per MMA)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 

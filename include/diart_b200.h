@@ -139,6 +139,10 @@ int dg_profile_enable(int enable);
 /* test hook: the same random shifted-window GEMM through the float32 SIMT kernel and the tcgen05 (bf16x3)
  * kernel; epi 0 = bias -> f32, 1 = bias+leaky+bn -> bf16 hi/lo planes, 2 = bias+leaky+bn -> f32. */
 int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int epi, float* max_abs_diff, float* out_rms);
+/* test hook (host only, no GPU): the weight-side split of float32 values into the two 16-bit operand planes
+ * (hi = rn16(x), lo = rn16(x - hi)); f16 = 1 -> IEEE fp16 (saturating), 0 -> bf16.  What the device does to
+ * activations with cvt.rn(.satfinite).f16/bf16.f32. */
+int dg_selftest_split_host(const float* x, long long n, int f16, unsigned short* hi, unsigned short* lo);
 int dg_profile_report(char* buf, int cap);
 
 /* ---- shared-identity mode (extension beyond the reference; SURVEY.md 8(e), BASELINE config 5): G ranks diarize
