@@ -1109,8 +1109,10 @@ extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int e
   DG_CUDA(cudaDeviceSynchronize());
   std::vector<float> c0((size_t)M * N), c1((size_t)M * N);
   DG_CUDA(cudaMemcpy(c0.data(), dC0.p, c0.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<uint16_t> oh, ol;
   if (epi == 1) {
-    std::vector<uint16_t> oh((size_t)M * N), ol((size_t)M * N);
+    oh.resize((size_t)M * N);
+    ol.resize((size_t)M * N);
     DG_CUDA(cudaMemcpy(oh.data(), dOh.p, oh.size() * 2, cudaMemcpyDeviceToHost));
     DG_CUDA(cudaMemcpy(ol.data(), dOl.p, ol.size() * 2, cudaMemcpyDeviceToHost));
     for (size_t i = 0; i < c1.size(); i++) c1[i] = host_h16_to_f32(oh[i], split_f16()) + host_h16_to_f32(ol[i], split_f16());
@@ -1118,10 +1120,26 @@ extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int e
     DG_CUDA(cudaMemcpy(c1.data(), dC1.p, c1.size() * 4, cudaMemcpyDeviceToHost));
   }
   double md = 0, ss = 0;
+  size_t worst = 0, n_big = 0;
   for (size_t i = 0; i < c0.size(); i++) {
     const double d = fabs((double)c0[i] - (double)c1[i]);
-    if (!(d <= md)) md = d;     // NaN-propagating max
+    if (!(d <= md)) {     // NaN-propagating max
+      md = d;
+      worst = i;
+    }
+    if (!(d <= 1e-2)) n_big++;
     ss += (double)c0[i] * c0[i];
+  }
+  if (n_big)
+    fprintf(stderr, "dg_selftest_gemm_tc: %zu of %zu outputs differ by more than 1e-2; worst at row %zu col %zu: simt %g, tcgen05 %g\n",
+            n_big, c0.size(), worst / N, worst % N, c0[worst], c1[worst]);
+  if (n_big && epi == 1) {
+    size_t shown = 0;
+    for (size_t i = 0; i < c0.size() && shown < 12; i++)
+      if (!(fabs((double)c0[i] - (double)c1[i]) <= 1e-2)) {
+        fprintf(stderr, "   row %zu col %zu: simt %g, planes hi 0x%04x lo 0x%04x\n", i / N, i % N, c0[i], oh[i], ol[i]);
+        shown++;
+      }
   }
   *max_abs_diff = (float)md;
   *out_rms = (float)sqrt(ss / c0.size());

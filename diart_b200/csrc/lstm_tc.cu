@@ -251,13 +251,18 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tm_whi /*smem-resident plane 
 //    shared memory, so 88 of the 96 tcgen05.mma of a step read their A operand from TMEM and only 8 pay the 4 KB
 //    shared-memory operand read of an SS MMA (32 in version 2 -- the MMA phase was bound by exactly those reads);
 //  * the MMAs are issued by ONE elected lane from warp-uniform descriptors (uniform registers, back-to-back UTCHMMA);
-//  * the cell update needs 7 MUFU operations instead of 10 (one reciprocal for f*c + i*g, one for o*tanh(c)) and
-//    ~50 instead of ~135 instructions per cell: with 2048 cells per step on one SM this phase is MUFU / issue bound;
+//  * h_t is the B operand in MN-MAJOR (batch-contiguous) layout: the thread that owns hidden unit u holds h_t[u] of its
+//    8 batch rows, which is exactly one 16-byte unit of an MN-major core matrix -> one 16-byte shared store per plane
+//    and thread instead of 16 scattered 2-byte stores (the fence.proxy.async that follows costs a MEMBAR whose latency
+//    grows with the stores in flight);
+//  * the cell update needs 7 MUFU operations instead of 10 (one reciprocal for f*c + i*g, one for o*tanh(c)), ~45
+//    instead of ~135 instructions per cell, and is branch-free for full tiles so the 8 cells of a thread overlap;
 //  * rows past the batch are skipped (batch-1 latency).
 constexpr int L3_THREADS = 288;                        // 8 cell-update warps + 1 issuing warp
 constexpr int L3_WS_BYTES = 2 * 128 * 128;             // W_lo of gate o: 2 k-blocks x (128 rows x 128 B)
 constexpr int L3_SMEM = L3_WS_BYTES + LT_H_BYTES + 256 + 1024;
 constexpr uint32_t L3_COL_D = 0, L3_COL_WHI = 64, L3_COL_WLO = 320;
+constexpr int L3_PLANE = 128 * LT_NB * 2;              // one plane of h_t: 128 units x 16 rows x 2 B = 4 KB
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -270,14 +275,107 @@ __device__ __forceinline__ float rcp_approx(float x) {
   return y;
 }
 
+struct L3Cell {
+  const float* gp;     // gate pre-activations of (first row, t, dir, u)
+  float* hp;           // output h of (first row, t, dir, u)
+  size_t row_gx, row_h;
+  ptrdiff_t dgx, dh;
+  uint32_t tlane;      // TMEM address of this thread's accumulator columns
+  uint32_t h_addr;     // shared address of this thread's 16-byte unit in buffer 0, hi plane (MN-major) / row 0 (K-major)
+  int rows, ch;
+};
+
+// the 293 dependent cell updates of one thread; FULL = all 8 batch rows of this warp are valid (no branches: the
+// eight independent dependency chains overlap)
+template <bool F16, bool BMN, bool FULL>
+__device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done, uint64_t* h_ready, int lane) {
+  constexpr int f16 = F16 ? 1 : 0;
+  const float L2E = 1.4426950408889634f;
+  float c[8];
+#pragma unroll
+  for (int n = 0; n < 8; n++) c[n] = 0.f;
+  for (int step = 0; step < T; step++) {
+    const int nxt = (step + 1) & 1;
+    float xg[4][8];
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      if (FULL || n < s.rows) {
+#pragma unroll
+        for (int g = 0; g < 4; g++) xg[g][n] = __ldg(s.gp + n * s.row_gx + g * 128);
+      } else {
+#pragma unroll
+        for (int g = 0; g < 4; g++) xg[g][n] = 0.f;
+      }
+    }
+    mbar_wait(mma_done, step & 1);
+    tc_fence_after();
+    uint32_t ri[8], rf[8], rg[8], ro[8];
+    tmem_ld8(s.tlane + 0 * LT_NB, ri);
+    tmem_ld8(s.tlane + 1 * LT_NB, rf);
+    tmem_ld8(s.tlane + 2 * LT_NB, rg);
+    tmem_ld8(s.tlane + 3 * LT_NB, ro);
+    tmem_ld_wait();
+    float h[8];
+    uint16_t hh[8], hl[8];
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      if (FULL || n < s.rows) {
+        // e^-i, e^-f, e^2g, e^-o (exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127)
+        const float ei = ex2_approx(fminf((__uint_as_float(ri[n]) + xg[0][n]) * -L2E, 40.f));
+        const float ef = ex2_approx(fminf((__uint_as_float(rf[n]) + xg[1][n]) * -L2E, 40.f));
+        const float eg = ex2_approx(fminf((__uint_as_float(rg[n]) + xg[2][n]) * (2.f * L2E), 40.f));
+        const float eo = ex2_approx(fminf((__uint_as_float(ro[n]) + xg[3][n]) * -L2E, 40.f));
+        // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(1 + eg))  over one common denominator
+        const float df = 1.f + ef, p = (1.f + ei) * (1.f + eg);
+        c[n] = fmaf(c[n], p, (eg - 1.f) * df) * rcp_approx(p * df);
+        // h = tanh(c') / (1 + eo)
+        const float ec = ex2_approx(fminf(c[n] * (2.f * L2E), 40.f));
+        h[n] = (ec - 1.f) * rcp_approx((1.f + eo) * (ec + 1.f));
+        split_h16(h[n], f16, hh[n], hl[n]);
+      } else {
+        h[n] = 0.f;
+        hh[n] = hl[n] = 0;
+      }
+    }
+    const uint32_t dst = s.h_addr + nxt * (LT_H_BYTES / 2);
+    if (BMN) {
+      st_shared_v4(dst, pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]), pack_u16x2(hh[4], hh[5]), pack_u16x2(hh[6], hh[7]));
+      st_shared_v4(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]), pack_u16x2(hl[2], hl[3]), pack_u16x2(hl[4], hl[5]),
+                   pack_u16x2(hl[6], hl[7]));
+    } else {
+#pragma unroll
+      for (int n = 0; n < 8; n++) {
+        if (FULL || n < s.rows) {
+          const int row = s.ch * 8 + n;
+          // s.h_addr already holds k-block and the (chunk, element) position; row and the 128B swizzle are added here
+          const uint32_t a = dst + row * 128;
+          st_shared_u16(a ^ ((uint32_t)(row & 7) << 4), hh[n]);
+          st_shared_u16((a + L3_PLANE) ^ ((uint32_t)(row & 7) << 4), hl[n]);
+        }
+      }
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&h_ready[nxt]);
+    // the float32 copy of h_t for the next layer leaves after the hand-off: it is not on the recurrence's critical path
+#pragma unroll
+    for (int n = 0; n < 8; n++)
+      if (FULL || n < s.rows) s.hp[n * s.row_h] = h[n];
+    s.gp += s.dgx;
+    s.hp += s.dh;
+  }
+}
+
+template <bool F16, bool BMN>
 __global__ void __launch_bounds__(L3_THREADS, 1)
 lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __restrict__ w_hi,
-                const uint16_t* __restrict__ w_lo /*both [2][512][128] bf16*/, const float* __restrict__ gx, int B, int T,
-                int stride, int groups_per_dir, float* __restrict__ hout, int f16) {
+                const uint16_t* __restrict__ w_lo /*both [2][512][128]*/, const float* __restrict__ gx, int B, int T,
+                int stride, int groups_per_dir, float* __restrict__ hout, int mn_swap) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                         // [k-block][128 x 128 B]   (W_lo, gate o)
-  unsigned char* hsm = smem + L3_WS_BYTES;           // [buffer][plane][k-block][16 x 128 B]
+  unsigned char* hsm = smem + L3_WS_BYTES;           // [buffer][plane][4 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L3_WS_BYTES + LT_H_BYTES);
   uint64_t* w_full = bars;
   uint64_t* mma_done = bars + 1;
@@ -314,7 +412,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     }
     __syncwarp();
   } else if (warp < 4) {
-    // lane r of gate tile g holds W[g*128 + r][0..127] as 64 packed bf16 pairs (low half = even k)
+    // lane r of gate tile g holds W[g*128 + r][0..127] as 64 packed 16-bit pairs (low half = even k)
     const int r = warp * 32 + lane;
     for (int plane = 0; plane < 2; plane++) {
       for (int g = 0; g < (plane ? 3 : 4); g++) {
@@ -341,9 +439,15 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
 
   if (warp == 8) {
     if (elect_one()) {
-      const uint32_t idesc = (1u << 4) | idesc_ab_format(f16) | ((uint32_t)(LT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | idesc_ab_format(F16 ? 1 : 0) | (BMN ? (1u << 16) : 0u) |
+                             ((uint32_t)(LT_NB >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       const uint64_t a_s = umma_desc(smem_u32(wsm));
-      const uint64_t bb0 = umma_desc(smem_u32(hsm)), bb1 = umma_desc(smem_u32(hsm + LT_H_BYTES / 2));
+      // B operand (h_t): MN-major = [k-group of 8][row-group of 8][8 k x 16 B]: LBO (k-groups) 256 B, SBO (row groups) 128 B,
+      // one k-step (16 k) = 512 B;  K-major = 128B-swizzled rows, two k-blocks of 16 rows x 128 B per plane
+      const uint32_t h0 = smem_u32(hsm);
+      const uint32_t lbo = mn_swap ? 128 : 256, sbo = mn_swap ? 256 : 128;     // (mn_swap: diagnostic A/B only)
+      const uint64_t bb0 = BMN ? umma_desc_mn(h0, lbo, sbo) : umma_desc(h0);
+      const uint64_t bb1 = BMN ? umma_desc_mn(h0 + LT_H_BYTES / 2, lbo, sbo) : umma_desc(h0 + LT_H_BYTES / 2);
       for (int step = 0; step < T; step++) {
         const int buf = step & 1;
         if (step > 0) {
@@ -355,8 +459,8 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
         for (int ks = 0; ks < 8; ks++) {
           constexpr int kTile = 16384 >> 4, kHTile = LT_H_TILE >> 4;
           const int kb = ks >> 2, kk = ks & 3;
-          const uint64_t b_hi = b0d + (uint64_t)(kb * kHTile + kk * 2);
-          const uint64_t b_lo = b0d + (uint64_t)(2 * kHTile + kb * kHTile + kk * 2);
+          const uint64_t b_hi = b0d + (uint64_t)(BMN ? ks * (512 >> 4) : kb * kHTile + kk * 2);
+          const uint64_t b_lo = b_hi + (uint64_t)(L3_PLANE >> 4);
 #pragma unroll
           for (int g = 0; g < 4; g++) {
             const uint32_t d = tmem_base + L3_COL_D + g * LT_NB;
@@ -375,70 +479,25 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     // ================================================================ cell update (warps 0..7)
     const int quad = warp & 3, ch = warp >> 2;
     const int u = quad * 32 + lane;                 // hidden unit == TMEM lane
-    const int rows = min(8, max(0, B - (b0 + ch * 8)));          // valid batch rows of this warp's 8 columns
-    float c[8];
-#pragma unroll
-    for (int n = 0; n < 8; n++) c[n] = 0.f;
-    const uint32_t tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + L3_COL_D + ch * 8;
-    const int kb_u = u >> 6, kq = u & 63, chunk = kq >> 3, e2 = (kq & 7) * 2;
-    const size_t row_gx = (size_t)stride * 1024, row_h = (size_t)stride * 256;
+    L3Cell s;
+    s.rows = min(8, max(0, B - (b0 + ch * 8)));     // valid batch rows of this warp's 8 columns
+    s.ch = ch;
+    s.tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + L3_COL_D + ch * 8;
+    s.row_gx = (size_t)stride * 1024;
+    s.row_h = (size_t)stride * 256;
     const int t0 = dir == 0 ? 0 : T - 1;
-    const float* gp = gx + ((size_t)(b0 + ch * 8) * stride + t0) * 1024 + dir * 512 + u;
-    float* hp = hout + ((size_t)(b0 + ch * 8) * stride + t0) * 256 + dir * 128 + u;
-    const ptrdiff_t dgx = dir == 0 ? 1024 : -1024, dh = dir == 0 ? 256 : -256;
-    const float L2E = 1.4426950408889634f;
-    for (int step = 0; step < T; step++) {
-      const int nxt = (step + 1) & 1;
-      float xg[4][8];
-#pragma unroll
-      for (int n = 0; n < 8; n++) {
-        if (n < rows) {
-#pragma unroll
-          for (int g = 0; g < 4; g++) xg[g][n] = __ldg(gp + n * row_gx + g * 128);
-        } else {
-#pragma unroll
-          for (int g = 0; g < 4; g++) xg[g][n] = 0.f;
-        }
-      }
-      mbar_wait(mma_done, step & 1);
-      tc_fence_after();
-      uint32_t ri[8], rf[8], rg[8], ro[8];
-      tmem_ld8(tlane + 0 * LT_NB, ri);
-      tmem_ld8(tlane + 1 * LT_NB, rf);
-      tmem_ld8(tlane + 2 * LT_NB, rg);
-      tmem_ld8(tlane + 3 * LT_NB, ro);
-      tmem_ld_wait();
-      unsigned char* hdst = hsm + nxt * (LT_H_BYTES / 2) + kb_u * LT_H_TILE;
-#pragma unroll
-      for (int n = 0; n < 8; n++) {
-        if (n < rows) {
-          // e^-i, e^-f, e^2g (exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127)
-          const float ei = ex2_approx(fminf((__uint_as_float(ri[n]) + xg[0][n]) * -L2E, 40.f));
-          const float ef = ex2_approx(fminf((__uint_as_float(rf[n]) + xg[1][n]) * -L2E, 40.f));
-          const float eg = ex2_approx(fminf((__uint_as_float(rg[n]) + xg[2][n]) * (2.f * L2E), 40.f));
-          const float eo = ex2_approx(fminf((__uint_as_float(ro[n]) + xg[3][n]) * -L2E, 40.f));
-          // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(1 + eg))  over one common denominator
-          const float df = 1.f + ef, p = (1.f + ei) * (1.f + eg);
-          c[n] = fmaf(c[n], p, (eg - 1.f) * df) * rcp_approx(p * df);
-          // h = tanh(c') / (1 + eo)
-          const float ec = ex2_approx(fminf(c[n] * (2.f * L2E), 40.f));
-          const float h = (ec - 1.f) * rcp_approx((1.f + eo) * (ec + 1.f));
-          hp[n * row_h] = h;
-          uint16_t hh, hl;
-          split_h16(h, f16, hh, hl);
-          const int row = ch * 8 + n;
-          const int off = row * 128 + ((chunk ^ (row & 7)) << 4) + e2;       // 128B swizzle of the K-major row
-          *reinterpret_cast<uint16_t*>(hdst + off) = hh;
-          *reinterpret_cast<uint16_t*>(hdst + 2 * LT_H_TILE + off) = hl;
-        }
-      }
-      gp += dgx;
-      hp += dh;
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&h_ready[nxt]);
+    s.gp = gx + ((size_t)(b0 + ch * 8) * stride + t0) * 1024 + dir * 512 + u;
+    s.hp = hout + ((size_t)(b0 + ch * 8) * stride + t0) * 256 + dir * 128 + u;
+    s.dgx = dir == 0 ? 1024 : -1024;
+    s.dh = dir == 0 ? 256 : -256;
+    if (BMN) {
+      s.h_addr = smem_u32(hsm) + (u >> 3) * 256 + ch * 128 + (u & 7) * 16;
+    } else {
+      const int kb_u = u >> 6, kq = u & 63;
+      s.h_addr = smem_u32(hsm) + kb_u * LT_H_TILE + ((kq >> 3) << 4) + (kq & 7) * 2;
     }
+    if (s.rows == 8) l3_cell_loop<F16, BMN, true>(s, T, mma_done, h_ready, lane);
+    else l3_cell_loop<F16, BMN, false>(s, T, mma_done, h_ready, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -477,19 +536,32 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     return -2;
   }
   static bool attr_done = false;
-  static int version = 3;
+  static int version = 3, bmn = 1, mn_swap = 0;
   if (!attr_done) {
     DG_CUDA(cudaFuncSetAttribute(lstm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, LT_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    const char* e = getenv("DG_LSTM_V2");      // A/B switch: the version-2 kernel (W_lo wholly in shared memory)
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    const char* e = getenv("DG_LSTM_V2");      // A/B switches: the version-2 kernel; K-major (scattered) h operand
     if (e && e[0] == '1') version = 2;
+    e = getenv("DG_LSTM_KMAJOR");
+    if (e && e[0] == '1') bmn = 0;
+    e = getenv("DG_LSTM_SWAP");
+    if (e && e[0] == '1') mn_swap = 1;
     attr_done = true;
   }
   const int gpd = (B + LT_NB - 1) / LT_NB;
   if (version == 3) {
-    lstm_tc3_kernel<<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, reinterpret_cast<const uint16_t*>(whh_hi),
-                                                         reinterpret_cast<const uint16_t*>(whh_lo), gx, B, T, stride, gpd, hout,
-                                                         split_f16());
+    const uint16_t* ph = reinterpret_cast<const uint16_t*>(whh_hi);
+    const uint16_t* pl = reinterpret_cast<const uint16_t*>(whh_lo);
+    const int f16 = split_f16();
+#define DG_L3(F, M) lstm_tc3_kernel<F, M><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, mn_swap)
+    if (f16 && bmn) DG_L3(true, true);
+    else if (f16) DG_L3(true, false);
+    else if (bmn) DG_L3(false, true);
+    else DG_L3(false, false);
+#undef DG_L3
     DG_LAUNCHED();
     return 0;
   }

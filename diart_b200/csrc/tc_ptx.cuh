@@ -87,6 +87,23 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
   d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
   return d;
 }
+// MN-major operand without swizzle ("interleaved" core matrices): a core matrix is 8 MN-elements (one 16-byte unit)
+// x 8 k-values (consecutive 16-byte units) = 128 contiguous bytes; `sbo` = byte stride between groups of 8
+// MN-elements, `lbo` = byte stride between groups of 8 k-values (cute::UMMA::make_umma_desc<Major::MN>, INTERLEAVE)
+__device__ __forceinline__ uint64_t umma_desc_mn(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;
+  return d;
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void st_shared_u16(uint32_t addr, uint16_t v) {
+  asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_c, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {
   asm volatile(

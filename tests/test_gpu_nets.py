@@ -11,8 +11,8 @@ from diart_b200 import models
 
 pytestmark = pytest.mark.gpu
 
-SEG_TOL = 5e-4
-EMB_TOL = 5e-4
+SEG_TOL = 1e-4
+EMB_TOL = 1e-4
 
 
 def _osp(seg, gamma=3, beta=10):

@@ -3,17 +3,21 @@
 # usage: tools/gpu_ab.sh <tag>
 tag=${1:-ab}
 out=gpurun_out
-mkdir -p $out
 cd "$(dirname "$0")/.."
-timeout 900 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_nets.py tests/test_gpu_pipeline.py -x -q -m gpu -s 2>&1 | grep -v "^$" | tail -40 > $out/${tag}_tests.log
-tail -5 $out/${tag}_tests.log
-timeout 300 python bench.py --steps 10 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err
-DG_LSTM_V2=1 timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_lstm2.json 2>> $out/${tag}_bench.err
-DG_SPLIT_BF16=1 timeout 200 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > $out/${tag}_bench_bf16.json 2>> $out/${tag}_bench.err
-timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --serial > $out/${tag}_bench_serial.json 2>> $out/${tag}_bench.err
-timeout 200 python bench.py --steps 30 --warmup 5 --no-cpu-baseline --serial --batch 1 > $out/${tag}_bench_b1.json 2>> $out/${tag}_bench.err
-DG_SPLIT_BF16=1 DG_LSTM_V2=1 timeout 600 python -m pytest tests/test_gpu_nets.py -x -q -m gpu -s 2>&1 | grep -i "err\|passed\|failed" | tail -8 > $out/${tag}_tests_old.log
-for f in $out/${tag}_bench*.json; do echo $f; python - "$f" <<'PY'
+mkdir -p $out
+nets() { timeout 600 python -m pytest tests/test_gpu_nets.py -x -q -m gpu -s 2>&1 | grep -i "err\|passed\|failed" | tail -6; }
+echo "== nets default" | tee $out/${tag}_tests.log; nets | tee -a $out/${tag}_tests.log
+if grep -q failed $out/${tag}_tests.log; then
+  echo "== nets DG_LSTM_SWAP=1" | tee -a $out/${tag}_tests.log; DG_LSTM_SWAP=1 nets | tee -a $out/${tag}_tests.log
+fi
+echo "== nets DG_LSTM_KMAJOR=1" | tee -a $out/${tag}_tests.log; DG_LSTM_KMAJOR=1 nets | tee -a $out/${tag}_tests.log
+b() { name=$1; shift; timeout 240 python bench.py --no-cpu-baseline "$@" > $out/${tag}_bench_$name.json 2>> $out/${tag}_bench.err; }
+b default --steps 10 --warmup 3
+DG_LSTM_KMAJOR=1 b kmajor --steps 10 --warmup 3
+b serial --steps 20 --warmup 3 --serial
+DG_LSTM_KMAJOR=1 b serial_kmajor --steps 20 --warmup 3 --serial
+b b1 --steps 30 --warmup 5 --serial --batch 1
+for f in $out/${tag}_bench_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
 try:
     d=json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
