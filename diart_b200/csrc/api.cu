@@ -521,10 +521,11 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
   for (int L = 0; L < 4; L++) {
     if (tc) {
       const int cin = L == 0 ? 64 : 256;
+      static const bool lstm_simt = getenv("DG_LSTM_SIMT") && getenv("DG_LSTM_SIMT")[0] == '1';
       if (L == 0)
         rc = launch_split_ex(w.work.out, M, 64, 64, 64, w.work.out_pool, g.S2, w.work.sc2.as<float>(),
                              w.work.sh2.as<float>(), w.xh.p, w.xl.p, st);
-      else
+      else if (lstm_simt)
         rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, w.xh.p, w.xl.p, st);
       if (rc) return rc;
       TcGemm t{};
@@ -533,11 +534,12 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
       t.out_f32 = w.gx.as<float>(); t.ldc = 1024; t.epi = 0; t.tag = "lstm_inproj";
       if ((rc = launch_gemm_tc(t, st))) return rc;
       float* hout = hbuf[L & 1];
-      static const bool lstm_simt = getenv("DG_LSTM_SIMT") && getenv("DG_LSTM_SIMT")[0] == '1';
+      // the tcgen05 recurrence writes h_t straight into the operand planes of the next GEMM (the in-projection that
+      // read them has completed in stream order); the SIMT recurrence (DG_LSTM_SIMT=1) goes through float32 + split
       if (lstm_simt)
         rc = launch_lstm_layer(w.gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st);
       else
-        rc = launch_lstm_layer_tc(w.gx.as<float>(), h->whh_hi[L].p, h->whh_lo[L].p, B, g.T2, g.S2, hout, st);
+        rc = launch_lstm_layer_tc(w.gx.as<float>(), h->whh_hi[L].p, h->whh_lo[L].p, B, g.T2, g.S2, nullptr, w.xh.p, w.xl.p, st);
       if (rc) return rc;
       hin = hout;
       continue;
@@ -560,7 +562,8 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
   if (tc) {
     // Linear(256,128) -> leaky -> Linear(128,128) -> leaky on the tcgen05 GEMM (identity "BatchNorm")
     if (w.y1h.ensure(rows * 128 * 2) || w.y1l.ensure(rows * 128 * 2)) return DG_ECUDA;
-    if ((rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, w.xh.p, w.xl.p, st))) return rc;
+    static const bool lstm_simt2 = getenv("DG_LSTM_SIMT") && getenv("DG_LSTM_SIMT")[0] == '1';
+    if (lstm_simt2 && (rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, w.xh.p, w.xl.p, st))) return rc;
     TcGemm t{};
     t.A_hi = w.xh.p; t.A_lo = w.xl.p; t.lda = 256; t.Cin = 256; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
     t.W_hi = h->l1_hi.p; t.W_lo = h->l1_lo.p; t.Npad = 128; t.N = 128; t.bias = h->l1b.as<float>();

@@ -161,8 +161,9 @@ void lstm_pack_whh(const float* whh_fwd /*[512][128]*/, const float* whh_bwd, fl
 // lstm_tc.cu -- recurrence on tcgen05 (W_hh hi plane in shared memory, lo plane in tensor memory)
 size_t lstm_tc_plane_elems();
 void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16);
+// `hout` (float32 [B*stride][256]) and/or the hi/lo planes `out_hi`, `out_lo` ([B*stride][256] 16-bit) receive h_t
 int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, int B, int T, int stride, float* hout,
-                         cudaStream_t st);
+                         void* out_hi, void* out_lo, cudaStream_t st);
 // heads.cu
 int launch_seg_final(const float* y /*[B*stride,128]*/, const float* wc /*[K][128]*/, const float* bc, int B, int T,
                      int stride, int K, float* seg /*[B,T,K]*/, cudaStream_t st);

@@ -46,6 +46,7 @@ struct TcArgs {
   __nv_bfloat16* out_lo;
   int ldc;
   int f16;              // operand planes are fp16 (1) or bf16 (0)
+  int vec8;             // output rows are 32-byte aligned: 256-bit stores
 };
 
 enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2 };
@@ -215,14 +216,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             }
             uint4* ph = reinterpret_cast<uint4*>(a.out_hi + m * a.ldc + n0 + c);
             uint4* pl = reinterpret_cast<uint4*>(a.out_lo + m * a.ldc + n0 + c);
+            if (a.vec8) {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-              ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-              pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              for (int i = 0; i < 2; i++) {
+                st_global_v8(ph + 2 * i, hi[8 * i], hi[8 * i + 1], hi[8 * i + 2], hi[8 * i + 3], hi[8 * i + 4], hi[8 * i + 5],
+                             hi[8 * i + 6], hi[8 * i + 7]);
+                st_global_v8(pl + 2 * i, lo[8 * i], lo[8 * i + 1], lo[8 * i + 2], lo[8 * i + 3], lo[8 * i + 4], lo[8 * i + 5],
+                             lo[8 * i + 6], lo[8 * i + 7]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
             }
           } else {
             float* po = a.out_f32 + m * a.ldc + n0 + c;
-            if (n0 + c + 32 <= a.N) {
+            if (n0 + c + 32 <= a.N && a.vec8) {
+#pragma unroll
+              for (int i = 0; i < 4; i++)
+                st_global_v8(po + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]),
+                             __float_as_uint(v[8 * i + 3]), __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]),
+                             __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
+            } else if (n0 + c + 32 <= a.N) {
 #pragma unroll
               for (int i = 0; i < 8; i++)
                 reinterpret_cast<float4*>(po)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -289,6 +306,12 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
   a.out_f32 = g.out_f32; a.out_hi = reinterpret_cast<__nv_bfloat16*>(g.out_hi);
   a.out_lo = reinterpret_cast<__nv_bfloat16*>(g.out_lo); a.ldc = g.ldc;
   a.f16 = split_f16();
+  {
+    static const bool no_v8 = getenv("DG_NO_V8") && getenv("DG_NO_V8")[0] == '1';     // A/B switch
+    const bool planes = EPI == TC_LEAKY_BN_SPLIT;
+    const uintptr_t base = planes ? ((uintptr_t)g.out_hi | (uintptr_t)g.out_lo) : (uintptr_t)g.out_f32;
+    a.vec8 = !no_v8 && base % 32 == 0 && (g.ldc * (planes ? 2 : 4)) % 32 == 0;
+  }
   static bool attr_done = false;
   if (!attr_done) {
     DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));

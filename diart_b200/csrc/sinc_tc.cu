@@ -178,9 +178,12 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
             v[i] = fmaxf(fmaxf(fabsf(fmaf(gamma, __uint_as_float(r0[i]), c0)), fabsf(fmaf(gamma, __uint_as_float(r1[i]), c0))),
                          fabsf(fmaf(gamma, __uint_as_float(r2[i]), c0)));
           }
+          // rows are 320 B and the buffer is 256-byte aligned: two full 32-byte sectors per lane
 #pragma unroll
-          for (int i = 0; i < 4; i++)
-            reinterpret_cast<float4*>(o + c)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 2; i++)
+            st_global_v8(o + c + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]),
+                         __float_as_uint(v[8 * i + 3]), __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]),
+                         __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
         }
       }
       tc_fence_before();

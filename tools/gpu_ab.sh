@@ -5,17 +5,12 @@ tag=${1:-ab}
 out=gpurun_out
 cd "$(dirname "$0")/.."
 mkdir -p $out
-nets() { timeout 600 python -m pytest tests/test_gpu_nets.py -x -q -m gpu -s 2>&1 | grep -i "err\|passed\|failed" | tail -6; }
-echo "== nets default" | tee $out/${tag}_tests.log; nets | tee -a $out/${tag}_tests.log
-if grep -q failed $out/${tag}_tests.log; then
-  echo "== nets DG_LSTM_SWAP=1" | tee -a $out/${tag}_tests.log; DG_LSTM_SWAP=1 nets | tee -a $out/${tag}_tests.log
-fi
-echo "== nets DG_LSTM_KMAJOR=1" | tee -a $out/${tag}_tests.log; DG_LSTM_KMAJOR=1 nets | tee -a $out/${tag}_tests.log
+timeout 900 python -m pytest tests/test_gpu_gemm_tc.py tests/test_gpu_nets.py tests/test_gpu_pipeline.py tests/test_gpu_shapes.py -q -m gpu -s 2>&1 | grep -i "err\|passed\|failed\|shape (" | tail -40 | tee $out/${tag}_tests.log
 b() { name=$1; shift; timeout 240 python bench.py --no-cpu-baseline "$@" > $out/${tag}_bench_$name.json 2>> $out/${tag}_bench.err; }
 b default --steps 10 --warmup 3
-DG_LSTM_KMAJOR=1 b kmajor --steps 10 --warmup 3
+DG_NO_V8=1 b nov8 --steps 10 --warmup 3
 b serial --steps 20 --warmup 3 --serial
-DG_LSTM_KMAJOR=1 b serial_kmajor --steps 20 --warmup 3 --serial
+DG_NO_V8=1 b serial_nov8 --steps 20 --warmup 3 --serial
 b b1 --steps 30 --warmup 5 --serial --batch 1
 for f in $out/${tag}_bench_*.json; do echo $f; python - "$f" <<'PY'
 import json,sys
