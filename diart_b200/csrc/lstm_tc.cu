@@ -23,8 +23,11 @@
 //
 // 288 threads: warps 0-7 cell update (TMEM lane quadrant = warp % 4, batch columns 8*(warp/4) ..), warp 8 loads W_lo
 // of gate o by TMA once and issues the 96 tcgen05.mma of every step.
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <vector>
 
 #include "dg_common.cuh"
 #include "tc_ptx.cuh"
@@ -88,8 +91,9 @@ struct L3Cell {
 
 // the 293 dependent cell updates of one thread; FULL = all 8 batch rows of this warp are valid (no branches: the
 // eight independent dependency chains overlap)
-template <bool F16, bool FULL>
-__device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done, uint64_t* h_ready, int lane) {
+template <bool F16, bool FULL, bool TIMING>
+__device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done, uint64_t* h_ready, int lane,
+                                             unsigned* dbg) {
   constexpr int f16 = F16 ? 1 : 0;
   const float L2E = 1.4426950408889634f;
   float c[8];
@@ -108,12 +112,33 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
         for (int g = 0; g < 4; g++) xg[g][n] = 0.f;
       }
     }
-    mbar_wait(mma_done, step & 1);
+    mbar_wait(&mma_done[0], step & 1);
     tc_fence_after();
+    if (TIMING && dbg) dbg[step * 8 + 2] = (unsigned)clock();
     uint32_t ri[8], rf[8], rg[8], ro[8];
     tmem_ld8(s.tlane + 0 * LT_NB, ri);
     tmem_ld8(s.tlane + 1 * LT_NB, rf);
     tmem_ld8(s.tlane + 2 * LT_NB, rg);
+    tmem_ld_wait();
+    if (TIMING && dbg) dbg[step * 8 + 3] = (unsigned)clock();
+    float num[8], den[8];     // tanh(c') = num / den
+#pragma unroll
+    for (int n = 0; n < 8; n++) {
+      if (FULL || n < s.rows) {
+        // e^-i, e^-f, e^2g (exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127)
+        const float ei = ex2_approx(fminf((__uint_as_float(ri[n]) + xg[0][n]) * -L2E, 40.f));
+        const float ef = ex2_approx(fminf((__uint_as_float(rf[n]) + xg[1][n]) * -L2E, 40.f));
+        const float eg = ex2_approx(fminf((__uint_as_float(rg[n]) + xg[2][n]) * (2.f * L2E), 40.f));
+        // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(1 + eg))  over one common denominator
+        const float df = 1.f + ef, p = (1.f + ei) * (1.f + eg);
+        c[n] = fmaf(c[n], p, (eg - 1.f) * df) * rcp_approx(p * df);
+        const float ec = ex2_approx(fminf(c[n] * (2.f * L2E), 40.f));
+        num[n] = ec - 1.f;
+        den[n] = ec + 1.f;
+      }
+    }
+    mbar_wait(&mma_done[1], step & 1);
+    tc_fence_after();
     tmem_ld8(s.tlane + 3 * LT_NB, ro);
     tmem_ld_wait();
     float h[8];
@@ -121,17 +146,9 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
 #pragma unroll
     for (int n = 0; n < 8; n++) {
       if (FULL || n < s.rows) {
-        // e^-i, e^-f, e^2g, e^-o (exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127)
-        const float ei = ex2_approx(fminf((__uint_as_float(ri[n]) + xg[0][n]) * -L2E, 40.f));
-        const float ef = ex2_approx(fminf((__uint_as_float(rf[n]) + xg[1][n]) * -L2E, 40.f));
-        const float eg = ex2_approx(fminf((__uint_as_float(rg[n]) + xg[2][n]) * (2.f * L2E), 40.f));
+        // h = tanh(c') / (1 + e^-o)
         const float eo = ex2_approx(fminf((__uint_as_float(ro[n]) + xg[3][n]) * -L2E, 40.f));
-        // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(1 + eg))  over one common denominator
-        const float df = 1.f + ef, p = (1.f + ei) * (1.f + eg);
-        c[n] = fmaf(c[n], p, (eg - 1.f) * df) * rcp_approx(p * df);
-        // h = tanh(c') / (1 + eo)
-        const float ec = ex2_approx(fminf(c[n] * (2.f * L2E), 40.f));
-        h[n] = (ec - 1.f) * rcp_approx((1.f + eo) * (ec + 1.f));
+        h[n] = num[n] * rcp_approx((1.f + eo) * den[n]);
         split_h16(h[n], f16, hh[n], hl[n]);
       } else {
         h[n] = 0.f;
@@ -139,10 +156,12 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
       }
     }
     const uint32_t dst = s.h_addr + nxt * (LT_H_BYTES / 2);
+    if (TIMING && dbg) dbg[step * 8 + 4] = (unsigned)clock() + (__float_as_uint(h[0]) & 0u);   // (keeps the math above the read)
     st_shared_v4(dst, pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]), pack_u16x2(hh[4], hh[5]), pack_u16x2(hh[6], hh[7]));
     st_shared_v4(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]), pack_u16x2(hl[2], hl[3]), pack_u16x2(hl[4], hl[5]),
                  pack_u16x2(hl[6], hl[7]));
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    if (TIMING && dbg) dbg[step * 8 + 5] = (unsigned)clock();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&h_ready[nxt]);
@@ -166,21 +185,21 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
   }
 }
 
-template <bool F16>
+template <bool F16, bool TIMING>
 __global__ void __launch_bounds__(L3_THREADS, 1)
 lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __restrict__ w_hi,
                 const uint16_t* __restrict__ w_lo /*both [2][512][128]*/, const float* __restrict__ gx, int B, int T,
                 int stride, int groups_per_dir, float* __restrict__ hout, uint16_t* __restrict__ out_hi,
-                uint16_t* __restrict__ out_lo) {
+                uint16_t* __restrict__ out_lo, unsigned* __restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                         // [k-block][128 x 128 B]   (W_lo, gate o)
   unsigned char* hsm = smem + L3_WS_BYTES;           // [buffer][plane][4 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L3_WS_BYTES + LT_H_BYTES);
   uint64_t* w_full = bars;
-  uint64_t* mma_done = bars + 1;
-  uint64_t* h_ready = bars + 2;                      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* mma_done = bars + 1;                     // [2]: gates i, f, g complete / gate o complete
+  uint64_t* h_ready = bars + 3;                      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int dir = blockIdx.x / groups_per_dir;
@@ -188,7 +207,8 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
-    mbar_init(mma_done, 1);
+    mbar_init(&mma_done[0], 1);
+    mbar_init(&mma_done[1], 1);
     mbar_init(&h_ready[0], 8);
     mbar_init(&h_ready[1], 8);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -253,24 +273,29 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
           mbar_wait(&h_ready[buf], ((step - 1) >> 1) & 1);
           tc_fence_after();
         }
+        if (TIMING && blockIdx.x == 0) dbg[step * 8 + 0] = (unsigned)clock();
         const uint64_t b0d = buf ? bb1 : bb0;
+        // gate-major order with two completion points: the cell update starts on i, f, g (72 MMAs) while the 24 MMAs
+        // of gate o -- the ones that read W_lo from shared memory -- are still in the pipe
 #pragma unroll
-        for (int ks = 0; ks < 8; ks++) {
-          constexpr int kTile = 16384 >> 4;
-          const int kb = ks >> 2, kk = ks & 3;
-          const uint64_t b_hi = b0d + (uint64_t)(ks * (512 >> 4));
-          const uint64_t b_lo = b_hi + (uint64_t)(L3_PLANE >> 4);
+        for (int g = 0; g < 4; g++) {
+          const uint32_t d = tmem_base + L3_COL_D + g * LT_NB;
 #pragma unroll
-          for (int g = 0; g < 4; g++) {
-            const uint32_t d = tmem_base + L3_COL_D + g * LT_NB;
+          for (int ks = 0; ks < 8; ks++) {
+            constexpr int kTile = 16384 >> 4;
+            const int kb = ks >> 2, kk = ks & 3;
+            const uint64_t b_hi = b0d + (uint64_t)(ks * (512 >> 4));
+            const uint64_t b_lo = b_hi + (uint64_t)(L3_PLANE >> 4);
             const uint32_t a_hi = tmem_base + L3_COL_WHI + g * 64 + ks * 8;
             umma_bf16_ts(d, a_hi, b_lo, idesc, ks != 0);                                     // W_hi . h_lo
             if (g < 3) umma_bf16_ts(d, tmem_base + L3_COL_WLO + g * 64 + ks * 8, b_hi, idesc, 1);   // W_lo . h_hi
             else umma_bf16(d, a_s + (uint64_t)(kb * kTile + kk * 2), b_hi, idesc, 1);
             umma_bf16_ts(d, a_hi, b_hi, idesc, 1);                                           // W_hi . h_hi
           }
+          if (g == 2) umma_commit(&mma_done[0]);
         }
-        umma_commit(mma_done);
+        if (TIMING && blockIdx.x == 0) dbg[step * 8 + 1] = (unsigned)clock();
+        umma_commit(&mma_done[1]);
       }
     }
     __syncwarp();
@@ -292,8 +317,9 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     s.dgx = dir == 0 ? 1024 : -1024;
     s.dh = dir == 0 ? 256 : -256;
     s.h_addr = smem_u32(hsm) + (u >> 3) * 256 + ch * 128 + (u & 7) * 16;
-    if (s.rows == 8) l3_cell_loop<F16, true>(s, T, mma_done, h_ready, lane);
-    else l3_cell_loop<F16, false>(s, T, mma_done, h_ready, lane);
+    unsigned* my_dbg = (TIMING && blockIdx.x == 0 && threadIdx.x == 0) ? dbg : nullptr;
+    if (s.rows == 8) l3_cell_loop<F16, true, TIMING>(s, T, mma_done, h_ready, lane, my_dbg);
+    else l3_cell_loop<F16, false, TIMING>(s, T, mma_done, h_ready, lane, my_dbg);
   }
   tc_fence_before();
   __syncthreads();
@@ -332,9 +358,12 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     return -2;
   }
   static bool attr_done = false;
+  static bool timing = false;
   if (!attr_done) {
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    timing = getenv("DG_LSTM_TIMING") && getenv("DG_LSTM_TIMING")[0] == '1';
     attr_done = true;
   }
   if (!hout && !out_hi) {
@@ -346,8 +375,41 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
   const uint16_t* pl = reinterpret_cast<const uint16_t*>(whh_lo);
   uint16_t* oh = reinterpret_cast<uint16_t*>(out_hi);
   uint16_t* ol = reinterpret_cast<uint16_t*>(out_lo);
-  if (split_f16()) lstm_tc3_kernel<true><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol);
-  else lstm_tc3_kernel<false><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol);
+  if (timing && split_f16()) {
+    // diagnostic (DG_LSTM_TIMING=1): SM-clock stamps of CTA 0's issuing lane and first cell-update thread, per step
+    static int reported = 0;
+    unsigned* dbg = nullptr;
+    DG_CUDA(cudaMalloc(&dbg, (size_t)T * 8 * sizeof(unsigned)));
+    DG_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(unsigned), st));
+    lstm_tc3_kernel<true, true><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, dbg);
+    DG_CUDA(cudaStreamSynchronize(st));
+    if (reported++ < 6) {
+      std::vector<unsigned> hbuf((size_t)T * 8);
+      DG_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
+      double acc[6] = {0, 0, 0, 0, 0, 0};
+      int n = 0;
+      for (int s2 = 20; s2 + 1 < T; s2++, n++) {
+        const unsigned* a = &hbuf[(size_t)s2 * 8];
+        const unsigned* nx = &hbuf[(size_t)(s2 + 1) * 8];
+        acc[0] += (double)(unsigned)(a[1] - a[0]);     // issue of the 96 MMAs
+        acc[1] += (double)(unsigned)(a[2] - a[1]);     // last issue -> cell threads see mma_done
+        acc[2] += (double)(unsigned)(a[3] - a[2]);     // tcgen05.ld of the accumulators
+        acc[3] += (double)(unsigned)(a[4] - a[3]);     // cell math
+        acc[4] += (double)(unsigned)(a[5] - a[4]);     // shared stores + fence.proxy.async
+        acc[5] += (double)(unsigned)(nx[0] - a[5]);    // arrive -> issuing lane resumes
+      }
+      fprintf(stderr, "lstm_rec timing (B=%d, cycles per step, CTA 0): issue %.0f | mma->cells %.0f | tmem ld %.0f | math %.0f | "
+                      "store+fence %.0f | hand-off %.0f | total %.0f\n",
+              B, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n,
+              (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / n);
+    }
+    cudaFree(dbg);
+    return 0;
+  }
+  if (split_f16())
+    lstm_tc3_kernel<true, false><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
+  else
+    lstm_tc3_kernel<false, false><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
   DG_LAUNCHED();
   return 0;
 }
