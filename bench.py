@@ -323,7 +323,7 @@ def run_ours(args):
                     "ms_per_launch": per_launch_ms}
         if dom == "lstm_rec":   # neither roofline binds a recurrence: report the dependent-step latency as well
             roofline["note"] = ("latency-bound: 293 dependent steps per launch (4 launches = 1172 per batch); "
-                                "tcgen05 bf16x3, 32 CTAs; compare us_per_dependent_step, not frac")
+                                "tcgen05 (fp16 hi/lo planes, 3 products), 32 CTAs; compare us_per_dependent_step, not frac")
             roofline["us_per_dependent_step"] = per_launch_ms * 1e3 / 293
         # the largest throughput-bound kernel next to it, for the tensor roofline proper
         gemms = {k: v for k, v in kernels.items() if k.startswith("tdnn")}
@@ -331,7 +331,7 @@ def run_ours(args):
             gk = max(gemms, key=lambda k: gemms[k]["ms"])
             g_ms = gemms[gk]["ms"] / gemms[gk]["count"]
             g_tf = FLOPS_PER_CHUNK[gk] * B / (g_ms * 1e-3) / 1e12
-            roofline["largest_gemm"] = {"kernel": gk, "achieved_algorithmic": g_tf, "executed_bf16x3": 3 * g_tf,
+            roofline["largest_gemm"] = {"kernel": gk, "achieved_algorithmic": g_tf, "executed_x3": 3 * g_tf,
                                         "frac_of_peak_executed": 3 * g_tf / pk["tf"], "ms_per_launch": g_ms}
     else:
         achieved = BYTES_PER_CHUNK * B / (per_launch_ms * 1e-3) / 1e9

@@ -1,7 +1,8 @@
 """Parity of the CUDA networks (through the C ABI) against the oracle restatement (oracle/nets.py).
 
-Tolerances (float32 everywhere, different summation order only): segmentation scores 5e-4 absolute (the float32 oracle itself is 0.84e-4 from a float64 evaluation of this synthetic net),
-unit-norm embeddings 5e-4 absolute (the synthetic embedding has a ~6x cancellation between its raw
+Tolerances (float32 everywhere, different summation order only): segmentation scores 1e-4 absolute (measured
+<= 3e-5; the float32 oracle itself is 0.84e-4 from a float64 evaluation of this synthetic net), unit-norm embeddings 1e-4
+absolute (measured <= 2e-5), raw embeddings 3e-4 relative (the synthetic embedding has a ~6x cancellation between its raw
 and centred components, see oracle/calibrate.py)."""
 import numpy as np
 import pytest
@@ -88,12 +89,12 @@ def test_embedding_reference_call_convention(cuda_nets, oracle_nets, audio_batch
     with torch.no_grad():
         ref = emb_o(rep, w_rows).reshape(B, K, -1)
     rel = ((out.cpu() - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item()
-    assert rel < 5e-4   # raw (un-normalised) embeddings: ~6x cancellation in the synthetic net
+    assert rel < 3e-4   # raw (un-normalised) embeddings: ~6x cancellation in the synthetic net
     # no weights: plain statistics pooling (mean, unbiased std)
     plain = emb_c(x[:, None, :].to(cuda_device), None).cpu()
     with torch.no_grad():
         ref_plain = emb_o(x[:, None, :], None)
-    assert ((plain - ref_plain).norm(dim=-1) / ref_plain.norm(dim=-1)).max().item() < 5e-4
+    assert ((plain - ref_plain).norm(dim=-1) / ref_plain.norm(dim=-1)).max().item() < 3e-4
 
 
 def test_embedding_pool_mode_21(cuda_device, oracle_nets, audio_batch):
@@ -108,7 +109,7 @@ def test_embedding_pool_mode_21(cuda_device, oracle_nets, audio_batch):
         w = _osp(seg_o(x[:, None, :]))
         ref = emb_o.forward_dedup(x[:, None, :], w)
     out = emb_c.forward_fused(x.to(cuda_device), w.to(cuda_device)).cpu()
-    assert ((out - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item() < 5e-4
+    assert ((out - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item() < 3e-4
 
 
 def test_bad_shapes_raise(cuda_nets, cuda_device):
