@@ -391,12 +391,12 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
       for (int s2 = 20; s2 + 1 < T; s2++, n++) {
         const unsigned* a = &hbuf[(size_t)s2 * 8];
         const unsigned* nx = &hbuf[(size_t)(s2 + 1) * 8];
-        acc[0] += (double)(unsigned)(a[1] - a[0]);     // issue of the 96 MMAs
-        acc[1] += (double)(unsigned)(a[2] - a[1]);     // last issue -> cell threads see mma_done
-        acc[2] += (double)(unsigned)(a[3] - a[2]);     // tcgen05.ld of the accumulators
-        acc[3] += (double)(unsigned)(a[4] - a[3]);     // cell math
-        acc[4] += (double)(unsigned)(a[5] - a[4]);     // shared stores + fence.proxy.async
-        acc[5] += (double)(unsigned)(nx[0] - a[5]);    // arrive -> issuing lane resumes
+        acc[0] += (double)(int)(a[1] - a[0]);     // issue of the 96 MMAs
+        acc[1] += (double)(int)(a[2] - a[1]);          // last issue -> cell threads see the FIRST completion point (negative: overlap)
+        acc[2] += (double)(int)(a[3] - a[2]);     // tcgen05.ld of the accumulators
+        acc[3] += (double)(int)(a[4] - a[3]);          // cell math incl. the wait for gate o
+        acc[4] += (double)(int)(a[5] - a[4]);     // shared stores + fence.proxy.async
+        acc[5] += (double)(int)(nx[0] - a[5]);    // arrive -> issuing lane resumes
       }
       fprintf(stderr, "lstm_rec timing (B=%d, cycles per step, CTA 0): issue %.0f | mma->cells %.0f | tmem ld %.0f | math %.0f | "
                       "store+fence %.0f | hand-off %.0f | total %.0f\n",
