@@ -1,4 +1,4 @@
-// Shifted-window GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), "bf16x3" precision.
+// Shifted-window GEMM on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), hi/lo split precision.
 //
 //     C[m, n] = epi( sum_{j<KW} sum_{c<Cin} A[m + j*dil, c] * W[n, j*Cin + c] + bias[n] )
 //
@@ -6,9 +6,10 @@
 // LeakyReLU -> BatchNorm1d(eval)) and the LSTM input projections of PyanNet (SURVEY.md Appendix
 // A.3/A.4; reached from the reference through src/diart/models.py:131-133) -- must stay at float32-level
 // accuracy because their outputs feed hard thresholds (tau_active, rho_update, delta_new).  Each float32
-// operand x is therefore carried as two bf16 planes, hi = bf16(x) and lo = bf16(x - hi) (16 significand
-// bits), and every k-step issues three tcgen05.mma (hi*hi + lo*hi + hi*lo) into the same float32 TMEM
-// accumulator.  Measured against float32 this costs < 1e-5 relative error per layer (oracle test).
+// operand x is therefore carried as two 16-bit planes, hi = rn16(x) and lo = rn16(x - hi) -- fp16 by default
+// (22 significand bits for the pair), bf16 with DG_SPLIT_BF16=1 (16 bits) -- and every k-step issues three
+// tcgen05.mma (hi*hi + lo*hi + hi*lo) into the same float32 TMEM accumulator.  Measured against the float32
+// SIMT GEMM: < 1e-5 relative (tests/test_gpu_gemm_tc.py).
 //
 // Because activations are stored time-major ([item][row][channel]) a Conv1d tap is just a TMA box whose
 // row coordinate is shifted by j*dil: no im2col is ever materialised.
@@ -388,7 +389,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
 
 int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld_out, int pool, int item_rows,
                     const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st) {
-  ProfScope _ps("split_bf16", st);
+  ProfScope _ps("split16", st);
   if (C % 4 || ld_in % 4 || ld_out % 4) {
     set_error("split: channel counts must be multiples of 4");
     return -1;
