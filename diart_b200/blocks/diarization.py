@@ -149,7 +149,7 @@ class SpeakerDiarization(base.Pipeline):
         return self._fused, F, K, D
 
     def submit(self, batch: torch.Tensor):
-        """Pipelined step (depth 2): enqueue a (B,S) device batch and return; clustering of this step overlaps the
+        """Pipelined step (at most three outstanding): enqueue a (B,S) device batch and return; clustering of this step overlaps the
         networks of the next one.  ``batch`` must stay alive until the matching :meth:`collect`."""
         device = self.segmentation.device
         h, F, K, D = self._ensure_fused(batch.shape[1])

@@ -1166,10 +1166,14 @@ struct dg_pipeline {
   SincPrep prep[2];
   cudaEvent_t e_prep[2] = {nullptr, nullptr};
   cudaEvent_t e_start = nullptr, e_osp = nullptr, e_emb = nullptr, e_done = nullptr;
-  // depth-2 pipelining (dg_pipeline_submit* / collect*)
-  DevBuf slot_wav[2], slot_seg[2], slot_emb[2], slot_map[2];
-  cudaEvent_t e_h2d[2] = {nullptr, nullptr}, e_slot_done[2] = {nullptr, nullptr};
-  int slot_B[2] = {0, 0}, slot_S[2] = {0, 0}, head = 0, outstanding = 0;
+  // pipelining (dg_pipeline_submit* / collect*): up to DG_MAX_INFLIGHT steps outstanding.  Step n uses result / input
+  // slot n % 3 and scratch lane n & 1: two steps compute concurrently (lanes), the third slot lets the host upload the
+  // waveforms of step n+2 while steps n and n+1 are on the device
+  DevBuf slot_wav[3], slot_seg[3], slot_emb[3], slot_map[3];
+  cudaEvent_t e_h2d[3] = {nullptr, nullptr, nullptr}, e_slot_done[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t e_lane_done[2] = {nullptr, nullptr};
+  int slot_B[3] = {0, 0, 0}, slot_S[3] = {0, 0, 0}, outstanding = 0;
+  long long next_step = 0;
 };
 
 extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
@@ -1206,10 +1210,11 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
   DG_CUDA(cudaEventCreateWithFlags(&h->e_prep[1], cudaEventDisableTiming));
   DG_CUDA(cudaStreamCreateWithFlags(&h->s_h2d, cudaStreamNonBlocking));
   DG_CUDA(cudaStreamCreateWithFlags(&h->s_d2h, cudaStreamNonBlocking));
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < 3; i++) {
     DG_CUDA(cudaEventCreateWithFlags(&h->e_h2d[i], cudaEventDisableTiming));
     DG_CUDA(cudaEventCreateWithFlags(&h->e_slot_done[i], cudaEventDisableTiming));
   }
+  for (int i = 0; i < 2; i++) DG_CUDA(cudaEventCreateWithFlags(&h->e_lane_done[i], cudaEventDisableTiming));
   DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));   // so that the first step's wait on it is well defined
   *out = h.release();
   return DG_OK;
@@ -1302,7 +1307,7 @@ extern "C" int dg_pipeline_step(dg_pipeline* h, const float* wav, int B, int S, 
   return DG_OK;
 }
 
-// ---- pipelined (depth 2) variants: the sequential clustering of step i and the host copies overlap the
+// ---- pipelined variants (up to three steps outstanding, two computing): the sequential clustering of step i and the host copies overlap the
 //      networks of step i+1.  Per stream the chunk order is preserved: clustering runs on one stream.
 static int pipeline_slot_prepare(dg_pipeline* h, int slot, int B, int S, int F, int K, bool host_in) {
   const int D = h->emb->D;
@@ -1313,23 +1318,31 @@ static int pipeline_slot_prepare(dg_pipeline* h, int slot, int B, int S, int F, 
   return DG_OK;
 }
 
+static const int DG_MAX_INFLIGHT = 3;
+
 static int pipeline_submit_common(dg_pipeline* h, const float* wav_dev, int B, int S, int F, int K, int slot,
                                   cudaEvent_t start) {
   int rc;
-  // the slot's previous occupant (two submits ago) must be fully clustered before its buffers are rewritten
-  DG_CUDA(cudaStreamWaitEvent(slot ? h->s_seg2 : h->s_seg, h->e_slot_done[slot], 0));
+  const int lane = (int)(h->next_step & 1);
+  cudaStream_t s_lane = lane ? h->s_seg2 : h->s_seg;
+  // the slot's previous occupant (three submits ago) and the lane's previous user (two submits ago) must be fully
+  // clustered before their buffers are rewritten
+  DG_CUDA(cudaStreamWaitEvent(s_lane, h->e_slot_done[slot], 0));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_slot_done[slot], 0));
+  DG_CUDA(cudaStreamWaitEvent(s_lane, h->e_lane_done[lane], 0));
+  DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_lane_done[lane], 0));
   if ((rc = pipeline_nets(h, wav_dev, B, S, F, K, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), start,
-                          slot)))
+                          lane)))
     return rc;
   DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_emb, 0));
   if ((rc = dg_cluster_step(h->clu, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), B, F, K,
                             h->slot_map[slot].as<int32_t>(), nullptr, h->s_clu)))
     return rc;
   DG_CUDA(cudaEventRecord(h->e_slot_done[slot], h->s_clu));
+  DG_CUDA(cudaEventRecord(h->e_lane_done[lane], h->s_clu));
   h->slot_B[slot] = B;
   h->slot_S[slot] = S;
-  h->head = (h->head + 1) & 1;
+  h->next_step++;
   h->outstanding++;
   return DG_OK;
 }
@@ -1339,14 +1352,14 @@ extern "C" int dg_pipeline_submit(dg_pipeline* h, const float* wav_dev, int B, i
     set_error("dg_pipeline_submit: bad arguments");
     return DG_EINVAL;
   }
-  if (h->outstanding >= 2) {
-    set_error("dg_pipeline_submit: two steps are already outstanding; collect one first");
+  if (h->outstanding >= DG_MAX_INFLIGHT) {
+    set_error("dg_pipeline_submit: three steps are already outstanding; collect one first");
     return DG_EINVAL;
   }
   int rc, F = 0, K = 0;
   if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
   DG_CUDA(cudaSetDevice(h->seg->device));
-  const int slot = h->head;
+  const int slot = (int)(h->next_step % 3);
   if ((rc = pipeline_slot_prepare(h, slot, B, S, F, K, false))) return rc;
   DG_CUDA(cudaEventRecord(h->e_start, (cudaStream_t)stream));
   return pipeline_submit_common(h, wav_dev, B, S, F, K, slot, h->e_start);
@@ -1358,7 +1371,7 @@ extern "C" int dg_pipeline_collect(dg_pipeline* h, const float** seg_dev, const 
     set_error("dg_pipeline_collect: nothing outstanding");
     return DG_EINVAL;
   }
-  const int slot = (h->head - h->outstanding) & 1;
+  const int slot = (int)((h->next_step - h->outstanding) % 3);
   DG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->e_slot_done[slot], 0));
   if (seg_dev) *seg_dev = h->slot_seg[slot].as<float>();
   if (emb_dev) *emb_dev = h->slot_emb[slot].as<float>();
@@ -1373,7 +1386,7 @@ extern "C" int dg_pipeline_collect_copy(dg_pipeline* h, float* seg_dev, float* e
     set_error("dg_pipeline_collect_copy: nothing outstanding");
     return DG_EINVAL;
   }
-  const int slot = (h->head - h->outstanding) & 1;
+  const int slot = (int)((h->next_step - h->outstanding) % 3);
   int F = 0, K = 0;
   const int B = h->slot_B[slot], D = h->emb->D;
   dg_seg_dims(h->seg, h->slot_S[slot], &F, &K);
@@ -1391,14 +1404,14 @@ extern "C" int dg_pipeline_submit_host(dg_pipeline* h, const float* wav_host, in
     set_error("dg_pipeline_submit_host: bad arguments");
     return DG_EINVAL;
   }
-  if (h->outstanding >= 2) {
-    set_error("dg_pipeline_submit_host: two steps are already outstanding; collect one first");
+  if (h->outstanding >= DG_MAX_INFLIGHT) {
+    set_error("dg_pipeline_submit_host: three steps are already outstanding; collect one first");
     return DG_EINVAL;
   }
   int rc, F = 0, K = 0;
   if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
   DG_CUDA(cudaSetDevice(h->seg->device));
-  const int slot = h->head;
+  const int slot = (int)(h->next_step % 3);
   if ((rc = pipeline_slot_prepare(h, slot, B, S, F, K, true))) return rc;
   DG_CUDA(cudaStreamWaitEvent(h->s_h2d, h->e_slot_done[slot], 0));
   DG_CUDA(cudaMemcpyAsync(h->slot_wav[slot].p, wav_host, (size_t)B * S * 4, cudaMemcpyHostToDevice, h->s_h2d));
@@ -1411,7 +1424,7 @@ extern "C" int dg_pipeline_collect_host(dg_pipeline* h, float* seg_host, float* 
     set_error("dg_pipeline_collect_host: nothing outstanding");
     return DG_EINVAL;
   }
-  const int slot = (h->head - h->outstanding) & 1;
+  const int slot = (int)((h->next_step - h->outstanding) % 3);
   int F = 0, K = 0;
   const int B = h->slot_B[slot], D = h->emb->D;
   dg_seg_dims(h->seg, h->slot_S[slot], &F, &K);
@@ -1465,8 +1478,8 @@ extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
     if (h->e_prep[1]) cudaEventDestroy(h->e_prep[1]);
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
-    for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done, h->e_h2d[0], h->e_h2d[1], h->e_slot_done[0],
-                          h->e_slot_done[1]})
+    for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done, h->e_h2d[0], h->e_h2d[1], h->e_h2d[2],
+                          h->e_slot_done[0], h->e_slot_done[1], h->e_slot_done[2], h->e_lane_done[0], h->e_lane_done[1]})
       if (e) cudaEventDestroy(e);
   }
   if (h && h->st) cudaStreamDestroy(h->st);

@@ -115,11 +115,12 @@ int dg_pipeline_step(dg_pipeline* h, const float* wav_dev /*[B,S]*/, int B, int 
  * (pinned staging owned by the handle); synchronous. */
 int dg_pipeline_step_host(dg_pipeline* h, const float* wav_host, int B, int S, float* seg_host,
                           float* emb_host, int32_t* map_host, float* permuted_host /*nullable*/);
-/* Pipelined (depth 2) variants for throughput: submit enqueues a step and returns; the sequential clustering
- * of step i and the host<->device copies overlap the networks of step i+1 (chunk order per stream is kept:
- * all clustering runs on one internal stream).  At most two steps may be outstanding; collect returns them
- * oldest first.  dg_pipeline_collect makes `stream` wait for the step and hands out device pointers that stay
- * valid until the second next submit; dg_pipeline_collect_host copies to host buffers and blocks. */
+/* Pipelined variants for throughput: submit enqueues a step and returns; the sequential clustering of step i and
+ * the host<->device copies overlap the networks of step i+1 (chunk order per stream is kept: all clustering runs on
+ * one internal stream).  At most THREE steps may be outstanding -- two compute concurrently, the third lets the
+ * waveforms of step i+2 be uploaded meanwhile -- and collect returns them oldest first.  dg_pipeline_collect makes
+ * `stream` wait for the step and hands out device pointers that stay valid until the third next submit;
+ * dg_pipeline_collect_host copies to host buffers and blocks. */
 int dg_pipeline_submit(dg_pipeline* h, const float* wav_dev /*[B,S], must stay valid until collected*/, int B, int S,
                        void* stream);
 int dg_pipeline_collect(dg_pipeline* h, const float** seg_dev, const float** emb_dev, const int32_t** map_dev,

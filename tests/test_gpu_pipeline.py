@@ -117,15 +117,19 @@ def test_pipelined_submit_collect_equals_sequential_steps(oracle_nets, stream, c
     what one-step-at-a-time dg_pipeline_step gives: chunk order per stream is preserved"""
     a = make_pipeline(oracle_nets, cuda_device)
     b = make_pipeline(oracle_nets, cuda_device)
-    batches = [torch.from_numpy(synth.windows(stream, BATCH, first=i * BATCH)).to(cuda_device) for i in range(3)]
+    batches = [torch.from_numpy(synth.windows(stream, BATCH, first=i * BATCH)).to(cuda_device) for i in range(6)]
     ref = [a.device_step(x) for x in batches]
     got = []
     b.submit(batches[0])
     b.submit(batches[1])
-    got.append(b.collect())
+    got.append(b.collect())          # two outstanding (what bench.py's device loop does)
     b.submit(batches[2])
+    b.submit(batches[3])             # three outstanding: slots 1, 2, 0 and lanes 1, 0, 1
     got.append(b.collect())
+    b.submit(batches[4])
     got.append(b.collect())
+    b.submit(batches[5])
+    got.extend(b.collect() for _ in range(3))
     torch.cuda.synchronize()
     for (s1, e1, m1), (s2, e2, m2) in zip(ref, got):
         assert torch.equal(s1, s2) and torch.equal(e1, e2) and torch.equal(m1, m2)
@@ -164,16 +168,14 @@ def test_voice_activity_detection_pipeline(oracle_nets, stream, cuda_device):
 
 
 def test_host_submit_collect_matches_step_host(oracle_nets, stream, cuda_device):
-    """C ABI with HOST buffers: dg_pipeline_submit_host / collect_host (two steps in flight) == dg_pipeline_step_host"""
-    import ctypes as C
-
+    """C ABI with HOST buffers: dg_pipeline_submit_host / collect_host (three steps outstanding) == dg_pipeline_step_host"""
     from diart_b200 import _lib
 
     lib = _lib.lib()
     a, b = make_pipeline(oracle_nets, cuda_device), make_pipeline(oracle_nets, cuda_device)
     ha, F, K, D = a._ensure_fused(80000)
     hb, _, _, _ = b._ensure_fused(80000)
-    batches = [np.ascontiguousarray(synth.windows(stream, BATCH, first=i * BATCH)) for i in range(3)]
+    batches = [np.ascontiguousarray(synth.windows(stream, BATCH, first=i * BATCH)) for i in range(5)]
 
     def bufs():
         return (np.empty((BATCH, F, K), np.float32), np.empty((BATCH, K, D), np.float32), np.empty((BATCH, K), np.int32))
@@ -184,14 +186,15 @@ def test_host_submit_collect_matches_step_host(oracle_nets, stream, cuda_device)
         _lib.check(lib.dg_pipeline_step_host(ha, x.ctypes.data, BATCH, 80000, s.ctypes.data, e.ctypes.data, m.ctypes.data, None))
         ref.append((s, e, m))
     got = []
-    _lib.check(lib.dg_pipeline_submit_host(hb, batches[0].ctypes.data, BATCH, 80000))
-    _lib.check(lib.dg_pipeline_submit_host(hb, batches[1].ctypes.data, BATCH, 80000))
-    assert lib.dg_pipeline_submit_host(hb, batches[2].ctypes.data, BATCH, 80000) == -1      # only two in flight
-    for nxt in (batches[2], None, None):
+    for x in batches[:3]:
+        _lib.check(lib.dg_pipeline_submit_host(hb, x.ctypes.data, BATCH, 80000))
+    assert lib.dg_pipeline_submit_host(hb, batches[3].ctypes.data, BATCH, 80000) == -1      # only three outstanding
+    for nxt in (batches[3], batches[4], None, None, None):
         s, e, m = bufs()
         _lib.check(lib.dg_pipeline_collect_host(hb, s.ctypes.data, e.ctypes.data, m.ctypes.data))
         got.append((s, e, m))
         if nxt is not None:
             _lib.check(lib.dg_pipeline_submit_host(hb, nxt.ctypes.data, BATCH, 80000))
+    assert lib.dg_pipeline_collect_host(hb, None, None, None) == -1                          # nothing outstanding
     for (s1, e1, m1), (s2, e2, m2) in zip(ref, got):
         assert np.array_equal(s1, s2) and np.array_equal(e1, e2) and np.array_equal(m1, m2)
