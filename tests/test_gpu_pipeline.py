@@ -117,7 +117,8 @@ def test_pipelined_submit_collect_equals_sequential_steps(oracle_nets, stream, c
     what one-step-at-a-time dg_pipeline_step gives: chunk order per stream is preserved"""
     a = make_pipeline(oracle_nets, cuda_device)
     b = make_pipeline(oracle_nets, cuda_device)
-    batches = [torch.from_numpy(synth.windows(stream, BATCH, first=i * BATCH)).to(cuda_device) for i in range(6)]
+    nb = N_CHUNKS // 6     # six consecutive batches out of the 48-chunk stream
+    batches = [torch.from_numpy(synth.windows(stream, nb, first=i * nb)).to(cuda_device) for i in range(6)]
     ref = [a.device_step(x) for x in batches]
     got = []
     b.submit(batches[0])
@@ -175,26 +176,27 @@ def test_host_submit_collect_matches_step_host(oracle_nets, stream, cuda_device)
     a, b = make_pipeline(oracle_nets, cuda_device), make_pipeline(oracle_nets, cuda_device)
     ha, F, K, D = a._ensure_fused(80000)
     hb, _, _, _ = b._ensure_fused(80000)
-    batches = [np.ascontiguousarray(synth.windows(stream, BATCH, first=i * BATCH)) for i in range(5)]
+    nb = N_CHUNKS // 6
+    batches = [np.ascontiguousarray(synth.windows(stream, nb, first=i * nb)) for i in range(5)]
 
     def bufs():
-        return (np.empty((BATCH, F, K), np.float32), np.empty((BATCH, K, D), np.float32), np.empty((BATCH, K), np.int32))
+        return (np.empty((nb, F, K), np.float32), np.empty((nb, K, D), np.float32), np.empty((nb, K), np.int32))
 
     ref = []
     for x in batches:
         s, e, m = bufs()
-        _lib.check(lib.dg_pipeline_step_host(ha, x.ctypes.data, BATCH, 80000, s.ctypes.data, e.ctypes.data, m.ctypes.data, None))
+        _lib.check(lib.dg_pipeline_step_host(ha, x.ctypes.data, nb, 80000, s.ctypes.data, e.ctypes.data, m.ctypes.data, None))
         ref.append((s, e, m))
     got = []
     for x in batches[:3]:
-        _lib.check(lib.dg_pipeline_submit_host(hb, x.ctypes.data, BATCH, 80000))
-    assert lib.dg_pipeline_submit_host(hb, batches[3].ctypes.data, BATCH, 80000) == -1      # only three outstanding
+        _lib.check(lib.dg_pipeline_submit_host(hb, x.ctypes.data, nb, 80000))
+    assert lib.dg_pipeline_submit_host(hb, batches[3].ctypes.data, nb, 80000) == -1      # only three outstanding
     for nxt in (batches[3], batches[4], None, None, None):
         s, e, m = bufs()
         _lib.check(lib.dg_pipeline_collect_host(hb, s.ctypes.data, e.ctypes.data, m.ctypes.data))
         got.append((s, e, m))
         if nxt is not None:
-            _lib.check(lib.dg_pipeline_submit_host(hb, nxt.ctypes.data, BATCH, 80000))
+            _lib.check(lib.dg_pipeline_submit_host(hb, nxt.ctypes.data, nb, 80000))
     assert lib.dg_pipeline_collect_host(hb, None, None, None) == -1                          # nothing outstanding
     for (s1, e1, m1), (s2, e2, m2) in zip(ref, got):
         assert np.array_equal(s1, s2) and np.array_equal(e1, e2) and np.array_equal(m1, m2)
