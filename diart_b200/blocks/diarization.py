@@ -145,6 +145,9 @@ class SpeakerDiarization(base.Pipeline):
             _lib.check(_lib.lib().dg_pipeline_create(seg_net.handle, emb_net.handle, self.clustering._handle(D),
                                                      float(self.config.gamma), float(self.config.beta),
                                                      int(self.config.normalize_embedding_weights), C.byref(h)))
+            # consecutive chunks of a batch are `step` seconds apart in one stream (reference operators.py:44-100): a
+            # hint for the stream form of the sinc layer; the device verifies it per batch
+            _lib.check(_lib.lib().dg_pipeline_set_hop(h, int(round(self.config.step * self.config.sample_rate))))
             self._fused = h
         return self._fused, F, K, D
 

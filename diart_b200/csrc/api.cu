@@ -127,6 +127,7 @@ struct SincWeights {
   DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: bf16 hi/lo planes [128][5*128] and [128][5*64]
   DevBuf filt_planes;                  // sinc filter bank as three bf16 planes [3][80][256] (hi, lo, lo2)
   DevBuf cf;                           // folded wav-norm affine: beta * sum_k h[f][k]
+  DevBuf hsum;                         // sum_k h[f][k] (stream form of the sinc layer)
 };
 
 // ParamSincFB.filters() in float32, as asteroid-filterbanks computes it with torch
@@ -175,6 +176,9 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
     std::vector<float> cf(80);
     sinc_tc_affine_consts(h.data(), w.wn_beta, cf.data());
     if (upload(w.cf, cf)) return DG_ECUDA;
+    std::vector<float> hs(80);
+    sinc_tc_affine_consts(h.data(), 1.f, hs.data());
+    if (upload(w.hsum, hs)) return DG_ECUDA;
   }
   auto pad_vec = [&](const std::string& name, int n, int npad, DevBuf& dst) -> int {
     const float* s = t.get(name, n);
@@ -221,14 +225,23 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
 // ones, so the fused pipeline computes them once per step
 struct SincPrep {
   DevBuf wmean, wrstd, wh, wl;
+  // stream form (DG_STREAM_SINC=1 and a hop hint): planes of the raw stream and the device flag "this batch is a run of
+  // overlapping windows"; `hop` > 0 means the stream-form launches were enqueued for this batch
+  DevBuf swh, swl, flag;
+  int hop = 0;
   int ensure(int B, const Geom& g) {
     const size_t bytes = 4 * sinc_tc_plane_elems(B, g) * 2;
     return (wmean.ensure(B * 4) || wrstd.ensure(B * 4) || wh.ensure(bytes) || wl.ensure(bytes)) ? DG_ECUDA : 0;
+  }
+  int ensure_stream(int B, const Geom& g, int hop_) {
+    const size_t bytes = 4 * sinc_stream_geom(B, g, hop_).plane * 2;
+    return (swh.ensure(bytes) || swl.ensure(bytes) || flag.ensure(16)) ? DG_ECUDA : 0;
   }
 };
 struct SincWork {
   DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
   DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: bf16 planes of the conv inputs, un-pooled conv outputs
+  DevBuf craw;                         // stream form: raw convolution of the stream [P][80]
   SincPrep own_prep;                   // statistics + waveform planes when no shared ones are supplied
   const float* out = nullptr;          // conv2 output that the next layer normalises on load ...
   int out_pool = 0;                    // ... 1: still un-pooled (rows = 3x), MaxPool1d(3) is applied on load
@@ -252,11 +265,22 @@ struct SincWork {
   }
 };
 
-static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cudaStream_t st) {
+static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cudaStream_t st, int hop = 0) {
   int rc;
   if ((rc = p.ensure(B, g))) return rc;
+  // stream form of the sinc layer: opt-in (DG_STREAM_SINC=1) and only with a hop hint from the caller; the device flag
+  // written by overlap_check decides per batch, so a wrong hint costs two empty launches, never a wrong result
+  static const bool stream_on = getenv("DG_STREAM_SINC") && getenv("DG_STREAM_SINC")[0] == '1';
+  p.hop = 0;
+  if (stream_on && hop > 0 && B >= 4 && hop % 40 == 0 && g.S % 4 == 0 && hop < g.S && ((uintptr_t)wav & 15) == 0) {
+    if ((rc = p.ensure_stream(B, g, hop))) return rc;
+    if ((rc = launch_overlap_check(wav, B, g.S, hop, p.flag.as<int>(), st))) return rc;
+    p.hop = hop;
+  }
   if ((rc = launch_wave_stats(wav, B, g.S, p.wmean.as<float>(), p.wrstd.as<float>(), st))) return rc;
-  return launch_sinc_prep(wav, p.wmean.as<float>(), p.wrstd.as<float>(), B, g, p.wh.p, p.wl.p, st);
+  if (p.hop && (rc = launch_stream_prep(wav, B, g, hop, p.swh.p, p.swl.p, p.flag.as<int>(), st))) return rc;
+  return launch_sinc_prep(wav, p.wmean.as<float>(), p.wrstd.as<float>(), B, g, p.wh.p, p.wl.p, st,
+                          p.hop ? p.flag.as<int>() : nullptr);
 }
 
 // waveform [B,S] -> k.out (pre-norm conv2 output, pooled [B*S2,64] or un-pooled [B*S1,64]) + its
@@ -278,8 +302,17 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
         if ((rc = run_sinc_prep(k.own_prep, wav, B, g, st))) return rc;
         prep = &k.own_prep;
       }
+      if (prep->hop) {   // stream form: one convolution of the unique samples + a per-window affine / |.| / pool pass
+        const SincStreamGeom sg = sinc_stream_geom(B, g, prep->hop);
+        if (k.craw.ensure(((size_t)sg.P + 16) * 80 * 4)) return DG_ECUDA;
+        if ((rc = launch_sinc0_tc_stream(w.filt_planes.p, B, g, prep->hop, prep->swh.p, prep->swl.p, k.craw.as<float>(),
+                                         prep->flag.as<int>(), st)) ||
+            (rc = launch_sinc_pool(k.craw.as<float>(), prep->wmean.as<float>(), prep->wrstd.as<float>(), w.cf.as<float>(),
+                                   w.hsum.as<float>(), w.wn_gamma, B, g, prep->hop, k.p0.as<float>(), prep->flag.as<int>(), st)))
+          return rc;
+      }
       rc = launch_sinc0_tc(w.wn_gamma, w.cf.as<float>(), w.filt_planes.p, B, g, prep->wh.p, prep->wl.p,
-                           k.p0.as<float>(), st);
+                           k.p0.as<float>(), st, prep->hop ? prep->flag.as<int>() : nullptr);
     }
     if (rc) return rc;
     if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),
@@ -1156,6 +1189,7 @@ struct dg_pipeline {
   dg_cluster* clu;
   float gamma, beta;
   int normalize_weights;
+  int hop = 0;          // samples between consecutive windows of a batch (hint, dg_pipeline_set_hop); 0 = unknown
   DevBuf osp, wav, segd, embd, mapd, permd;
   cudaStream_t st = nullptr;
   // two-stream overlap inside a step: the segmentation chain (critical path, high priority) and the
@@ -1238,7 +1272,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
   const SincPrep* shared = nullptr;
   if (!sinc_simt) {
-    if ((rc = run_sinc_prep(h->prep[lane], wav, B, g, s_seg))) return rc;
+    if ((rc = run_sinc_prep(h->prep[lane], wav, B, g, s_seg, h->hop))) return rc;
     DG_CUDA(cudaEventRecord(h->e_prep[lane], s_seg));
     DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_prep[lane], 0));
     shared = &h->prep[lane];
@@ -1273,6 +1307,15 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     return rc;
   if ((rc = emb_project(h->emb, B * K, 1, 1.f, emb, h->s_emb))) return rc;
   DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_set_hop(dg_pipeline* h, int hop_samples) {
+  if (!h || hop_samples < 0) {
+    set_error("dg_pipeline_set_hop: bad arguments");
+    return DG_EINVAL;
+  }
+  h->hop = hop_samples;
   return DG_OK;
 }
 

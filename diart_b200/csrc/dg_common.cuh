@@ -150,9 +150,24 @@ size_t sinc_tc_plane_elems(int B, const Geom& g);
 void sinc_tc_pack_filters(const float* filt, uint16_t* planes /*[3][80][256]*/, int f16);
 void sinc_tc_affine_consts(const float* filt, float beta, float* cf);
 int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int B, const Geom& g, void* planes_hi,
-                     void* planes_lo, cudaStream_t st);
+                     void* planes_lo, cudaStream_t st, const int* skip_flag = nullptr);
 int launch_sinc0_tc(float gamma, const float* cf_dev, const void* w_planes, int B, const Geom& g, const void* planes_hi,
-                    const void* planes_lo, float* p0, cudaStream_t st);
+                    const void* planes_lo, float* p0, cudaStream_t st, const int* skip_flag = nullptr);
+// stream form of the sinc layer (sinc_tc.cu): the batch is B windows of one stream, `hop` samples apart
+struct SincStreamGeom {
+  int Ls;        // unique samples (B-1)*hop + S
+  int P;         // conv positions of the stream
+  int rows;      // rows of the overlapping-row view (one "item")
+  size_t plane;  // elements per shifted copy
+};
+SincStreamGeom sinc_stream_geom(int B, const Geom& g, int hop);
+int launch_overlap_check(const float* wav, int B, int S, int hop, int* flag, cudaStream_t st);
+int launch_stream_prep(const float* wav, int B, const Geom& g, int hop, void* planes_hi, void* planes_lo, const int* flag,
+                       cudaStream_t st);
+int launch_sinc0_tc_stream(const void* w_planes, int B, const Geom& g, int hop, const void* planes_hi, const void* planes_lo,
+                           float* craw, const int* flag, cudaStream_t st);
+int launch_sinc_pool(const float* craw, const float* mean, const float* rstd, const float* cf, const float* hsum, float gamma,
+                     int B, const Geom& g, int hop, float* p0, const int* flag, cudaStream_t st);
 // lstm.cu
 int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_packed, int B, int T, int stride,
                       float* hout /*[B*stride,256]*/, cudaStream_t st);

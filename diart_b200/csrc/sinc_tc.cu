@@ -41,7 +41,11 @@ struct SincTcMaps {
 
 __global__ void __launch_bounds__(192, 1)
 sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows_total, int rows_per_item, int T0,
-                int S0, float* __restrict__ p0, float gamma, const float* __restrict__ cf, int f16) {
+                int S0, float* __restrict__ p0, float gamma, const float* __restrict__ cf, int f16,
+                float* __restrict__ craw, int P, const int* __restrict__ flag, int want) {
+  // stream form (see the end of this file): the per-window launch and the stream launch are both enqueued and a device
+  // flag -- "the batch is a run of overlapping windows of one stream" -- decides which of the two does the work
+  if (flag && ((*flag != 0) != (want != 0))) return;
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                       // [kb][plane][80 x 128 B]
@@ -161,6 +165,25 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * 256;
+      if (craw) {
+        // stream form: the raw convolution outputs of the three classes, conv position 12 t'' + 3 q + j
+        const long long pos0 = 12LL * R + 3 * q;
+#pragma unroll 1
+        for (int c = 0; c < ST_N; c += 16) {
+          uint32_t r[3][16];
+          tmem_ld16(taddr + c, r[0]);
+          tmem_ld16(taddr + ST_N + c, r[1]);
+          tmem_ld16(taddr + 2 * ST_N + c, r[2]);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 3; j++)
+            if (R < rows_total && pos0 + j < P) {
+              float* o2 = craw + (size_t)(pos0 + j) * ST_N + c;
+              st_global_v8(o2, r[j][0], r[j][1], r[j][2], r[j][3], r[j][4], r[j][5], r[j][6], r[j][7]);
+              st_global_v8(o2 + 8, r[j][8], r[j][9], r[j][10], r[j][11], r[j][12], r[j][13], r[j][14], r[j][15]);
+            }
+        }
+      } else
 #pragma unroll 1
       for (int c = 0; c < ST_N; c += 16) {
         uint32_t r0[16], r1[16], r2[16];
@@ -206,7 +229,9 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
 // normalised waveform -> four shifted copies, bf16 hi / lo planes:  plane[c][b*Lp + i] = split(xn[b][i + 2c])
 __global__ void __launch_bounds__(256) sinc_prep_kernel(const float* __restrict__ wav, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, int S, int Lp, size_t plane_elems,
-                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int f16) {
+                                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int f16,
+                                                        const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;     // the stream form does the work
   const int b = blockIdx.y;
   const float mu = mean[b], sc = rstd[b];
   const float* x = wav + (size_t)b * S;
@@ -277,24 +302,21 @@ void sinc_tc_affine_consts(const float* filt /*[251][80]*/, float beta, float* c
 
 // standardised waveform -> four shifted bf16 hi/lo copies (shared by every SincNet that reads this batch)
 int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int B, const Geom& g, void* planes_hi,
-                     void* planes_lo, cudaStream_t st) {
+                     void* planes_lo, cudaStream_t st, const int* skip_flag) {
   const int rpi = sinc_tc_rows_per_item(g), Lp = rpi * 120;
   const size_t plane = sinc_tc_plane_elems(B, g);
   ProfScope _ps("sinc0_prep", st);
   dim3 grid((Lp + 8 + 255) / 256, B);
   sinc_prep_kernel<<<grid, 256, 0, st>>>(wav, mean, rstd, g.S, Lp, plane, reinterpret_cast<uint16_t*>(planes_hi),
-                                         reinterpret_cast<uint16_t*>(planes_lo), split_f16());
+                                         reinterpret_cast<uint16_t*>(planes_lo), split_f16(), skip_flag);
   DG_LAUNCHED();
   return 0;
 }
 
-int launch_sinc0_tc(float gamma, const float* cf_dev, const void* w_planes, int B, const Geom& g, const void* planes_hi,
-                    const void* planes_lo, float* p0, cudaStream_t st) {
-  const int rpi = sinc_tc_rows_per_item(g);
-  const size_t plane = sinc_tc_plane_elems(B, g);
-  ProfScope _ps("sinc0", st);
+static int sinc0_launch_common(const void* w_planes, uint64_t rows, int rpi, size_t plane, const void* planes_hi,
+                               const void* planes_lo, int T0, int S0, float* p0, float gamma, const float* cf_dev, float* craw,
+                               int P, const int* flag, int want, cudaStream_t st) {
   SincTcMaps maps;
-  const uint64_t rows = (uint64_t)B * rpi;
   for (int c = 0; c < 4; c++) {
     const __nv_bfloat16* bh = reinterpret_cast<const __nv_bfloat16*>(planes_hi) + (size_t)c * plane;
     const __nv_bfloat16* bl = reinterpret_cast<const __nv_bfloat16*>(planes_lo) + (size_t)c * plane;
@@ -312,8 +334,134 @@ int launch_sinc0_tc(float gamma, const float* cf_dev, const void* w_planes, int 
   const int sms = usable_sms();
   const int row_tiles = (int)((rows + ST_ROWS - 1) / ST_ROWS);
   const int tiles = row_tiles * 4;
-  sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, g.T0, g.S0, p0,
-                                                                    gamma, cf_dev, split_f16());
+  sinc0_tc_kernel<<<tiles < sms ? tiles : sms, 192, ST_SMEM, st>>>(maps, row_tiles, (int)rows, rpi, T0, S0, p0, gamma, cf_dev,
+                                                                    split_f16(), craw, P, flag, want);
+  DG_LAUNCHED();
+  return 0;
+}
+
+// `skip_flag` (device, nullable): when it is non-zero the stream form below produces p0 and this launch returns at once
+int launch_sinc0_tc(float gamma, const float* cf_dev, const void* w_planes, int B, const Geom& g, const void* planes_hi,
+                    const void* planes_lo, float* p0, cudaStream_t st, const int* skip_flag) {
+  const int rpi = sinc_tc_rows_per_item(g);
+  ProfScope _ps("sinc0", st);
+  return sinc0_launch_common(w_planes, (uint64_t)B * rpi, rpi, sinc_tc_plane_elems(B, g), planes_hi, planes_lo, g.T0, g.S0, p0,
+                             gamma, cf_dev, nullptr, 0, skip_flag, 0, st);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stream form.  The batches of the hot path are runs of 90 %-overlapping windows of ONE audio stream (window b = samples
+// [b*hop, b*hop + S), reference src/diart/operators.py:44-100), and the sinc layer is the only one before the first
+// per-window normalisation.  Because InstanceNorm1d(1) is an affine map per window,
+//     conv((x - mu_b) * rstd_b * gamma + beta)[t, f] = gamma * rstd_b * conv(x)[t, f] + (beta - gamma * rstd_b * mu_b) * sum_k h[f, k],
+// the convolution of the RAW stream is shared by every window that contains the sample: it is computed once over the
+// (B-1)*hop + S unique samples (9.6x fewer conv positions at B = 256) and a streaming kernel applies the per-window
+// affine, |.| and MaxPool1d(3) from the L2-resident result.  A device-side bit comparison of the overlapping parts
+// (`overlap_check`) decides per batch whether this form or the per-window form runs, so arbitrary batches stay exact.
+__global__ void __launch_bounds__(256) overlap_check_kernel(const float* __restrict__ wav, int S, int hop, int* flag) {
+  const int b = blockIdx.y, n4 = (S - hop) >> 2;
+  const uint4* a = reinterpret_cast<const uint4*>(wav + (size_t)b * S + hop);
+  const uint4* c = reinterpret_cast<const uint4*>(wav + (size_t)(b + 1) * S);
+  bool bad = false;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += gridDim.x * blockDim.x) {
+    const uint4 x = a[i], y = c[i];
+    bad |= (x.x != y.x) | (x.y != y.y) | (x.z != y.z) | (x.w != y.w);
+  }
+  if (bad) *flag = 0;
+}
+
+int launch_overlap_check(const float* wav, int B, int S, int hop, int* flag, cudaStream_t st) {
+  ProfScope _ps("overlap_check", st);
+  DG_CUDA(cudaMemsetAsync(flag, 1, sizeof(int), st));       // non-zero = "overlapping run"; cleared on the first mismatch
+  dim3 grid(8, B - 1);
+  overlap_check_kernel<<<grid, 256, 0, st>>>(wav, S, hop, flag);
+  DG_LAUNCHED();
+  return 0;
+}
+
+SincStreamGeom sinc_stream_geom(int B, const Geom& g, int hop) {
+  SincStreamGeom sg;
+  sg.Ls = (B - 1) * hop + g.S;
+  sg.P = (B - 1) * (hop / 10) + g.T0c;
+  const int by_rows = (sg.P + 11) / 12, by_len = (sg.Ls + 8 + 119) / 120;
+  sg.rows = by_rows > by_len ? by_rows : by_len;
+  sg.plane = (size_t)sg.rows * 120 + 1024;
+  return sg;
+}
+
+// raw stream -> four shifted 16-bit hi / lo copies:  plane[c][i] = split(stream[i + 2c])
+__global__ void __launch_bounds__(256) stream_prep_kernel(const float* __restrict__ wav, int S, int hop, int Ls, int Lp,
+                                                          size_t plane_elems, uint16_t* __restrict__ hi,
+                                                          uint16_t* __restrict__ lo, int f16, const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < Lp + 8; i += gridDim.x * blockDim.x) {
+    float v = 0.f;
+    if (i < Ls) {
+      const int b = i < S ? 0 : (i - S) / hop + 1;          // the window that ends with this sample
+      v = wav[(size_t)b * S + (i - b * hop)];
+    }
+    uint16_t h, l;
+    split_h16(v, f16, h, l);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+      const int j = i - 2 * c;
+      if (j >= 0 && j < Lp) {
+        hi[(size_t)c * plane_elems + j] = h;
+        lo[(size_t)c * plane_elems + j] = l;
+      }
+    }
+  }
+}
+
+int launch_stream_prep(const float* wav, int B, const Geom& g, int hop, void* planes_hi, void* planes_lo, const int* flag,
+                       cudaStream_t st) {
+  const SincStreamGeom sg = sinc_stream_geom(B, g, hop);
+  ProfScope _ps("sinc0_prep", st);
+  const int Lp = sg.rows * 120;
+  stream_prep_kernel<<<(Lp + 8 + 255) / 256, 256, 0, st>>>(wav, g.S, hop, sg.Ls, Lp, sg.plane, reinterpret_cast<uint16_t*>(planes_hi),
+                                                          reinterpret_cast<uint16_t*>(planes_lo), split_f16(), flag);
+  DG_LAUNCHED();
+  return 0;
+}
+
+// raw convolution of the stream: craw[P][80]
+int launch_sinc0_tc_stream(const void* w_planes, int B, const Geom& g, int hop, const void* planes_hi, const void* planes_lo,
+                           float* craw, const int* flag, cudaStream_t st) {
+  const SincStreamGeom sg = sinc_stream_geom(B, g, hop);
+  ProfScope _ps("sinc0", st);
+  return sinc0_launch_common(w_planes, (uint64_t)sg.rows, sg.rows, sg.plane, planes_hi, planes_lo, 0, 0, nullptr, 1.f, nullptr,
+                             craw, sg.P, flag, 1, st);
+}
+
+// p0[b][p][f] = max_{j<3} | A_b * craw[b*hop/10 + 3p + j][f] + cf[f] - A_b * mu_b * hsum[f] |,  A_b = gamma * rstd_b
+__global__ void __launch_bounds__(256) sinc_pool_kernel(const float* __restrict__ craw, const float* __restrict__ mean,
+                                                        const float* __restrict__ rstd, const float* __restrict__ cf,
+                                                        const float* __restrict__ hsum, float gamma, int hop10, int T0, int S0,
+                                                        float* __restrict__ p0, const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  const int b = blockIdx.y;
+  const float A = gamma * rstd[b], Am = A * mean[b];
+  const float4* src = reinterpret_cast<const float4*>(craw + (size_t)b * hop10 * ST_N);
+  float4* dst = reinterpret_cast<float4*>(p0 + (size_t)b * S0 * ST_N);
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < T0 * 20; idx += gridDim.x * blockDim.x) {
+    const int p = idx / 20, f4 = idx - p * 20;
+    const float4 c4 = reinterpret_cast<const float4*>(cf)[f4], h4 = reinterpret_cast<const float4*>(hsum)[f4];
+    const float bx = fmaf(-Am, h4.x, c4.x), by = fmaf(-Am, h4.y, c4.y), bz = fmaf(-Am, h4.z, c4.z), bw = fmaf(-Am, h4.w, c4.w);
+    const float4 u0 = src[(size_t)(3 * p) * 20 + f4], u1 = src[(size_t)(3 * p + 1) * 20 + f4], u2 = src[(size_t)(3 * p + 2) * 20 + f4];
+    float4 v;
+    v.x = fmaxf(fmaxf(fabsf(fmaf(A, u0.x, bx)), fabsf(fmaf(A, u1.x, bx))), fabsf(fmaf(A, u2.x, bx)));
+    v.y = fmaxf(fmaxf(fabsf(fmaf(A, u0.y, by)), fabsf(fmaf(A, u1.y, by))), fabsf(fmaf(A, u2.y, by)));
+    v.z = fmaxf(fmaxf(fabsf(fmaf(A, u0.z, bz)), fabsf(fmaf(A, u1.z, bz))), fabsf(fmaf(A, u2.z, bz)));
+    v.w = fmaxf(fmaxf(fabsf(fmaf(A, u0.w, bw)), fabsf(fmaf(A, u1.w, bw))), fabsf(fmaf(A, u2.w, bw)));
+    dst[(size_t)p * 20 + f4] = v;
+  }
+}
+
+int launch_sinc_pool(const float* craw, const float* mean, const float* rstd, const float* cf, const float* hsum, float gamma,
+                     int B, const Geom& g, int hop, float* p0, const int* flag, cudaStream_t st) {
+  ProfScope _ps("sinc0_pool", st);
+  dim3 grid((g.T0 * 20 + 255) / 256 < 64 ? (g.T0 * 20 + 255) / 256 : 64, B);
+  sinc_pool_kernel<<<grid, 256, 0, st>>>(craw, mean, rstd, cf, hsum, gamma, hop / 10, g.T0, g.S0, p0, flag);
   DG_LAUNCHED();
   return 0;
 }
