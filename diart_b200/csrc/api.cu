@@ -225,7 +225,7 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
 // ones, so the fused pipeline computes them once per step
 struct SincPrep {
   DevBuf wmean, wrstd, wh, wl;
-  // stream form (DG_STREAM_SINC=1 and a hop hint): planes of the raw stream and the device flag "this batch is a run of
+  // stream form (needs a hop hint; DG_STREAM_SINC=0 disables it): planes of the raw stream and the device flag "this batch is a run of
   // overlapping windows"; `hop` > 0 means the stream-form launches were enqueued for this batch
   DevBuf swh, swl, flag;
   int hop = 0;
@@ -268,9 +268,10 @@ struct SincWork {
 static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cudaStream_t st, int hop = 0) {
   int rc;
   if ((rc = p.ensure(B, g))) return rc;
-  // stream form of the sinc layer: opt-in (DG_STREAM_SINC=1) and only with a hop hint from the caller; the device flag
-  // written by overlap_check decides per batch, so a wrong hint costs two empty launches, never a wrong result
-  static const bool stream_on = getenv("DG_STREAM_SINC") && getenv("DG_STREAM_SINC")[0] == '1';
+  // stream form of the sinc layer: on by default (DG_STREAM_SINC=0 disables it), only with a hop hint from the caller;
+  // the device flag written by overlap_check decides per batch, so a wrong hint costs a few empty launches, never a
+  // wrong result
+  static const bool stream_on = !(getenv("DG_STREAM_SINC") && getenv("DG_STREAM_SINC")[0] == '0');
   p.hop = 0;
   if (stream_on && hop > 0 && B >= 4 && hop % 40 == 0 && g.S % 4 == 0 && hop < g.S && ((uintptr_t)wav & 15) == 0) {
     if ((rc = p.ensure_stream(B, g, hop))) return rc;

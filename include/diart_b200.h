@@ -112,10 +112,9 @@ int dg_pipeline_step(dg_pipeline* h, const float* wav_dev /*[B,S]*/, int B, int 
                      float* seg_dev /*[B,F,K]*/, float* emb_dev /*[B,K,D]*/,
                      int32_t* map_dev /*[B,K]*/, float* permuted_dev /*[B,F,M] or NULL*/, void* stream);
 /* Hint: consecutive windows of a batch are `hop_samples` apart in ONE stream (reference config.step x sample_rate;
- * windows as `rearrange_audio_stream` emits them, src/diart/operators.py:44-100).  With DG_STREAM_SINC=1 the
- * pipeline then verifies the overlap on the device for every batch (bit comparison) and, when it holds, runs the
- * sinc layer once over the unique samples instead of once per window.  0 = no hint (default).  Results never depend
- * on the hint being right. */
+ * windows as `rearrange_audio_stream` emits them, src/diart/operators.py:44-100).  The pipeline then verifies the overlap on the device for every batch (bit comparison) and, when it holds, runs the
+ * sinc layer once over the unique samples instead of once per window (DG_STREAM_SINC=0 disables this).  0 = no hint
+ * (default).  Results never depend on the hint being right. */
 int dg_pipeline_set_hop(dg_pipeline* h, int hop_samples);
 /* Same with HOST buffers: H2D of the waveforms and D2H of the results inside the call
  * (pinned staging owned by the handle); synchronous. */
