@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from diart_b200 import blocks, models, synth
+from diart_b200 import _lib, blocks, models, synth
 from diart_b200.core import SlidingWindow, SlidingWindowFeature
 from oracle.clustering import OracleClustering
 from oracle.pipeline import OraclePipeline
@@ -31,9 +31,21 @@ def make_pipeline(oracle_nets, device, **kw):
     return blocks.SpeakerDiarization(config)
 
 
+def window_form(pipe, num_samples=80000):
+    """withdraw the hop hint: the sinc layer then runs once per window instead of once over the stream's unique samples"""
+    h = pipe._ensure_fused(num_samples)[0]
+    _lib.check(_lib.lib().dg_pipeline_set_hop(h, 0))
+    return pipe
+
+
+@pytest.mark.parametrize("sinc_form", ["stream", "window"])
 @pytest.mark.parametrize("params", [dict(), dict(tau_active=0.5, rho_update=0.2, delta_new=0.8, max_speakers=4)])
-def test_fused_step_matches_oracle(params, oracle_nets, stream, cuda_device):
+def test_fused_step_matches_oracle(params, sinc_form, oracle_nets, stream, cuda_device):
+    """the batches are consecutive windows of one stream: with the hop hint (default) the sinc layer takes the stream
+    form, without it the per-window form; both must meet the same bars"""
     pipe = make_pipeline(oracle_nets, cuda_device, **params)
+    if sinc_form == "window":
+        window_form(pipe)
     cfg = pipe.config
     oracle = OraclePipeline(*oracle_nets, tau_active=cfg.tau_active, rho_update=cfg.rho_update,
                             delta_new=cfg.delta_new, max_speakers=cfg.max_speakers, as_reference=False)
@@ -110,6 +122,22 @@ def test_foreign_models_behind_loader_api(oracle_nets, stream, cuda_device):
     # torch's cuDNN / cuBLAS float32 kernels re-associate differently from both the CPU oracle and this path
     assert (s1 - s2).abs().max().item() < 1e-3 and (e1 - e2).abs().max().item() < 2e-3
     assert m1.shape == m2.shape and m1.dtype == torch.int32
+
+
+def test_hop_hint_is_only_a_hint(oracle_nets, stream, cuda_device):
+    """a batch that is NOT a run of overlapping windows (here: the windows in reverse order) must give exactly the
+    per-window results although the hop hint is set -- the overlap is verified on the device for every batch -- and a
+    batch that is one gives the same speaker maps and scores within the parity bar in both forms"""
+    a, b = make_pipeline(oracle_nets, cuda_device), window_form(make_pipeline(oracle_nets, cuda_device))
+    fwd = synth.windows(stream, BATCH)
+    rev = torch.from_numpy(np.ascontiguousarray(fwd[::-1])).to(cuda_device)
+    (s1, e1, m1), (s2, e2, m2) = a.device_step(rev), b.device_step(rev)
+    assert torch.equal(s1, s2) and torch.equal(e1, e2) and torch.equal(m1, m2)
+    a, b = make_pipeline(oracle_nets, cuda_device), window_form(make_pipeline(oracle_nets, cuda_device))   # fresh clustering state
+    x = torch.from_numpy(fwd).to(cuda_device)
+    (s1, e1, m1), (s2, e2, m2) = a.device_step(x), b.device_step(x)
+    assert (s1 - s2).abs().max().item() < 1e-4 and (e1 - e2).abs().max().item() < 1e-4
+    assert torch.equal(m1, m2)
 
 
 def test_pipelined_submit_collect_equals_sequential_steps(oracle_nets, stream, cuda_device):
