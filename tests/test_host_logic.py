@@ -96,3 +96,30 @@ def test_loader_plugin_contract():
     assert calls == ["load", ("to", "cpu")] and m.is_in_memory()
     e = models.EmbeddingModel(lambda: (lambda w, x=None: np.zeros((2, 4), dtype=np.float32)))
     assert isinstance(e(torch.zeros(2, 1, 10)), torch.Tensor)      # ndarray results become tensors (models.py:262-264)
+
+
+def test_stream_form_identity_of_the_sinc_layer():
+    """The identity the stream form of the sinc layer rests on (diart_b200/csrc/sinc_tc.cu): for window b of a stream,
+        maxpool3(|conv(wav_norm(x_b))|) == maxpool3(|A_b * conv(x)[b*hop/10 + t] + (beta - A_b * mu_b) * sum_k h|),
+    A_b = gamma * rstd_b, with ONE convolution of the raw stream shared by all overlapping windows (float64 here)."""
+    import torch
+
+    from oracle import nets
+
+    S, hop, B = 4000, 400, 5
+    g = torch.Generator().manual_seed(3)
+    stream = torch.randn((B - 1) * hop + S, generator=g, dtype=torch.float64) * 0.1 + 0.02
+    filt = nets.ParamSincFB().filters().detach().double()                    # (80, 1, 251)
+    gamma, beta = 1.25, 0.05
+    c_stream = torch.nn.functional.conv1d(stream[None, None], filt, stride=10)[0].T      # (P, 80)
+    hsum = filt[:, 0, :].sum(-1)
+    for b in range(B):
+        x = stream[b * hop:b * hop + S]
+        mu, var = x.mean(), x.var(unbiased=False)
+        rstd = 1.0 / torch.sqrt(var + 1e-5)
+        ref = torch.nn.functional.conv1d(((x - mu) * rstd * gamma + beta)[None, None], filt, stride=10)[0].T.abs()
+        T0 = ref.shape[0] // 3
+        ref = ref[:3 * T0].reshape(T0, 3, 80).amax(1)
+        A = gamma * rstd
+        got = (A * c_stream[b * hop // 10:b * hop // 10 + 3 * T0] + (beta - A * mu) * hsum).abs().reshape(T0, 3, 80).amax(1)
+        assert torch.allclose(got, ref, rtol=1e-10, atol=1e-12)
