@@ -107,7 +107,7 @@ static int upload_u16(DevBuf& b, const std::vector<uint16_t>& h) {
   return 0;
 }
 
-// float32 [N][K] host weights -> zero-padded bf16 hi/lo device planes [Npad][K]
+// float32 [N][K] host weights -> zero-padded 16-bit hi/lo device planes [Npad][K]
 static int upload_split(DevBuf& hi, DevBuf& lo, const std::vector<float>& w_nk, int N, int Npad, int K) {
   std::vector<uint16_t> h((size_t)Npad * K), l((size_t)Npad * K);
   split_weights_host(w_nk.data(), N, Npad, K, h.data(), l.data(), split_f16());
@@ -124,8 +124,8 @@ static int upload(DevBuf& b, const std::vector<float>& h) {
 struct SincWeights {
   float wn_gamma = 1.f, wn_beta = 0.f;
   DevBuf filt, g0, b0, w1, bias1, g1, b1, w2, bias2, g2, b2;
-  DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: bf16 hi/lo planes [128][5*128] and [128][5*64]
-  DevBuf filt_planes;                  // sinc filter bank as three bf16 planes [3][80][256] (hi, lo, lo2)
+  DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: 16-bit hi/lo planes [128][5*128] and [128][5*64]
+  DevBuf filt_planes;                  // sinc filter bank as 16-bit planes [3][80][256] (hi, lo; lo2 for the bf16 mode)
   DevBuf cf;                           // folded wav-norm affine: beta * sum_k h[f][k]
   DevBuf hsum;                         // sum_k h[f][k] (stream form of the sinc layer)
 };
@@ -240,7 +240,7 @@ struct SincPrep {
 };
 struct SincWork {
   DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
-  DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: bf16 planes of the conv inputs, un-pooled conv outputs
+  DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: 16-bit planes of the conv inputs, un-pooled conv outputs
   DevBuf craw;                         // stream form: raw convolution of the stream [P][80]
   SincPrep own_prep;                   // statistics + waveform planes when no shared ones are supplied
   const float* out = nullptr;          // conv2 output that the next layer normalises on load ...
@@ -319,7 +319,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
     if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),
                                     k.sc0.as<float>(), k.sh0.as<float>(), st)))
       return rc;
-    // Conv1d(80,60,5): normalised input as bf16 planes (80 -> 128 channels), un-pooled float32 output
+    // Conv1d(80,60,5): normalised input as 16-bit hi/lo planes (80 -> 128 channels), un-pooled float32 output
     const long long M0 = (long long)B * g.S0, M1 = (long long)B * g.S1;
     if ((rc = launch_split_ex(k.p0.as<float>(), M0, 80, 80, 128, 0, g.S0, k.sc0.as<float>(), k.sh0.as<float>(),
                               k.a0h.p, k.a0l.p, st)))
@@ -383,10 +383,10 @@ struct dg_seg {
   int device = 0, K = 3;
   SincWeights sw;
   DevBuf wih[4], bih[4], whh[4];   // input projections [in_pad][1024], bias [1024], packed W_hh
-  DevBuf wih_hi[4], wih_lo[4];     // the same as bf16 hi/lo planes [1024][in_pad] for the tcgen05 path
-  DevBuf whh_hi[4], whh_lo[4];     // W_hh as bf16 hi/lo planes [2][512][128] for the tcgen05 recurrence
+  DevBuf wih_hi[4], wih_lo[4];     // the same as 16-bit hi/lo planes [1024][in_pad] for the tcgen05 path
+  DevBuf whh_hi[4], whh_lo[4];     // W_hh as 16-bit hi/lo planes [2][512][128] for the tcgen05 recurrence
   DevBuf l1w, l1b, l2w, l2b, cw, cb;
-  DevBuf l1_hi, l1_lo, l2_hi, l2_lo, ones128, zeros128;   // head Linears as bf16 planes [128][in] (tcgen05 path)
+  DevBuf l1_hi, l1_lo, l2_hi, l2_lo, ones128, zeros128;   // head Linears as 16-bit hi/lo planes [128][in] (tcgen05 path)
   // activations: two independent sets ("lanes") so that the fused pipeline can run the segmentation chains of
   // two consecutive steps concurrently (the recurrence occupies only 32 SMs)
   struct Scratch {
@@ -1094,7 +1094,7 @@ extern "C" int dg_selftest_split_host(const float* x, long long n, int f16, unsi
   return DG_OK;
 }
 
-// Runs the same shifted-window GEMM through the float32 SIMT kernel and through the tcgen05 bf16x3
+// Runs the same shifted-window GEMM through the float32 SIMT kernel and through the tcgen05 split-precision
 // kernel on seeded random data and reports the largest absolute difference and the output scale.
 extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int epi, float* max_abs_diff,
                                    float* out_rms) {
@@ -1269,7 +1269,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   if (osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
   DG_CUDA(cudaStreamWaitEvent(s_seg, start, 0));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, start, 0));
-  // waveform statistics + standardised bf16 planes once, for both networks' SincNets
+  // waveform statistics + standardised 16-bit planes once, for both networks' SincNets
   static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
   const SincPrep* shared = nullptr;
   if (!sinc_simt) {

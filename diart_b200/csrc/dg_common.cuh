@@ -115,7 +115,7 @@ struct GemmArgs {
   const char* tag;   // kernel label for profiling (layer name)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
-// gemm_tc.cu -- tcgen05 / TMEM / TMA path (bf16x3 split precision)
+// gemm_tc.cu -- tcgen05 / TMEM / TMA path (hi/lo split precision, three products)
 struct TcGemm {
   const void* A_hi;    // bf16 [Mtot, lda]
   const void* A_lo;

@@ -20,7 +20,7 @@
 //   warp 1      MMA issuer (one elected lane): 12 tcgen05.mma per k-block into one of two TMEM
 //               accumulators (128 lanes x BN fp32 columns each); tcgen05.commit frees the smem slot
 //   warps 2-5   epilogue: tcgen05.ld the finished accumulator (one TMEM lane quadrant per warp), bias,
-//               LeakyReLU, BatchNorm affine, then either float32 rows or the next layer's hi/lo bf16
+//               LeakyReLU, BatchNorm affine, then either float32 rows or the next layer's hi/lo 16-bit
 //               planes; overlaps the next tile's MMAs through the second accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -134,7 +134,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     // ===================================================================== MMA issuer
     // (elect_one, not lane == 0: descriptors stay in uniform registers and the tcgen05.mma issue back to back)
     if (elect_one()) {
-      // instruction descriptor: D=f32, A=B=bf16, both K-major, N = BN, M = 128
+      // instruction descriptor: D=f32, A=B=fp16 (or bf16), both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | idesc_ab_format(a.f16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -150,9 +150,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 16; ks++) {
             const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 bytes per 16-element k-step
-            umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, (kb | ks) != 0);
-            umma_bf16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
-            umma_bf16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
+            umma_f16(tmem_c, a_lo + adv, w_hi + adv, idesc, (kb | ks) != 0);
+            umma_f16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
+            umma_f16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
           }
           umma_commit(&empty[stage]);           // smem slot reusable once these MMAs have read it
           if (++stage == NSTAGE) {
@@ -345,8 +345,8 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
   }
 }
 
-// ------------------------------------------------------------------------------------ bf16 hi/lo split
-// x [rows_in, ld_in] float32 -> hi/lo bf16 planes [rows_out, ld_out]; optionally MaxPool1d(3) over rows
+// ------------------------------------------------------------------------------------ 16-bit hi/lo split
+// x [rows_in, ld_in] float32 -> hi/lo 16-bit planes [rows_out, ld_out]; optionally MaxPool1d(3) over rows
 // (out row r <- max of in rows 3r..3r+2) and the previous InstanceNorm1d + LeakyReLU (scale/shift per
 // (item, channel), item = out row / item_rows); channels [C, ld_out) are written as zeros.
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, long long rows_out, int C, int ld_in,

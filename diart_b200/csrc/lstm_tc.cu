@@ -36,7 +36,7 @@ namespace dg {
 
 constexpr int LT_NB = 16;                               // batch rows per CTA (= N of every MMA)
 
-__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
   asm volatile(
       "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}"
@@ -287,10 +287,10 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
             const uint64_t b_hi = b0d + (uint64_t)(ks * (512 >> 4));
             const uint64_t b_lo = b_hi + (uint64_t)(L3_PLANE >> 4);
             const uint32_t a_hi = tmem_base + L3_COL_WHI + g * 64 + ks * 8;
-            umma_bf16_ts(d, a_hi, b_lo, idesc, ks != 0);                                     // W_hi . h_lo
-            if (g < 3) umma_bf16_ts(d, tmem_base + L3_COL_WLO + g * 64 + ks * 8, b_hi, idesc, 1);   // W_lo . h_hi
-            else umma_bf16(d, a_s + (uint64_t)(kb * kTile + kk * 2), b_hi, idesc, 1);
-            umma_bf16_ts(d, a_hi, b_hi, idesc, 1);                                           // W_hi . h_hi
+            umma_f16_ts(d, a_hi, b_lo, idesc, ks != 0);                                     // W_hi . h_lo
+            if (g < 3) umma_f16_ts(d, tmem_base + L3_COL_WLO + g * 64 + ks * 8, b_hi, idesc, 1);   // W_lo . h_hi
+            else umma_f16(d, a_s + (uint64_t)(kb * kTile + kk * 2), b_hi, idesc, 1);
+            umma_f16_ts(d, a_hi, b_hi, idesc, 1);                                           // W_hi . h_hi
           }
           if (g == 2) umma_commit(&mma_done[0]);
         }
@@ -331,7 +331,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
 
 size_t lstm_tc_plane_elems() { return (size_t)2 * 512 * 128; }
 
-// torch weight_hh_l{L}[_reverse] ([512][128], gate order i,f,g,o) -> bf16 hi / lo planes [2][512][128]
+// torch weight_hh_l{L}[_reverse] ([512][128], gate order i,f,g,o) -> 16-bit hi / lo planes [2][512][128]
 void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16) {
   split_weights_host(whh_fwd, 512, 512, 128, hi, lo, f16);
   split_weights_host(whh_bwd, 512, 512, 128, hi + 512 * 128, lo + 512 * 128, f16);

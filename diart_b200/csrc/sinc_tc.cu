@@ -36,7 +36,7 @@ constexpr int ST_SMEM = ST_W_TOTAL + ST_NSTAGE * ST_STAGE + 256 + 1024;
 
 struct SincTcMaps {
   CUtensorMap a_hi[4], a_lo[4];   // shifted copies of the normalised waveform, hi / lo planes
-  CUtensorMap w[3];               // filter bank [80][256]: bf16 hi, lo and second-order lo2 planes
+  CUtensorMap w[3];               // filter bank [80][256]: 16-bit hi, lo and (bf16 mode) second-order lo2 planes
 };
 
 __global__ void __launch_bounds__(192, 1)
@@ -131,12 +131,12 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
               // layer's error is amplified by every later layer, so the filters carry 24 significand bits.
               // (fp16 planes: hi + lo already carry 22 bits of both operands, three products suffice)
               if (!f16) {
-                umma_bf16(tmem_c, a_lo + adv, w_lo + adv, idesc, (kb | ks) != 0);
-                umma_bf16(tmem_c, a_hi + adv, w_l2 + adv, idesc, 1);
+                umma_f16(tmem_c, a_lo + adv, w_lo + adv, idesc, (kb | ks) != 0);
+                umma_f16(tmem_c, a_hi + adv, w_l2 + adv, idesc, 1);
               }
-              umma_bf16(tmem_c, a_lo + adv, w_hi + adv, idesc, f16 ? (uint32_t)((kb | ks) != 0) : 1u);
-              umma_bf16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
-              umma_bf16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
+              umma_f16(tmem_c, a_lo + adv, w_hi + adv, idesc, f16 ? (uint32_t)((kb | ks) != 0) : 1u);
+              umma_f16(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
+              umma_f16(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
             }
             umma_commit(&empty[stage]);
             if (++stage == ST_NSTAGE) {
@@ -226,7 +226,7 @@ sinc0_tc_kernel(const __grid_constant__ SincTcMaps maps, int row_tiles, int rows
   }
 }
 
-// normalised waveform -> four shifted copies, bf16 hi / lo planes:  plane[c][b*Lp + i] = split(xn[b][i + 2c])
+// normalised waveform -> four shifted copies, 16-bit hi / lo planes:  plane[c][b*Lp + i] = split(xn[b][i + 2c])
 __global__ void __launch_bounds__(256) sinc_prep_kernel(const float* __restrict__ wav, const float* __restrict__ mean,
                                                         const float* __restrict__ rstd, int S, int Lp, size_t plane_elems,
                                                         uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int f16,
@@ -277,8 +277,8 @@ int sinc_tc_rows_per_item(const Geom& g) {
 }
 size_t sinc_tc_plane_elems(int B, const Geom& g) { return (size_t)B * sinc_tc_rows_per_item(g) * 120 + 1024; }
 
-// filt [251][80] float32 (k-major) -> three bf16 planes [3][80][256] (n-major, K padded with zeros):
-// hi = bf16(w), lo = bf16(w - hi), lo2 = bf16(w - hi - lo)
+// filt [251][80] float32 (k-major) -> three 16-bit planes [3][80][256] (n-major, K padded with zeros):
+// hi = rn16(w), lo = rn16(w - hi), lo2 = rn16(w - hi - lo)
 void sinc_tc_pack_filters(const float* filt, uint16_t* planes, int f16) {
   static float w[80 * 256], r[80 * 256];
   static uint16_t dummy[80 * 256];
@@ -300,7 +300,7 @@ void sinc_tc_affine_consts(const float* filt /*[251][80]*/, float beta, float* c
   }
 }
 
-// standardised waveform -> four shifted bf16 hi/lo copies (shared by every SincNet that reads this batch)
+// standardised waveform -> four shifted 16-bit hi/lo copies (shared by every SincNet that reads this batch)
 int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int B, const Geom& g, void* planes_hi,
                      void* planes_lo, cudaStream_t st, const int* skip_flag) {
   const int rpi = sinc_tc_rows_per_item(g), Lp = rpi * 120;
