@@ -1,3 +1,4 @@
+"""Manual diagnostic (GPU): repeatability of the segmentation network, checked against the oracle."""
 import sys, os, torch, numpy as np
 sys.path.insert(0, os.getcwd())
 from diart_b200 import models, synth

@@ -17,8 +17,8 @@ timeout 400 $NCU --metrics gpu__time_duration.sum --clock-control none -c 600 --
 full() { name=$1; pat=$2; skip=$3; timeout 300 $NCU --set full --clock-control none --import-source on -k "regex:$pat" -s $skip -c 1 -f -o $out/final_$name $B > $out/ncu_$name.log 2>&1; }
 full lstm 'lstm_tc3' 5
 full sinc0 'sinc0_tc' 2
-full tdnn 'gemm_tc_kernel<\(int\)256, \(int\)1>' 5
-full inproj 'gemm_tc_kernel<\(int\)256, \(int\)0>' 3
+# (-k matches the base name only: the templated GEMM launches are picked by index)
+timeout 400 $NCU --set full --clock-control none --import-source on -k regex:gemm_tc_kernel -s 3 -c 8 -f -o $out/final_gemm $B > $out/ncu_gemm.log 2>&1
 ls -la $out/final_* | awk '{print $5, $9}'
 for f in $out/final_bench*.json $out/final_ref.json; do echo $f; python - "$f" <<'PY'
 import json,sys
