@@ -377,7 +377,9 @@ def run_ours(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "batch": B, "streams": world, "parallelism": (f"{world} independent streams, "
                    "1 per GPU, no collectives" if shared is None else f"{world} streams, 1 per GPU, shared speaker "
-                   "identity: one NCCL all-gather of centroid-delta records per step + deterministic merge"), "l2": "inputs rotate over 3 distinct 82 MB batches (246 MB > 126 MB L2)"},
+                   "identity: one NCCL all-gather of centroid-delta records per step + deterministic merge"), "l2": "inputs rotate over 3 distinct 82 MB batches (246 MB > 126 MB L2)",
+                   "arithmetic": "float32 results: every dense layer as fp16 hi/lo operand planes x 3 tcgen05 products with float32 "
+                                 "accumulation (22 significand bits per operand), float64 clustering"},
         "chunks_per_s": value / STEP_SECONDS,
         "step_tflops": step_flops / (ms_max / args.steps * 1e-3) / 1e12,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": B * CHUNK * 4,
