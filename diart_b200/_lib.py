@@ -35,6 +35,7 @@ SIGNATURES = {
     "dg_selftest_split_host": (C.c_int, [_P, C.c_longlong, C.c_int, _P, _P]),
     "dg_seg_create": (C.c_int, [C.POINTER(DgTensor), C.c_int, C.c_int, C.POINTER(_P)]),
     "dg_seg_dims": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dg_seg_set_powerset": (C.c_int, [_P, C.c_int, C.c_int]),
     "dg_seg_forward": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P]),
     "dg_seg_destroy": (C.c_int, [_P]),
     "dg_emb_create": (C.c_int, [C.POINTER(DgTensor), C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),

@@ -4,6 +4,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <sstream>
@@ -380,7 +381,9 @@ using namespace dg;
 
 // ================================================================================== segmentation
 struct dg_seg {
-  int device = 0, K = 3;
+  int device = 0, K = 3;           // K = classifier outputs (local speakers; powerset classes for powerset models)
+  int ps_speakers = 0;             // > 0: powerset model with this many local speakers (dg_seg_set_powerset)
+  DevBuf ps_masks;                 // speaker bit set of every powerset class
   SincWeights sw;
   DevBuf wih[4], bih[4], whh[4];   // input projections [in_pad][1024], bias [1024], packed W_hh
   DevBuf wih_hi[4], wih_lo[4];     // the same as 16-bit hi/lo planes [1024][in_pad] for the tcgen05 path
@@ -528,8 +531,55 @@ extern "C" int dg_seg_dims(const dg_seg* h, int num_samples, int* frames, int* s
   }
   Geom g = make_geom(num_samples);
   if (frames) *frames = g.T2;
-  if (speakers) *speakers = h->K;
+  if (speakers) *speakers = h->ps_speakers ? h->ps_speakers : h->K;
   return DG_OK;
+}
+
+// Declares the model a powerset model (pyannote/segmentation-3.0 style): its classifier has one output per subset of
+// the `num_speakers` local speakers of size <= `max_per_frame`, in itertools.combinations order (pyannote
+// Powerset.build_mapping); the forward then returns hard multilabel scores (reference models.py:29-39).
+extern "C" int dg_seg_set_powerset(dg_seg* h, int num_speakers, int max_per_frame) {
+  if (!h || num_speakers < 1 || num_speakers > 8 || max_per_frame < 0 || max_per_frame > num_speakers) {
+    set_error("dg_seg_set_powerset: bad arguments");
+    return DG_EINVAL;
+  }
+  std::vector<uint32_t> masks;
+  for (int size = 0; size <= max_per_frame; size++)          // subsets by size, each size in lexicographic order
+    for (uint32_t m = 0; m < (1u << num_speakers); m++) {
+      if (__builtin_popcount(m) != size) continue;
+      masks.push_back(m);
+    }
+  // lexicographic order of combinations (0,1) < (0,2) < (1,2) is NOT numeric order of the bit masks in general: sort each
+  // size class by the sorted member tuples
+  auto members = [&](uint32_t m) {
+    std::vector<int> v;
+    for (int i = 0; i < num_speakers; i++)
+      if (m >> i & 1u) v.push_back(i);
+    return v;
+  };
+  std::stable_sort(masks.begin(), masks.end(), [&](uint32_t a, uint32_t b) {
+    const int sa = __builtin_popcount(a), sb = __builtin_popcount(b);
+    if (sa != sb) return sa < sb;
+    return members(a) < members(b);
+  });
+  if ((int)masks.size() != h->K) {
+    set_error("dg_seg_set_powerset: the classifier has " + std::to_string(h->K) + " outputs but the powerset has " +
+              std::to_string(masks.size()) + " classes");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  if (h->ps_masks.ensure(masks.size() * 4)) return DG_ECUDA;
+  DG_CUDA(cudaMemcpy(h->ps_masks.p, masks.data(), masks.size() * 4, cudaMemcpyHostToDevice));
+  h->ps_speakers = num_speakers;
+  return DG_OK;
+}
+
+// classifier + sigmoid, or classifier + powerset decoding
+static int seg_head_final(dg_seg* h, const float* y2, int B, const Geom& g, float* seg, cudaStream_t st) {
+  if (h->ps_speakers)
+    return launch_seg_powerset(y2, h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, h->ps_speakers,
+                               h->ps_masks.as<unsigned>(), seg, st);
+  return launch_seg_final(y2, h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
 }
 
 extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* seg, void* stream) {
@@ -608,7 +658,7 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
     t.W_hi = h->l2_hi.p; t.W_lo = h->l2_lo.p; t.bias = h->l2b.as<float>();
     t.out_hi = nullptr; t.out_lo = nullptr; t.out_f32 = w.y2.as<float>(); t.epi = 2;
     if ((rc = launch_gemm_tc(t, st))) return rc;
-    return launch_seg_final(w.y2.as<float>(), h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
+    return seg_head_final(h, w.y2.as<float>(), B, g, seg, st);
   }
   GemmArgs a{};
   a.A = hin; a.lda = 256; a.Cin = 256; a.KW = 1; a.dil = 1; a.Mtot = M; a.M = M;
@@ -618,7 +668,7 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
   a.A = w.y1.as<float>(); a.lda = 128; a.Cin = 128;
   a.W = h->l2w.as<float>(); a.bias = h->l2b.as<float>(); a.C = w.y2.as<float>();
   if ((rc = launch_gemm(a, st))) return rc;
-  return launch_seg_final(w.y2.as<float>(), h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
+  return seg_head_final(h, w.y2.as<float>(), B, g, seg, st);
 }
 
 extern "C" int dg_seg_destroy(dg_seg* h) {

@@ -182,6 +182,8 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
 // heads.cu
 int launch_seg_final(const float* y /*[B*stride,128]*/, const float* wc /*[K][128]*/, const float* bc, int B, int T,
                      int stride, int K, float* seg /*[B,T,K]*/, cudaStream_t st);
+int launch_seg_powerset(const float* y, const float* wc, const float* bc, int B, int T, int stride, int C, int num_speakers,
+                        const unsigned* masks_dev, float* seg /*[B,T,num_speakers]*/, cudaStream_t st);
 int launch_osp(const float* seg, int B, int F, int K, float gamma, float beta, int normalize, float* out,
                cudaStream_t st);
 int launch_stats_pool(const float* x /*[B*stride,C]*/, int B, int stride, int T, int C, const float* w /*[B,F,K]*/,

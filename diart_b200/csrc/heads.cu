@@ -51,6 +51,56 @@ int launch_seg_final(const float* y, const float* wc, const float* bc, int B, in
   return 0;
 }
 
+// powerset models (pyannote/segmentation-3.0): Linear(128, C) -> log_softmax over C classes (= subsets of the local
+// speakers of size <= max_per_frame) -> Powerset.to_multilabel = one_hot(argmax) @ mapping, i.e. hard {0,1} scores
+// (reference PowersetAdapter, src/diart/models.py:29-39).  argmax of log_softmax = argmax of the logits (first maximum,
+// like torch.argmax); `masks[c]` = speaker bit set of class c.
+__global__ void __launch_bounds__(256) seg_powerset_kernel(const float* __restrict__ y, const float* __restrict__ wc,
+                                                           const float* __restrict__ bc, int T, int stride, int C,
+                                                           int num_speakers, const unsigned* __restrict__ masks,
+                                                           float* __restrict__ seg) {
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float4 w[8];
+  float bias[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    w[k] = k < C ? *reinterpret_cast<const float4*>(wc + k * 128 + lane * 4) : make_float4(0, 0, 0, 0);
+    bias[k] = k < C ? bc[k] : 0.f;
+  }
+  for (int t = warp; t < T; t += 8) {
+    const float4 v = *reinterpret_cast<const float4*>(y + ((size_t)b * stride + t) * 128 + lane * 4);
+    int best = 0;
+    float best_v = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (k >= C) break;
+      float d = v.x * w[k].x;
+      d = fmaf(v.y, w[k].y, d);
+      d = fmaf(v.z, w[k].z, d);
+      d = fmaf(v.w, w[k].w, d);
+      for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+      d += bias[k];
+      if (d > best_v) {     // strict: the first maximum wins
+        best_v = d;
+        best = k;
+      }
+    }
+    if (lane < num_speakers) seg[((size_t)b * T + t) * num_speakers + lane] = (masks[best] >> lane) & 1u ? 1.f : 0.f;
+  }
+}
+
+int launch_seg_powerset(const float* y, const float* wc, const float* bc, int B, int T, int stride, int C, int num_speakers,
+                        const unsigned* masks_dev, float* seg, cudaStream_t st) {
+  ProfScope _ps("seg_final", st);
+  if (C > 8 || num_speakers > 8) {
+    set_error("seg_powerset: at most 8 classes / speakers");
+    return -1;
+  }
+  seg_powerset_kernel<<<B, 256, 0, st>>>(y, wc, bc, T, stride, C, num_speakers, masks_dev, seg);
+  DG_LAUNCHED();
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------------- osp
 __device__ __forceinline__ float pow_like_torch(float x, float g) {
   if (g == 3.f) return x * x * x;

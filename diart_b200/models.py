@@ -16,7 +16,7 @@ from __future__ import annotations
 
 import ctypes as C
 from pathlib import Path
-from typing import Callable, Dict, Optional, Union
+from typing import Callable, Dict, Optional, Tuple, Union
 
 import numpy as np
 import torch
@@ -93,12 +93,26 @@ class _Handle:
 
 
 class B200PyanNet(_Handle):
-    """pyannote/segmentation forward on the GPU: ``(B, 1, S) cuda float32 -> (B, F, K)``."""
+    """pyannote/segmentation forward on the GPU: ``(B, 1, S) cuda float32 -> (B, F, K)``.
+
+    ``powerset=(num_speakers, max_speakers_per_frame)`` declares a powerset model (pyannote/segmentation-3.0): the
+    classifier's outputs are subsets of the local speakers and the forward returns the hard multilabel scores the
+    reference's ``PowersetAdapter`` produces (reference ``src/diart/models.py:29-39``)."""
+
+    def __init__(self, state: StateDict, powerset: Optional[Tuple[int, int]] = None):
+        super().__init__(state)
+        self.powerset = powerset
 
     def _create(self, device):
         arr, n, keep = _lib.pack_state_dict(self._state)
         h = C.c_void_p()
         _lib.check(_lib.lib().dg_seg_create(arr, n, device.index, C.byref(h)))
+        if self.powerset is not None:
+            try:
+                _lib.check(_lib.lib().dg_seg_set_powerset(h, int(self.powerset[0]), int(self.powerset[1])))
+            except Exception:
+                _lib.lib().dg_seg_destroy(h)
+                raise
         return h
 
     def _destroy(self, h):
@@ -190,14 +204,27 @@ class B200XVectorSincNet(_Handle):
         return out
 
 
-class B200SegmentationLoader:
-    """``loader`` argument for ``SegmentationModel`` (ours or the reference's)."""
+def _powerset_of(source) -> Optional[Tuple[int, int]]:
+    """(num_speakers, max_speakers_per_frame) when ``source`` is a pyannote model with powerset specifications (what the
+    reference's loader checks, ``src/diart/models.py:50-53``), else None"""
+    specs = getattr(source, "specifications", None)
+    if specs is not None and getattr(specs, "powerset", False):
+        return len(specs.classes), int(specs.powerset_max_classes)
+    return None
 
-    def __init__(self, source):
+
+class B200SegmentationLoader:
+    """``loader`` argument for ``SegmentationModel`` (ours or the reference's).  ``powerset=(num_speakers,
+    max_speakers_per_frame)`` for powerset checkpoints given as plain state dicts (it is read from the model's
+    specifications when ``source`` is a pyannote model)."""
+
+    def __init__(self, source, powerset: Optional[Tuple[int, int]] = None):
         self.source = source
+        self.powerset = powerset
 
     def __call__(self) -> B200PyanNet:
-        return B200PyanNet(_load_state(self.source))
+        powerset = self.powerset if self.powerset is not None else _powerset_of(self.source)
+        return B200PyanNet(_load_state(self.source), powerset=powerset)
 
 
 class B200EmbeddingLoader:

@@ -55,6 +55,11 @@ int dg_version(void);
 int dg_seg_create(const dg_tensor* tensors, int n_tensors, int device, dg_seg** out);
 /* frames / local speakers produced for `num_samples`-sample chunks (293 / 3 for 80000) */
 int dg_seg_dims(const dg_seg* h, int num_samples, int* frames, int* speakers);
+/* Powerset models (pyannote/segmentation-3.0; reference PowersetAdapter, src/diart/models.py:29-39): the classifier has
+ * one output per subset of the `num_speakers` local speakers of size <= `max_per_frame` (pyannote Powerset order: by
+ * size, then lexicographic); forward then returns the hard multilabel scores one_hot(argmax) @ mapping, (B, F,
+ * num_speakers), and dg_seg_dims reports num_speakers. */
+int dg_seg_set_powerset(dg_seg* h, int num_speakers, int max_per_frame);
 int dg_seg_forward(dg_seg* h, const float* wav_dev /*[B,S]*/, int B, int S,
                    float* seg_dev /*[B,F,K]*/, void* stream);
 int dg_seg_destroy(dg_seg* h);

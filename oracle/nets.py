@@ -123,15 +123,43 @@ class SincNet(nn.Module):
         return outputs
 
 
+def powerset_mapping(num_classes: int, max_set_size: int) -> torch.Tensor:
+    """pyannote.audio.utils.powerset.Powerset.build_mapping (pyannote.audio >= 3.0; un-vendored dependency of the reference,
+    ``setup.cfg:34``): one row per subset of the ``num_classes`` speakers of size <= ``max_set_size``, ordered by size and
+    then as ``itertools.combinations`` yields them; mapping[row, speaker] = 1 when the speaker is in the subset."""
+    import itertools
+
+    rows = [subset for size in range(max_set_size + 1) for subset in itertools.combinations(range(num_classes), size)]
+    mapping = torch.zeros(len(rows), num_classes)
+    for r, subset in enumerate(rows):
+        mapping[r, list(subset)] = 1.0
+    return mapping
+
+
+def to_multilabel(powerset_log_probabilities: torch.Tensor, mapping: torch.Tensor) -> torch.Tensor:
+    """Powerset.to_multilabel(soft=False): one_hot(argmax over classes) @ mapping -> hard {0, 1} scores (B, F, speakers)"""
+    hard = F.one_hot(torch.argmax(powerset_log_probabilities, dim=-1), mapping.shape[0]).float()
+    return hard @ mapping
+
+
 class PyanNet(nn.Module):
     """pyannote.audio.models.segmentation.PyanNet with the pyannote/segmentation hyper-parameters."""
 
-    def __init__(self, num_speakers: int = 3, sample_rate: int = 16000):
+    def __init__(self, num_speakers: int = 3, sample_rate: int = 16000, powerset_max_classes: Optional[int] = None):
+        """``powerset_max_classes`` (pyannote/segmentation-3.0: 2 with ``num_speakers`` = 3): the classifier then has one
+        output per subset of the speakers of size <= that number, the last activation is ``log_softmax`` and ``forward``
+        applies what the reference's ``PowersetAdapter`` applies, ``Powerset.to_multilabel`` (reference
+        ``src/diart/models.py:29-39``)."""
         super().__init__()
         self.sincnet = SincNet(sample_rate=sample_rate, stride=10)
         self.lstm = nn.LSTM(60, 128, num_layers=4, bidirectional=True, batch_first=True, dropout=0.0)
         self.linear = nn.ModuleList([nn.Linear(256, 128), nn.Linear(128, 128)])
-        self.classifier = nn.Linear(128, num_speakers)
+        self.powerset_mapping = None
+        if powerset_max_classes is not None:
+            self.powerset_mapping = powerset_mapping(num_speakers, powerset_max_classes)
+            self.classifier = nn.Linear(128, self.powerset_mapping.shape[0])
+        else:
+            self.classifier = nn.Linear(128, num_speakers)
 
     def forward(self, waveforms: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
         x = self.sincnet(waveforms, taps)                 # (B, 60, 293)
@@ -143,6 +171,11 @@ class PyanNet(nn.Module):
             taps["lstm"] = x
         for linear in self.linear:
             x = F.leaky_relu(linear(x))
+        if self.powerset_mapping is not None:
+            logp = F.log_softmax(self.classifier(x), dim=-1)
+            if taps is not None:
+                taps["log_probabilities"] = logp
+            return to_multilabel(logp, self.powerset_mapping)
         return torch.sigmoid(self.classifier(x))
 
 
@@ -235,6 +268,16 @@ def _load(net: nn.Module, state) -> nn.Module:
 def make_segmentation(seed: int = 4321, num_speakers: int = 3, calibrated: bool = True) -> PyanNet:
     from diart_b200 import synth
     return _load(PyanNet(num_speakers=num_speakers), synth.segmentation_state(seed, num_speakers, calibrated))
+
+
+def make_powerset_segmentation(seed: int = 5151, num_speakers: int = 3, max_per_frame: int = 2, scale: float = 6.0) -> PyanNet:
+    """random-init powerset PyanNet (pyannote/segmentation-3.0 layout: 7 classes for 3 speakers, at most 2 per frame); the
+    classifier is scaled up so that the arg-max class varies over time instead of idling on one subset"""
+    from diart_b200 import synth
+    net = PyanNet(num_speakers=num_speakers, powerset_max_classes=max_per_frame)
+    state = synth.segmentation_state(seed, net.classifier.out_features, calibrated=False)
+    state["classifier.weight"] = state["classifier.weight"] * scale
+    return _load(net, state)
 
 
 def make_embedding(seed: int = 8765, pool_mode: str = "3.1", calibrated: bool = True) -> XVectorSincNet:
