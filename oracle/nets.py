@@ -250,6 +250,97 @@ class XVectorSincNet(nn.Module):
 
 
 # --------------------------------------------------------------------------------------
+# Variant B of the embedding row (SURVEY.md section 8(a) A8', Appendix A.6): pyannote/wespeaker-voxceleb-resnet34-LM.
+# ORACLE ONLY in this round -- there is no CUDA path for it yet; this restatement (from the published WeSpeaker /
+# pyannote.audio 3.1 definitions, un-vendored by the reference: setup.cfg:34) is the checker the next round builds to.
+# --------------------------------------------------------------------------------------
+class _BasicBlock(nn.Module):
+    """wespeaker.models.resnet.BasicBlock: conv3x3-bn-relu-conv3x3-bn + shortcut (1x1 conv + bn when the shape changes) -> relu"""
+
+    def __init__(self, in_planes: int, planes: int, stride: int):
+        super().__init__()
+        self.conv1 = nn.Conv2d(in_planes, planes, 3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = nn.Conv2d(planes, planes, 3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.shortcut = nn.Sequential()
+        if stride != 1 or in_planes != planes:
+            self.shortcut = nn.Sequential(nn.Conv2d(in_planes, planes, 1, stride=stride, bias=False), nn.BatchNorm2d(planes))
+
+    def forward(self, x):
+        out = F.relu(self.bn1(self.conv1(x)))
+        out = self.bn2(self.conv2(out))
+        return F.relu(out + self.shortcut(x))
+
+
+class _ResNet34(nn.Module):
+    """wespeaker ResNet34(feat_dim=80, embed_dim=256, m_channels=32, pooling TSTP, two_emb_layer=False)"""
+
+    def __init__(self, feat_dim: int = 80, embed_dim: int = 256, m_channels: int = 32, pool_mode: str = "3.1"):
+        super().__init__()
+        self.conv1 = nn.Conv2d(1, m_channels, 3, stride=1, padding=1, bias=False)
+        self.bn1 = nn.BatchNorm2d(m_channels)
+        in_planes = m_channels
+        for i, (mult, blocks, stride) in enumerate(((1, 3, 1), (2, 4, 2), (4, 6, 2), (8, 3, 2)), start=1):
+            layers = []
+            for s in [stride] + [1] * (blocks - 1):
+                layers.append(_BasicBlock(in_planes, m_channels * mult, s))
+                in_planes = m_channels * mult
+            setattr(self, f"layer{i}", nn.Sequential(*layers))
+        self.stats_dim = (feat_dim // 8) * m_channels * 8          # 10 x 256 = 2560
+        self.pool = StatsPool(pool_mode)                           # TSTP = StatsPool over (channel x frequency, time)
+        self.seg_1 = nn.Linear(self.stats_dim * 2, embed_dim)
+
+    def maps(self, fbank: torch.Tensor) -> torch.Tensor:
+        x = fbank.permute(0, 2, 1).unsqueeze(1)                   # (N, T, F) -> (N, 1, F, T)
+        x = F.relu(self.bn1(self.conv1(x)))
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))   # (N, 256, F/8, T/8)
+
+    def forward(self, fbank: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        x = self.maps(fbank)
+        x = x.reshape(x.shape[0], x.shape[1] * x.shape[2], x.shape[3])   # "batch dimension channel frames -> batch (dimension channel) frames"
+        return self.seg_1(self.pool(x, weights))
+
+
+class WeSpeakerResNet34(nn.Module):
+    """pyannote.audio.models.embedding.WeSpeakerResNet34: int16-scaled waveform -> kaldi fbank (80 mel bins, 25 ms / 10 ms,
+    Hamming, no dither, no energy) -> per-item mean normalisation over time -> ResNet34 -> TSTP(weights) -> Linear(5120, 256)"""
+
+    def __init__(self, sample_rate: int = 16000, pool_mode: str = "3.1"):
+        super().__init__()
+        self.sample_rate = sample_rate
+        self.resnet = _ResNet34(pool_mode=pool_mode)
+
+    def compute_fbank(self, waveforms: torch.Tensor) -> torch.Tensor:
+        from torchaudio.compliance import kaldi
+
+        x = waveforms * (1 << 15)
+        feats = torch.stack([kaldi.fbank(w, num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0,
+                                         sample_frequency=self.sample_rate, window_type="hamming", use_energy=False)
+                             for w in x])                           # (N, 498, 80) for 80 000 samples
+        return feats - feats.mean(dim=1, keepdim=True)
+
+    def forward(self, waveforms: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """waveforms (N, 1, S), weights (N, F) or None -> (N, 256)"""
+        return self.resnet(self.compute_fbank(waveforms), weights)
+
+
+def make_wespeaker(seed: int = 2468, pool_mode: str = "3.1") -> WeSpeakerResNet34:
+    """seeded random-init variant-B net (torch's default initialisers; BatchNorm statistics randomised so that the eval-mode
+    affine is not the identity)"""
+    torch.manual_seed(seed)
+    net = WeSpeakerResNet34(pool_mode=pool_mode)
+    g = torch.Generator().manual_seed(seed)
+    for m in net.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.running_mean.copy_(0.1 * torch.randn(m.num_features, generator=g))
+            m.running_var.copy_(0.5 + torch.rand(m.num_features, generator=g))
+            m.weight.data.copy_(1.0 + 0.1 * torch.randn(m.num_features, generator=g))
+            m.bias.data.copy_(0.1 * torch.randn(m.num_features, generator=g))
+    return net.eval()
+
+
+# --------------------------------------------------------------------------------------
 # Seeded synthetic weights / audio (SURVEY.md section 8(d)): generated by diart_b200.synth so
 # that the oracle and the CUDA side are fed the very same state dicts.
 # --------------------------------------------------------------------------------------

@@ -84,3 +84,30 @@ def test_numpy_reduction_semantics():
         run = (run + seg[f]).astype(np.float32)
     assert np.array_equal(np.mean(seg, axis=0), run / np.float32(293))
     assert (np.float32(0.6) >= 0.6) and not (np.float32(0.59999996) >= 0.6)   # float32 comparison (weak scalar)
+
+
+def test_variant_b_oracle_wespeaker_resnet34():
+    """Variant B of the embedding row (SURVEY.md 8(a) A8', Appendix A.6) exists as an ORACLE only so far: pinned by the
+    published size of WeSpeaker ResNet34 (6.63 M parameters), the feature-map sizes 80x498 -> 10x63, the 5120-d TSTP
+    statistics, and the pooling semantics (constant weights = no weights)."""
+    import torch
+
+    from diart_b200 import synth
+    from oracle import nets
+
+    net = nets.make_wespeaker()
+    assert nets.n_params(net) == 6_634_336
+    x = torch.from_numpy(synth.windows(synth.synth_audio(80000 + 8000, seed=5), 2))[:, None, :]
+    with torch.no_grad():
+        fb = net.compute_fbank(x)
+        assert fb.shape == (2, 498, 80) and fb.mean(dim=1).abs().max() < 1e-4        # CMN
+        maps = net.resnet.maps(fb)
+        assert maps.shape == (2, 256, 10, 63)
+        assert net.resnet.seg_1.in_features == 5120
+        e = net(x)
+        e_const = net(x, torch.full((2, 293), 0.37))
+        w = torch.rand(2, 293, generator=torch.Generator().manual_seed(1))
+        e_w = net(x, w)
+    assert e.shape == (2, 256)
+    assert torch.allclose(e, e_const, rtol=1e-3, atol=1e-4)       # scale-free weights (+1e-8 terms of the 3.1 StatsPool)
+    assert not torch.allclose(e, e_w, rtol=1e-3, atol=1e-4)
