@@ -111,3 +111,20 @@ def test_variant_b_oracle_wespeaker_resnet34():
     assert e.shape == (2, 256)
     assert torch.allclose(e, e_const, rtol=1e-3, atol=1e-4)       # scale-free weights (+1e-8 terms of the 3.1 StatsPool)
     assert not torch.allclose(e, e_w, rtol=1e-3, atol=1e-4)
+
+
+def test_fbank_as_two_matrix_products_equals_kaldi():
+    """the B200 mapping of variant B's front end (oracle/fbank_linear.py): one [514, 400] operator on an overlapping-row
+    view of the waveform, power, one [80, 257] mel matrix, log -- against torchaudio's kaldi.fbank"""
+    import torch
+    from torchaudio.compliance import kaldi
+
+    from diart_b200 import synth
+    from oracle import fbank_linear
+
+    x = synth.synth_audio(80000, seed=11) * 32768.0
+    ref = kaldi.fbank(torch.from_numpy(x)[None], num_mel_bins=80, frame_length=25, frame_shift=10, dither=0.0,
+                      sample_frequency=16000, window_type="hamming", use_energy=False).numpy()
+    got = fbank_linear.fbank(x)
+    assert got.shape == ref.shape == (498, 80)
+    assert np.abs(got - ref).max() < 2e-3 and np.abs(got - ref).mean() < 1e-4     # log-mel values are O(10)
