@@ -128,3 +128,23 @@ def test_fbank_as_two_matrix_products_equals_kaldi():
     got = fbank_linear.fbank(x)
     assert got.shape == ref.shape == (498, 80)
     assert np.abs(got - ref).max() < 2e-3 and np.abs(got - ref).mean() < 1e-4     # log-mel values are O(10)
+
+
+def test_resnet34_in_shifted_window_gemm_form_equals_the_oracle():
+    """the B200 mapping of variant B's trunk (oracle/resnet_gemm_form.py): time-major channels-last maps, 3x3 / 1x1 convolutions
+    as 9- / 1-tap shifted-window GEMMs with zero out-of-bounds rows, folded BatchNorm, permuted Linear columns"""
+    import torch
+
+    from diart_b200 import synth
+    from oracle import nets, resnet_gemm_form
+
+    net = nets.make_wespeaker()
+    x = torch.from_numpy(synth.windows(synth.synth_audio(80000 + 8000, seed=5), 2))[:, None, :]
+    w = torch.rand(2, 293, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        fb = net.compute_fbank(x)
+        for weights in (None, w):
+            ref = net.resnet(fb, weights)
+            got = resnet_gemm_form.forward(net, fb, weights)
+            assert got.shape == ref.shape == (2, 256)
+            assert (got - ref).abs().max() < 2e-4 * ref.abs().max()
