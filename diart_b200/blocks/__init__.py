@@ -5,5 +5,5 @@ from .diarization import SpeakerDiarization, SpeakerDiarizationConfig
 from .embedding import (EmbeddingNormalization, OverlapAwareSpeakerEmbedding, OverlappedSpeechPenalty,
                         SpeakerEmbedding)
 from .segmentation import SpeakerSegmentation
-from .utils import Binarize
+from .utils import AdjustVolume, Binarize, Resample
 from .vad import VoiceActivityDetection, VoiceActivityDetectionConfig

@@ -71,3 +71,25 @@ def test_formatter_equals_reference(ref):
     assert torch.equal(a.cast(swf), b.cast(swf))
     ra, rb = a.restore_type(torch.ones(1, 25, 2)), b.restore_type(torch.ones(1, 25, 2))
     assert ra.sliding_window.start == rb.sliding_window.start and ra.sliding_window.step == rb.sliding_window.step
+
+
+def test_preprocessing_blocks_equal_reference(ref):
+    """Resample and AdjustVolume (optional pre-processing next to the path) against the reference implementations"""
+    import importlib
+
+    from diart_b200 import blocks
+    from diart_b200.core import SlidingWindow, SlidingWindowFeature
+
+    ref_utils = importlib.import_module("diart.blocks.utils")
+    rng = np.random.default_rng(5)
+    batch = torch.from_numpy(rng.standard_normal((3, 8000, 1)).astype(np.float32) * 0.05)
+    loud = batch * 100
+    for target in (-20.0, 3.0):
+        for x in (batch, loud):
+            np.testing.assert_allclose(blocks.AdjustVolume(target)(x).numpy(), ref_utils.AdjustVolume(target)(x).numpy(), rtol=1e-6)
+    swf = SlidingWindowFeature(batch[0].numpy(), SlidingWindow(start=1.5, duration=1 / 8000, step=1 / 8000))
+    a, b = blocks.Resample(8000, 16000)(swf), ref_utils.Resample(8000, 16000)(swf)
+    assert a.data.shape == b.data.shape == (16000, 1)
+    np.testing.assert_allclose(a.data, b.data, rtol=1e-6, atol=1e-7)
+    assert a.sliding_window.start == b.sliding_window.start and a.sliding_window.step == b.sliding_window.step
+    np.testing.assert_allclose(blocks.Resample(16000, 8000)(batch).numpy(), ref_utils.Resample(16000, 8000)(batch).numpy(), rtol=1e-6, atol=1e-7)
