@@ -123,3 +123,36 @@ def test_stream_form_identity_of_the_sinc_layer():
         A = gamma * rstd
         got = (A * c_stream[b * hop // 10:b * hop // 10 + 3 * T0] + (beta - A * mu) * hsum).abs().reshape(T0, 3, 80).amax(1)
         assert torch.allclose(got, ref, rtol=1e-10, atol=1e-12)
+
+
+def test_rttm_sinks(tmp_path):
+    """RTTMWriter / PredictionAccumulator (reference sinks.py:25-88): per-chunk turns are appended as they arrive, and
+    same-speaker turns closer than the collar are merged when the stream ends; both sinks end with the same RTTM text"""
+    from diart_b200 import sinks
+    from diart_b200.core import Annotation, Segment
+
+    chunks = []
+    for i in range(6):                                        # speaker0: 0.0-0.48 | 0.50-0.98 | ... (20 ms gaps), speaker1 once
+        a = Annotation(modality="speech")
+        a[Segment(0.5 * i, 0.5 * i + 0.48), 0] = "speaker0"
+        if i == 3:
+            a[Segment(1.6, 1.9), 1] = "speaker1"
+        chunks.append((a, None))
+    path = tmp_path / "out.rttm"
+    path.write_text("stale\n")
+    writer, acc = sinks.RTTMWriter("file1", path), sinks.PredictionAccumulator("file1")
+    assert not path.exists()                                  # an existing file is removed up front
+    for c in chunks:
+        writer.on_next(c)
+        acc.on_next(c)
+    assert len(path.read_text().splitlines()) == 7            # un-patched: one line per turn
+    writer.on_completed()
+    acc.on_completed()
+    text = path.read_text()
+    assert text == acc.get_prediction().to_rttm()
+    assert text.splitlines() == ["SPEAKER file1 1 0.000 2.980 <NA> <NA> speaker0 <NA> <NA>",
+                                 "SPEAKER file1 1 1.600 0.300 <NA> <NA> speaker1 <NA> <NA>"]
+    with pytest.raises(ValueError):
+        acc.on_next("not a prediction")
+    loaded = sinks.load_rttm(path)
+    assert list(loaded) == ["file1"] and loaded["file1"].to_rttm() == text
