@@ -324,6 +324,14 @@ class WeSpeakerResNet34(nn.Module):
         """waveforms (N, 1, S), weights (N, F) or None -> (N, 256)"""
         return self.resnet(self.compute_fbank(waveforms), weights)
 
+    def forward_dedup(self, waveforms: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
+        """Trunk once per waveform, K poolings: ``weights`` (B, F, K) -> (B, K, 256); arithmetically identical to the
+        reference's K-fold repeat (``src/diart/blocks/embedding.py:57-59``) because the weights only enter at pooling."""
+        r = self.resnet
+        x = r.maps(self.compute_fbank(waveforms))
+        x = x.reshape(x.shape[0], x.shape[1] * x.shape[2], x.shape[3])
+        return torch.stack([r.seg_1(r.pool(x, weights[:, :, k])) for k in range(weights.shape[2])], dim=1)
+
 
 def make_wespeaker(seed: int = 2468, pool_mode: str = "3.1") -> WeSpeakerResNet34:
     """seeded random-init variant-B net (torch's default initialisers; BatchNorm statistics randomised so that the eval-mode

@@ -109,6 +109,10 @@ def test_variant_b_oracle_wespeaker_resnet34():
         w = torch.rand(2, 293, generator=torch.Generator().manual_seed(1))
         e_w = net(x, w)
     assert e.shape == (2, 256)
+    with torch.no_grad():
+        w2 = torch.stack([w, 1.0 - w], dim=-1)
+        dedup = net.forward_dedup(x, w2)
+    assert dedup.shape == (2, 2, 256) and torch.allclose(dedup[:, 0], e_w, rtol=1e-4, atol=1e-5)
     assert torch.allclose(e, e_const, rtol=1e-3, atol=1e-4)       # scale-free weights (+1e-8 terms of the 3.1 StatsPool)
     assert not torch.allclose(e, e_w, rtol=1e-3, atol=1e-4)
 
