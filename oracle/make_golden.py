@@ -10,6 +10,9 @@ Fixtures
                        normalize_embeddings known answers from reference functional.py, blocks/embedding.py
   nets.npz             segmentation scores and unit-norm embeddings of the oracle networks, computed
                        THROUGH the reference's SpeakerSegmentation / OverlapAwareSpeakerEmbedding blocks
+  net_layers.npz       per-layer fingerprints (mean, std, |max|, 32 samples) of PyanNet / XVectorSincNet / the powerset
+                       PyanNet / WeSpeakerResNet34 on one seeded chunk (SURVEY.md 8(c) golden kind 1); needs no reference tree:
+                       python oracle/make_golden.py --layers
 """
 import hashlib
 import os
@@ -37,7 +40,42 @@ def digest(a: np.ndarray) -> str:
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
+def fingerprint(t: torch.Tensor) -> np.ndarray:
+    a = t.detach().double().reshape(-1)
+    idx = torch.linspace(0, a.numel() - 1, 32).long()
+    return np.concatenate([[a.mean().item(), a.std().item(), a.abs().max().item()], a[idx].numpy()])
+
+
+def layer_fingerprints() -> dict:
+    """{tap name: fingerprint} of the four oracle networks on window 0 of synth_audio(seed=1234)"""
+    x = torch.from_numpy(synth.windows(synth.synth_audio(80000 + 8000, seed=1234), 1))[:, None, :]
+    w = torch.rand(1, 293, generator=torch.Generator().manual_seed(7))
+    out = {}
+    with torch.no_grad():
+        taps = {}
+        out["seg/out"] = fingerprint(nets.make_segmentation()(x, taps))
+        out.update({f"seg/{k}": fingerprint(v) for k, v in taps.items()})
+        taps = {}
+        emb = nets.make_embedding()
+        trunk = emb.trunk(x, taps)
+        out.update({f"emb/{k}": fingerprint(v) for k, v in taps.items()})
+        out["emb/out_weighted"] = fingerprint(emb.embedding(emb.stats_pool(trunk, w)))
+        taps = {}
+        nets.make_powerset_segmentation()(x, taps)
+        out["powerset/log_probabilities"] = fingerprint(taps["log_probabilities"])
+        wes = nets.make_wespeaker()
+        fb = wes.compute_fbank(x)
+        out["wespeaker/fbank"] = fingerprint(fb)
+        out["wespeaker/maps"] = fingerprint(wes.resnet.maps(fb))
+        out["wespeaker/out_weighted"] = fingerprint(wes(x, w))
+    return out
+
+
 def main():
+    if "--layers" in sys.argv:
+        np.savez_compressed(os.path.join(OUT, "net_layers.npz"), **{k.replace("/", "__"): v for k, v in layer_fingerprints().items()})
+        print("golden written: net_layers.npz")
+        return
     ref = ref_import.load()
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)

@@ -152,3 +152,21 @@ def test_resnet34_in_shifted_window_gemm_form_equals_the_oracle():
             got = resnet_gemm_form.forward(net, fb, weights)
             assert got.shape == ref.shape == (2, 256)
             assert (got - ref).abs().max() < 2e-4 * ref.abs().max()
+
+
+def test_per_layer_fingerprints_of_the_oracle_networks():
+    """golden kind 1 of SURVEY.md 8(c): per-layer tensors of the (restated, third-party) networks on seeded synthetic weights
+    and audio -- stored as fingerprints (mean, std, |max|, 32 samples per layer) in tests/golden/net_layers.npz by
+    `python oracle/make_golden.py --layers`; any change of the restatement or of the synthetic weights shows up here"""
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(GOLD), "..", "oracle", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    g = np.load(os.path.join(GOLD, "net_layers.npz"))
+    now = mg.layer_fingerprints()
+    assert sorted(k.replace("/", "__") for k in now) == sorted(g.files) and len(g.files) == 19
+    for name, fp in now.items():
+        ref = g[name.replace("/", "__")]
+        scale = max(ref[1], 1e-6)                       # the layer's standard deviation
+        assert np.abs(fp - ref).max() < 2e-4 * max(scale, ref[2]), name
