@@ -124,22 +124,6 @@ def test_foreign_models_behind_loader_api(oracle_nets, stream, cuda_device):
     assert m1.shape == m2.shape and m1.dtype == torch.int32
 
 
-def test_hop_hint_is_only_a_hint(oracle_nets, stream, cuda_device):
-    """a batch that is NOT a run of overlapping windows (here: the windows in reverse order) must give exactly the
-    per-window results although the hop hint is set -- the overlap is verified on the device for every batch -- and a
-    batch that is one gives the same speaker maps and scores within the parity bar in both forms"""
-    a, b = make_pipeline(oracle_nets, cuda_device), window_form(make_pipeline(oracle_nets, cuda_device))
-    fwd = synth.windows(stream, BATCH)
-    rev = torch.from_numpy(np.ascontiguousarray(fwd[::-1])).to(cuda_device)
-    (s1, e1, m1), (s2, e2, m2) = a.device_step(rev), b.device_step(rev)
-    assert torch.equal(s1, s2) and torch.equal(e1, e2) and torch.equal(m1, m2)
-    a, b = make_pipeline(oracle_nets, cuda_device), window_form(make_pipeline(oracle_nets, cuda_device))   # fresh clustering state
-    x = torch.from_numpy(fwd).to(cuda_device)
-    (s1, e1, m1), (s2, e2, m2) = a.device_step(x), b.device_step(x)
-    assert (s1 - s2).abs().max().item() < 1e-4 and (e1 - e2).abs().max().item() < 1e-4
-    assert torch.equal(m1, m2)
-
-
 def test_pipelined_submit_collect_equals_sequential_steps(oracle_nets, stream, cuda_device):
     """dg_pipeline_submit / collect (clustering of step i overlapping the networks of step i+1) must give exactly
     what one-step-at-a-time dg_pipeline_step gives: chunk order per stream is preserved"""
