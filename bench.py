@@ -57,9 +57,12 @@ HBM_BYTES_PER_CHUNK = {
     # (both nets / all call sites pooled) float32 map in, two 16-bit planes out: mean over the 7 launches of a step
     "split16": (2 * (2658 * 80 * 4 + 2658 * 128 * 4) + 2 * (2654 * 64 * 4 + 884 * 64 * 4) + 2 * (880 * 64 * 4 + 293 * 64 * 4)
                 + 3 * (3000 + 3008) * 4) / 7,
+    # sequential clustering: scores + embeddings in, speaker map out (latency-bound: 256 dependent chunks per launch)
+    "cluster_step": 293 * 3 * 4 + 3 * 512 * 4 + 3 * 4,
 }
 # compulsory HBM bytes per chunk of the whole step: waveform in, seg + emb out
 BYTES_PER_CHUNK = 80000 * 4 + 293 * 3 * 4 + 3 * 512 * 4
+STEP_FLOPS_PER_CHUNK = 3.359e9      # segmentation 1.312 + embedding (de-duplicated trunk) 2.047 GFLOP
 
 
 def peaks():
@@ -314,19 +317,138 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * args.steps * B * STEP_SECONDS / float(t.item())
 
+    # ---------------- end to end with the ring buffer in HBM: the host pushes every sample once
+    # (B x 8000 new samples per step instead of B stacked windows), windows are formed on the device
+    stream_line = None
+    if not args.serial and not args.no_stream_leg:
+        from diart_b200 import synth as _synth
+        from diart_b200.operators import DeviceAudioStream
+
+        n_total = max(2, args.warmup) + args.steps
+        audio = _synth.synth_audio(CHUNK + STEP * (n_total * B - 1), seed=1234 + rank)
+        dst = DeviceAudioStream(CHUNK / SR, STEP / SR, SR, max_windows=B, device=device)
+        pipe.reset()
+        fused, F, K, D = pipe._ensure_fused(CHUNK)
+        dst.push(audio[:CHUNK - STEP])
+        cursor = [CHUNK - STEP]
+
+        def stream_steps(n):
+            depth = 3
+            for i in range(n):
+                blk = audio[cursor[0]:cursor[0] + B * STEP]
+                cursor[0] += B * STEP
+                _lib.check(lib.dg_stream_push_host(dst.handle, blk.ctypes.data, len(blk)))
+                _lib.check(lib.dg_pipeline_submit_stream(fused, dst.handle, B))
+                if i >= depth - 1:
+                    j = (i - depth + 1) % 3
+                    _lib.check(lib.dg_pipeline_collect_host(fused, seg_h[j].data_ptr(), emb_h[j].data_ptr(), map_h[j].data_ptr()))
+            for i in range(max(0, n - depth + 1), n):
+                j = i % 3
+                _lib.check(lib.dg_pipeline_collect_host(fused, seg_h[j].data_ptr(), emb_h[j].data_ptr(), map_h[j].data_ptr()))
+
+        stream_steps(max(2, args.warmup))
+        barrier()
+        t0 = time.perf_counter()
+        stream_steps(args.steps)
+        torch.cuda.synchronize(device)
+        st_s = time.perf_counter() - t0
+        t = torch.tensor([st_s], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        stream_line = {"value": world * args.steps * B * STEP_SECONDS / float(t.item()), "unit": UNIT,
+                       "ms_per_step": 1e3 * float(t.item()) / args.steps, "h2d_bytes_per_step": B * STEP * 4,
+                       "d2h_bytes_per_step": B * F * K * 4 + B * K * D * 4 + B * K * 4,
+                       "api": "dg_stream_push_host (pageable host block -> pinned mirror -> ring in HBM) + dg_pipeline_submit_stream / "
+                              "collect_host, three steps outstanding"}
+        del dst
+
+    # ---------------- R3: the drop-in call itself, SpeakerDiarization.__call__ on B separate SlidingWindowFeatures (the
+    # reference's Chronometer bracket, src/diart/inference.py:130-137): gather + H2D, fused step, device post-path, D2H of
+    # the turn list, Annotation objects -- everything a StreamingInference user pays per batch
+    call_line = None
+    if not args.no_pipeline_call:
+        from diart_b200.core import SlidingWindow, SlidingWindowFeature
+
+        pipe.reset()
+        sw_of = lambda n: SlidingWindow(start=STEP_SECONDS * n, duration=1 / SR, step=1 / SR)
+        rows = [[np.ascontiguousarray(host[j][b][:, None]) for b in range(B)] for j in range(NB)]
+        n_calls = max(3, min(args.steps, 10))
+
+        def call_steps(n, first):
+            turns = 0
+            for i in range(n):
+                g0 = (first + i) * B
+                chunks = [SlidingWindowFeature(rows[i % NB][b], sw_of(g0 + b)) for b in range(B)]
+                out = pipe(chunks)
+                turns += sum(len(a) for a, _ in out)
+            return turns
+
+        call_steps(2, 0)
+        barrier()
+        t0 = time.perf_counter()
+        n_turn_objs = call_steps(n_calls, 2)
+        call_s = time.perf_counter() - t0
+        t = torch.tensor([call_s], device=device, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        call_line = {"value": world * n_calls * B * STEP_SECONDS / float(t.item()), "unit": UNIT,
+                     "ms_per_call": 1e3 * float(t.item()) / n_calls, "calls": n_calls,
+                     "h2d_bytes_per_step": B * CHUNK * 4, "d2h_bytes_per_step": B * 16 + 4 + 4 * (n_turn_objs // n_calls),
+                     "api": "SpeakerDiarization.__call__(Sequence[SlidingWindowFeature]) -> Sequence[(Annotation, SlidingWindowFeature)], "
+                            "synchronous per batch (dg_pipeline_call_host: threaded gather + upload of B separate pageable host "
+                            "windows, fused step, device aggregation/binarisation, one D2H of the turn list)"}
+
+    # ---------------- parity of the benchmarked configuration (outside every timed region): the pipelined path over NB
+    # batches of B windows from a fresh state; speaker maps against the oracle clustering replayed on the same scores /
+    # embeddings, float64 centroids bit for bit, a sample of the scores against the oracle network
+    parity = None
+    if rank == 0 and not args.no_parity_check:
+        from oracle import nets as onets
+        from oracle.clustering import OracleClustering
+
+        pipe.reset()
+        fused, F, K, D = pipe._ensure_fused(CHUNK)
+        got = []
+        for i in range(NB):
+            pipe.submit(dev[i])
+            if i > 0:
+                got.append(pipe.collect())
+        got.append(pipe.collect())
+        torch.cuda.synchronize(device)
+        cfg = pipe.config
+        replay = OracleClustering(cfg.tau_active, cfg.rho_update, cfg.delta_new, "cosine", cfg.max_speakers)
+        ok, bad = True, None
+        for j, (sg, em, mp) in enumerate(got):
+            sg, em, mp = sg.cpu().numpy(), em.cpu().numpy(), mp.cpu().numpy()
+            want = np.stack([replay(s_, e_)[0] for s_, e_ in zip(sg, em)])
+            if not np.array_equal(want, mp):
+                ok, bad = False, (j, int(np.where((want != mp).any(axis=1))[0][0]))
+                break
+        centers_equal = bool(ok and np.array_equal(pipe.clustering.centers, replay.centers))
+        with torch.no_grad():
+            torch.set_num_threads(min(16, os.cpu_count() or 1))
+            o_seg = onets.make_segmentation()(torch.from_numpy(host[0][:4])[:, None, :]).numpy()
+        seg_err = float(np.abs(got[0][0][:4].cpu().numpy() - o_seg).max())
+        parity = {"chunks": NB * B, "maps_equal_oracle_replay": ok, "centroids_bit_equal": centers_equal,
+                  "seg_max_abs_err_4_windows": seg_err, "first_difference": bad}
+        if not (ok and centers_equal and seg_err < 1e-4):
+            raise SystemExit(f"bench.py: the benchmarked configuration fails its parity check: {parity}")
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
     # ---------------- roofline of the dominant kernel
-    # "dominant" = largest share of the step's SM-time: event time x the fraction of the 148 SMs the kernel occupies.
-    # The two sequential kernels are long but narrow -- cluster_step is ONE CTA on its own stream, lstm_rec 2 x ceil(B/16)
-    # CTAs -- and overlap everything else; ranking by plain duration would flip between them from run to run.
+    # `roofline` = the kernel with the largest CUDA-event time inside the timed region.  At B = 256 that is one of the two
+    # sequential kernels -- cluster_step (ONE CTA on its own stream) or lstm_rec (2 x ceil(B/16) CTAs) -- which are long but narrow
+    # and overlap everything else; `by_sm_time` therefore also ranks by event time x the fraction of the 148 SMs a kernel occupies,
+    # and `step` puts the whole step against both rooflines.
     pk = peaks()
     narrow = {"cluster_step": 1 / 148, "cluster_merge": 1 / 148, "cluster_export": 1 / 148, "relabel_maps": 1 / 148,
               "lstm_rec": min(1.0, 2 * ((B + 15) // 16) / 148)}
     sm_time = {k: v["ms"] * narrow.get(k, 1.0) for k, v in kernels.items()}
-    dom = max(sm_time, key=sm_time.get)
+    dom = max(kernels, key=lambda k: kernels[k]["ms"])        # the dominant kernel BY EVENT DURATION inside the timed region
+    dom_sm = max(sm_time, key=sm_time.get)                     # ... and by SM-time (extra key `by_sm_time`)
     per_launch_ms = kernels[dom]["ms"] / kernels[dom]["count"]
     traffic_tab = {}
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -347,16 +469,22 @@ def run_ours(args):
         return {"kernel": k, "bound": "hbm", "achieved": gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": gbs / pk["hbm_gbs"],
                 "traffic": traffic_tab.get(k), "peak_source": pk["src"], "ms_per_launch": ms_l}
 
-    if dom in HBM_BYTES_PER_CHUNK:
-        roofline = hbm_line(dom)
-    elif dom in FLOPS_PER_CHUNK:
-        roofline = tensor_line(dom)
-    else:
-        achieved = BYTES_PER_CHUNK * B / (per_launch_ms * 1e-3) / 1e9
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                    "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_source": pk["src"],
-                    "ms_per_launch": per_launch_ms}
-    roofline["dominant_by"] = "SM-time (event ms x SMs occupied / 148)"
+    def line_of(k):
+        if k in HBM_BYTES_PER_CHUNK:
+            return hbm_line(k)
+        if k in FLOPS_PER_CHUNK:
+            return tensor_line(k)
+        ms_l = kernels[k]["ms"] / kernels[k]["count"]
+        achieved = BYTES_PER_CHUNK * B / (ms_l * 1e-3) / 1e9
+        return {"kernel": k, "bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                "frac": achieved / pk["hbm_gbs"], "traffic": traffic_tab.get(k), "peak_source": pk["src"], "ms_per_launch": ms_l}
+
+    roofline = line_of(dom)
+    roofline["dominant_by"] = "CUDA-event duration summed over the timed region"
+    if dom in ("lstm_rec", "cluster_step"):
+        roofline["note"] = ("latency-bound sequential kernel (293 dependent steps per launch / one dependent step per chunk) on a few SMs, "
+                            "overlapped by the wide kernels of the other streams: neither roofline binds it; see `recurrence`, `by_sm_time` and `step`")
+    roofline["by_sm_time"] = dict(line_of(dom_sm), dominant_by="SM-time (event ms x SMs occupied / 148)")
     roofline["sm_time_ms_per_step"] = {k: round(v / args.steps, 4) for k, v in sorted(sm_time.items(), key=lambda kv: -kv[1])[:6]}
     if "lstm_rec" in kernels:   # the longest kernel by duration: neither roofline binds a recurrence
         r_ms = kernels["lstm_rec"]["ms"] / kernels["lstm_rec"]["count"]
@@ -371,6 +499,15 @@ def run_ours(args):
         roofline["largest_gemm"] = tensor_line(gk)
     step_flops = sum(FLOPS_PER_CHUNK[k] * (4 if k == "lstm_inproj" or k == "lstm_rec" else 2 if k in
                      ("sinc0", "sinc_conv1", "sinc_conv2", "seg_linear") else 1) for k in FLOPS_PER_CHUNK) * B
+    step_ms = ms_max / args.steps
+    roofline["step"] = {
+        "bound": "tensor", "flops_per_step": STEP_FLOPS_PER_CHUNK * B, "achieved": STEP_FLOPS_PER_CHUNK * B / (step_ms * 1e-3) / 1e12,
+        "peak": pk["tf"], "unit": "TFLOP/s", "frac": STEP_FLOPS_PER_CHUNK * B / (step_ms * 1e-3) / 1e12 / pk["tf"],
+        "peak_source": pk["src"] + " (bf16 sustained)", "compulsory_bytes_per_step": BYTES_PER_CHUNK * B,
+        "hbm_frac": BYTES_PER_CHUNK * B / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
+        "traffic": traffic_tab.get("_step"),
+        "note": "SURVEY.md 8(d) algorithmic FLOPs of the de-duplicated path (3.359 GFLOP per chunk) / ms_per_step; the path executes 3 "
+                "tcgen05 products per algorithmic product (fp16 hi/lo split) and contains 1172 + 256 dependent steps per batch"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -386,6 +523,9 @@ def run_ours(args):
                 "d2h_bytes_per_step": B * F * K * 4 + B * K * D * 4 + B * K * 4,
                 "api": ("dg_pipeline_step_host" if args.serial else "dg_pipeline_submit_host / collect_host, three steps outstanding") +
                        " (C ABI, pinned host buffers)"},
+        "e2e_stream": stream_line,
+        "e2e_pipeline_call": call_line,
+        "parity": parity,
         "gpu_launches": int(launches),
         "clocks": clocks.summary(),
         "roofline": roofline,
@@ -427,6 +567,9 @@ def _main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ref-batch", type=int, default=32)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stream-leg", action="store_true", help="skip the device ring-buffer leg (e2e_stream)")
+    ap.add_argument("--no-pipeline-call", action="store_true", help="skip the SpeakerDiarization.__call__ leg (e2e_pipeline_call)")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the oracle replay of the benchmarked configuration")
     ap.add_argument("--shared-identity", action="store_true",
                     help="BASELINE config 5: share the global speaker table across ranks (one all-gather per step)")
     ap.add_argument("--serial", action="store_true", help="one step at a time (dg_pipeline_step) instead of depth-2 pipelining")

@@ -64,6 +64,19 @@ SIGNATURES = {
     "dg_pipeline_submit_host": (C.c_int, [_P, _P, C.c_int, C.c_int]),
     "dg_pipeline_collect_host": (C.c_int, [_P, _P, _P, _P]),
     "dg_pipeline_destroy": (C.c_int, [_P]),
+    "dg_post_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, C.c_double, C.c_int, C.POINTER(_P)]),
+    "dg_post_step": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.POINTER(C.c_int), _P]),
+    "dg_post_reset": (C.c_int, [_P]),
+    "dg_post_destroy": (C.c_int, [_P]),
+    "dg_stream_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
+    "dg_stream_push_host": (C.c_int, [_P, _P, C.c_int]),
+    "dg_stream_available": (C.c_int, [_P]),
+    "dg_stream_windows": (C.c_int, [_P, C.c_int, _P, _P]),
+    "dg_stream_reset": (C.c_int, [_P]),
+    "dg_stream_destroy": (C.c_int, [_P]),
+    "dg_pipeline_submit_stream": (C.c_int, [_P, _P, C.c_int]),
+    "dg_pipeline_call_stream": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P]),
+    "dg_pipeline_call_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P]),
 }
 
 

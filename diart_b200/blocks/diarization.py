@@ -3,8 +3,8 @@
 Lines 177-203 of the reference -- segmentation, overlapped-speech penalty, embedding, normalisation
 and the sequential clustering loop -- run as ONE fused device step (``dg_pipeline_step``): the
 waveform batch is uploaded once, nothing returns to the host in between, and only the
-(B,F,K) scores and the (B,K) speaker map come back.  Lines 205-232 (aggregation, binarisation,
-buffer bookkeeping) are host-side numpy for now ("next").
+(B,F,K) scores and the (B,K) speaker map come back.  Lines 205-232 (SpeakerMap.apply, aggregation, binarisation) run
+on the device too (``blocks/post.py``, ``csrc/post.cu``); the host only attaches time stamps.
 """
 from __future__ import annotations
 
@@ -21,6 +21,7 @@ from . import base
 from .aggregation import DelayedAggregation
 from .clustering import OnlineSpeakerClustering
 from .embedding import OverlapAwareSpeakerEmbedding
+from .post import DevicePostPath, aggregate_audio
 from .segmentation import SpeakerSegmentation
 from .utils import Binarize
 
@@ -81,6 +82,7 @@ class SpeakerDiarization(base.Pipeline):
         self.chunk_buffer, self.pred_buffer = [], []
         self._fused: Optional[C.c_void_p] = None
         self._pinned: Optional[torch.Tensor] = None
+        self._post: Optional[DevicePostPath] = None
         self.reset()
 
     @staticmethod
@@ -111,6 +113,8 @@ class SpeakerDiarization(base.Pipeline):
                                                   self.config.delta_new, "cosine", self.config.max_speakers,
                                                   device=self.segmentation.device)
         self.chunk_buffer, self.pred_buffer = [], []
+        if self._post is not None:
+            self._post.reset()
 
     # ------------------------------------------------------------------ fused device step
     def _drop_fused(self):
@@ -207,10 +211,79 @@ class SpeakerDiarization(base.Pipeline):
 
     # ------------------------------------------------------------------ the pipeline call
     def __call__(self, waveforms: Sequence[SlidingWindowFeature]) -> Sequence[Tuple[Annotation, SlidingWindowFeature]]:
+        """reference diarization.py:157-234.  With the B200 models the whole body is ONE library call
+        (``dg_pipeline_call_host``): the B separate host windows are gathered and uploaded by worker threads, the fused
+        step and the post-path (aggregation, binarisation, run-length turns) run on the device, and only the packed turn
+        list returns; the host attaches time stamps."""
         batch_size = len(waveforms)
         assert batch_size >= 1, "Pipeline expected at least 1 input"
-        batch = np.stack([np.asarray(w.data, dtype=np.float32) for w in waveforms])   # (batch, samples, channels)
         expected = int(np.rint(self.config.duration * self.config.sample_rate))
+        if self._native_models() is None:
+            return self._call_blockwise(waveforms, expected)
+        rows = []
+        for w in waveforms:
+            d = w.data
+            assert d.shape[0] == expected, f"Expected {expected} samples per chunk, but got {d.shape[0]}"
+            assert d.ndim == 1 or d.shape[1] == 1, "expected mono audio"
+            if d.dtype != np.float32 or not d.flags.c_contiguous:
+                d = np.ascontiguousarray(d, dtype=np.float32)
+            rows.append(d)
+        h, F, K, D = self._ensure_fused(expected)
+        post = self._ensure_post(F, K)
+        starts = np.array([w.extent.start for w in waveforms], dtype=np.float64)
+        seg_resolution = waveforms[0].extent.duration / F
+        plan, out_start, out_res = post.plan(starts, seg_resolution)
+        header, turns = post.buffers(batch_size)
+        ptrs = (C.c_void_p * batch_size)(*[r.__array_interface__["data"][0] for r in rows])
+        n_turns = C.c_int()
+        with torch.cuda.device(self.segmentation.device):
+            _lib.check(_lib.lib().dg_pipeline_call_host(h, post.handle, ptrs, batch_size, expected, plan.ctypes.data,
+                                                        header.ctypes.data, turns.ctypes.data, len(turns),
+                                                        C.byref(n_turns), None, None))
+        annotations = post.annotations(header, turns, n_turns.value, out_start, out_res, self.timestamp_shift)
+        audio, self.chunk_buffer = aggregate_audio(self.chunk_buffer, waveforms, post.nw, self.config.step,
+                                                   self.config.latency)
+        return list(zip(annotations, audio))
+
+    def call_stream(self, stream, batch_size: Optional[int] = None):
+        """``__call__`` for the next ``batch_size`` windows (default: all available) of a
+        :class:`diart_b200.operators.DeviceAudioStream`: the windows never exist on the host, only each new sample was
+        uploaded once.  Returns the same ``[(Annotation, SlidingWindowFeature), ...]`` as ``__call__`` on the windows
+        ``rearrange_audio_stream`` would have emitted."""
+        B = stream.available if batch_size is None else int(batch_size)
+        assert B >= 1, "Pipeline expected at least 1 input"
+        expected = int(np.rint(self.config.duration * self.config.sample_rate))
+        assert stream.chunk_samples == expected, f"Expected {expected} samples per chunk, but got {stream.chunk_samples}"
+        if self._native_models() is None:
+            raise _lib.DiartB200Error("call_stream needs the B200 segmentation and embedding models")
+        h, F, K, D = self._ensure_fused(expected)
+        post = self._ensure_post(F, K)
+        sr = stream.sample_rate
+        first = stream.windows_emitted
+        sws = [SlidingWindow(start=stream.window_start_time(first + i), duration=1 / sr, step=1 / sr) for i in range(B)]
+        waves = [SlidingWindowFeature(stream.host_window(first + i), sw) for i, sw in enumerate(sws)]
+        starts = np.array([w.extent.start for w in waves], dtype=np.float64)
+        plan, out_start, out_res = post.plan(starts, waves[0].extent.duration / F)
+        header, turns = post.buffers(B)
+        n_turns = C.c_int()
+        with torch.cuda.device(self.segmentation.device):
+            _lib.check(_lib.lib().dg_pipeline_call_stream(h, post.handle, stream.handle, B, plan.ctypes.data,
+                                                          header.ctypes.data, turns.ctypes.data, len(turns),
+                                                          C.byref(n_turns), None, None))
+        annotations = post.annotations(header, turns, n_turns.value, out_start, out_res, self.timestamp_shift)
+        audio, self.chunk_buffer = aggregate_audio(self.chunk_buffer, waves, post.nw, self.config.step, self.config.latency)
+        stream.advance(B, keep_windows=post.nw)
+        return list(zip(annotations, audio))
+
+    def _ensure_post(self, F: int, K: int) -> DevicePostPath:
+        if self._post is None:
+            self._post = DevicePostPath(self.config.step, self.config.latency, self.config.tau_active, F, K,
+                                        self.config.max_speakers, self.segmentation.device)
+        return self._post
+
+    def _call_blockwise(self, waveforms, expected):
+        """foreign models behind the loader API: block by block, host-side aggregation (numpy mirrors of the reference)"""
+        batch = np.stack([np.asarray(w.data, dtype=np.float32) for w in waveforms])   # (batch, samples, channels)
         assert batch.shape[1] == expected, f"Expected {expected} samples per chunk, but got {batch.shape[1]}"
         assert batch.shape[2] == 1, "expected mono audio"
         seg, _, maps = self.host_step(np.ascontiguousarray(batch[:, :, 0]))

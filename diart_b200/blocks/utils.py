@@ -19,7 +19,8 @@ class Binarize:
         grid = segmentation.sliding_window
         active = segmentation.data > self.threshold
         annotation = Annotation(uri=self.uri, modality="speech")
-        middles = grid.start + grid.step * np.arange(num_frames + 1) + 0.5 * grid.duration
+        lefts = grid.start + grid.step * np.arange(num_frames + 1)
+        middles = 0.5 * (lefts + (lefts + grid.duration))        # SlidingWindow[i].middle, as the reference evaluates it
         for spk in np.where(active.any(axis=0))[0]:
             col = np.concatenate([[False], active[:, spk], [False]])
             change = np.flatnonzero(col[1:] != col[:-1])       # on/off boundaries, in frame units

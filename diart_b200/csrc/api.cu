@@ -5,9 +5,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <deque>
 #include <map>
 #include <memory>
 #include <sstream>
+#include <thread>
 #include <vector>
 
 #include "../../include/diart_b200.h"
@@ -266,7 +268,8 @@ struct SincWork {
   }
 };
 
-static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cudaStream_t st, int hop = 0) {
+static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cudaStream_t st, int hop = 0,
+                         bool overlap_known = false) {
   int rc;
   if ((rc = p.ensure(B, g))) return rc;
   // stream form of the sinc layer: on by default (DG_STREAM_SINC=0 disables it), only with a hop hint from the caller;
@@ -276,7 +279,11 @@ static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cu
   p.hop = 0;
   if (stream_on && hop > 0 && B >= 4 && hop % 40 == 0 && g.S % 4 == 0 && hop < g.S && ((uintptr_t)wav & 15) == 0) {
     if ((rc = p.ensure_stream(B, g, hop))) return rc;
-    if ((rc = launch_overlap_check(wav, B, g.S, hop, p.flag.as<int>(), st))) return rc;
+    if (overlap_known) {   // the batch was formed on the device from ONE stream (dg_stream): nothing to verify
+      DG_CUDA(cudaMemsetAsync(p.flag.p, 1, sizeof(int), st));
+    } else if ((rc = launch_overlap_check(wav, B, g.S, hop, p.flag.as<int>(), st))) {
+      return rc;
+    }
     p.hop = hop;
   }
   if ((rc = launch_wave_stats(wav, B, g.S, p.wmean.as<float>(), p.wrstd.as<float>(), st))) return rc;
@@ -1259,6 +1266,9 @@ struct dg_pipeline {
   cudaEvent_t e_lane_done[2] = {nullptr, nullptr};
   int slot_B[3] = {0, 0, 0}, slot_S[3] = {0, 0, 0}, outstanding = 0;
   long long next_step = 0;
+  bool overlap_known = false;     // the current dg_pipeline_step batch was formed from a dg_stream (windows overlap by construction)
+  void* pin_wav = nullptr;        // pinned staging of dg_pipeline_call_host (B separate host windows -> one upload)
+  size_t pin_wav_bytes = 0;
 };
 
 extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
@@ -1308,7 +1318,7 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
 // segmentation chain on s_seg and embedding chain on s_emb, both starting after `start`; on return
 // e_emb (recorded on s_emb) marks seg, osp and emb complete
 static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, int K, float* seg, float* emb,
-                         cudaEvent_t start, int lane = 0) {
+                         cudaEvent_t start, int lane = 0, int stream_hop = 0) {
   int rc;
   const Geom g = make_geom(S);
   // lane 0 / 1: segmentation stream, scratch set, OSP buffer and event of this step (consecutive pipelined steps
@@ -1323,7 +1333,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
   const SincPrep* shared = nullptr;
   if (!sinc_simt) {
-    if ((rc = run_sinc_prep(h->prep[lane], wav, B, g, s_seg, h->hop))) return rc;
+    if ((rc = run_sinc_prep(h->prep[lane], wav, B, g, s_seg, stream_hop ? stream_hop : h->hop, stream_hop != 0))) return rc;
     DG_CUDA(cudaEventRecord(h->e_prep[lane], s_seg));
     DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_prep[lane], 0));
     shared = &h->prep[lane];
@@ -1393,7 +1403,7 @@ extern "C" int dg_pipeline_step(dg_pipeline* h, const float* wav, int B, int S, 
   cudaStream_t st = (cudaStream_t)stream;
   DG_CUDA(cudaSetDevice(h->seg->device));
   DG_CUDA(cudaEventRecord(h->e_start, st));
-  if ((rc = pipeline_nets(h, wav, B, S, F, K, seg, emb, h->e_start))) return rc;
+  if ((rc = pipeline_nets(h, wav, B, S, F, K, seg, emb, h->e_start, 0, h->overlap_known ? h->hop : 0))) return rc;
   DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_emb, 0));
   if ((rc = dg_cluster_step(h->clu, seg, emb, B, F, K, map, permuted, h->s_clu))) return rc;
   DG_CUDA(cudaEventRecord(h->e_done, h->s_clu));
@@ -1415,7 +1425,7 @@ static int pipeline_slot_prepare(dg_pipeline* h, int slot, int B, int S, int F, 
 static const int DG_MAX_INFLIGHT = 3;
 
 static int pipeline_submit_common(dg_pipeline* h, const float* wav_dev, int B, int S, int F, int K, int slot,
-                                  cudaEvent_t start) {
+                                  cudaEvent_t start, int stream_hop = 0) {
   int rc;
   const int lane = (int)(h->next_step & 1);
   cudaStream_t s_lane = lane ? h->s_seg2 : h->s_seg;
@@ -1426,7 +1436,7 @@ static int pipeline_submit_common(dg_pipeline* h, const float* wav_dev, int B, i
   DG_CUDA(cudaStreamWaitEvent(s_lane, h->e_lane_done[lane], 0));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_lane_done[lane], 0));
   if ((rc = pipeline_nets(h, wav_dev, B, S, F, K, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), start,
-                          lane)))
+                          lane, stream_hop)))
     return rc;
   DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_emb, 0));
   if ((rc = dg_cluster_step(h->clu, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), B, F, K,
@@ -1561,6 +1571,425 @@ extern "C" int dg_pipeline_step_host(dg_pipeline* h, const float* wav_host, int 
   return DG_OK;
 }
 
+// ======================================================================== device-side audio stream
+// rearrange_audio_stream (reference src/diart/operators.py:44-100) on the device: the host pushes each sample ONCE
+// (8 000 new samples per chunk instead of the 80 000 of a stacked window: 8.2 MB instead of 82 MB per 256-chunk step),
+// windows are formed from a circular ring in HBM.
+struct dg_stream {
+  int device = 0, S = 0, hop = 0, C = 0;
+  long long wpos = 0, rpos = 0;          // absolute sample counters: pushed / start of the next window
+  DevBuf ring;
+  float* pin = nullptr;                  // pinned mirror of the ring (staging for the uploads)
+  cudaStream_t st = nullptr;             // uploads
+  cudaEvent_t e_up = nullptr, e_read = nullptr;
+  // uploads still reading the pinned mirror: (first absolute sample, event); a region of the mirror is rewritten only
+  // after the upload that last used it has completed
+  std::deque<std::pair<long long, cudaEvent_t>> inflight;
+  std::vector<cudaEvent_t> spare;
+  ~dg_stream() {
+    for (auto& e : inflight) cudaEventDestroy(e.second);
+    for (auto& e : spare) cudaEventDestroy(e);
+    if (pin) cudaFreeHost(pin);
+    if (st) cudaStreamDestroy(st);
+    if (e_up) cudaEventDestroy(e_up);
+    if (e_read) cudaEventDestroy(e_read);
+  }
+};
+
+extern "C" int dg_stream_create(int chunk_samples, int step_samples, int max_windows, int device, dg_stream** out) {
+  if (!out || chunk_samples < 4 || step_samples < 4 || chunk_samples % 4 || step_samples % 4 || max_windows < 1 ||
+      step_samples > chunk_samples) {
+    set_error("dg_stream_create: chunk and step must be positive multiples of 4 samples, step <= chunk");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(device));
+  std::unique_ptr<dg_stream> h(new dg_stream());
+  h->device = device; h->S = chunk_samples; h->hop = step_samples;
+  // room for the windows being read, a full batch being uploaded meanwhile, and the overlap tail
+  h->C = ((chunk_samples + 2 * max_windows * step_samples + 1023) / 1024) * 1024;
+  if (h->ring.ensure((size_t)h->C * 4)) return DG_ECUDA;
+  DG_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&h->pin), (size_t)h->C * 4, cudaHostAllocDefault));
+  DG_CUDA(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_up, cudaEventDisableTiming));
+  DG_CUDA(cudaEventCreateWithFlags(&h->e_read, cudaEventDisableTiming));
+  DG_CUDA(cudaEventRecord(h->e_read, h->st));
+  *out = h.release();
+  return DG_OK;
+}
+
+extern "C" int dg_stream_destroy(dg_stream* h) {
+  delete h;
+  return DG_OK;
+}
+
+extern "C" int dg_stream_reset(dg_stream* h) {
+  if (!h) return DG_EINVAL;
+  DG_CUDA(cudaSetDevice(h->device));
+  DG_CUDA(cudaStreamSynchronize(h->st));
+  h->wpos = h->rpos = 0;
+  for (auto& e : h->inflight) h->spare.push_back(e.second);
+  h->inflight.clear();
+  return DG_OK;
+}
+
+// complete windows that have been pushed but not yet consumed
+extern "C" int dg_stream_available(const dg_stream* h) {
+  if (!h) return 0;
+  const long long have = h->wpos - h->rpos;
+  return have < h->S ? 0 : (int)((have - h->S) / h->hop + 1);
+}
+
+// appends n samples (host memory, any kind) to the stream; returns once they are staged (the upload is asynchronous)
+extern "C" int dg_stream_push_host(dg_stream* h, const float* samples, int n) {
+  if (!h || !samples || n < 0) {
+    set_error("dg_stream_push_host: bad arguments");
+    return DG_EINVAL;
+  }
+  if (h->wpos + n - h->rpos > h->C) {
+    set_error("dg_stream_push_host: ring full (" + std::to_string(h->wpos - h->rpos) + " samples buffered, capacity " +
+              std::to_string(h->C) + "): consume windows first");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  // samples older than rpos may be overwritten: uploads are ordered after the last kernel that read the ring
+  DG_CUDA(cudaStreamWaitEvent(h->st, h->e_read, 0));
+  // the mirror region [wpos, wpos + n) was last used by the uploads of samples one lap earlier: wait for those
+  while (!h->inflight.empty() && h->inflight.front().first < h->wpos + n - h->C) {
+    DG_CUDA(cudaEventSynchronize(h->inflight.front().second));
+    h->spare.push_back(h->inflight.front().second);
+    h->inflight.pop_front();
+  }
+  int done = 0;
+  while (done < n) {
+    const int at = (int)((h->wpos + done) % h->C);
+    const int len = std::min(n - done, h->C - at);
+    memcpy(h->pin + at, samples + done, (size_t)len * 4);
+    DG_CUDA(cudaMemcpyAsync(h->ring.as<float>() + at, h->pin + at, (size_t)len * 4, cudaMemcpyHostToDevice, h->st));
+    done += len;
+  }
+  cudaEvent_t ev;
+  if (!h->spare.empty()) {
+    ev = h->spare.back();
+    h->spare.pop_back();
+  } else {
+    DG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  }
+  DG_CUDA(cudaEventRecord(ev, h->st));
+  h->inflight.emplace_back(h->wpos, ev);
+  h->wpos += n;
+  DG_CUDA(cudaEventRecord(h->e_up, h->st));
+  return DG_OK;
+}
+
+// materialises the next B windows as a dense [B, S] batch on `st` and advances the stream by B steps
+static int stream_expand(dg_stream* h, int B, float* wav_dev, cudaStream_t st) {
+  if (dg_stream_available(h) < B) {
+    set_error("dg_stream: " + std::to_string(B) + " windows requested, " + std::to_string(dg_stream_available(h)) + " available");
+    return DG_EINVAL;
+  }
+  if (h->rpos % 4) {
+    set_error("dg_stream: window start is not 16-byte aligned");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaStreamWaitEvent(st, h->e_up, 0));
+  int rc;
+  if ((rc = launch_expand_windows(h->ring.as<float>(), h->rpos, h->C, h->hop, h->S, B, wav_dev, st))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_read, st));
+  h->rpos += (long long)B * h->hop;
+  return 0;
+}
+
+extern "C" int dg_stream_windows(dg_stream* h, int B, float* wav_dev, void* stream) {
+  if (!h || !wav_dev || B < 1) {
+    set_error("dg_stream_windows: bad arguments");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  return stream_expand(h, B, wav_dev, (cudaStream_t)stream);
+}
+
+// =============================================================================== device post-path
+// DelayedAggregation (hamming, loose) + Binarize of reference diarization.py:205-232 on the device (post.cu).  The handle keeps
+// the scores and speaker maps of the last `num_windows - 1` chunks (the reference's pred_buffer) on the device.
+struct dg_post {
+  int device = 0, F = 0, K = 0, M = 0, nw = 1;
+  double tau = 0.5;
+  DevBuf hamming, hist_seg[2], hist_map[2], plan, header, turns, total;
+  int cur = 0, n_hist = 0, cap_B = 0;
+  int turn_cap = 0;
+  void* pin = nullptr;            // pinned staging: plan in, header + total + turn prefix out
+  size_t pin_bytes = 0;
+  ~dg_post() {
+    if (pin) cudaFreeHost(pin);
+  }
+};
+
+static const int DG_POST_PREFIX = 16384;   // turns copied back together with the header (one D2H in the common case)
+
+extern "C" int dg_post_create(int frames, int local_speakers, int max_speakers, int num_windows, const double* hamming_host,
+                              double tau, int device, dg_post** out) {
+  if (!out || !hamming_host || frames < 1 || frames > 1023 || local_speakers < 1 || max_speakers < 1 || max_speakers > 64 ||
+      num_windows < 1 || num_windows > 256) {
+    set_error("dg_post_create: need 1 <= frames <= 1023, 1 <= max_speakers <= 64, 1 <= num_windows <= 256");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(device));
+  std::unique_ptr<dg_post> h(new dg_post());
+  h->device = device; h->F = frames; h->K = local_speakers; h->M = max_speakers; h->nw = num_windows; h->tau = tau;
+  if (h->hamming.ensure((size_t)frames * 8) || h->total.ensure(16)) return DG_ECUDA;
+  DG_CUDA(cudaMemcpy(h->hamming.p, hamming_host, (size_t)frames * 8, cudaMemcpyHostToDevice));
+  const size_t hs = (size_t)std::max(1, num_windows - 1);
+  for (int i = 0; i < 2; i++)
+    if (h->hist_seg[i].ensure(hs * frames * local_speakers * 4) || h->hist_map[i].ensure(hs * local_speakers * 4)) return DG_ECUDA;
+  *out = h.release();
+  return DG_OK;
+}
+
+extern "C" int dg_post_reset(dg_post* h) {
+  if (!h) return DG_EINVAL;
+  h->n_hist = 0;
+  return DG_OK;
+}
+
+extern "C" int dg_post_destroy(dg_post* h) {
+  delete h;
+  return DG_OK;
+}
+
+static int post_ensure(dg_post* h, int B) {
+  if (B <= h->cap_B) return 0;
+  const int stride = 4 + h->nw;
+  // worst case: every second frame of every speaker starts a turn
+  h->turn_cap = B * h->M * ((h->F + 1) / 2);
+  if (h->plan.ensure((size_t)B * stride * 4) || h->header.ensure((size_t)B * 16 + 16) ||
+      h->turns.ensure((size_t)h->turn_cap * 4))
+    return DG_ECUDA;
+  const size_t need = (size_t)B * stride * 4 + (size_t)B * 16 + 16 + (size_t)DG_POST_PREFIX * 4;
+  if (need > h->pin_bytes) {
+    if (h->pin) cudaFreeHost(h->pin);
+    h->pin = nullptr;
+    DG_CUDA(cudaHostAlloc(&h->pin, need, cudaHostAllocDefault));
+    h->pin_bytes = need;
+  }
+  h->cap_B = B;
+  return 0;
+}
+
+// enqueues plan upload, aggregation + binarisation + run-length kernel, history update and the D2H of the results on `st`
+static int post_enqueue(dg_post* h, const float* seg_dev, const int32_t* map_dev, int B, const int32_t* plan_host,
+                        cudaStream_t st) {
+  int rc;
+  if ((rc = post_ensure(h, B))) return rc;
+  const int stride = 4 + h->nw;
+  unsigned char* pin = reinterpret_cast<unsigned char*>(h->pin);
+  const size_t plan_bytes = (size_t)B * stride * 4;
+  memcpy(pin, plan_host, plan_bytes);
+  DG_CUDA(cudaMemcpyAsync(h->plan.p, pin, plan_bytes, cudaMemcpyHostToDevice, st));
+  DG_CUDA(cudaMemsetAsync(h->total.p, 0, 4, st));
+  if ((rc = launch_post(seg_dev, map_dev, h->hist_seg[h->cur].as<float>(), h->hist_map[h->cur].as<int32_t>(), h->n_hist, B,
+                        h->F, h->K, h->M, h->nw, h->plan.as<int32_t>(), stride, h->hamming.as<double>(), h->tau,
+                        h->header.as<int32_t>(), h->turns.as<uint32_t>(), h->turn_cap, h->total.as<unsigned int>(), st)))
+    return rc;
+  const int keep = std::min(h->nw - 1, h->n_hist + B);
+  if (keep > 0) {
+    if ((rc = launch_post_history(seg_dev, map_dev, h->hist_seg[h->cur].as<float>(), h->hist_map[h->cur].as<int32_t>(),
+                                  h->n_hist, B, h->F, h->K, keep, h->hist_seg[h->cur ^ 1].as<float>(),
+                                  h->hist_map[h->cur ^ 1].as<int32_t>(), st)))
+      return rc;
+    h->cur ^= 1;
+  }
+  h->n_hist = keep;
+  unsigned char* out = pin + plan_bytes;
+  DG_CUDA(cudaMemcpyAsync(out, h->header.p, (size_t)B * 16, cudaMemcpyDeviceToHost, st));
+  DG_CUDA(cudaMemcpyAsync(out + (size_t)B * 16, h->total.p, 4, cudaMemcpyDeviceToHost, st));
+  DG_CUDA(cudaMemcpyAsync(out + (size_t)B * 16 + 16, h->turns.p, (size_t)std::min(DG_POST_PREFIX, h->turn_cap) * 4,
+                          cudaMemcpyDeviceToHost, st));
+  return 0;
+}
+
+// after `st` has been synchronised: hands the results to the caller
+static int post_finish(dg_post* h, int B, int32_t* header_host, uint32_t* turns_host, int turn_cap_host, int* n_turns,
+                       cudaStream_t st) {
+  const int stride = 4 + h->nw;
+  unsigned char* out = reinterpret_cast<unsigned char*>(h->pin) + (size_t)B * stride * 4;
+  unsigned int total = 0;
+  memcpy(&total, out + (size_t)B * 16, 4);
+  if (n_turns) *n_turns = (int)total;
+  memcpy(header_host, out, (size_t)B * 16);
+  if ((int)total > turn_cap_host) {
+    set_error("dg_post_step: turn buffer too small (" + std::to_string(total) + " turns)");
+    return DG_EINVAL;
+  }
+  const unsigned int pre = std::min<unsigned int>(total, (unsigned int)DG_POST_PREFIX);
+  memcpy(turns_host, out + (size_t)B * 16 + 16, (size_t)pre * 4);
+  if (total > pre) {
+    DG_CUDA(cudaMemcpyAsync(turns_host + pre, h->turns.as<uint32_t>() + pre, (size_t)(total - pre) * 4,
+                            cudaMemcpyDeviceToHost, st));
+    DG_CUDA(cudaStreamSynchronize(st));
+  }
+  return DG_OK;
+}
+
+extern "C" int dg_post_step(dg_post* h, const float* seg_dev, const int32_t* map_dev, int B, const int32_t* plan_host,
+                            int32_t* header_host, uint32_t* turns_host, int turn_cap_host, int* n_turns, void* stream) {
+  if (!h || !seg_dev || !map_dev || !plan_host || !header_host || !turns_host || B < 1) {
+    set_error("dg_post_step: bad arguments");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = post_enqueue(h, seg_dev, map_dev, B, plan_host, st))) return rc;
+  DG_CUDA(cudaStreamSynchronize(st));
+  return post_finish(h, B, header_host, turns_host, turn_cap_host, n_turns, st);
+}
+
+// ---- the whole body of SpeakerDiarization.__call__ (reference diarization.py:172-232) in one call: B separate host windows
+//      (as rearrange_audio_stream emits them) are gathered into pinned staging by worker threads while earlier rows are
+//      already on their way to the device, then fused step + post-path, one D2H of the turn list.
+static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, float* dst_dev, cudaStream_t st) {
+  const size_t bytes = (size_t)B * S * 4;
+  if (bytes > h->pin_wav_bytes) {
+    if (h->pin_wav) cudaFreeHost(h->pin_wav);
+    h->pin_wav = nullptr;
+    DG_CUDA(cudaHostAlloc(&h->pin_wav, bytes, cudaHostAllocDefault));
+    h->pin_wav_bytes = bytes;
+  }
+  float* pin = reinterpret_cast<float*>(h->pin_wav);
+  const int R = 8;                                    // rows per work item
+  const int items = (B + R - 1) / R;
+  int nthreads = (int)std::thread::hardware_concurrency();
+  nthreads = std::max(1, std::min({nthreads, 16, items}));
+  std::vector<std::atomic<int>> done(items);
+  for (auto& d : done) d.store(0, std::memory_order_relaxed);
+  std::atomic<int> next{0};
+  auto work = [&]() {
+    for (;;) {
+      const int it = next.fetch_add(1, std::memory_order_relaxed);
+      if (it >= items) return;
+      const int r0 = it * R, r1 = std::min(B, r0 + R);
+      for (int r = r0; r < r1; r++) memcpy(pin + (size_t)r * S, rows[r], (size_t)S * 4);
+      done[it].store(1, std::memory_order_release);
+    }
+  };
+  std::vector<std::thread> pool;
+  for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+  cudaError_t err = cudaSuccess;
+  if (nthreads == 1) work();
+  // the calling thread forwards finished items, in order, in runs of up to 4 (256-row batches: 8 copies of ~10 MB)
+  int sent = 0;
+  while (sent < items) {
+    int upto = sent;
+    while (upto < items && upto - sent < 4 && done[upto].load(std::memory_order_acquire)) upto++;
+    if (upto == sent) {
+      std::this_thread::yield();
+      continue;
+    }
+    const int r0 = sent * R, r1 = std::min(B, upto * R);
+    if (err == cudaSuccess)
+      err = cudaMemcpyAsync(dst_dev + (size_t)r0 * S, pin + (size_t)r0 * S, (size_t)(r1 - r0) * S * 4, cudaMemcpyHostToDevice, st);
+    sent = upto;
+  }
+  for (auto& t : pool) t.join();
+  DG_CUDA(err);
+  return 0;
+}
+
+extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float* const* rows_host, int B, int S,
+                                     const int32_t* plan_host, int32_t* header_host, uint32_t* turns_host, int turn_cap_host,
+                                     int* n_turns, float* seg_host, int32_t* map_host) {
+  if (!h || !post || !rows_host || !plan_host || !header_host || !turns_host || B < 1) {
+    set_error("dg_pipeline_call_host: bad arguments");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  if (F != post->F || K != post->K || h->clu->p.M != post->M || post->device != h->seg->device) {
+    set_error("dg_pipeline_call_host: post handle was created for other dimensions");
+    return DG_EINVAL;
+  }
+  const int D = h->emb->D;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  if (h->wav.ensure((size_t)B * S * 4) || h->segd.ensure((size_t)B * F * K * 4) || h->embd.ensure((size_t)B * K * D * 4) ||
+      h->mapd.ensure((size_t)B * K * 4))
+    return DG_ECUDA;
+  if ((rc = upload_rows(h, rows_host, B, S, h->wav.as<float>(), h->st))) return rc;
+  if ((rc = dg_pipeline_step(h, h->wav.as<float>(), B, S, h->segd.as<float>(), h->embd.as<float>(), h->mapd.as<int32_t>(),
+                             nullptr, h->st)))
+    return rc;
+  if ((rc = post_enqueue(post, h->segd.as<float>(), h->mapd.as<int32_t>(), B, plan_host, h->st))) return rc;
+  if (seg_host) DG_CUDA(cudaMemcpyAsync(seg_host, h->segd.p, (size_t)B * F * K * 4, cudaMemcpyDeviceToHost, h->st));
+  if (map_host) DG_CUDA(cudaMemcpyAsync(map_host, h->mapd.p, (size_t)B * K * 4, cudaMemcpyDeviceToHost, h->st));
+  DG_CUDA(cudaStreamSynchronize(h->st));
+  return post_finish(post, B, header_host, turns_host, turn_cap_host, n_turns, h->st);
+}
+
+// pipelined step whose batch is the next B windows of a device-side stream (no window upload at all; the sinc layer takes
+// its stream form without the overlap check: the windows overlap by construction)
+extern "C" int dg_pipeline_submit_stream(dg_pipeline* h, dg_stream* s, int B) {
+  if (!h || !s || B < 1) {
+    set_error("dg_pipeline_submit_stream: bad arguments");
+    return DG_EINVAL;
+  }
+  if (h->outstanding >= DG_MAX_INFLIGHT) {
+    set_error("dg_pipeline_submit_stream: three steps are already outstanding; collect one first");
+    return DG_EINVAL;
+  }
+  if (s->device != h->seg->device) {
+    set_error("dg_pipeline_submit_stream: stream and pipeline live on different devices");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  const int S = s->S;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  const int slot = (int)(h->next_step % 3);
+  if ((rc = pipeline_slot_prepare(h, slot, B, S, F, K, true))) return rc;
+  DG_CUDA(cudaStreamWaitEvent(h->s_h2d, h->e_slot_done[slot], 0));
+  if ((rc = stream_expand(s, B, h->slot_wav[slot].as<float>(), h->s_h2d))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_h2d[slot], h->s_h2d));
+  return pipeline_submit_common(h, h->slot_wav[slot].as<float>(), B, S, F, K, slot, h->e_h2d[slot], s->hop);
+}
+
+// SpeakerDiarization.__call__ for the next B windows of a device-side stream: fused step + post-path, synchronous
+extern "C" int dg_pipeline_call_stream(dg_pipeline* h, dg_post* post, dg_stream* s, int B, const int32_t* plan_host,
+                                       int32_t* header_host, uint32_t* turns_host, int turn_cap_host, int* n_turns,
+                                       float* seg_host, int32_t* map_host) {
+  if (!h || !post || !s || !plan_host || !header_host || !turns_host || B < 1) {
+    set_error("dg_pipeline_call_stream: bad arguments");
+    return DG_EINVAL;
+  }
+  if (h->outstanding) {
+    set_error("dg_pipeline_call_stream: submitted steps are outstanding; collect them first");
+    return DG_EINVAL;
+  }
+  int rc, F = 0, K = 0;
+  const int S = s->S;
+  if ((rc = dg_seg_dims(h->seg, S, &F, &K))) return rc;
+  if (F != post->F || K != post->K || h->clu->p.M != post->M || post->device != h->seg->device || s->device != h->seg->device) {
+    set_error("dg_pipeline_call_stream: handles were created for other dimensions / devices");
+    return DG_EINVAL;
+  }
+  const int D = h->emb->D;
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  if (h->wav.ensure((size_t)B * S * 4) || h->segd.ensure((size_t)B * F * K * 4) || h->embd.ensure((size_t)B * K * D * 4) ||
+      h->mapd.ensure((size_t)B * K * 4))
+    return DG_ECUDA;
+  if ((rc = stream_expand(s, B, h->wav.as<float>(), h->st))) return rc;
+  const int hop_saved = h->hop;
+  h->hop = s->hop;
+  h->overlap_known = true;
+  rc = dg_pipeline_step(h, h->wav.as<float>(), B, S, h->segd.as<float>(), h->embd.as<float>(), h->mapd.as<int32_t>(), nullptr, h->st);
+  h->overlap_known = false;
+  h->hop = hop_saved;
+  if (rc) return rc;
+  if ((rc = post_enqueue(post, h->segd.as<float>(), h->mapd.as<int32_t>(), B, plan_host, h->st))) return rc;
+  if (seg_host) DG_CUDA(cudaMemcpyAsync(seg_host, h->segd.p, (size_t)B * F * K * 4, cudaMemcpyDeviceToHost, h->st));
+  if (map_host) DG_CUDA(cudaMemcpyAsync(map_host, h->mapd.p, (size_t)B * K * 4, cudaMemcpyDeviceToHost, h->st));
+  DG_CUDA(cudaStreamSynchronize(h->st));
+  return post_finish(post, B, header_host, turns_host, turn_cap_host, n_turns, h->st);
+}
+
 extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
   if (h) {
     if (h->s_seg) cudaStreamDestroy(h->s_seg);
@@ -1577,6 +2006,7 @@ extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
       if (e) cudaEventDestroy(e);
   }
   if (h && h->st) cudaStreamDestroy(h->st);
+  if (h && h->pin_wav) cudaFreeHost(h->pin_wav);
   delete h;
   return DG_OK;
 }

@@ -208,6 +208,13 @@ int launch_cluster_merge(const double* records, int world, int rank, const Clust
                          cudaStream_t st);
 int launch_relabel_maps(int32_t* maps, int n, const int32_t* relabel, cudaStream_t st);
 size_t cluster_prep_floats(int B, int K);
+// post.cu -- aggregation + binarisation + run-length turns (reference diarization.py:205-232)
+int launch_post(const float* seg, const int32_t* map, const float* hist_seg, const int32_t* hist_map, int n_hist, int B,
+                int F, int K, int M, int nw, const int32_t* plan, int plan_stride, const double* hamming, double tau,
+                int32_t* header, uint32_t* turns, int turn_cap, unsigned int* total, cudaStream_t st);
+int launch_expand_windows(const float* ring, long long r0, int C, int hop, int S, int B, float* wav, cudaStream_t st);
+int launch_post_history(const float* seg, const int32_t* map, const float* hist_seg, const int32_t* hist_map, int n_hist,
+                        int B, int F, int K, int keep, float* new_seg, int32_t* new_map, cudaStream_t st);
 size_t cluster_prep_doubles(int B, int K);
 
 }  // namespace dg

@@ -45,6 +45,8 @@ typedef struct dg_seg dg_seg;
 typedef struct dg_emb dg_emb;
 typedef struct dg_cluster dg_cluster;
 typedef struct dg_pipeline dg_pipeline;
+typedef struct dg_post dg_post;
+typedef struct dg_stream dg_stream;
 
 const char* dg_last_error(void);
 int dg_version(void);
@@ -140,6 +142,61 @@ int dg_pipeline_collect_copy(dg_pipeline* h, float* seg_dev, float* emb_dev, int
 int dg_pipeline_submit_host(dg_pipeline* h, const float* wav_host /*pinned memory recommended*/, int B, int S);
 int dg_pipeline_collect_host(dg_pipeline* h, float* seg_host, float* emb_host, int32_t* map_host);
 int dg_pipeline_destroy(dg_pipeline* h);
+
+/* ---- post-path of SpeakerDiarization.__call__ on the device (reference src/diart/blocks/diarization.py:205-232):
+ *      SpeakerMap.apply (mapping.py:341-360) -> DelayedAggregation(step, latency, "hamming", "loose")
+ *      (blocks/aggregation.py:73-92,120-218, incl. the first-buffer prepend rule :188-212) -> Binarize(tau)
+ *      (blocks/utils.py:11-59), run-length encoded.  The handle keeps the scores / maps of the last num_windows - 1
+ *      chunks (the reference's pred_buffer) on the device; num_windows = round(latency / step).
+ *      hamming_host = np.hamming(frames) in float64.  Arithmetic is float64 in numpy's order without fused
+ *      multiply-add: the thresholded result is bit-identical to the reference's.
+ *
+ *      plan_host int32 [B][4 + num_windows], one row per chunk, computed by the host with pyannote.core's
+ *      SlidingWindow.crop index arithmetic (diart_b200/blocks/post.py):
+ *        [0] nb   buffers aggregated for this chunk (1 .. num_windows)
+ *        [1] nf   frames of the aggregated region
+ *        [2] first_nf  > 0 only for the first buffer of a stream: output = first_nf frames, the last nf aggregated
+ *        [3] first_lo  first frame of that prepended crop (may be negative: edge-padded)
+ *        [4 + j]  first frame of buffer j's crop (oldest buffer first; may leave [0, frames): edge-padded)
+ *      header_host int32 [B][4] = {offset into turns, number of turns, output frames, 0};
+ *      turns_host  uint32 [turn_cap_host], packed speaker << 20 | on << 10 | off (frame indices; the turn covers the
+ *      frame MIDDLES on .. off as in Binarize), each chunk's turns contiguous, by speaker then time.
+ *      dg_post_step synchronises `stream`. ---- */
+int dg_post_create(int frames, int local_speakers, int max_speakers, int num_windows, const double* hamming_host,
+                   double tau, int device, dg_post** out);
+int dg_post_step(dg_post* h, const float* seg_dev /*[B,F,K]*/, const int32_t* map_dev /*[B,K]*/, int B,
+                 const int32_t* plan_host, int32_t* header_host, uint32_t* turns_host, int turn_cap_host, int* n_turns,
+                 void* stream);
+int dg_post_reset(dg_post* h);
+int dg_post_destroy(dg_post* h);
+/* The whole body of SpeakerDiarization.__call__ (reference diarization.py:172-232) in ONE call: rows_host[b] points to the
+ * S float32 samples of window b (B separate host arrays, as rearrange_audio_stream emits them); they are gathered into
+ * pinned staging by worker threads and uploaded while the gather is still running, then fused step + post-path; only the
+ * turn list (and, if asked for, scores and maps) returns to the host.  Synchronous. */
+int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float* const* rows_host, int B, int S,
+                          const int32_t* plan_host, int32_t* header_host, uint32_t* turns_host, int turn_cap_host,
+                          int* n_turns, float* seg_host /*nullable*/, int32_t* map_host /*nullable*/);
+
+/* ---- device-side audio stream: rearrange_audio_stream (reference src/diart/operators.py:44-100) with the ring buffer in
+ *      HBM.  The host pushes every sample ONCE (step_samples new samples per chunk instead of chunk_samples: 8.2 MB
+ *      instead of 82 MB per 256-chunk step at 5 s / 0.5 s); window i of the stream is samples
+ *      [i * step_samples, i * step_samples + chunk_samples).  max_windows = largest batch that will be requested.
+ *      dg_stream_push_host may be called with any block size (the reference's sources emit arbitrary blocks); it
+ *      fails with DG_EINVAL when the ring is full, i.e. windows must be consumed first. ---- */
+int dg_stream_create(int chunk_samples, int step_samples, int max_windows, int device, dg_stream** out);
+int dg_stream_push_host(dg_stream* h, const float* samples_host, int n);
+/* complete windows pushed but not yet consumed */
+int dg_stream_available(const dg_stream* h);
+/* the next B windows as a dense [B, chunk_samples] device batch on `stream`; advances the stream by B steps */
+int dg_stream_windows(dg_stream* h, int B, float* wav_dev, void* stream);
+int dg_stream_reset(dg_stream* h);
+int dg_stream_destroy(dg_stream* h);
+/* dg_pipeline_submit_host / dg_pipeline_call_host whose batch is the next B windows of `stream` (no window upload; the
+ * sinc layer takes its stream form directly: the windows overlap by construction).  Collect with dg_pipeline_collect*. */
+int dg_pipeline_submit_stream(dg_pipeline* h, dg_stream* stream, int B);
+int dg_pipeline_call_stream(dg_pipeline* h, dg_post* post, dg_stream* stream, int B, const int32_t* plan_host,
+                            int32_t* header_host, uint32_t* turns_host, int turn_cap_host, int* n_turns,
+                            float* seg_host /*nullable*/, int32_t* map_host /*nullable*/);
 
 /* number of kernels launched by this library since load (bench.py's gpu_launches) */
 int64_t dg_launch_count(void);
