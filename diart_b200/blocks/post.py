@@ -135,7 +135,7 @@ class DevicePostPath:
             out.append(ann)
         return out
 
-    def step(self, seg: torch.Tensor, maps: torch.Tensor, starts: np.ndarray, res: float, shift: float = 0.0):
+    def run(self, seg: torch.Tensor, maps: torch.Tensor, starts: np.ndarray, res: float, shift: float = 0.0):
         """device scores (B,F,K) + maps (B,K) -> list of Annotation (block-level entry; the fused pipeline uses
         dg_pipeline_call_host instead)"""
         plan, out_start, out_res = self.plan(np.asarray(starts, dtype=np.float64), res)

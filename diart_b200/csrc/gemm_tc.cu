@@ -27,6 +27,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
+
 #include "dg_common.cuh"
 #include "tc_ptx.cuh"
 
@@ -48,9 +50,15 @@ struct TcArgs {
   int ldc;
   int f16;              // operand planes are fp16 (1) or bf16 (0)
   int vec8;             // output rows are 32-byte aligned: 256-bit stores
+  int tap_off[9];       // row offset of every tap (Conv1d: j * dil; Conv2d on a zero-padded map: (dw-1) * Hp + (dh-1))
+  // TC_CONV2D: rows are positions (item, w, h) of a zero-padded [Wp][Hp] map; outputs go to the padded map [Wop][Hop] of the
+  // next layer (stride 1: same geometry; stride 2: computed at every centre, only odd (w, h) are kept)
+  int Wp, Hp, Wop, Hop, stride2, relu;
+  const __nv_bfloat16* res_hi;   // residual planes in the output geometry, or null
+  const __nv_bfloat16* res_lo;
 };
 
-enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2 };
+enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2, TC_CONV2D = 3 };
 
 // ------------------------------------------------------------------------------------ the kernel
 template <int BN>
@@ -58,7 +66,7 @@ struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB per plane
   static constexpr int W_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int NSTAGE = BN == 256 ? 2 : (BN == 128 ? 3 : 4);
+  static constexpr int NSTAGE = BN == 256 ? 2 : (BN == 128 ? 3 : 4);   // BN = 64 / 32: 4 stages
   static constexpr int PARAM_BYTES = 3 * BN * 4;
   static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
@@ -118,8 +126,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             unsigned char* st = smem + stage * S::STAGE_BYTES;
             mbar_expect_tx(&full[stage], S::STAGE_BYTES);
             const int kcol = (j * a.cin_blocks + cb) * TC_BK;
-            tma_load_2d(st, &tmA_hi, cb * TC_BK, m0 + j * a.dil, &full[stage]);
-            tma_load_2d(st + S::A_BYTES, &tmA_lo, cb * TC_BK, m0 + j * a.dil, &full[stage]);
+            tma_load_2d(st, &tmA_hi, cb * TC_BK, m0 + a.tap_off[j], &full[stage]);
+            tma_load_2d(st + S::A_BYTES, &tmA_lo, cb * TC_BK, m0 + a.tap_off[j], &full[stage]);
             tma_load_2d(st + 2 * S::A_BYTES, &tmW_hi, kcol, n0, &full[stage]);
             tma_load_2d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, kcol, n0, &full[stage]);
             if (++stage == NSTAGE) {
@@ -189,12 +197,74 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      long long mo = m;                 // output row
+      bool row_ok = m < a.M;
+      if (EPI == TC_CONV2D) {
+        const long long per = (long long)a.Wp * a.Hp;
+        const long long item = m / per;
+        const int rem = (int)(m - item * per), w = rem / a.Hp, h = rem - w * a.Hp;
+        row_ok = row_ok && w >= 1 && w <= a.Wp - 2 && h >= 1 && h <= a.Hp - 2;     // a centre inside the un-padded map
+        if (a.stride2) {
+          row_ok = row_ok && (w & 1) && (h & 1);
+          mo = (item * a.Wop + ((w - 1) >> 1) + 1) * a.Hop + ((h - 1) >> 1) + 1;
+        }
+      }
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
         if (n0 + c >= a.N) continue;
         float v[32];
+        if (EPI == TC_CONV2D) {
+          // BatchNorm2d(eval) affine -> (+ residual) -> ReLU
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = fmaf(__uint_as_float(r[i]), params[BN + c + i], params[2 * BN + c + i]);
+          if (row_ok && a.res_hi) {
+            const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + mo * a.ldc + n0 + c);
+            const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + mo * a.ldc + n0 + c);
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const uint4 hq = rh[q], lq = rl[q];
+              const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
+#pragma unroll
+              for (int e = 0; e < 4; e++) {
+                v[8 * q + 2 * e] += h16_to_f32((uint16_t)(hw[e] & 0xFFFFu), a.f16) + h16_to_f32((uint16_t)(lw[e] & 0xFFFFu), a.f16);
+                v[8 * q + 2 * e + 1] += h16_to_f32((uint16_t)(hw[e] >> 16), a.f16) + h16_to_f32((uint16_t)(lw[e] >> 16), a.f16);
+              }
+            }
+          }
+          if (a.relu) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
+          }
+          if (row_ok) {
+            if (a.out_f32) {
+              float* po = a.out_f32 + mo * a.ldc + n0 + c;
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                reinterpret_cast<float4*>(po)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            if (a.out_hi) {
+              uint32_t hi[16], lo[16];
+#pragma unroll
+              for (int i = 0; i < 16; i++) {
+                uint16_t h0, l0, h1, l1;
+                split_h16(v[2 * i], a.f16, h0, l0);
+                split_h16(v[2 * i + 1], a.f16, h1, l1);
+                hi[i] = pack_u16x2(h0, h1);
+                lo[i] = pack_u16x2(l0, l1);
+              }
+              uint4* ph = reinterpret_cast<uint4*>(a.out_hi + mo * a.ldc + n0 + c);
+              uint4* pl = reinterpret_cast<uint4*>(a.out_lo + mo * a.ldc + n0 + c);
+#pragma unroll
+              for (int i = 0; i < 4; i++) {
+                ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+                pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+              }
+            }
+          }
+          continue;
+        }
 #pragma unroll
         for (int i = 0; i < 32; i++) {
           float x = __uint_as_float(r[i]) + params[c + i];
@@ -307,18 +377,26 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
   a.out_f32 = g.out_f32; a.out_hi = reinterpret_cast<__nv_bfloat16*>(g.out_hi);
   a.out_lo = reinterpret_cast<__nv_bfloat16*>(g.out_lo); a.ldc = g.ldc;
   a.f16 = split_f16();
+  for (int j = 0; j < 9; j++) a.tap_off[j] = j < g.KW ? (g.tap_off ? g.tap_off[j] : j * g.dil) : 0;
+  a.Wp = g.Wp; a.Hp = g.Hp; a.Wop = g.Wop; a.Hop = g.Hop; a.stride2 = g.stride2; a.relu = g.relu;
+  a.res_hi = reinterpret_cast<const __nv_bfloat16*>(g.res_hi);
+  a.res_lo = reinterpret_cast<const __nv_bfloat16*>(g.res_lo);
   {
     static const bool no_v8 = getenv("DG_NO_V8") && getenv("DG_NO_V8")[0] == '1';     // A/B switch
     const bool planes = EPI == TC_LEAKY_BN_SPLIT;
     const uintptr_t base = planes ? ((uintptr_t)g.out_hi | (uintptr_t)g.out_lo) : (uintptr_t)g.out_f32;
     a.vec8 = !no_v8 && base % 32 == 0 && (g.ldc * (planes ? 2 : 4)) % 32 == 0;
   }
-  static bool attr_done = false;
-  if (!attr_done) {
-    DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    attr_done = true;
+  {   // function attributes are per device: one flag per (instantiation, device)
+    static bool attr_done[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+      DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+      if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
   }
-  const int sms = usable_sms();
+  const int sms = g.sm_limit > 0 ? std::min(g.sm_limit, usable_sms()) : usable_sms();
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
   gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
@@ -328,12 +406,22 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
 
 int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
   ProfScope _ps(g.tag ? g.tag : "gemm_tc", st);
-  if (g.Cin % TC_BK || g.lda % 8 || g.ldc % (g.epi == TC_LEAKY_BN_SPLIT ? 8 : 4) || (g.Npad % 128 && g.Npad != 64)) {
+  if (g.Cin % TC_BK || g.lda % 8 || g.ldc % (g.epi == TC_LEAKY_BN_SPLIT ? 8 : 4) || (g.Npad % 128 && g.Npad != 64 && g.Npad != 32) ||
+      g.KW < 1 || g.KW > 9) {
     set_error("gemm_tc: Cin must be a multiple of 64, A pitch a multiple of 8, output pitch a multiple of 4 "
-              "(8 for bf16 planes), padded N a multiple of 128");
+              "(8 for bf16 planes), padded N 32, 64 or a multiple of 128, at most 9 taps");
     return -1;
   }
   const bool wide = g.Npad % 256 == 0;
+  if (g.epi == TC_CONV2D) {
+    if (g.ldc % 32 || g.N % 32 || g.Wp < 3 || g.Hp < 3 || (!g.out_hi && !g.out_f32)) {
+      set_error("gemm_tc (conv2d): channel counts must be multiples of 32");
+      return -1;
+    }
+    if (g.Npad == 32) return launch_tc<32, TC_CONV2D>(g, st);
+    if (g.Npad == 64) return launch_tc<64, TC_CONV2D>(g, st);
+    return wide ? launch_tc<256, TC_CONV2D>(g, st) : launch_tc<128, TC_CONV2D>(g, st);
+  }
   if (g.Npad == 64 && g.epi == TC_BIAS_F32) return launch_tc<64, TC_BIAS_F32>(g, st);
   switch (g.epi) {
     case TC_BIAS_F32:

@@ -47,7 +47,7 @@ def test_device_post_path_equals_reference_blocks(latency, splits, cuda_device):
     for b in splits:
         seg = torch.from_numpy(seg_all[first:first + b]).to(cuda_device)
         maps = torch.from_numpy(map_all[first:first + b]).to(cuda_device)
-        got += post.step(seg, maps, np.array(starts[first:first + b]), res)
+        got += post.run(seg, maps, np.array(starts[first:first + b]), res)
         first += b
     lines = 0
     for i, (a, b) in enumerate(zip(want, got)):
@@ -58,7 +58,7 @@ def test_device_post_path_equals_reference_blocks(latency, splits, cuda_device):
     post.reset()
     seg = torch.from_numpy(seg_all[:splits[0]]).to(cuda_device)
     maps = torch.from_numpy(map_all[:splits[0]]).to(cuda_device)
-    again = post.step(seg, maps, np.array(starts[:splits[0]]), res)
+    again = post.run(seg, maps, np.array(starts[:splits[0]]), res)
     assert [tracks(a) for a in again] == [tracks(a) for a in want[:splits[0]]]
 
 
@@ -71,7 +71,7 @@ def test_many_turns_need_a_second_copy(cuda_device):
     post = DevicePostPath(5.0, 5.0, tau, F, K, M, cuda_device)       # step = latency = duration: whole chunks are emitted
     starts = np.arange(n) * 5.0
     res = 5.0 / F
-    got = post.step(torch.from_numpy(seg).to(cuda_device), torch.from_numpy(maps).to(cuda_device), starts, res)
+    got = post.run(torch.from_numpy(seg).to(cuda_device), torch.from_numpy(maps).to(cuda_device), starts, res)
     total = sum(len(tracks(a)) for a in got)
     assert total > 16384
     agg, binarize = DelayedAggregation(5.0, 5.0, "hamming", "loose"), Binarize(tau)
