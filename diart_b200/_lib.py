@@ -43,6 +43,7 @@ SIGNATURES = {
     "dg_emb_forward": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dg_emb_forward_rows": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P]),
     "dg_emb_destroy": (C.c_int, [_P]),
+    "dg_emb_debug_trunk": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int64, _P]),
     "dg_osp": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _P, _P]),
     "dg_normalize_embeddings": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dg_cluster_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(_P)]),

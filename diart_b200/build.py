@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libdiartb200.so")
-SOURCES = ["api.cu", "sincnet.cu", "gemm.cu", "gemm_tc.cu", "sinc_tc.cu", "lstm.cu", "lstm_tc.cu", "heads.cu", "cluster.cu", "post.cu"]
+SOURCES = ["api.cu", "sincnet.cu", "gemm.cu", "gemm_tc.cu", "sinc_tc.cu", "lstm.cu", "lstm_tc.cu", "heads.cu", "cluster.cu", "post.cu", "resnet.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 

@@ -42,7 +42,8 @@ ProfScope::~ProfScope() {
 
 int launch_stats_pool_ex(const float* x, int stride, int T, int C, const float* w, int F, int K, int layout,
                          int n_groups, const int* grp_item, const int* grp_q0, const int* grp_nq, const int* idx0,
-                         const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st);
+                         const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st,
+                         long long item_pitch = 0, int row_pitch = 0);
 
 // ------------------------------------------------------------------------------ small utilities
 struct DevBuf {
@@ -698,14 +699,46 @@ struct dg_emb {
   int tab_F = -1, tab_T = -1;
   DevBuf flags, uniq, grp, gathered;   // compatibility path
   const SincPrep* shared_prep = nullptr;
+  // what the pooling reads after a trunk pass: x(item, t, c) = pool_x[item * pool_item_pitch + t * pool_row_pitch + c], c < pool_C
+  const float* pool_x = nullptr;
+  long long pool_item_pitch = 0;
+  int pool_row_pitch = 0, pool_C = 1500;
+  int variant = 0;                     // 0: XVectorSincNet (pyannote/embedding), 1: WeSpeaker ResNet34 (variant B)
+  std::unique_ptr<struct ResNet> rn;
 };
+
+// ---- variant B: WeSpeaker ResNet34 (SURVEY.md 8(a) A8'; kernels in resnet.cu + the Conv2d epilogue of gemm_tc.cu)
+struct ResConv {                       // Conv2d (3x3 pad 1 or 1x1, no bias) + folded BatchNorm2d(eval)
+  int cin = 0, cout = 0, ksize = 3, stride = 1;
+  int KW = 9, cin_gemm = 0, lda = 0;   // GEMM view: taps, channels consumed per tap, row pitch of the input planes
+  DevBuf w_hi, w_lo, sc, sh;
+};
+struct ResBlock {
+  ResConv c1, c2, sc;
+  bool has_sc = false;
+};
+struct ResNet {
+  DevBuf fb_hi, fb_lo, banks, k_lo, k_hi, stem_w, stem_sc, stem_sh;
+  std::vector<ResBlock> blocks;
+  int stage_of[16];
+  // work buffers: planes of the waveform, spectrum, log-mel map, three plane pairs per stage, float32 final map
+  DevBuf wav_hi, wav_lo, spec, logmel, mean, act[4][3][2], fin;
+  int last_S = 0;                // the padding rings are only valid for one geometry: buffers are cleared when it changes
+  int stop_after = 99;           // test hook (dg_emb_debug_trunk): stop after the stem (-1) / after block k
+  int dbg_stage = 0, dbg_buf = 0;
+};
+static const int RN_CH[4] = {32, 64, 128, 256};
+static const int RN_BLOCKS[4] = {3, 4, 6, 3};
 
 static const int TD_OUT[5] = {512, 512, 512, 512, 1500};
 static const int TD_K[5] = {5, 3, 3, 1, 1};
 static const int TD_DIL[5] = {1, 2, 3, 1, 1};
 
+static int resnet_prepare(dg_emb* h, const Tensors& t);
+
 static int emb_prepare(dg_emb* h, const Tensors& t) {
   int rc;
+  if (t.numel("resnet.conv1.weight") > 0) return resnet_prepare(h, t);     // variant B checkpoint
   if ((rc = prep_sincnet(t, "sincnet.", h->sw))) return rc;
   int in = 60, in_pad = 64;
   for (int L = 0; L < 5; L++) {
@@ -759,6 +792,294 @@ static int emb_prepare(dg_emb* h, const Tensors& t) {
   return 0;
 }
 
+// Conv2d weight [co][ci][kh (mel)][kw (time)] + BatchNorm2d -> GEMM weight planes [Npad][K] (tap-major K) + scale / shift.
+// Maps are [item][w = time][h = mel][C]: tap (dw, dh) multiplies w[co][ci][dh][dw].  With 32 input channels the three dh
+// taps of one dw are 96 CONTIGUOUS values of the input planes (rows h-1, h, h+1 follow each other in memory), so they are
+// read as one 128-wide K slab through an overlapping-row view (row pitch 32): 3 taps x 128 instead of 9 taps x 64.
+static int resnet_conv_prepare(const Tensors& t, const std::string& conv, const std::string& bn, int cin, int cout, int ksize,
+                               int stride, ResConv& c) {
+  const float* w = t.get(conv + ".weight", (int64_t)cout * cin * ksize * ksize);
+  const float* gm = t.get(bn + ".weight", cout);
+  const float* bt = t.get(bn + ".bias", cout);
+  const float* rm = t.get(bn + ".running_mean", cout);
+  const float* rv = t.get(bn + ".running_var", cout);
+  if (!w || !gm || !bt || !rm || !rv) return DG_EWEIGHT;
+  c.cin = cin; c.cout = cout; c.ksize = ksize; c.stride = stride;
+  const bool narrow = cin == 32;
+  if (ksize == 3) {
+    c.KW = narrow ? 3 : 9;
+    c.cin_gemm = narrow ? 128 : cin;
+  } else {
+    c.KW = 1;
+    c.cin_gemm = narrow ? 64 : cin;
+  }
+  c.lda = cin;
+  const int K = c.KW * c.cin_gemm;
+  const int npad = cout <= 64 ? cout : (cout + 127) / 128 * 128;
+  std::vector<float> w_nk((size_t)cout * K, 0.f), sc(cout), sh(cout);
+  for (int o = 0; o < cout; o++) {
+    for (int ci = 0; ci < cin; ci++)
+      for (int dh = 0; dh < ksize; dh++)
+        for (int dw = 0; dw < ksize; dw++) {
+          const float v = w[(((size_t)o * cin + ci) * ksize + dh) * ksize + dw];
+          size_t k;
+          if (ksize == 1) k = ci;
+          else if (narrow) k = (size_t)dw * 128 + dh * 32 + ci;
+          else k = (size_t)(dw * 3 + dh) * cin + ci;
+          w_nk[(size_t)o * K + k] = v;
+        }
+    sc[o] = gm[o] / sqrtf(rv[o] + 1e-5f);
+    sh[o] = bt[o] - rm[o] * sc[o];
+  }
+  if (upload_split(c.w_hi, c.w_lo, w_nk, cout, npad, K) || upload(c.sc, sc) || upload(c.sh, sh)) return DG_ECUDA;
+  return 0;
+}
+
+static int resnet_prepare(dg_emb* h, const Tensors& t) {
+  int rc;
+  h->variant = 1;
+  h->rn.reset(new ResNet());
+  ResNet& r = *h->rn;
+  {
+    std::vector<float> op;
+    fbank_frame_operator(op);                                   // [514][400]
+    std::vector<float> w_nk((size_t)514 * 448, 0.f);
+    for (int n = 0; n < 514; n++) memcpy(&w_nk[(size_t)n * 448], &op[(size_t)n * 400], 400 * sizeof(float));
+    if (upload_split(r.fb_hi, r.fb_lo, w_nk, 514, 640, 448)) return DG_ECUDA;
+    std::vector<float> banks;
+    std::vector<int> lo, hi;
+    fbank_mel_banks(banks, lo, hi);
+    if (upload(r.banks, banks) || r.k_lo.ensure(80 * 4) || r.k_hi.ensure(80 * 4)) return DG_ECUDA;
+    DG_CUDA(cudaMemcpy(r.k_lo.p, lo.data(), 80 * 4, cudaMemcpyHostToDevice));
+    DG_CUDA(cudaMemcpy(r.k_hi.p, hi.data(), 80 * 4, cudaMemcpyHostToDevice));
+  }
+  {
+    const float* w = t.get("resnet.conv1.weight", 32 * 9);
+    const float* gm = t.get("resnet.bn1.weight", 32);
+    const float* bt = t.get("resnet.bn1.bias", 32);
+    const float* rm = t.get("resnet.bn1.running_mean", 32);
+    const float* rv = t.get("resnet.bn1.running_var", 32);
+    if (!w || !gm || !bt || !rm || !rv) return DG_EWEIGHT;
+    std::vector<float> sc(32), sh(32);
+    for (int o = 0; o < 32; o++) {
+      sc[o] = gm[o] / sqrtf(rv[o] + 1e-5f);
+      sh[o] = bt[o] - rm[o] * sc[o];
+    }
+    if (upload(r.stem_w, std::vector<float>(w, w + 288)) || upload(r.stem_sc, sc) || upload(r.stem_sh, sh)) return DG_ECUDA;
+  }
+  int in_planes = 32, bi = 0;
+  r.blocks.resize(16);
+  for (int st = 0; st < 4; st++)
+    for (int b = 0; b < RN_BLOCKS[st]; b++, bi++) {
+      const int planes = RN_CH[st], stride = (b == 0 && st > 0) ? 2 : 1;
+      const std::string pre = "resnet.layer" + std::to_string(st + 1) + "." + std::to_string(b) + ".";
+      ResBlock& blk = r.blocks[bi];
+      r.stage_of[bi] = st;
+      if ((rc = resnet_conv_prepare(t, pre + "conv1", pre + "bn1", in_planes, planes, 3, stride, blk.c1)) ||
+          (rc = resnet_conv_prepare(t, pre + "conv2", pre + "bn2", planes, planes, 3, 1, blk.c2)))
+        return rc;
+      blk.has_sc = stride != 1 || in_planes != planes;
+      if (blk.has_sc && (rc = resnet_conv_prepare(t, pre + "shortcut.0", pre + "shortcut.1", in_planes, planes, 1, stride, blk.sc)))
+        return rc;
+      in_planes = planes;
+    }
+  // Linear(5120, D): pyannote's feature order is (channel, mel) -- "batch (dimension channel) frames" -- ours (mel, channel)
+  const int64_t dn = t.numel("resnet.seg_1.bias");
+  if (dn < 4 || dn % 4) {
+    set_error("resnet.seg_1.bias missing or dimension not a multiple of 4");
+    return DG_EWEIGHT;
+  }
+  h->D = (int)dn;
+  const float* ew = t.get("resnet.seg_1.weight", dn * 5120);
+  const float* eb = t.get("resnet.seg_1.bias", dn);
+  if (!ew || !eb) return DG_EWEIGHT;
+  std::vector<float> w_nk((size_t)dn * 5120);
+  for (int o = 0; o < dn; o++)
+    for (int half = 0; half < 2; half++)
+      for (int hh = 0; hh < 10; hh++)
+        for (int c = 0; c < 256; c++) w_nk[(size_t)o * 5120 + half * 2560 + hh * 256 + c] = ew[(size_t)o * 5120 + half * 2560 + c * 10 + hh];
+  if (upload_split(h->ew_hi, h->ew_lo, w_nk, (int)dn, ((int)dn + 255) / 256 * 256, 5120) ||
+      upload(h->eb, std::vector<float>(eb, eb + dn)))
+    return DG_ECUDA;
+  h->pool_C = 2560;
+  return 0;
+}
+
+// geometry of variant B for S samples: fbank frames and the four map sizes (time x mel)
+struct ResGeom {
+  int T0, W[4], H[4];
+};
+static int resnet_geom(int S, ResGeom& g) {
+  if (S < 800 || S % 160) {
+    set_error("WeSpeaker embedding: chunk length must be a multiple of 160 samples (>= 800)");
+    return DG_EINVAL;
+  }
+  g.T0 = S / 160 - 2;                          // 1 + (S - 400) / 160, snip_edges
+  g.W[0] = g.T0;
+  g.H[0] = 80;
+  for (int s = 1; s < 4; s++) {
+    g.W[s] = (g.W[s - 1] - 1) / 2 + 1;
+    g.H[s] = (g.H[s - 1] - 1) / 2 + 1;
+  }
+  return 0;
+}
+
+static int resnet_conv(const ResConv& c, const void* in_hi, const void* in_lo, int U, int Wp, int Hp, int Wop, int Hop,
+                       void* out_hi, void* out_lo, float* out_f32, const void* res_hi, const void* res_lo, int relu,
+                       const char* tag, cudaStream_t st) {
+  int taps[9];
+  if (c.ksize == 1) taps[0] = 0;
+  else if (c.KW == 3)
+    for (int dw = 0; dw < 3; dw++) taps[dw] = (dw - 1) * Hp - 1;           // three dh taps folded into one K slab
+  else
+    for (int dw = 0; dw < 3; dw++)
+      for (int dh = 0; dh < 3; dh++) taps[dw * 3 + dh] = (dw - 1) * Hp + (dh - 1);
+  TcGemm t{};
+  const long long rows = (long long)U * Wp * Hp;
+  t.A_hi = in_hi; t.A_lo = in_lo; t.lda = c.lda; t.Cin = c.cin_gemm; t.KW = c.KW; t.dil = 1; t.Mtot = rows; t.M = rows;
+  t.W_hi = c.w_hi.p; t.W_lo = c.w_lo.p; t.Npad = c.cout <= 64 ? c.cout : (c.cout + 127) / 128 * 128; t.N = c.cout;
+  t.bn_scale = c.sc.as<float>(); t.bn_shift = c.sh.as<float>();
+  t.out_hi = out_hi; t.out_lo = out_lo; t.out_f32 = out_f32; t.ldc = c.cout; t.epi = 3; t.tag = tag;
+  t.tap_off = taps; t.Wp = Wp; t.Hp = Hp; t.Wop = Wop; t.Hop = Hop; t.stride2 = c.stride == 2; t.relu = relu;
+  t.res_hi = res_hi; t.res_lo = res_lo;
+  return launch_gemm_tc(t, st);
+}
+
+// waveform [U,S] -> float32 final map [U][W3 + 2][H3 + 2][256] (h->pool_x descriptor), frames W3
+static int resnet_trunk(dg_emb* h, const float* wav, int U, int S, cudaStream_t st, int* T_out) {
+  int rc;
+  ResNet& r = *h->rn;
+  ResGeom g;
+  if ((rc = resnet_geom(S, g))) return rc;
+  const int rpi = S / 160;                                      // spectrum rows per item (the last two are not frames)
+  const long long n = (long long)U * S;
+  if (r.wav_hi.ensure(((size_t)n + 1024) * 2) || r.wav_lo.ensure(((size_t)n + 1024) * 2) ||
+      r.spec.ensure(((size_t)U * rpi + 128) * 640 * 4) || r.logmel.ensure((size_t)U * g.T0 * 80 * 4) ||
+      r.mean.ensure((size_t)U * 80 * 4))
+    return DG_ECUDA;
+  for (int s = 0; s < 4; s++) {
+    const size_t rows = (size_t)U * (g.W[s] + 2) * (g.H[s] + 2) + 256;      // + tail: overlapping-row reads of the last rows
+    for (int b = 0; b < 3; b++)
+      for (int p = 0; p < 2; p++)
+        if (r.act[s][b][p].ensure(rows * RN_CH[s] * 2)) return DG_ECUDA;    // zero-initialised: the padding ring stays zero
+  }
+  if (r.fin.ensure(((size_t)U * (g.W[3] + 2) * (g.H[3] + 2) + 64) * 256 * 4)) return DG_ECUDA;
+  if (r.last_S != S) {
+    if (r.last_S)
+      for (int s = 0; s < 4; s++)
+        for (int b = 0; b < 3; b++)
+          for (int p = 0; p < 2; p++) DG_CUDA(cudaMemsetAsync(r.act[s][b][p].p, 0, r.act[s][b][p].bytes, st));
+    r.last_S = S;
+  }
+  // ---- kaldi fbank: planes of x * 2^15, [rows, 448] x [448, 640] on the tensor cores, power -> mel -> log, time mean
+  if ((rc = launch_fb_planes(wav, n, r.wav_hi.p, r.wav_lo.p, st))) return rc;
+  {
+    TcGemm t{};
+    t.A_hi = r.wav_hi.p; t.A_lo = r.wav_lo.p; t.lda = 160; t.Cin = 448; t.KW = 1; t.dil = 1;
+    t.Mtot = (long long)U * rpi; t.M = (long long)U * rpi;
+    t.W_hi = r.fb_hi.p; t.W_lo = r.fb_lo.p; t.Npad = 640; t.N = 640; t.out_f32 = r.spec.as<float>(); t.ldc = 640; t.epi = 0;
+    t.tag = "fbank_dft";
+    if ((rc = launch_gemm_tc(t, st))) return rc;
+  }
+  if ((rc = launch_fb_mel(r.spec.as<float>(), 640, rpi, g.T0, U, r.banks.as<float>(), r.k_lo.as<int>(), r.k_hi.as<int>(),
+                          r.logmel.as<float>(), st)) ||
+      (rc = launch_fb_mean(r.logmel.as<float>(), U, g.T0, r.mean.as<float>(), st)) ||
+      (rc = launch_rn_stem(r.logmel.as<float>(), r.mean.as<float>(), U, g.T0, r.stem_w.as<float>(), r.stem_sc.as<float>(),
+                           r.stem_sh.as<float>(), r.act[0][0][0].p, r.act[0][0][1].p, st)))
+    return rc;
+  // ---- 16 BasicBlocks: y = relu(bn1(conv1(x))); out = relu(bn2(conv2(y)) + shortcut(x))
+  int cur = 0;                      // buffer (0 / 2) of the current stage that holds x
+  int prev_stage = 0;
+  static const char* kTags[4] = {"resnet_l1", "resnet_l2", "resnet_l3", "resnet_l4"};
+  r.dbg_stage = 0;
+  r.dbg_buf = 0;
+  for (size_t bi = 0; bi < r.blocks.size() && (int)bi <= r.stop_after; bi++) {
+    const ResBlock& blk = r.blocks[bi];
+    const int s = r.stage_of[bi];
+    const int Wp = g.W[s] + 2, Hp = g.H[s] + 2;
+    DevBuf* x = r.act[prev_stage][cur];
+    const int xWp = g.W[prev_stage] + 2, xHp = g.H[prev_stage] + 2;
+    if (s != prev_stage) cur = 0;   // first block of a stage: x comes from the previous stage, the output goes to buffer 0
+    DevBuf* y = r.act[s][1];
+    DevBuf* out = s != prev_stage ? r.act[s][0] : r.act[s][cur ^ 2];
+    const void *res_hi = x[0].p, *res_lo = x[1].p;
+    if (blk.has_sc) {               // BatchNorm(Conv1x1 stride 2 (x)) into buffer 2 of this stage
+      DevBuf* z = r.act[s][2];
+      if ((rc = resnet_conv(blk.sc, x[0].p, x[1].p, U, xWp, xHp, Wp, Hp, z[0].p, z[1].p, nullptr, nullptr, nullptr, 0, kTags[s], st)))
+        return rc;
+      res_hi = z[0].p;
+      res_lo = z[1].p;
+    }
+    if ((rc = resnet_conv(blk.c1, x[0].p, x[1].p, U, xWp, xHp, Wp, Hp, y[0].p, y[1].p, nullptr, nullptr, nullptr, 1, kTags[s], st)))
+      return rc;
+    const bool last = bi + 1 == r.blocks.size();
+    if ((rc = resnet_conv(blk.c2, y[0].p, y[1].p, U, Wp, Hp, Wp, Hp, last ? nullptr : out[0].p, last ? nullptr : out[1].p,
+                          last ? r.fin.as<float>() : nullptr, res_hi, res_lo, 1, kTags[s], st)))
+      return rc;
+    if (s == prev_stage) cur ^= 2;
+    prev_stage = s;
+    r.dbg_stage = s;
+    r.dbg_buf = cur;
+  }
+  const int Wp3 = g.W[3] + 2, Hp3 = g.H[3] + 2;
+  h->pool_x = r.fin.as<float>() + ((size_t)1 * Hp3 + 1) * 256;       // position (w = 1, h = 1) of item 0
+  h->pool_item_pitch = (long long)Wp3 * Hp3 * 256;
+  h->pool_row_pitch = Hp3 * 256;
+  h->pool_C = g.H[3] * 256;
+  *T_out = g.W[3];
+  return 0;
+}
+
+// test hook: runs the variant-B trunk up to a given point and returns the intermediate map as float32 on the host.
+// stop_after = -2: log-mel features [U][T0][80] (before mean normalisation), -1: stem output, k >= 0: output of BasicBlock k
+// (dims = {U, W, H, C}, un-padded, layout [item][w = time][h = mel][channel]); 15 = the final map.
+extern "C" int dg_emb_debug_trunk(dg_emb* h, const float* wav_dev, int U, int S, int stop_after, float* out_host, int64_t cap,
+                                  int* dims) {
+  if (!h || h->variant != 1 || !wav_dev || !out_host || !dims || U < 1) {
+    set_error("dg_emb_debug_trunk: needs a WeSpeaker (variant B) handle");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->device));
+  ResNet& r = *h->rn;
+  ResGeom g;
+  int rc, T = 0;
+  if ((rc = resnet_geom(S, g))) return rc;
+  r.stop_after = stop_after < -1 ? -1 : stop_after;
+  rc = resnet_trunk(h, wav_dev, U, S, nullptr, &T);
+  r.stop_after = 99;
+  if (rc) return rc;
+  DG_CUDA(cudaDeviceSynchronize());
+  if (stop_after == -2) {
+    dims[0] = U; dims[1] = g.T0; dims[2] = 80; dims[3] = 1;
+    const int64_t n = (int64_t)U * g.T0 * 80;
+    if (n > cap) return DG_EINVAL;
+    DG_CUDA(cudaMemcpy(out_host, r.logmel.p, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    return DG_OK;
+  }
+  const int s = r.dbg_stage, W = g.W[s], H = g.H[s], C = RN_CH[s], Wp = W + 2, Hp = H + 2;
+  dims[0] = U; dims[1] = W; dims[2] = H; dims[3] = C;
+  const int64_t n = (int64_t)U * W * H * C;
+  if (n > cap) {
+    set_error("dg_emb_debug_trunk: buffer too small");
+    return DG_EINVAL;
+  }
+  const size_t rows = (size_t)U * Wp * Hp;
+  std::vector<float> full(rows * C);
+  if (stop_after >= 15) {
+    DG_CUDA(cudaMemcpy(full.data(), r.fin.p, rows * C * 4, cudaMemcpyDeviceToHost));
+  } else {
+    std::vector<uint16_t> hi(rows * C), lo(rows * C);
+    DG_CUDA(cudaMemcpy(hi.data(), r.act[s][r.dbg_buf][0].p, rows * C * 2, cudaMemcpyDeviceToHost));
+    DG_CUDA(cudaMemcpy(lo.data(), r.act[s][r.dbg_buf][1].p, rows * C * 2, cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < rows * C; i++) full[i] = host_h16_to_f32(hi[i], split_f16()) + host_h16_to_f32(lo[i], split_f16());
+  }
+  for (int u = 0; u < U; u++)
+    for (int w = 0; w < W; w++)
+      for (int hh = 0; hh < H; hh++)
+        memcpy(out_host + (((size_t)u * W + w) * H + hh) * C, &full[(((size_t)u * Wp + w + 1) * Hp + hh + 1) * C], (size_t)C * 4);
+  return DG_OK;
+}
+
 extern "C" int dg_emb_create(const dg_tensor* tensors, int n, int pool_mode, int device, dg_emb** out) {
   if (!tensors || !out || (pool_mode != 31 && pool_mode != 21)) {
     set_error("dg_emb_create: bad arguments (pool_mode must be 31 or 21)");
@@ -779,6 +1100,14 @@ extern "C" int dg_emb_dims(const dg_emb* h, int num_samples, int* frames, int* d
   if (!h || num_samples < 3000) {
     set_error("dg_emb_dims: bad arguments");
     return DG_EINVAL;
+  }
+  if (h->variant == 1) {
+    ResGeom rg;
+    int rc = resnet_geom(num_samples, rg);
+    if (rc) return rc;
+    if (frames) *frames = rg.W[3];
+    if (dimension) *dimension = h->D;
+    return DG_OK;
   }
   Geom g = make_geom(num_samples);
   if (frames) *frames = g.T2 - 14;
@@ -824,9 +1153,14 @@ static int build_tables(dg_emb* h, int F, int T, cudaStream_t st) {
 // waveform [U,S] -> t5 [U*S2, 1500]; returns the number of valid frames
 static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStream_t st, int* T_out) {
   int rc;
+  if (h->variant == 1) return resnet_trunk(h, wav, U, g.S, st, T_out);
   if ((rc = run_sincnet(h->sw, h->work, wav, U, g, st, h->shared_prep))) return rc;
   const size_t rows = (size_t)U * g.S2 + 64;
   if (h->tA.ensure(rows * 512 * 4) || h->tB.ensure(rows * 512 * 4) || h->t5.ensure(rows * 1500 * 4)) return DG_ECUDA;
+  h->pool_x = h->t5.as<float>();
+  h->pool_item_pitch = (long long)g.S2 * 1500;
+  h->pool_row_pitch = 1500;
+  h->pool_C = 1500;
   const long long M = (long long)U * g.S2;
   if (use_tensor_cores()) {
     if (h->xh.ensure(rows * 64 * 2) || h->xl.ensure(rows * 64 * 2) || h->aH.ensure(rows * 512 * 2) ||
@@ -885,11 +1219,11 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
 }
 
 static int emb_project(dg_emb* h, int rows, int normalize, float norm, float* out, cudaStream_t st) {
-  if (use_tensor_cores()) {
+  if (use_tensor_cores() || h->variant == 1) {
     int rc;
-    if (h->ph.ensure(((size_t)rows + 128) * 3008 * 2) || h->pl.ensure(((size_t)rows + 128) * 3008 * 2)) return DG_ECUDA;
-    if ((rc = launch_split_ex(h->pooled.as<float>(), rows, 3000, 3000, 3008, 0, 1, nullptr, nullptr, h->ph.p, h->pl.p,
-                              st)))
+    const int nfeat = 2 * h->pool_C, kpad = (nfeat + 63) / 64 * 64;     // 3000 -> 3008, 5120 -> 5120
+    if (h->ph.ensure(((size_t)rows + 128) * kpad * 2) || h->pl.ensure(((size_t)rows + 128) * kpad * 2)) return DG_ECUDA;
+    if ((rc = launch_split_ex(h->pooled.as<float>(), rows, nfeat, nfeat, kpad, 0, 1, nullptr, nullptr, h->ph.p, h->pl.p, st)))
       return rc;
     float* dst = out;
     if (normalize) {
@@ -897,7 +1231,7 @@ static int emb_project(dg_emb* h, int rows, int normalize, float norm, float* ou
       dst = h->eraw.as<float>();
     }
     TcGemm t{};
-    t.A_hi = h->ph.p; t.A_lo = h->pl.p; t.lda = 3008; t.Cin = 3008; t.KW = 1; t.dil = 1; t.Mtot = rows; t.M = rows;
+    t.A_hi = h->ph.p; t.A_lo = h->pl.p; t.lda = kpad; t.Cin = kpad; t.KW = 1; t.dil = 1; t.Mtot = rows; t.M = rows;
     t.W_hi = h->ew_hi.p; t.W_lo = h->ew_lo.p; t.Npad = (h->D + 255) / 256 * 256; t.N = h->D;
     t.bias = h->eb.as<float>(); t.out_f32 = dst; t.ldc = h->D; t.epi = 0; t.tag = "emb_linear";
     if ((rc = launch_gemm_tc(t, st))) return rc;
@@ -930,11 +1264,11 @@ extern "C" int dg_emb_forward(dg_emb* h, const float* wav, const float* weights,
   int rc, T = 0;
   if ((rc = emb_trunk(h, wav, B, g, st, &T))) return rc;
   if (weights && (rc = build_tables(h, F, T, st))) return rc;
-  if (h->pooled.ensure((size_t)B * K * 3000 * 4)) return DG_ECUDA;
+  if (h->pooled.ensure((size_t)B * K * 2 * h->pool_C * 4)) return DG_ECUDA;
   const float eps = h->pool_mode == 31 ? 1e-8f : 0.f;
-  if ((rc = launch_stats_pool(h->t5.as<float>(), B, g.S2, T, 1500, weights, F, K, h->idx0.as<int>(),
+  if ((rc = launch_stats_pool(h->pool_x, B, g.S2, T, h->pool_C, weights, F, K, h->idx0.as<int>(),
                               h->idx1.as<int>(), h->lam1.as<float>(), weights ? eps : 0.f,
-                              h->pooled.as<float>(), st)))
+                              h->pooled.as<float>(), st, h->pool_item_pitch, h->pool_row_pitch)))
     return rc;
   return emb_project(h, B * K, normalize, norm, out, st);
 }
@@ -984,12 +1318,12 @@ extern "C" int dg_emb_forward_rows(dg_emb* h, const float* wav, const float* wei
   DG_CUDA(cudaMemcpyAsync(h->grp.p, packed.data(), (size_t)3 * G * 4, cudaMemcpyHostToDevice, st));
   if ((rc = emb_trunk(h, trunk_in, U, g, st, &T))) return rc;
   if (weights && (rc = build_tables(h, F, T, st))) return rc;
-  if (h->pooled.ensure((size_t)N * 3000 * 4)) return DG_ECUDA;
+  if (h->pooled.ensure((size_t)N * 2 * h->pool_C * 4)) return DG_ECUDA;
   const float eps = (weights && h->pool_mode == 31) ? 1e-8f : 0.f;
   const int* gp = h->grp.as<int>();
-  if ((rc = launch_stats_pool_ex(h->t5.as<float>(), g.S2, T, 1500, weights, F, 1, 1, G, gp, gp + G, gp + 2 * G,
+  if ((rc = launch_stats_pool_ex(h->pool_x, g.S2, T, h->pool_C, weights, F, 1, 1, G, gp, gp + G, gp + 2 * G,
                                  h->idx0.as<int>(), h->idx1.as<int>(), h->lam1.as<float>(), eps,
-                                 h->pooled.as<float>(), st)))
+                                 h->pooled.as<float>(), st, h->pool_item_pitch, h->pool_row_pitch)))
     return rc;
   rc = emb_project(h, N, 0, 1.f, out, st);
   DG_CUDA(cudaStreamSynchronize(st));   // host staging vectors above must outlive the async copies
@@ -1361,10 +1695,11 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   DG_CUDA(cudaEventRecord(e_osp, s_seg));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, e_osp, 0));
   if ((rc = build_tables(h->emb, F, T, h->s_emb))) return rc;
-  if (h->emb->pooled.ensure((size_t)B * K * 3000 * 4)) return DG_ECUDA;
-  if ((rc = launch_stats_pool(h->emb->t5.as<float>(), B, g.S2, T, 1500, osp.as<float>(), F, K,
+  if (h->emb->pooled.ensure((size_t)B * K * 2 * h->emb->pool_C * 4)) return DG_ECUDA;
+  if ((rc = launch_stats_pool(h->emb->pool_x, B, g.S2, T, h->emb->pool_C, osp.as<float>(), F, K,
                               h->emb->idx0.as<int>(), h->emb->idx1.as<int>(), h->emb->lam1.as<float>(),
-                              h->emb->pool_mode == 31 ? 1e-8f : 0.f, h->emb->pooled.as<float>(), h->s_emb)))
+                              h->emb->pool_mode == 31 ? 1e-8f : 0.f, h->emb->pooled.as<float>(), h->s_emb,
+                              h->emb->pool_item_pitch, h->emb->pool_row_pitch)))
     return rc;
   if ((rc = emb_project(h->emb, B * K, 1, 1.f, emb, h->s_emb))) return rc;
   DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));

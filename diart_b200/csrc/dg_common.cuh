@@ -6,6 +6,7 @@
 
 #include <atomic>
 #include <string>
+#include <vector>
 
 namespace dg {
 
@@ -196,10 +197,17 @@ int launch_osp(const float* seg, int B, int F, int K, float gamma, float beta, i
                cudaStream_t st);
 int launch_stats_pool(const float* x /*[B*stride,C]*/, int B, int stride, int T, int C, const float* w /*[B,F,K]*/,
                       int F, int K, const int* idx0, const int* idx1, const float* lam1, float eps,
-                      float* pooled /*[B*K, 2C]*/, cudaStream_t st);
+                      float* pooled /*[B*K, 2C]*/, cudaStream_t st, long long item_pitch = 0, int row_pitch = 0);
 int launch_l2norm(const float* in, int rows, int D, float norm, float* out, cudaStream_t st);
 int launch_row_equal_flags(const float* wav, int N, int S, int* flags, cudaStream_t st);
 int launch_gather_rows(const float* src, const int* index, int rows, int cols, float* dst, cudaStream_t st);
+// resnet.cu -- variant B of the embedding (WeSpeaker ResNet34): fbank front end and stem around the Conv2d GEMMs
+int launch_fb_planes(const float* wav, long long n, void* hi, void* lo, cudaStream_t st);
+int launch_fb_mel(const float* spec, int ld, int rows_per_item, int T, int B, const float* banks, const int* k_lo, const int* k_hi,
+                  float* logmel, cudaStream_t st);
+int launch_fb_mean(const float* logmel, int B, int T, float* mean, cudaStream_t st);
+int launch_rn_stem(const float* logmel, const float* mean, int B, int T, const float* w, const float* sc, const float* sh,
+                   void* hi, void* lo, cudaStream_t st);
 // cluster.cu
 struct ClusterParams {
   int M, D;
@@ -224,5 +232,8 @@ int launch_expand_windows(const float* ring, long long r0, int C, int hop, int S
 int launch_post_history(const float* seg, const int32_t* map, const float* hist_seg, const int32_t* hist_map, int n_hist,
                         int B, int F, int K, int keep, float* new_seg, int32_t* new_map, cudaStream_t st);
 size_t cluster_prep_doubles(int B, int K);
+
+void fbank_frame_operator(std::vector<float>& op /*[514][400]*/);
+void fbank_mel_banks(std::vector<float>& banks /*[80][257]*/, std::vector<int>& k_lo, std::vector<int>& k_hi);
 
 }  // namespace dg

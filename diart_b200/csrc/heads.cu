@@ -175,7 +175,7 @@ int launch_osp(const float* seg, int B, int F, int K, float gamma, float beta, i
 // (idx0, idx1, lam1): nearest has lam1 = 0, linear interpolates (F.interpolate semantics).
 constexpr int PK = 4;
 __global__ void __launch_bounds__(256)
-stats_pool_kernel(const float* __restrict__ x, int stride, int T, int C, const float* __restrict__ w, int F, int K,
+stats_pool_kernel(const float* __restrict__ x, long long item_pitch, int row_pitch, int T, int C, const float* __restrict__ w, int F, int K,
                   int layout /*0: [B,F,K], 1: [N,F]*/, const int* __restrict__ grp_item, const int* __restrict__ grp_q0,
                   const int* __restrict__ grp_nq, const int* __restrict__ idx0, const int* __restrict__ idx1,
                   const float* __restrict__ lam1, float eps, float* __restrict__ pooled) {
@@ -226,11 +226,11 @@ stats_pool_kernel(const float* __restrict__ x, int stride, int T, int C, const f
   const int cl = threadIdx.x & 63, tg = threadIdx.x >> 6;
   const int c = blockIdx.x * 64 + cl;
   const bool ok = c < C;
-  const float* xb = x + (size_t)item * stride * C + c;
+  const float* xb = x + (size_t)item * item_pitch + c;
   float acc[PK] = {0.f, 0.f, 0.f, 0.f};
   if (ok)
     for (int t = tg; t < T; t += 4) {
-      const float xv = xb[(size_t)t * C];
+      const float xv = xb[(size_t)t * row_pitch];
       const float4 wv = *reinterpret_cast<const float4*>(&wr[t * PK]);
       acc[0] = fmaf(xv, wv.x, acc[0]); acc[1] = fmaf(xv, wv.y, acc[1]);
       acc[2] = fmaf(xv, wv.z, acc[2]); acc[3] = fmaf(xv, wv.w, acc[3]);
@@ -249,7 +249,7 @@ stats_pool_kernel(const float* __restrict__ x, int stride, int T, int C, const f
   __syncthreads();
   if (ok)
     for (int t = tg; t < T; t += 4) {
-      const float xv = xb[(size_t)t * C];
+      const float xv = xb[(size_t)t * row_pitch];
       const float4 wv = *reinterpret_cast<const float4*>(&wr[t * PK]);
       float d;
       d = xv - mean[0]; acc[0] = fmaf(d * d, wv.x, acc[0]);
@@ -276,21 +276,25 @@ stats_pool_kernel(const float* __restrict__ x, int stride, int T, int C, const f
 
 int launch_stats_pool_ex(const float* x, int stride, int T, int C, const float* w, int F, int K, int layout,
                          int n_groups, const int* grp_item, const int* grp_q0, const int* grp_nq, const int* idx0,
-                         const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st) {
+                         const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st, long long item_pitch,
+                         int row_pitch) {
   ProfScope _ps("stats_pool", st);
   const size_t smem = ((size_t)T * PK + 4 * 64 * PK) * sizeof(float);
   dim3 grid((C + 63) / 64, n_groups);
-  stats_pool_kernel<<<grid, 256, smem, st>>>(x, stride, T, C, w, F, K, layout, grp_item, grp_q0, grp_nq, idx0, idx1,
+  if (!item_pitch) item_pitch = (long long)stride * C;       // dense [item][stride rows][C]
+  if (!row_pitch) row_pitch = C;
+  stats_pool_kernel<<<grid, 256, smem, st>>>(x, item_pitch, row_pitch, T, C, w, F, K, layout, grp_item, grp_q0, grp_nq, idx0, idx1,
                                              lam1, eps, pooled);
   DG_LAUNCHED();
   return 0;
 }
 
 int launch_stats_pool(const float* x, int B, int stride, int T, int C, const float* w, int F, int K, const int* idx0,
-                      const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st) {
+                      const int* idx1, const float* lam1, float eps, float* pooled, cudaStream_t st, long long item_pitch,
+                      int row_pitch) {
   const int per = (K + PK - 1) / PK;
   return launch_stats_pool_ex(x, stride, T, C, w, F, K, 0, B * per, nullptr, nullptr, nullptr, idx0, idx1, lam1, eps,
-                              pooled, st);
+                              pooled, st, item_pitch, row_pitch);
 }
 
 // ---------------------------------------------------------------------------------------- l2norm

@@ -84,6 +84,13 @@ int dg_emb_forward(dg_emb* h, const float* wav_dev /*[B,S]*/, const float* weigh
 int dg_emb_forward_rows(dg_emb* h, const float* wav_dev /*[N,S]*/, const float* weights_dev /*[N,F] or NULL*/,
                         int N, int S, int F, float* out_dev /*[N,D]*/, void* stream);
 int dg_emb_destroy(dg_emb* h);
+/* Variant B -- pyannote/wespeaker-voxceleb-resnet34-LM (reference README.md:172-173, loaded through src/diart/models.py:50,59):
+ * dg_emb_create recognises the checkpoint by its key names (resnet.conv1.weight, resnet.layer1.0.conv1.weight, ...,
+ * resnet.seg_1.weight) and every dg_emb_* entry point then runs kaldi fbank -> ResNet34 -> TSTP -> Linear(5120, 256);
+ * chunk lengths must be multiples of 160 samples.  Test hook: the trunk up to the stem (stop_after = -1) or BasicBlock
+ * stop_after (0..15), returned as float32 [U][W][H][C] (time, mel, channel) on the host; -2 = log-mel features [U][T][80].
+ * dims receives {U, W, H, C}.  Synchronises the device. */
+int dg_emb_debug_trunk(dg_emb* h, const float* wav_dev, int U, int S, int stop_after, float* out_host, int64_t cap, int* dims);
 
 /* ---- element-wise blocks ---- */
 /* OverlappedSpeechPenalty (reference src/diart/blocks/embedding.py:98-107, functional.py:6-13) */
