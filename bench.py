@@ -63,6 +63,15 @@ HBM_BYTES_PER_CHUNK = {
 # compulsory HBM bytes per chunk of the whole step: waveform in, seg + emb out
 BYTES_PER_CHUNK = 80000 * 4 + 293 * 3 * 4 + 3 * 512 * 4
 STEP_FLOPS_PER_CHUNK = 3.359e9      # segmentation 1.312 + embedding (de-duplicated trunk) 2.047 GFLOP
+# variant B (WeSpeaker ResNet34, SURVEY.md 8(a) A8'): algorithmic FLOPs per chunk of all launches under one tag
+FLOPS_PER_CHUNK_STEP = {
+    "fbank_dft": 2 * 498 * 400 * 514,
+    "resnet_l1": 6 * 2 * 39840 * 32 * 32 * 9,
+    "resnet_l2": 2 * 9960 * 64 * (32 * 9 + 32 + 7 * 64 * 9),
+    "resnet_l3": 2 * 2500 * 128 * (64 * 9 + 64 + 11 * 128 * 9),
+    "resnet_l4": 2 * 630 * 256 * (128 * 9 + 128 + 5 * 256 * 9),
+}
+STEP_FLOPS_PER_CHUNK_WESPEAKER = 1.312e9 + sum(FLOPS_PER_CHUNK_STEP.values()) + 3 * (2 * 5120 * 256 + 2 * 2 * 2560 * 63)
 
 
 def peaks():
@@ -219,7 +228,8 @@ def run_ours(args):
     B = args.batch
     config = blocks.SpeakerDiarizationConfig(
         segmentation=models.SegmentationModel(models.B200SegmentationLoader(synth.segmentation_state())),
-        embedding=models.EmbeddingModel(models.B200EmbeddingLoader(synth.embedding_state())),
+        embedding=models.EmbeddingModel(models.B200EmbeddingLoader(
+            synth.wespeaker_state() if args.embedding == "wespeaker" else synth.embedding_state())),
         device=device)
     pipe = blocks.SpeakerDiarization(config)
     NB = 3                                                  # 3 x 82 MB of distinct inputs > 126 MB L2
@@ -458,7 +468,10 @@ def run_ours(args):
 
     def tensor_line(k):
         ms_l = kernels[k]["ms"] / kernels[k]["count"]
-        tf = FLOPS_PER_CHUNK[k] * B / (ms_l * 1e-3) / 1e12
+        if k in FLOPS_PER_CHUNK_STEP:       # several launches per step under one tag: total FLOPs of the step / total time
+            tf = FLOPS_PER_CHUNK_STEP[k] * B * args.steps / (kernels[k]["ms"] * 1e-3) / 1e12
+        else:
+            tf = FLOPS_PER_CHUNK[k] * B / (ms_l * 1e-3) / 1e12
         return {"kernel": k, "bound": "tensor", "achieved": tf, "peak": pk["tf"], "unit": "TFLOP/s", "frac": tf / pk["tf"],
                 "traffic": traffic_tab.get(k), "peak_source": pk["src"] + " (bf16 sustained)", "ms_per_launch": ms_l,
                 "executed_x3": 3 * tf, "frac_of_peak_executed": 3 * tf / pk["tf"]}
@@ -472,7 +485,7 @@ def run_ours(args):
     def line_of(k):
         if k in HBM_BYTES_PER_CHUNK:
             return hbm_line(k)
-        if k in FLOPS_PER_CHUNK:
+        if k in FLOPS_PER_CHUNK or k in FLOPS_PER_CHUNK_STEP:
             return tensor_line(k)
         ms_l = kernels[k]["ms"] / kernels[k]["count"]
         achieved = BYTES_PER_CHUNK * B / (ms_l * 1e-3) / 1e9
@@ -493,16 +506,17 @@ def run_ours(args):
             "achieved_tflops": FLOPS_PER_CHUNK["lstm_rec"] * B / (r_ms * 1e-3) / 1e12, "traffic": traffic_tab.get("lstm_rec"),
             "note": "latency-bound: 293 dependent steps per launch (4 launches = 1172 per batch), 2 x ceil(B/16) CTAs; "
                     "tcgen05 with fp16 hi/lo planes; see profiles/r1_lstm_step_timing.log"}
-    gemms = {k: v for k, v in kernels.items() if k.startswith("tdnn")}
+    gemms = {k: v for k, v in kernels.items() if k.startswith("tdnn") or k.startswith("resnet_l")}
     if gemms:   # the largest throughput-bound tensor kernel, for the tensor roofline proper
         gk = max(gemms, key=lambda k: gemms[k]["ms"])
         roofline["largest_gemm"] = tensor_line(gk)
     step_flops = sum(FLOPS_PER_CHUNK[k] * (4 if k == "lstm_inproj" or k == "lstm_rec" else 2 if k in
                      ("sinc0", "sinc_conv1", "sinc_conv2", "seg_linear") else 1) for k in FLOPS_PER_CHUNK) * B
     step_ms = ms_max / args.steps
+    sfc = STEP_FLOPS_PER_CHUNK_WESPEAKER if args.embedding == "wespeaker" else STEP_FLOPS_PER_CHUNK
     roofline["step"] = {
-        "bound": "tensor", "flops_per_step": STEP_FLOPS_PER_CHUNK * B, "achieved": STEP_FLOPS_PER_CHUNK * B / (step_ms * 1e-3) / 1e12,
-        "peak": pk["tf"], "unit": "TFLOP/s", "frac": STEP_FLOPS_PER_CHUNK * B / (step_ms * 1e-3) / 1e12 / pk["tf"],
+        "bound": "tensor", "flops_per_step": sfc * B, "achieved": sfc * B / (step_ms * 1e-3) / 1e12,
+        "peak": pk["tf"], "unit": "TFLOP/s", "frac": sfc * B / (step_ms * 1e-3) / 1e12 / pk["tf"],
         "peak_source": pk["src"] + " (bf16 sustained)", "compulsory_bytes_per_step": BYTES_PER_CHUNK * B,
         "hbm_frac": BYTES_PER_CHUNK * B / (step_ms * 1e-3) / 1e9 / pk["hbm_gbs"],
         "traffic": traffic_tab.get("_step"),
@@ -512,7 +526,9 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "batch": B, "streams": world, "parallelism": (f"{world} independent streams, "
+        "config": {"workload": WORKLOAD if args.embedding == "xvector" else WORKLOAD.replace(
+                       "pyannote/embedding architectures", "pyannote/wespeaker-voxceleb-resnet34-LM (variant B) architectures"),
+                   "embedding": args.embedding, "batch": B, "streams": world, "parallelism": (f"{world} independent streams, "
                    "1 per GPU, no collectives" if shared is None else f"{world} streams, 1 per GPU, shared speaker "
                    "identity: one NCCL all-gather of centroid-delta records per step + deterministic merge"), "l2": "inputs rotate over 3 distinct 82 MB batches (246 MB > 126 MB L2)",
                    "arithmetic": "float32 results: every dense layer as fp16 hi/lo operand planes x 3 tcgen05 products with float32 "
@@ -566,6 +582,9 @@ def _main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--ref-batch", type=int, default=32)
+    ap.add_argument("--embedding", default="xvector", choices=["xvector", "wespeaker"],
+                    help="embedding network: pyannote/embedding (XVectorSincNet, the quoted configuration) or variant B, "
+                         "pyannote/wespeaker-voxceleb-resnet34-LM (ResNet34, reference README.md:172-173)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stream-leg", action="store_true", help="skip the device ring-buffer leg (e2e_stream)")
     ap.add_argument("--no-pipeline-call", action="store_true", help="skip the SpeakerDiarization.__call__ leg (e2e_pipeline_call)")

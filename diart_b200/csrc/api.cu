@@ -128,7 +128,7 @@ static int upload(DevBuf& b, const std::vector<float>& h) {
 struct SincWeights {
   float wn_gamma = 1.f, wn_beta = 0.f;
   DevBuf filt, g0, b0, w1, bias1, g1, b1, w2, bias2, g2, b2;
-  DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: 16-bit hi/lo planes [128][5*128] and [128][5*64]
+  DevBuf w1_hi, w1_lo, w2_hi, w2_lo;   // tcgen05 path: 16-bit hi/lo planes [64][448] (taps folded into K: 5 x 80 + pad) and [64][5*64]
   DevBuf filt_planes;                  // sinc filter bank as 16-bit planes [3][80][256] (hi, lo; lo2 for the bf16 mode)
   DevBuf cf;                           // folded wav-norm affine: beta * sum_k h[f][k]
   DevBuf hsum;                         // sum_k h[f][k] (stream form of the sinc layer)
@@ -219,9 +219,18 @@ static int prep_sincnet(const Tensors& t, const std::string& pre, SincWeights& w
         for (int j = 0; j < k; j++) w_nk[(size_t)o * k * in_pad + j * in_pad + c] = s[((size_t)o * in + c) * k + j];
     return upload_split(hi, lo, w_nk, out, 64, k * in_pad);
   };
-  if ((rc = conv_w_tc(pre + "conv1d.1.weight", 60, 80, 5, 128, w.w1_hi, w.w1_lo)) ||
-      (rc = conv_w_tc(pre + "conv1d.2.weight", 60, 60, 5, 64, w.w2_hi, w.w2_lo)))
-    return rc;
+  {
+    // Conv1d(80, 60, 5) with its taps folded into K: the input planes are 80-channel rows (pitch 160 B), so the im2col row of
+    // output row m is the 400 CONTIGUOUS values starting at row m -- read through an overlapping-row TMA view, K = 448
+    const float* s1 = t.get(pre + "conv1d.1.weight", (int64_t)60 * 80 * 5);
+    if (!s1) return DG_EWEIGHT;
+    std::vector<float> w_nk((size_t)60 * 448, 0.f);
+    for (int o = 0; o < 60; o++)
+      for (int c = 0; c < 80; c++)
+        for (int j = 0; j < 5; j++) w_nk[(size_t)o * 448 + j * 80 + c] = s1[((size_t)o * 80 + c) * 5 + j];
+    if (upload_split(w.w1_hi, w.w1_lo, w_nk, 60, 64, 448)) return DG_ECUDA;
+  }
+  if ((rc = conv_w_tc(pre + "conv1d.2.weight", 60, 60, 5, 64, w.w2_hi, w.w2_lo))) return rc;
   return 0;
 }
 
@@ -231,7 +240,7 @@ struct SincPrep {
   DevBuf wmean, wrstd, wh, wl;
   // stream form (needs a hop hint; DG_STREAM_SINC=0 disables it): planes of the raw stream and the device flag "this batch is a run of
   // overlapping windows"; `hop` > 0 means the stream-form launches were enqueued for this batch
-  DevBuf swh, swl, flag;
+  DevBuf swh, swl, flag, spart;
   int hop = 0;
   int ensure(int B, const Geom& g) {
     const size_t bytes = 4 * sinc_tc_plane_elems(B, g) * 2;
@@ -245,7 +254,7 @@ struct SincPrep {
 struct SincWork {
   DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
   DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: 16-bit planes of the conv inputs, un-pooled conv outputs
-  DevBuf craw;                         // stream form: raw convolution of the stream [P][80]
+  DevBuf craw, part;                   // stream form: raw convolution of the stream [P][80], statistics partials
   SincPrep own_prep;                   // statistics + waveform planes when no shared ones are supplied
   const float* out = nullptr;          // conv2 output that the next layer normalises on load ...
   int out_pool = 0;                    // ... 1: still un-pooled (rows = 3x), MaxPool1d(3) is applied on load
@@ -287,7 +296,15 @@ static int run_sinc_prep(SincPrep& p, const float* wav, int B, const Geom& g, cu
     }
     p.hop = hop;
   }
-  if ((rc = launch_wave_stats(wav, B, g.S, p.wmean.as<float>(), p.wrstd.as<float>(), st))) return rc;
+  const bool fast_stats = p.hop && stream_stats_ok(g.S, p.hop);
+  if (fast_stats) {
+    if (p.spart.ensure(stream_stats_doubles(B, g.S, p.hop) * 8)) return DG_ECUDA;
+    if ((rc = launch_stream_stats(wav, B, g.S, p.hop, p.spart.as<double>(), p.wmean.as<float>(), p.wrstd.as<float>(),
+                                  p.flag.as<int>(), st)))
+      return rc;
+  }
+  if ((rc = launch_wave_stats(wav, B, g.S, p.wmean.as<float>(), p.wrstd.as<float>(), st, fast_stats ? p.flag.as<int>() : nullptr)))
+    return rc;
   if (p.hop && (rc = launch_stream_prep(wav, B, g, hop, p.swh.p, p.swl.p, p.flag.as<int>(), st))) return rc;
   return launch_sinc_prep(wav, p.wmean.as<float>(), p.wrstd.as<float>(), B, g, p.wh.p, p.wl.p, st,
                           p.hop ? p.flag.as<int>() : nullptr);
@@ -301,6 +318,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
   if ((rc = k.ensure(B, g))) return rc;
   if (use_tensor_cores()) {
     if ((rc = k.ensure_tc(B, g))) return rc;
+    const int* stream_flag = nullptr;      // device flag "the stream form produced the conv1 operand planes of this batch"
     static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
     if (sinc_simt) {
       if ((rc = launch_wave_stats(wav, B, g.S, k.wmean.as<float>(), k.wrstd.as<float>(), st))) return rc;
@@ -314,27 +332,31 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
       }
       if (prep->hop) {   // stream form: one convolution of the unique samples + a per-window affine / |.| / pool pass
         const SincStreamGeom sg = sinc_stream_geom(B, g, prep->hop);
-        if (k.craw.ensure(((size_t)sg.P + 16) * 80 * 4)) return DG_ECUDA;
+        if (k.craw.ensure(((size_t)sg.P + 16) * 80 * 4) || k.part.ensure(sinc_pool_part_floats(B) * 4)) return DG_ECUDA;
+        // raw convolution of the stream, then statistics and normalised operand planes straight from it (p0 is never written)
         if ((rc = launch_sinc0_tc_stream(w.filt_planes.p, B, g, prep->hop, prep->swh.p, prep->swl.p, k.craw.as<float>(),
                                          prep->flag.as<int>(), st)) ||
-            (rc = launch_sinc_pool(k.craw.as<float>(), prep->wmean.as<float>(), prep->wrstd.as<float>(), w.cf.as<float>(),
-                                   w.hsum.as<float>(), w.wn_gamma, B, g, prep->hop, k.p0.as<float>(), prep->flag.as<int>(), st)))
+            (rc = launch_sinc_pool_fused(k.craw.as<float>(), prep->wmean.as<float>(), prep->wrstd.as<float>(), w.cf.as<float>(),
+                                         w.hsum.as<float>(), w.wn_gamma, B, g, prep->hop, w.g0.as<float>(), w.b0.as<float>(),
+                                         k.part.as<float>(), k.sc0.as<float>(), k.sh0.as<float>(), k.a0h.p, k.a0l.p,
+                                         prep->flag.as<int>(), st)))
           return rc;
+        stream_flag = prep->flag.as<int>();
       }
       rc = launch_sinc0_tc(w.wn_gamma, w.cf.as<float>(), w.filt_planes.p, B, g, prep->wh.p, prep->wl.p,
                            k.p0.as<float>(), st, prep->hop ? prep->flag.as<int>() : nullptr);
     }
     if (rc) return rc;
     if ((rc = launch_instnorm_stats(k.p0.as<float>(), B, g.S0, g.T0, 80, 80, w.g0.as<float>(), w.b0.as<float>(),
-                                    k.sc0.as<float>(), k.sh0.as<float>(), st)))
+                                    k.sc0.as<float>(), k.sh0.as<float>(), st, 0, stream_flag)))
       return rc;
-    // Conv1d(80,60,5): normalised input as 16-bit hi/lo planes (80 -> 128 channels), un-pooled float32 output
+    // Conv1d(80,60,5): normalised input as 16-bit hi/lo planes (80-channel rows), un-pooled float32 output
     const long long M0 = (long long)B * g.S0, M1 = (long long)B * g.S1;
-    if ((rc = launch_split_ex(k.p0.as<float>(), M0, 80, 80, 128, 0, g.S0, k.sc0.as<float>(), k.sh0.as<float>(),
-                              k.a0h.p, k.a0l.p, st)))
+    if ((rc = launch_split_ex(k.p0.as<float>(), M0, 80, 80, 80, 0, g.S0, k.sc0.as<float>(), k.sh0.as<float>(),
+                              k.a0h.p, k.a0l.p, st, stream_flag)))
       return rc;
     TcGemm t{};
-    t.A_hi = k.a0h.p; t.A_lo = k.a0l.p; t.lda = 128; t.Cin = 128; t.KW = 5; t.dil = 1; t.Mtot = M0; t.M = M0;
+    t.A_hi = k.a0h.p; t.A_lo = k.a0l.p; t.lda = 80; t.Cin = 448; t.KW = 1; t.dil = 1; t.Mtot = M0; t.M = M0;
     t.W_hi = w.w1_hi.p; t.W_lo = w.w1_lo.p; t.Npad = 64; t.N = 64; t.bias = w.bias1.as<float>();
     t.out_f32 = k.c1.as<float>(); t.ldc = 64; t.epi = 0; t.tag = "sinc_conv1";
     if ((rc = launch_gemm_tc(t, st))) return rc;

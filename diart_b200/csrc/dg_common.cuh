@@ -87,11 +87,15 @@ __device__ __forceinline__ float leaky(float x) { return x > 0.f ? x : 0.01f * x
 
 // ------------------------------------------------------------------ launchers (defined per .cu)
 // sincnet.cu
-int launch_wave_stats(const float* wav, int B, int S, float* mean, float* rstd, cudaStream_t st);
+int launch_wave_stats(const float* wav, int B, int S, float* mean, float* rstd, cudaStream_t st, const int* skip_flag = nullptr);
+bool stream_stats_ok(int S, int hop);
+size_t stream_stats_doubles(int B, int S, int hop);
+int launch_stream_stats(const float* wav, int B, int S, int hop, double* part, float* mean, float* rstd, const int* flag,
+                        cudaStream_t st);
 int launch_sinc0(const float* wav, const float* mean, const float* rstd, float wn_gamma, float wn_beta,
                  const float* filt /*[251][80]*/, int B, const Geom& g, float* p0 /*[B,S0,80]*/, cudaStream_t st);
 int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
-                          const float* beta, float* sc, float* sh, cudaStream_t st, int pool = 0);
+                          const float* beta, float* sc, float* sh, cudaStream_t st, int pool = 0, const int* skip_flag = nullptr);
 // gemm.cu
 enum Epi { EPI_BIAS = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_LEAKY_BN = 2, EPI_BIAS_POOL3 = 3 };
 struct GemmArgs {
@@ -147,7 +151,7 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st);
 int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
                  void* lo, cudaStream_t st);
 int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld_out, int pool, int item_rows,
-                    const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st);
+                    const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st, const int* skip_flag = nullptr);
 // element type of the 16-bit operand planes: 1 = fp16 (default), 0 = bf16 (DG_SPLIT_BF16=1); fixed at first use
 int split_f16();
 void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo, int f16);
@@ -177,6 +181,10 @@ int launch_sinc0_tc_stream(const void* w_planes, int B, const Geom& g, int hop, 
                            float* craw, const int* flag, cudaStream_t st);
 int launch_sinc_pool(const float* craw, const float* mean, const float* rstd, const float* cf, const float* hsum, float gamma,
                      int B, const Geom& g, int hop, float* p0, const int* flag, cudaStream_t st);
+size_t sinc_pool_part_floats(int B);
+int launch_sinc_pool_fused(const float* craw, const float* mean, const float* rstd, const float* cf, const float* hsum, float gamma,
+                           int B, const Geom& g, int hop, const float* g0, const float* b0, float* part, float* sc, float* sh,
+                           void* planes_hi, void* planes_lo, const int* flag, cudaStream_t st);
 // lstm.cu
 int launch_lstm_layer(const float* gx /*[B*stride,1024]*/, const float* whh_packed, int B, int T, int stride,
                       float* hout /*[B*stride,256]*/, cudaStream_t st);

@@ -440,7 +440,8 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
 __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x, long long rows_out, int C, int ld_in,
                                                     int ld_out, int pool, int item_rows, const float* __restrict__ sc,
                                                     const float* __restrict__ sh, __nv_bfloat16* __restrict__ hi,
-                                                    __nv_bfloat16* __restrict__ lo, int f16) {
+                                                    __nv_bfloat16* __restrict__ lo, int f16, const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;
   const int q_per_row = ld_out >> 2;
   const long long n4 = rows_out * q_per_row;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -476,7 +477,7 @@ __global__ void __launch_bounds__(256) split_kernel(const float* __restrict__ x,
 }
 
 int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld_out, int pool, int item_rows,
-                    const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st) {
+                    const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st, const int* skip_flag) {
   ProfScope _ps("split16", st);
   if (C % 4 || ld_in % 4 || ld_out % 4) {
     set_error("split: channel counts must be multiples of 4");
@@ -486,7 +487,7 @@ int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld
   const long long want = (n4 + 255) / 256;
   const int grid = (int)(want < 148 * 16 ? want : 148 * 16);
   split_kernel<<<grid, 256, 0, st>>>(x, rows_out, C, ld_in, ld_out, pool, item_rows, sc, sh,
-                                     reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), split_f16());
+                                     reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), split_f16(), skip_flag);
   DG_LAUNCHED();
   return 0;
 }

@@ -23,7 +23,8 @@ __device__ __forceinline__ double block_sum_d(double v, double* sm) {
 }
 
 __global__ void __launch_bounds__(512) wave_stats_kernel(const float* __restrict__ wav, int S, float* __restrict__ mean,
-                                                         float* __restrict__ rstd) {
+                                                         float* __restrict__ rstd, const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;     // the stream form computes the statistics from per-hop partial sums
   __shared__ double sm[32];
   const float* x = wav + (size_t)blockIdx.x * S;
   float s = 0.f;
@@ -41,9 +42,67 @@ __global__ void __launch_bounds__(512) wave_stats_kernel(const float* __restrict
   }
 }
 
-int launch_wave_stats(const float* wav, int B, int S, float* mean, float* rstd, cudaStream_t st) {
+int launch_wave_stats(const float* wav, int B, int S, float* mean, float* rstd, cudaStream_t st, const int* skip_flag) {
   ProfScope _ps("wave_stats", st);
-  wave_stats_kernel<<<B, 512, 0, st>>>(wav, S, mean, rstd);
+  wave_stats_kernel<<<B, 512, 0, st>>>(wav, S, mean, rstd, skip_flag);
+  DG_LAUNCHED();
+  return 0;
+}
+
+// ---- stream form: the B windows are a run of one stream (window b = samples [b*hop, b*hop + S)), so every sample is summed
+// ONCE: partial (sum x, sum x^2) per quarter hop in double, then each window adds its 4 S / hop partials.
+// (B x S = 82 MB read by 256 CTAs becomes 8.5 MB read by ~1000.)
+__global__ void __launch_bounds__(256) stream_sums_kernel(const float* __restrict__ wav, int B, int S, int hop, int sub,
+                                                          double* __restrict__ part, const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  __shared__ double sm[32];
+  const long long first = (long long)blockIdx.x * sub;           // first stream sample of this block
+  int b = (int)(first / hop);
+  if (b > B - 1) b = B - 1;
+  const float4* x = reinterpret_cast<const float4*>(wav + (size_t)b * S + (first - (long long)b * hop));
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < (sub >> 2); i += blockDim.x) {
+    const float4 v = x[i];
+    s1 += (v.x + v.y) + (v.z + v.w);
+    s2 = fmaf(v.x, v.x, fmaf(v.y, v.y, fmaf(v.z, v.z, fmaf(v.w, v.w, s2))));
+  }
+  const double t1 = block_sum_d((double)s1, sm);
+  const double t2 = block_sum_d((double)s2, sm);
+  if (threadIdx.x == 0) {
+    part[2 * blockIdx.x] = t1;
+    part[2 * blockIdx.x + 1] = t2;
+  }
+}
+
+__global__ void stream_stats_kernel(const double* __restrict__ part, int B, int S, int hop, int sub, float* __restrict__ mean,
+                                    float* __restrict__ rstd, const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int per_hop = hop / sub, n = S / sub;
+  double t1 = 0, t2 = 0;
+  for (int i = 0; i < n; i++) {
+    t1 += part[2 * (b * per_hop + i)];
+    t2 += part[2 * (b * per_hop + i) + 1];
+  }
+  const double m = t1 / S;
+  double var = t2 / S - m * m;
+  if (var < 0) var = 0;
+  mean[b] = (float)m;
+  rstd[b] = (float)(1.0 / sqrt(var + 1e-5));
+}
+
+bool stream_stats_ok(int S, int hop) { return hop % 16 == 0 && S % (hop / 4) == 0; }
+size_t stream_stats_doubles(int B, int S, int hop) { return 2 * ((size_t)(B - 1) * 4 + (size_t)S / (hop / 4)) + 8; }
+
+int launch_stream_stats(const float* wav, int B, int S, int hop, double* part, float* mean, float* rstd, const int* flag,
+                        cudaStream_t st) {
+  ProfScope _ps("wave_stats", st);
+  const int sub = hop / 4;
+  const int blocks = (B - 1) * 4 + S / sub;
+  stream_sums_kernel<<<blocks, 256, 0, st>>>(wav, B, S, hop, sub, part, flag);
+  DG_LAUNCHED();
+  stream_stats_kernel<<<(B + 127) / 128, 128, 0, st>>>(part, B, S, hop, sub, mean, rstd, flag);
   DG_LAUNCHED();
   return 0;
 }
@@ -145,7 +204,9 @@ int launch_sinc0(const float* wav, const float* mean, const float* rstd, float w
 __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __restrict__ x, int stride_rows, int T, int C,
                                                              int ldc, const float* __restrict__ gamma,
                                                              const float* __restrict__ beta, float* __restrict__ sc,
-                                                             float* __restrict__ sh, int pool) {
+                                                             float* __restrict__ sh, int pool,
+                                                             const int* __restrict__ skip_flag) {
+  if (skip_flag && *skip_flag != 0) return;       // the fused stream-form tail produced these statistics
   __shared__ double s1[8][32], s2[8][32];
   const int b = blockIdx.y, c = blockIdx.x * 32 + (threadIdx.x & 31), w = threadIdx.x >> 5;
   const bool ok = c < C;
@@ -183,10 +244,10 @@ __global__ void __launch_bounds__(256) instnorm_stats_kernel(const float* __rest
 }
 
 int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
-                          const float* beta, float* sc, float* sh, cudaStream_t st, int pool) {
+                          const float* beta, float* sc, float* sh, cudaStream_t st, int pool, const int* skip_flag) {
   ProfScope _ps("instnorm_stats", st);
   dim3 grid((C + 31) / 32, B);
-  instnorm_stats_kernel<<<grid, 256, 0, st>>>(x, stride_rows, T, C, ldc, gamma, beta, sc, sh, pool);
+  instnorm_stats_kernel<<<grid, 256, 0, st>>>(x, stride_rows, T, C, ldc, gamma, beta, sc, sh, pool, skip_flag);
   DG_LAUNCHED();
   return 0;
 }

@@ -98,6 +98,38 @@ def embedding_state(seed: int = 8765, dimension: int = 512, calibrated: bool = T
     return s
 
 
+def wespeaker_state(seed: int = 2468, dimension: int = 256) -> Dict[str, torch.Tensor]:
+    """state_dict of pyannote's WeSpeakerResNet34 (pyannote/wespeaker-voxceleb-resnet34-LM layout, 6 634 336 parameters):
+    seeded uniform(+-1/sqrt(fan_in)) convolutions, randomised BatchNorm statistics (so that the eval-mode affine is not
+    the identity)."""
+    g = torch.Generator().manual_seed(seed)
+    s: Dict[str, torch.Tensor] = {}
+
+    def bn(prefix: str, c: int):
+        s[prefix + ".weight"] = 1.0 + 0.1 * torch.randn(c, generator=g)
+        s[prefix + ".bias"] = 0.1 * torch.randn(c, generator=g)
+        s[prefix + ".running_mean"] = 0.1 * torch.randn(c, generator=g)
+        s[prefix + ".running_var"] = 0.5 + torch.rand(c, generator=g)
+
+    s["resnet.conv1.weight"] = _uniform(g, (32, 1, 3, 3), 9, 1.7)
+    bn("resnet.bn1", 32)
+    in_planes = 32
+    for i, (planes, blocks, stride) in enumerate(((32, 3, 1), (64, 4, 2), (128, 6, 2), (256, 3, 2)), start=1):
+        for b, st in enumerate([stride] + [1] * (blocks - 1)):
+            pre = f"resnet.layer{i}.{b}."
+            s[pre + "conv1.weight"] = _uniform(g, (planes, in_planes, 3, 3), in_planes * 9, 1.7)
+            bn(pre + "bn1", planes)
+            s[pre + "conv2.weight"] = _uniform(g, (planes, planes, 3, 3), planes * 9, 1.7)
+            bn(pre + "bn2", planes)
+            if st != 1 or in_planes != planes:
+                s[pre + "shortcut.0.weight"] = _uniform(g, (planes, in_planes, 1, 1), in_planes, 1.7)
+                bn(pre + "shortcut.1", planes)
+            in_planes = planes
+    s["resnet.seg_1.weight"] = _uniform(g, (dimension, 5120), 5120)
+    s["resnet.seg_1.bias"] = _uniform(g, (dimension,), 5120)
+    return s
+
+
 def synth_audio(num_samples: int, seed: int = 1234, sample_rate: int = 16000, num_speakers: int = 4) -> np.ndarray:
     """Mono float32 stream in [-1,1]: harmonic 'speakers' (f0 in 90..250 Hz, three formant-like
     resonances) gated by a seeded two-state turn-taking chain with some overlap, plus -40 dB noise."""

@@ -53,7 +53,7 @@ def test_device_post_path_equals_reference_blocks(latency, splits, cuda_device):
     for i, (a, b) in enumerate(zip(want, got)):
         assert tracks(a) == tracks(b), f"chunk {i}"
         lines += len(tracks(a))
-    assert lines > n // 2
+    assert lines > n // 4
     # reset: the same stream again gives the same answer (history cleared on both sides)
     post.reset()
     seg = torch.from_numpy(seg_all[:splits[0]]).to(cuda_device)
