@@ -55,6 +55,8 @@ SIGNATURES = {
     "dg_cluster_record_len": (C.c_int, [_P]),
     "dg_cluster_export_delta": (C.c_int, [_P, _P, _P]),
     "dg_cluster_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, C.c_int, _P]),
+    "dg_pipeline_identity_export": (C.c_int, [_P, _P, _P]),
+    "dg_pipeline_identity_merge": (C.c_int, [_P, _P, C.c_int, C.c_int, _P]),
     "dg_pipeline_create": (C.c_int, [_P, _P, _P, C.c_float, C.c_float, C.c_int, C.POINTER(_P)]),
     "dg_pipeline_set_hop": (C.c_int, [_P, C.c_int]),
     "dg_pipeline_step": (C.c_int, [_P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P]),

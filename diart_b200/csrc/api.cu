@@ -367,7 +367,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
     if ((rc = launch_split_ex(k.c1.as<float>(), M1, 64, 64, 64, 1, g.S1, k.sc1.as<float>(), k.sh1.as<float>(),
                               k.a1h.p, k.a1l.p, st)))
       return rc;
-    t.A_hi = k.a1h.p; t.A_lo = k.a1l.p; t.lda = 64; t.Cin = 64; t.Mtot = M1; t.M = M1;
+    t.A_hi = k.a1h.p; t.A_lo = k.a1l.p; t.lda = 64; t.Cin = 64; t.KW = 5; t.Mtot = M1; t.M = M1;
     t.W_hi = w.w2_hi.p; t.W_lo = w.w2_lo.p; t.bias = w.bias2.as<float>();
     t.out_f32 = k.c2.as<float>(); t.tag = "sinc_conv2";
     if ((rc = launch_gemm_tc(t, st))) return rc;
@@ -1622,6 +1622,10 @@ struct dg_pipeline {
   cudaEvent_t e_lane_done[2] = {nullptr, nullptr};
   int slot_B[3] = {0, 0, 0}, slot_S[3] = {0, 0, 0}, outstanding = 0;
   long long next_step = 0;
+  // shared-identity mode inside the pipelined flow: export / merge run on the clustering stream, in order with the clustering
+  // of the submitted steps, so the networks of the next steps keep running meanwhile
+  cudaEvent_t e_ident = nullptr, e_ident_in = nullptr;
+  long long ident_merged_upto = 0;      // steps below this index have had their maps relabelled by a merge
   bool overlap_known = false;     // the current dg_pipeline_step batch was formed from a dg_stream (windows overlap by construction)
   void* pin_wav = nullptr;        // pinned staging of dg_pipeline_call_host (B separate host windows -> one upload)
   size_t pin_wav_bytes = 0;
@@ -2281,6 +2285,61 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
   return post_finish(post, B, header_host, turns_host, turn_cap_host, n_turns, h->st);
 }
 
+// ---- shared-identity mode (BASELINE config 5) without leaving the pipelined flow.  After dg_pipeline_submit*:
+//   dg_pipeline_identity_export  enqueues the export of this rank's centroid changes behind the clustering of every submitted
+//                                step (clustering stream) and makes `stream` wait for it -> the caller all-gathers the records
+//   dg_pipeline_identity_merge   makes the clustering stream wait for `stream` (the all-gather), merges all ranks' records and
+//                                relabels the speaker maps of the steps clustered since the previous merge (still on the device)
+// The clustering of the NEXT submitted step is ordered behind the merge, exactly as in the one-step-at-a-time protocol; only
+// the networks of the next steps overlap the exchange.  Call the pair once after every submit, before collecting that step.
+extern "C" int dg_pipeline_identity_export(dg_pipeline* h, double* record_dev, void* stream) {
+  if (!h || !record_dev) {
+    set_error("dg_pipeline_identity_export: bad arguments");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  if (!h->e_ident) {
+    DG_CUDA(cudaEventCreateWithFlags(&h->e_ident, cudaEventDisableTiming));
+    DG_CUDA(cudaEventCreateWithFlags(&h->e_ident_in, cudaEventDisableTiming));
+  }
+  int rc;
+  if ((rc = dg_cluster_export_delta(h->clu, record_dev, h->s_clu))) return rc;
+  DG_CUDA(cudaEventRecord(h->e_ident, h->s_clu));
+  DG_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, h->e_ident, 0));
+  return DG_OK;
+}
+
+extern "C" int dg_pipeline_identity_merge(dg_pipeline* h, const double* records_dev, int world, int rank, void* stream) {
+  if (!h || !records_dev || world < 1 || rank < 0 || rank >= world || !h->e_ident) {
+    set_error("dg_pipeline_identity_merge: bad arguments (or no export before it)");
+    return DG_EINVAL;
+  }
+  DG_CUDA(cudaSetDevice(h->seg->device));
+  DG_CUDA(cudaEventRecord(h->e_ident_in, (cudaStream_t)stream));
+  DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_ident_in, 0));
+  int rc;
+  long long first = h->ident_merged_upto;
+  if (first < h->next_step - DG_MAX_INFLIGHT) first = h->next_step - DG_MAX_INFLIGHT;
+  bool merged = false;
+  for (long long step = first; step < h->next_step; step++) {
+    const int slot = (int)(step % 3);
+    int F = 0, K = 0;
+    dg_seg_dims(h->seg, h->slot_S[slot], &F, &K);
+    int32_t* maps = h->slot_map[slot].as<int32_t>();
+    const int n = h->slot_B[slot] * K;
+    if (!merged) {
+      if ((rc = dg_cluster_merge(h->clu, records_dev, world, rank, maps, n, h->s_clu))) return rc;
+      merged = true;
+    } else if ((rc = launch_relabel_maps(maps, n, h->clu->relabel.as<int32_t>(), h->s_clu))) {
+      return rc;
+    }
+    DG_CUDA(cudaEventRecord(h->e_slot_done[slot], h->s_clu));      // collect must see the relabelled maps
+  }
+  if (!merged && (rc = dg_cluster_merge(h->clu, records_dev, world, rank, nullptr, 0, h->s_clu))) return rc;
+  h->ident_merged_upto = h->next_step;
+  return DG_OK;
+}
+
 // pipelined step whose batch is the next B windows of a device-side stream (no window upload at all; the sinc layer takes
 // its stream form without the overlap check: the windows overlap by construction)
 extern "C" int dg_pipeline_submit_stream(dg_pipeline* h, dg_stream* s, int B) {
@@ -2359,7 +2418,8 @@ extern "C" int dg_pipeline_destroy(dg_pipeline* h) {
     if (h->s_h2d) cudaStreamDestroy(h->s_h2d);
     if (h->s_d2h) cudaStreamDestroy(h->s_d2h);
     for (cudaEvent_t e : {h->e_start, h->e_osp, h->e_emb, h->e_done, h->e_h2d[0], h->e_h2d[1], h->e_h2d[2],
-                          h->e_slot_done[0], h->e_slot_done[1], h->e_slot_done[2], h->e_lane_done[0], h->e_lane_done[1]})
+                          h->e_slot_done[0], h->e_slot_done[1], h->e_slot_done[2], h->e_lane_done[0], h->e_lane_done[1],
+                          h->e_ident, h->e_ident_in})
       if (e) cudaEventDestroy(e);
   }
   if (h && h->st) cudaStreamDestroy(h->st);

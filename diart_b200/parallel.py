@@ -93,6 +93,25 @@ class SharedIdentity:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
 
+    def sync_submitted(self, pipeline_handle) -> None:
+        """The same exchange for steps submitted with ``dg_pipeline_submit*`` (call after every submit, before that step's
+        collect): export, all-gather and merge are stream-ordered behind the clustering of the submitted steps and ahead of
+        the next one -- the one-step-at-a-time protocol -- while the networks of the following steps keep running.  No host
+        synchronisation; the maps are relabelled in their device slots."""
+        lib, clu = self._lib.lib(), self.clustering
+        device = clu.device
+        n = lib.dg_cluster_record_len(clu._h)
+        if getattr(self, "_rec", None) is None or self._rec.numel() != n:
+            self._rec = torch.empty(n, dtype=torch.float64, device=device)
+            self._gathered = torch.empty(self.world * n, dtype=torch.float64, device=device) if self.world > 1 else self._rec
+        stream = self._lib.stream_ptr(device)
+        with torch.cuda.device(device):
+            self._lib.check(lib.dg_pipeline_identity_export(pipeline_handle, self._rec.data_ptr(), stream))
+            if self.world > 1:
+                dist.all_gather_into_tensor(self._gathered, self._rec, group=self.group)
+            self._lib.check(lib.dg_pipeline_identity_merge(pipeline_handle, self._gathered.data_ptr(), self.world, self.rank,
+                                                           stream))
+
     def sync(self, maps: torch.Tensor) -> torch.Tensor:
         lib, clu = self._lib.lib(), self.clustering
         if clu._h is None:

@@ -231,6 +231,15 @@ int dg_cluster_record_len(const dg_cluster* h);
 int dg_cluster_export_delta(dg_cluster* h, double* record_dev, void* stream);
 int dg_cluster_merge(dg_cluster* h, const double* records_dev /*[world, record_len]*/, int world, int rank,
                      int32_t* maps_dev /*nullable*/, int n_maps, void* stream);
+/* The same exchange inside the pipelined flow (dg_pipeline_submit* / collect*): both calls are stream-ordered on the
+ * pipeline's clustering stream, behind the clustering of every submitted step and ahead of the next one, so the protocol is
+ * exactly the one-step-at-a-time protocol while the networks of the following steps keep running.
+ *   dg_pipeline_identity_export: record_dev [record_len] float64 receives this rank's changes; `stream` waits for it
+ *     (issue the all-gather on `stream`);
+ *   dg_pipeline_identity_merge: the clustering stream waits for `stream`, merges, and relabels the maps of the steps
+ *     clustered since the previous merge in their device slots (call the pair after every submit, before that step's collect). */
+int dg_pipeline_identity_export(dg_pipeline* h, double* record_dev, void* stream);
+int dg_pipeline_identity_merge(dg_pipeline* h, const double* records_dev, int world, int rank, void* stream);
 
 #ifdef __cplusplus
 }

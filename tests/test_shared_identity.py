@@ -89,3 +89,62 @@ def test_cuda_merge_matches_oracle_simulation(cuda_device):
         assert np.array_equal(np.concatenate(got[r]), ref_maps[r]), f"rank {r}"
         assert np.array_equal(clus[r].centers, ref_table), f"rank {r}: shared table is not bit-identical"
         assert clus[r].active_centers == ref_active
+
+
+@pytest.mark.gpu
+def test_pipelined_identity_exchange_equals_the_serial_protocol(oracle_nets, cuda_device):
+    """dg_pipeline_identity_export / merge inside the three-deep submit / collect flow (exchange ordered on the clustering
+    stream) == one step at a time with dg_cluster_export_delta / dg_cluster_merge: identical maps and bit-identical tables.
+    Two simulated ranks on one device; the all-gather is a concatenation."""
+    from diart_b200 import _lib, synth
+    from test_gpu_pipeline import make_pipeline
+
+    lib = _lib.lib()
+    G, nb, B = 2, 5, 12
+    audio = [synth.synth_audio(80000 + 8000 * (nb * B - 1), seed=900 + r, num_speakers=3) for r in range(G)]
+    batches = [[torch.from_numpy(synth.windows(audio[r], B, first=i * B)).to(cuda_device) for i in range(nb)] for r in range(G)]
+    # --- serial protocol
+    ser = [make_pipeline(oracle_nets, cuda_device) for _ in range(G)]
+    want = [[] for _ in range(G)]
+    for i in range(nb):
+        recs, maps = [], []
+        for r in range(G):
+            _, _, m = ser[r].device_step(batches[r][i])
+            maps.append(m)
+            n = lib.dg_cluster_record_len(ser[r].clustering._h)
+            rec = torch.empty(n, dtype=torch.float64, device=cuda_device)
+            _lib.check(lib.dg_cluster_export_delta(ser[r].clustering._h, rec.data_ptr(), _lib.stream_ptr(cuda_device)))
+            recs.append(rec)
+        gathered = torch.cat(recs)
+        for r in range(G):
+            _lib.check(lib.dg_cluster_merge(ser[r].clustering._h, gathered.data_ptr(), G, r, maps[r].data_ptr(), maps[r].numel(),
+                                            _lib.stream_ptr(cuda_device)))
+            want[r].append(maps[r].cpu().numpy())
+    # --- pipelined: submit, exchange, collect two steps later
+    pip = [make_pipeline(oracle_nets, cuda_device) for _ in range(G)]
+    hs = [p._ensure_fused(80000)[0] for p in pip]
+    n = lib.dg_cluster_record_len(pip[0].clustering._h)
+    got = [[] for _ in range(G)]
+    st = _lib.stream_ptr(cuda_device)
+    for i in range(nb):
+        recs = []
+        for r in range(G):
+            pip[r].submit(batches[r][i])
+            rec = torch.empty(n, dtype=torch.float64, device=cuda_device)
+            _lib.check(lib.dg_pipeline_identity_export(hs[r], rec.data_ptr(), st))
+            recs.append(rec)
+        gathered = torch.cat(recs)
+        for r in range(G):
+            _lib.check(lib.dg_pipeline_identity_merge(hs[r], gathered.data_ptr(), G, r, st))
+        if i >= 2:
+            for r in range(G):
+                got[r].append(pip[r].collect()[2].cpu().numpy())
+    for r in range(G):
+        while len(got[r]) < nb:
+            got[r].append(pip[r].collect()[2].cpu().numpy())
+    torch.cuda.synchronize()
+    for r in range(G):
+        for i in range(nb):
+            assert np.array_equal(want[r][i], got[r][i]), f"rank {r} step {i}"
+        assert np.array_equal(ser[r].clustering.centers, pip[r].clustering.centers)
+    assert np.array_equal(pip[0].clustering.centers, pip[1].clustering.centers)
