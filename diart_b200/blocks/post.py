@@ -153,35 +153,44 @@ def aggregate_audio(chunk_buffer: List[SlidingWindowFeature], new: Sequence[Slid
                     latency: float) -> Tuple[List[SlidingWindowFeature], List[SlidingWindowFeature]]:
     """``DelayedAggregation(step, latency, "first", "center")`` over the waveform buffers (reference
     diarization.py:76-77,228), for the whole batch: per chunk the crop of the OLDEST buffered waveform over the
-    output region, as a view where the range lies inside the chunk.  Returns (outputs, new chunk_buffer)."""
-    buf = list(chunk_buffer)
+    output region, as a view where the range lies inside the chunk.  The crop indices of all chunks are evaluated at once
+    (numpy float64, the operation order of pyannote.core's ``crop(mode="center", fixed=...)``).
+    Returns (outputs, new chunk_buffer)."""
+    H, B = len(chunk_buffer), len(new)
+    buf = list(chunk_buffer) + list(new)
+    ext = [w.extent for w in new]
+    w_start = np.array([e.start for e in ext])
+    w_end = np.array([e.end for e in ext])
+    first_idx = np.maximum(H + np.arange(B) + 1 - nw, 0) if nw > 1 else H + np.arange(B)     # oldest buffer of each chunk
+    nbuf = np.minimum(H + np.arange(B) + 1, nw)
+    sw0 = [buf[i].sliding_window for i in first_idx]
+    s0 = np.array([sw.start for sw in sw0])
+    d0 = np.array([sw.duration for sw in sw0])
+    p0 = np.array([sw.step for sw in sw0])
+    start = w_end - latency
+    end = start + step
+    fixed = np.where(end > start, end - start, 0.0)
+    lo = np.rint((start - s0 - 0.5 * d0) / p0).astype(np.int64)          # SlidingWindow.closest_frame
+    cnt = np.rint(fixed / p0).astype(np.int64)                           # SlidingWindow.samples(fixed, mode="center")
+    is_first = (nbuf == 1) & (w_start == 0)
     outs = []
-    for wav in new:
-        buf.append(wav)
-        first = buf[0]
-        sw = first.sliding_window
-        n = first.data.shape[0]
-        ext = wav.extent
-        start = ext.end - latency
-        end = start + step
-        fixed = end - start if end > start else 0.0
-        lo = int(np.rint((start - sw.start - 0.5 * sw.duration) / sw.step))     # closest_frame
-        cnt = int(np.rint(fixed / sw.step))
-        if len(buf) == 1 and ext.start == 0:
+    for c in range(B):
+        first = buf[first_idx[c]]
+        data, n = first.data, first.data.shape[0]
+        if is_first[c]:
             # first buffer of a stream: [0, region.end) with the region pasted over its tail (aggregation.py:188-212)
-            lo1 = int(np.rint((0.0 - sw.start - 0.5 * sw.duration) / sw.step))
-            cnt1 = int(np.rint(end / sw.step))
-            data = _crop(first.data, lo1, cnt1, n).copy()
-            data[-cnt:] = _crop(first.data, lo, cnt, n)
-            res = end / data.shape[0]
-            outs.append(SlidingWindowFeature(data, SlidingWindow(start=0, duration=res, step=res)))
+            lo1 = int(np.rint((0.0 - s0[c] - 0.5 * d0[c]) / p0[c]))
+            cnt1 = int(np.rint(end[c] / p0[c]))
+            out = _crop(data, lo1, cnt1, n).copy()
+            out[-int(cnt[c]):] = _crop(data, int(lo[c]), int(cnt[c]), n)
+            res = end[c] / out.shape[0]
+            outs.append(SlidingWindowFeature(out, SlidingWindow(start=0, duration=res, step=res)))
         else:
-            data = _crop(first.data, lo, cnt, n)
-            res = fixed / data.shape[0]
-            outs.append(SlidingWindowFeature(data, SlidingWindow(start=start, duration=res, step=res)))
-        if len(buf) == nw:
-            buf = buf[1:]
-    return outs, buf
+            out = _crop(data, int(lo[c]), int(cnt[c]), n)
+            res = fixed[c] / out.shape[0]
+            outs.append(SlidingWindowFeature(out, SlidingWindow(start=start[c], duration=res, step=res)))
+    keep = min(nw - 1, H + B)
+    return outs, (buf[len(buf) - keep:] if keep else [])
 
 
 def _crop(data: np.ndarray, lo: int, cnt: int, n: int) -> np.ndarray:

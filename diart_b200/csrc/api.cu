@@ -725,6 +725,8 @@ struct dg_emb {
   const float* pool_x = nullptr;
   long long pool_item_pitch = 0;
   int pool_row_pitch = 0, pool_C = 1500;
+  const void *t4h = nullptr, *t4l = nullptr;   // operand planes of TDNN5 after a trunk pass that stopped before it
+  DevBuf pool_rw, pool_vs, pool_part;           // fused TDNN5 + pooling: row weights, weight sums, per-tile partial sums
   int variant = 0;                     // 0: XVectorSincNet (pyannote/embedding), 1: WeSpeaker ResNet34 (variant B)
   std::unique_ptr<struct ResNet> rn;
 };
@@ -1173,7 +1175,14 @@ static int build_tables(dg_emb* h, int F, int T, cudaStream_t st) {
 }
 
 // waveform [U,S] -> t5 [U*S2, 1500]; returns the number of valid frames
-static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStream_t st, int* T_out) {
+// DG_NO_POOL_FUSE=1: A/B switch, TDNN5 writes its map and stats_pool reads it back (the round-1 path)
+static bool pool_fusion_on() {
+  static const bool off = getenv("DG_NO_POOL_FUSE") && getenv("DG_NO_POOL_FUSE")[0] == '1';
+  return !off && use_tensor_cores();
+}
+
+// `defer_last`: stop before TDNN5 (its operand planes are left in h->t4h / t4l) -- the caller runs it fused with the pooling
+static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStream_t st, int* T_out, bool defer_last = false) {
   int rc;
   if (h->variant == 1) return resnet_trunk(h, wav, U, g.S, st, T_out);
   if ((rc = run_sincnet(h->sw, h->work, wav, U, g, st, h->shared_prep))) return rc;
@@ -1197,6 +1206,12 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
     void* ol[2] = {h->aL.p, h->bL.p};
     static const char* kTags[5] = {"tdnn1", "tdnn2", "tdnn3", "tdnn4", "tdnn5"};
     for (int L = 0; L < 5; L++) {
+      if (L == 4 && defer_last) {
+        h->t4h = ih;
+        h->t4l = il;
+        T -= (TD_K[L] - 1) * TD_DIL[L];
+        break;
+      }
       TcGemm t{};
       t.A_hi = ih; t.A_lo = il; t.lda = cin; t.Cin = cin; t.KW = TD_K[L]; t.dil = TD_DIL[L]; t.Mtot = M; t.M = M;
       t.W_hi = h->tw_hi[L].p; t.W_lo = h->tw_lo[L].p; t.Npad = (TD_OUT[L] + 255) / 256 * 256; t.N = TD_OUT[L];
@@ -1238,6 +1253,31 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
   }
   *T_out = T;
   return 0;
+}
+
+// TDNN5 (Conv1d(512, 1500, 1) -> LeakyReLU -> BatchNorm) fused with the K weighted statistics poolings: the [rows, 1500] map
+// (455 MB at B = 256) is never written; the epilogue leaves per-tile partial sums, pool_finalize turns them into mean / std.
+static int emb_tdnn5_pool(dg_emb* h, int U, const Geom& g, const float* weights, int F, int K, int T, cudaStream_t st) {
+  int rc;
+  const long long M = (long long)U * g.S2;
+  const int m_tiles = (int)((M + 127) / 128);
+  const float eps = h->pool_mode == 31 ? 1e-8f : 0.f;
+  if (h->pool_rw.ensure(((size_t)M + 128) * 16) || h->pool_vs.ensure((size_t)U * K * 8) ||
+      h->pool_part.ensure((size_t)m_tiles * 2 * 8 * 1500 * 4) || h->pooled.ensure((size_t)U * K * 3000 * 4))
+    return DG_ECUDA;
+  if ((rc = launch_pool_weights(weights, U, F, K, g.S2, T, h->idx0.as<int>(), h->idx1.as<int>(), h->lam1.as<float>(), eps,
+                                h->pool_rw.as<float>(), h->pool_vs.as<float>(), st)))
+    return rc;
+  TcGemm t{};
+  t.A_hi = h->t4h; t.A_lo = h->t4l; t.lda = 512; t.Cin = 512; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
+  t.W_hi = h->tw_hi[4].p; t.W_lo = h->tw_lo[4].p; t.Npad = 1536; t.N = 1500;
+  t.bias = h->tb[4].as<float>(); t.bn_scale = h->bns[4].as<float>(); t.bn_shift = h->bnh[4].as<float>();
+  t.ldc = 1500; t.epi = 4; t.tag = "tdnn5";
+  t.pool_w = h->pool_rw.as<float>(); t.pool_part = h->pool_part.as<float>(); t.pool_item_rows = g.S2; t.pool_K = K;
+  if ((rc = launch_gemm_tc(t, st))) return rc;
+  h->pool_C = 1500;
+  return launch_pool_finalize(h->pool_part.as<float>(), h->pool_vs.as<float>(), h->bnh[4].as<float>(), U, K, 1500, g.S2, T, eps,
+                              h->pooled.as<float>(), st);
 }
 
 static int emb_project(dg_emb* h, int rows, int normalize, float norm, float* out, cudaStream_t st) {
@@ -1284,8 +1324,13 @@ extern "C" int dg_emb_forward(dg_emb* h, const float* wav, const float* weights,
   DG_CUDA(cudaSetDevice(h->device));
   const Geom g = make_geom(S);
   int rc, T = 0;
-  if ((rc = emb_trunk(h, wav, B, g, st, &T))) return rc;
+  const bool fuse = weights && h->variant == 0 && K <= 4 && g.S2 >= 128 && pool_fusion_on();
+  if ((rc = emb_trunk(h, wav, B, g, st, &T, fuse))) return rc;
   if (weights && (rc = build_tables(h, F, T, st))) return rc;
+  if (fuse) {
+    if ((rc = emb_tdnn5_pool(h, B, g, weights, F, K, T, st))) return rc;
+    return emb_project(h, B * K, normalize, norm, out, st);
+  }
   if (h->pooled.ensure((size_t)B * K * 2 * h->pool_C * 4)) return DG_ECUDA;
   const float eps = h->pool_mode == 31 ? 1e-8f : 0.f;
   if ((rc = launch_stats_pool(h->pool_x, B, g.S2, T, h->pool_C, weights, F, K, h->idx0.as<int>(),
@@ -1700,13 +1745,14 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   }
   // embedding trunk first in host order (low-priority stream, grid capped to the SMs the LSTM leaves free)
   int T = 0;
+  const bool fuse_pool = h->emb->variant == 0 && K <= 4 && g.S2 >= 128 && pool_fusion_on();
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->seg->device);
     const int lstm_ctas = 2 * ((B + 15) / 16);
     g_sm_limit = sms - lstm_ctas > sms / 2 ? sms - lstm_ctas : 0;
     h->emb->shared_prep = shared;
-    rc = emb_trunk(h->emb, wav, B, g, h->s_emb, &T);
+    rc = emb_trunk(h->emb, wav, B, g, h->s_emb, &T, fuse_pool);
     h->emb->shared_prep = nullptr;
     g_sm_limit = 0;
     if (rc) return rc;
@@ -1721,6 +1767,20 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   DG_CUDA(cudaEventRecord(e_osp, s_seg));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, e_osp, 0));
   if ((rc = build_tables(h->emb, F, T, h->s_emb))) return rc;
+  if (fuse_pool) {
+    // TDNN5 needs the pooling weights: it runs here, after the segmentation of this step, fused with the pooling
+    // (persistent grid capped like the trunk's: the other lane's recurrence may hold 2 x ceil(B/16) SMs at this point)
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->seg->device);
+    const int lstm_ctas = 2 * ((B + 15) / 16);
+    g_sm_limit = sms - lstm_ctas > sms / 2 ? sms - lstm_ctas : 0;
+    rc = emb_tdnn5_pool(h->emb, B, g, osp.as<float>(), F, K, T, h->s_emb);
+    if (!rc) rc = emb_project(h->emb, B * K, 1, 1.f, emb, h->s_emb);
+    g_sm_limit = 0;
+    if (rc) return rc;
+    DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));
+    return DG_OK;
+  }
   if (h->emb->pooled.ensure((size_t)B * K * 2 * h->emb->pool_C * 4)) return DG_ECUDA;
   if ((rc = launch_stats_pool(h->emb->pool_x, B, g.S2, T, h->emb->pool_C, osp.as<float>(), F, K,
                               h->emb->idx0.as<int>(), h->emb->idx1.as<int>(), h->emb->lam1.as<float>(),
@@ -2208,15 +2268,7 @@ extern "C" int dg_post_step(dg_post* h, const float* seg_dev, const int32_t* map
 // ---- the whole body of SpeakerDiarization.__call__ (reference diarization.py:172-232) in one call: B separate host windows
 //      (as rearrange_audio_stream emits them) are gathered into pinned staging by worker threads while earlier rows are
 //      already on their way to the device, then fused step + post-path, one D2H of the turn list.
-static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, float* dst_dev, cudaStream_t st) {
-  const size_t bytes = (size_t)B * S * 4;
-  if (bytes > h->pin_wav_bytes) {
-    if (h->pin_wav) cudaFreeHost(h->pin_wav);
-    h->pin_wav = nullptr;
-    DG_CUDA(cudaHostAlloc(&h->pin_wav, bytes, cudaHostAllocDefault));
-    h->pin_wav_bytes = bytes;
-  }
-  float* pin = reinterpret_cast<float*>(h->pin_wav);
+static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, float* pin, float* dst_dev, cudaStream_t st) {
   const int R = 8;                                    // rows per work item
   const int items = (B + R - 1) / R;
   int nthreads = (int)std::thread::hardware_concurrency();
@@ -2237,7 +2289,7 @@ static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, f
   for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
   cudaError_t err = cudaSuccess;
   if (nthreads == 1) work();
-  // the calling thread forwards finished items, in order, in runs of up to 4 (256-row batches: 8 copies of ~10 MB)
+  // the calling thread forwards finished items, in order, in runs of up to 4 (~10 MB per copy)
   int sent = 0;
   while (sent < items) {
     int upto = sent;
@@ -2270,14 +2322,49 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
     return DG_EINVAL;
   }
   const int D = h->emb->D;
+  (void)D;
+  if (h->outstanding) {
+    set_error("dg_pipeline_call_host: submitted steps are outstanding; collect them first");
+    return DG_EINVAL;
+  }
   DG_CUDA(cudaSetDevice(h->seg->device));
-  if (h->wav.ensure((size_t)B * S * 4) || h->segd.ensure((size_t)B * F * K * 4) || h->embd.ensure((size_t)B * K * D * 4) ||
-      h->mapd.ensure((size_t)B * K * 4))
-    return DG_ECUDA;
-  if ((rc = upload_rows(h, rows_host, B, S, h->wav.as<float>(), h->st))) return rc;
-  if ((rc = dg_pipeline_step(h, h->wav.as<float>(), B, S, h->segd.as<float>(), h->embd.as<float>(), h->mapd.as<int32_t>(),
-                             nullptr, h->st)))
-    return rc;
+  if (h->segd.ensure((size_t)B * F * K * 4) || h->mapd.ensure((size_t)B * K * 4)) return DG_ECUDA;
+  const size_t bytes = (size_t)B * S * 4;
+  if (bytes > h->pin_wav_bytes) {
+    if (h->pin_wav) cudaFreeHost(h->pin_wav);
+    h->pin_wav = nullptr;
+    DG_CUDA(cudaHostAlloc(&h->pin_wav, bytes, cudaHostAllocDefault));
+    h->pin_wav_bytes = bytes;
+  }
+  // The batch runs as up to three sub-batches through the pipelined machinery (dg_pipeline_submit_host): the upload of
+  // sub-batch j+1 and its front end overlap the recurrence of sub-batch j; clustering stays in chunk order on its one stream,
+  // so the result is exactly that of one step over the whole batch.  DG_CALL_SPLIT = 1..3 (default 2 from 128 windows on).
+  static const int split_env = getenv("DG_CALL_SPLIT") ? atoi(getenv("DG_CALL_SPLIT")) : 0;
+  int nsplit = split_env > 0 ? std::min(split_env, DG_MAX_INFLIGHT) : (B >= 128 ? 2 : 1);
+  nsplit = std::max(1, std::min(nsplit, B / 8 > 0 ? B / 8 : 1));
+  const int Bs = (B + nsplit - 1) / nsplit;
+  int slots[DG_MAX_INFLIGHT], nbs[DG_MAX_INFLIGHT], ns = 0;
+  for (int r0 = 0; r0 < B; r0 += Bs, ns++) {
+    const int nb = std::min(Bs, B - r0);
+    const int slot = (int)(h->next_step % 3);
+    if ((rc = pipeline_slot_prepare(h, slot, nb, S, F, K, true))) return rc;
+    DG_CUDA(cudaStreamWaitEvent(h->s_h2d, h->e_slot_done[slot], 0));
+    if ((rc = upload_rows(h, rows_host + r0, nb, S, reinterpret_cast<float*>(h->pin_wav) + (size_t)r0 * S,
+                          h->slot_wav[slot].as<float>(), h->s_h2d)))
+      return rc;
+    DG_CUDA(cudaEventRecord(h->e_h2d[slot], h->s_h2d));
+    if ((rc = pipeline_submit_common(h, h->slot_wav[slot].as<float>(), nb, S, F, K, slot, h->e_h2d[slot]))) return rc;
+    slots[ns] = slot;
+    nbs[ns] = nb;
+  }
+  for (int j = 0, r0 = 0; j < ns; r0 += nbs[j], j++) {     // gather the sub-batches' scores / maps, in order
+    DG_CUDA(cudaStreamWaitEvent(h->st, h->e_slot_done[slots[j]], 0));
+    DG_CUDA(cudaMemcpyAsync(h->segd.as<float>() + (size_t)r0 * F * K, h->slot_seg[slots[j]].p, (size_t)nbs[j] * F * K * 4,
+                            cudaMemcpyDeviceToDevice, h->st));
+    DG_CUDA(cudaMemcpyAsync(h->mapd.as<int32_t>() + (size_t)r0 * K, h->slot_map[slots[j]].p, (size_t)nbs[j] * K * 4,
+                            cudaMemcpyDeviceToDevice, h->st));
+    h->outstanding--;
+  }
   if ((rc = post_enqueue(post, h->segd.as<float>(), h->mapd.as<int32_t>(), B, plan_host, h->st))) return rc;
   if (seg_host) DG_CUDA(cudaMemcpyAsync(seg_host, h->segd.p, (size_t)B * F * K * 4, cudaMemcpyDeviceToHost, h->st));
   if (map_host) DG_CUDA(cudaMemcpyAsync(map_host, h->mapd.p, (size_t)B * K * 4, cudaMemcpyDeviceToHost, h->st));

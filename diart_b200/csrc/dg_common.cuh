@@ -146,6 +146,11 @@ struct TcGemm {
   int Wp, Hp, Wop, Hop, stride2, relu;
   const void* res_hi;
   const void* res_lo;
+  // epi 4 (TDNN5 + weighted statistics pooling, heads.cu: pool_finalize): bias -> LeakyReLU -> BatchNorm, then per 128-row tile
+  // and item the sums  S1 = sum_t w_k[t] d,  S2 = sum_t w_k[t] d^2  of d = x - bn_shift  for the K local speakers
+  const float* pool_w;   // [Mtot][4]
+  float* pool_part;      // [m_tiles][2][4][2][N]
+  int pool_item_rows, pool_K;
 };
 int launch_gemm_tc(const TcGemm& g, cudaStream_t st);
 int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
@@ -206,6 +211,11 @@ int launch_osp(const float* seg, int B, int F, int K, float gamma, float beta, i
 int launch_stats_pool(const float* x /*[B*stride,C]*/, int B, int stride, int T, int C, const float* w /*[B,F,K]*/,
                       int F, int K, const int* idx0, const int* idx1, const float* lam1, float eps,
                       float* pooled /*[B*K, 2C]*/, cudaStream_t st, long long item_pitch = 0, int row_pitch = 0);
+// fused pooling (epi 4 of gemm_tc): row weights + their sums, and the final mean / std from the per-tile partial sums
+int launch_pool_weights(const float* w /*[B,F,K]*/, int B, int F, int K, int item_rows, int T, const int* idx0, const int* idx1,
+                        const float* lam1, float eps, float* row_w /*[B*item_rows][4]*/, float* vsum /*[B*K][2]*/, cudaStream_t st);
+int launch_pool_finalize(const float* part, const float* vsum, const float* pivot, int B, int K, int C, int item_rows, int T,
+                         float eps, float* pooled /*[B*K][2C]*/, cudaStream_t st);
 int launch_l2norm(const float* in, int rows, int D, float norm, float* out, cudaStream_t st);
 int launch_row_equal_flags(const float* wav, int N, int S, int* flags, cudaStream_t st);
 int launch_gather_rows(const float* src, const int* index, int rows, int cols, float* dst, cudaStream_t st);

@@ -56,9 +56,28 @@ struct TcArgs {
   int Wp, Hp, Wop, Hop, stride2, relu;
   const __nv_bfloat16* res_hi;   // residual planes in the output geometry, or null
   const __nv_bfloat16* res_lo;
+  // TC_POOL: weighted statistics pooling fused into the epilogue (the activation map is never written)
+  const float* pool_w;     // [rows][4]: pooling weight of (row, speaker), zero for rows past an item's valid frames
+  float* pool_part;        // [m_tiles][2 (item of the tile)][4 (speaker)][2 (sum w d, sum w d^2)][N]
+  int pool_item_rows, pool_K;
 };
 
-enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2, TC_CONV2D = 3 };
+enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2, TC_CONV2D = 3, TC_POOL = 4 };
+
+// sum over the 32 lanes of a warp of 32 per-lane values: afterwards lane L holds the total of v[L] (31 shuffles)
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; i++) {
+      const float send = up ? v[i] : v[i + s];
+      const float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
 
 // ------------------------------------------------------------------------------------ the kernel
 template <int BN>
@@ -68,6 +87,7 @@ struct TcSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int NSTAGE = BN == 256 ? 2 : (BN == 128 ? 3 : 4);   // BN = 64 / 32: 4 stages
   static constexpr int PARAM_BYTES = 3 * BN * 4;
+  static constexpr int POOL_BYTES = 2 * 4 * 2 * 8 * 32 * 4;                       // TC_POOL staging: [buffer][warp][item][8][32] floats
   static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
 
@@ -86,6 +106,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* acc_full = bars + 2 * NSTAGE;      // [2] MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  float* pool_stage = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES + 256);   // TC_POOL only
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int num_tiles = a.m_tiles * a.n_tiles;
@@ -209,12 +230,69 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mo = (item * a.Wop + ((w - 1) >> 1) + 1) * a.Hop + ((h - 1) >> 1) + 1;
         }
       }
+      // TC_POOL: this row's pooling weights and which of the tile's (at most two) items it belongs to
+      float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
+      int pseg = 0;
+      bool warp_has[2] = {true, false};
+      if (EPI == TC_POOL) {
+        const long long first_item = ((long long)mt * TC_BM) / a.pool_item_rows;
+        if (m < a.M) {
+          pw = *reinterpret_cast<const float4*>(a.pool_w + m * 4);
+          pseg = (int)(m / a.pool_item_rows - first_item);
+        }
+        warp_has[0] = __any_sync(0xffffffffu, pseg == 0);
+        warp_has[1] = __any_sync(0xffffffffu, pseg == 1);
+      }
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
         tmem_ld32(taddr + c, r);
-        if (n0 + c >= a.N) continue;
+        if (EPI != TC_POOL && n0 + c >= a.N) continue;
         float v[32];
+        if (EPI == TC_POOL) {
+          // bias -> LeakyReLU -> BatchNorm affine, then deviation from the per-channel pivot (the BatchNorm shift)
+          float d[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            float x = leaky(__uint_as_float(r[i]) + params[c + i]);
+            x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
+            d[i] = x - params[2 * BN + c + i];
+          }
+          float* stg = pool_stage + ((c >> 5) & 1) * (4 * 2 * 8 * 32) + (quad * 2) * (8 * 32);
+#pragma unroll
+          for (int sg = 0; sg < 2; sg++) {
+            if (!warp_has[sg]) {
+              for (int k = 0; k < a.pool_K; k++) {
+                stg[(sg * 8 + 2 * k) * 32 + lane] = 0.f;
+                stg[(sg * 8 + 2 * k + 1) * 32 + lane] = 0.f;
+              }
+              continue;
+            }
+#pragma unroll 1
+            for (int k = 0; k < a.pool_K; k++) {
+              const float wsel = k == 0 ? pw.x : (k == 1 ? pw.y : (k == 2 ? pw.z : pw.w));
+              const float wv = pseg == sg ? wsel : 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; i++) v[i] = wv * d[i];
+              float v2[32];
+#pragma unroll
+              for (int i = 0; i < 32; i++) v2[i] = v[i] * d[i];
+              stg[(sg * 8 + 2 * k) * 32 + lane] = warp_transpose_reduce(v, lane);
+              stg[(sg * 8 + 2 * k + 1) * 32 + lane] = warp_transpose_reduce(v2, lane);
+            }
+          }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          // 2 items x K speakers x 2 sums x 32 columns: the four warps' totals are added in a fixed order
+          const float* sb = pool_stage + ((c >> 5) & 1) * (4 * 2 * 8 * 32);
+          for (int idx = et; idx < 2 * a.pool_K * 2 * 32; idx += 128) {
+            const int col = idx & 31, j = (idx >> 5) % (2 * a.pool_K), sg = idx / (64 * a.pool_K);
+            const float tot = ((sb[((0 * 2 + sg) * 8 + j) * 32 + col] + sb[((1 * 2 + sg) * 8 + j) * 32 + col]) +
+                               sb[((2 * 2 + sg) * 8 + j) * 32 + col]) + sb[((3 * 2 + sg) * 8 + j) * 32 + col];
+            const int n = n0 + c + col;
+            if (n < a.N) a.pool_part[(((size_t)mt * 2 + sg) * 8 + j) * a.N + n] = tot;
+          }
+          continue;
+        }
         if (EPI == TC_CONV2D) {
           // BatchNorm2d(eval) affine -> (+ residual) -> ReLU
 #pragma unroll
@@ -381,6 +459,7 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
   a.Wp = g.Wp; a.Hp = g.Hp; a.Wop = g.Wop; a.Hop = g.Hop; a.stride2 = g.stride2; a.relu = g.relu;
   a.res_hi = reinterpret_cast<const __nv_bfloat16*>(g.res_hi);
   a.res_lo = reinterpret_cast<const __nv_bfloat16*>(g.res_lo);
+  a.pool_w = g.pool_w; a.pool_part = g.pool_part; a.pool_item_rows = g.pool_item_rows; a.pool_K = g.pool_K;
   {
     static const bool no_v8 = getenv("DG_NO_V8") && getenv("DG_NO_V8")[0] == '1';     // A/B switch
     const bool planes = EPI == TC_LEAKY_BN_SPLIT;
@@ -392,14 +471,15 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-      DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+      DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   S::TOTAL + (EPI == TC_POOL ? S::POOL_BYTES : 0)));
       if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
   }
   const int sms = g.sm_limit > 0 ? std::min(g.sm_limit, usable_sms()) : usable_sms();
   const int tiles = a.m_tiles * a.n_tiles;
   const int grid = tiles < sms ? tiles : sms;
-  gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
+  gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL + (EPI == TC_POOL ? S::POOL_BYTES : 0), st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
   DG_LAUNCHED();
   return 0;
 }
@@ -421,6 +501,13 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
     if (g.Npad == 32) return launch_tc<32, TC_CONV2D>(g, st);
     if (g.Npad == 64) return launch_tc<64, TC_CONV2D>(g, st);
     return wide ? launch_tc<256, TC_CONV2D>(g, st) : launch_tc<128, TC_CONV2D>(g, st);
+  }
+  if (g.epi == TC_POOL) {
+    if (!wide || !g.pool_w || !g.pool_part || g.pool_K < 1 || g.pool_K > 4 || g.pool_item_rows < TC_BM) {
+      set_error("gemm_tc (pool): needs 256-wide tiles, 1..4 speakers and items of at least 128 rows");
+      return -1;
+    }
+    return launch_tc<256, TC_POOL>(g, st);
   }
   if (g.Npad == 64 && g.epi == TC_BIAS_F32) return launch_tc<64, TC_BIAS_F32>(g, st);
   switch (g.epi) {

@@ -297,6 +297,87 @@ int launch_stats_pool(const float* x, int B, int stride, int T, int C, const flo
                               pooled, st, item_pitch, row_pitch);
 }
 
+// ------------------------------------------------------------------ fused pooling: weights and finalisation
+// Row weights of the fused TDNN5 + pooling epilogue (gemm_tc.cu, TC_POOL): the OSP weights resized from F to T frames exactly
+// like stats_pool_kernel does, one float4 per trunk row (zero past the T valid frames of an item / for absent speakers), and
+// v1 = sum w (+ eps), v2 = sum w^2 per (item, speaker) in the same summation order as stats_pool_kernel.
+__global__ void __launch_bounds__(256) pool_weights_kernel(const float* __restrict__ w, int F, int K, int item_rows, int T,
+                                                           const int* __restrict__ idx0, const int* __restrict__ idx1,
+                                                           const float* __restrict__ lam1, float eps, float* __restrict__ row_w,
+                                                           float* __restrict__ vsum) {
+  extern __shared__ float wr[];      // [T][4]
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < item_rows * 4; i += blockDim.x) {
+    const int t = i >> 2, k = i & 3;
+    float v = 0.f;
+    if (t < T && k < K) {
+      const size_t base = (size_t)b * F * K + k;
+      const float a = w[base + (size_t)idx0[t] * K];
+      const float l1 = lam1[t];
+      v = l1 == 0.f ? a : (1.f - l1) * a + l1 * w[base + (size_t)idx1[t] * K];
+    }
+    if (t < T) wr[i] = v;
+    row_w[((size_t)b * item_rows + t) * 4 + k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) {
+    float s1 = 0.f, s2 = 0.f;
+    for (int t = 0; t < T; t++) {
+      const float v = wr[t * 4 + threadIdx.x];
+      s1 += v;
+      s2 = fmaf(v, v, s2);
+    }
+    vsum[((size_t)b * K + threadIdx.x) * 2] = s1 + eps;
+    vsum[((size_t)b * K + threadIdx.x) * 2 + 1] = s2;
+  }
+}
+
+int launch_pool_weights(const float* w, int B, int F, int K, int item_rows, int T, const int* idx0, const int* idx1,
+                        const float* lam1, float eps, float* row_w, float* vsum, cudaStream_t st) {
+  ProfScope _ps("pool_weights", st);
+  pool_weights_kernel<<<B, 256, (size_t)T * 4 * sizeof(float), st>>>(w, F, K, item_rows, T, idx0, idx1, lam1, eps, row_w, vsum);
+  DG_LAUNCHED();
+  return 0;
+}
+
+// pyannote StatsPool from the partial sums of the fused epilogue (d = x - pivot):
+//   mean = sum(w x) / v1,  std = sqrt( sum(w (x - mean)^2) / (v1 - v2 / v1 + eps) ),  v1 = sum w + eps, v2 = sum w^2
+// with sum(w (x - mean)^2) = S2 - 2 dm S1 + dm^2 S0, dm = mean - pivot = (S1 - pivot * eps) / v1, S0 = v1 - eps.  The partials of
+// the tiles that cover an item are added in tile order in float64.
+__global__ void __launch_bounds__(128) pool_finalize_kernel(const float* __restrict__ part, const float* __restrict__ vsum,
+                                                            const float* __restrict__ pivot, int K, int C, int item_rows, int T,
+                                                            float eps, float* __restrict__ pooled) {
+  const int q = blockIdx.y, b = q / K, k = q - b * K;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long r0 = (long long)b * item_rows, r1 = r0 + T - 1;
+  double s1 = 0, s2 = 0;
+  for (long long mt = r0 / 128; mt <= r1 / 128; mt++) {
+    const int sg = (int)(b - (mt * 128) / item_rows);
+    const float* p = part + (((size_t)mt * 2 + sg) * 8 + 2 * k) * C + c;
+    s1 += p[0];
+    s2 += p[C];
+  }
+  const double v1 = vsum[(size_t)q * 2], v2 = vsum[(size_t)q * 2 + 1], pv = pivot[c];
+  const double s0 = v1 - (double)eps;
+  const double dm = (s1 - pv * (double)eps) / v1;
+  double num = s2 - 2.0 * dm * s1 + dm * dm * s0;
+  if (num < 0) num = 0;
+  const double var = num / (v1 - v2 / v1 + (double)eps);
+  float* o = pooled + (size_t)q * 2 * C;
+  o[c] = (float)(pv + dm);
+  o[C + c] = (float)sqrt(var);
+}
+
+int launch_pool_finalize(const float* part, const float* vsum, const float* pivot, int B, int K, int C, int item_rows, int T,
+                         float eps, float* pooled, cudaStream_t st) {
+  ProfScope _ps("pool_finalize", st);
+  dim3 grid((C + 127) / 128, B * K);
+  pool_finalize_kernel<<<grid, 128, 0, st>>>(part, vsum, pivot, K, C, item_rows, T, eps, pooled);
+  DG_LAUNCHED();
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------- l2norm
 __global__ void __launch_bounds__(256) l2norm_kernel(const float* __restrict__ in, int rows, int D, float norm,
                                                      float* __restrict__ out) {
