@@ -1859,12 +1859,14 @@ static int pipeline_submit_common(dg_pipeline* h, const float* wav_dev, int B, i
   if ((rc = pipeline_nets(h, wav_dev, B, S, F, K, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), start,
                           lane, stream_hop)))
     return rc;
+  // the lane's scratch (waveform planes, segmentation activations, OSP weights) is free as soon as this step's embeddings
+  // exist -- the clustering reads only the slot buffers -- so the step after next may start before this one is clustered
+  DG_CUDA(cudaEventRecord(h->e_lane_done[lane], h->s_emb));
   DG_CUDA(cudaStreamWaitEvent(h->s_clu, h->e_emb, 0));
   if ((rc = dg_cluster_step(h->clu, h->slot_seg[slot].as<float>(), h->slot_emb[slot].as<float>(), B, F, K,
                             h->slot_map[slot].as<int32_t>(), nullptr, h->s_clu)))
     return rc;
   DG_CUDA(cudaEventRecord(h->e_slot_done[slot], h->s_clu));
-  DG_CUDA(cudaEventRecord(h->e_lane_done[lane], h->s_clu));
   h->slot_B[slot] = B;
   h->slot_S[slot] = S;
   h->next_step++;

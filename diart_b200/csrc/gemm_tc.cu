@@ -64,21 +64,6 @@ struct TcArgs {
 
 enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2, TC_CONV2D = 3, TC_POOL = 4 };
 
-// sum over the 32 lanes of a warp of 32 per-lane values: afterwards lane L holds the total of v[L] (31 shuffles)
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; i++) {
-      const float send = up ? v[i] : v[i + s];
-      const float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 // ------------------------------------------------------------------------------------ the kernel
 template <int BN>
 struct TcSmem {
@@ -87,7 +72,8 @@ struct TcSmem {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int NSTAGE = BN == 256 ? 2 : (BN == 128 ? 3 : 4);   // BN = 64 / 32: 4 stages
   static constexpr int PARAM_BYTES = 3 * BN * 4;
-  static constexpr int POOL_BYTES = 2 * 4 * 2 * 8 * 32 * 4;                       // TC_POOL staging: [buffer][warp][item][8][32] floats
+  // TC_POOL: activation chunk [128][33] + row weights [128][4] + cross-row-group staging [4][2][8][32], all float
+  static constexpr int POOL_BYTES = (128 * 33 + 128 * 4 + 4 * 2 * 8 * 32) * 4;
   static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
 
@@ -205,43 +191,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
       const int n0 = nt * BN;
       const long long m = (long long)mt * TC_BM + quad * 32 + lane;
-      // stage the per-column parameters of this tile (named barrier 1: the 128 epilogue threads only)
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      for (int i = et; i < BN; i += 128) {
-        const int n = n0 + i;
-        const bool ok = n < a.N;
-        params[i] = (ok && a.bias) ? a.bias[n] : 0.f;
-        params[BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_scale[n] : 1.f;
-        params[2 * BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_shift[n] : 0.f;
+      // stage the per-column parameters of this tile (named barrier 1: the 128 epilogue threads only); with a single
+      // column tile they are the same for every tile of this CTA: staged once
+      if (a.n_tiles > 1 || tile == (int)blockIdx.x) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = et; i < BN; i += 128) {
+          const int n = n0 + i;
+          const bool ok = n < a.N;
+          params[i] = (ok && a.bias) ? a.bias[n] : 0.f;
+          params[BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_scale[n] : 1.f;
+          params[2 * BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_shift[n] : 0.f;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      // TC_CONV2D: output position of this row, and the residual of the first 32 columns requested before the wait
       long long mo = m;                 // output row
       bool row_ok = m < a.M;
+      uint4 rh0[4], rl0[4];
       if (EPI == TC_CONV2D) {
-        const long long per = (long long)a.Wp * a.Hp;
-        const long long item = m / per;
-        const int rem = (int)(m - item * per), w = rem / a.Hp, h = rem - w * a.Hp;
+        const unsigned mu = (unsigned)m, per = (unsigned)(a.Wp * a.Hp);     // (the launcher checks M < 2^31)
+        const unsigned item = mu / per, rem = mu - item * per;
+        const int w = (int)(rem / (unsigned)a.Hp), h = (int)(rem - (unsigned)w * (unsigned)a.Hp);
         row_ok = row_ok && w >= 1 && w <= a.Wp - 2 && h >= 1 && h <= a.Hp - 2;     // a centre inside the un-padded map
         if (a.stride2) {
           row_ok = row_ok && (w & 1) && (h & 1);
-          mo = (item * a.Wop + ((w - 1) >> 1) + 1) * a.Hop + ((h - 1) >> 1) + 1;
+          mo = ((long long)item * a.Wop + ((w - 1) >> 1) + 1) * a.Hop + ((h - 1) >> 1) + 1;
+        }
+        if (row_ok && a.res_hi) {
+          const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + mo * a.ldc + n0);
+          const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + mo * a.ldc + n0);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            rh0[q] = rh[q];
+            rl0[q] = rl[q];
+          }
         }
       }
-      // TC_POOL: this row's pooling weights and which of the tile's (at most two) items it belongs to
-      float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
-      int pseg = 0;
-      bool warp_has[2] = {true, false};
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
+      // TC_POOL: the rows' pooling weights go to shared memory; `brow` = first row of the tile that belongs to the NEXT item
+      // (a 128-row tile covers at most two items)
+      int brow = TC_BM;
       if (EPI == TC_POOL) {
-        const long long first_item = ((long long)mt * TC_BM) / a.pool_item_rows;
-        if (m < a.M) {
-          pw = *reinterpret_cast<const float4*>(a.pool_w + m * 4);
-          pseg = (int)(m / a.pool_item_rows - first_item);
-        }
-        warp_has[0] = __any_sync(0xffffffffu, pseg == 0);
-        warp_has[1] = __any_sync(0xffffffffu, pseg == 1);
+        float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < a.M) pw = *reinterpret_cast<const float4*>(a.pool_w + m * 4);
+        reinterpret_cast<float4*>(pool_stage + 128 * 33)[et] = pw;
+        const long long first = (long long)mt * TC_BM;
+        const long long nxt = (first / a.pool_item_rows + 1) * a.pool_item_rows;
+        brow = nxt - first < TC_BM ? (int)(nxt - first) : TC_BM;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
       }
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
@@ -250,44 +249,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
         if (EPI != TC_POOL && n0 + c >= a.N) continue;
         float v[32];
         if (EPI == TC_POOL) {
-          // bias -> LeakyReLU -> BatchNorm affine, then deviation from the per-channel pivot (the BatchNorm shift)
-          float d[32];
+          // bias -> LeakyReLU -> BatchNorm affine, then the deviation from the per-channel pivot (the BatchNorm shift) goes to
+          // shared memory; thread (row group rg, column col) then sums its 32 rows for the K speakers -- independent
+          // accumulators, no cross-lane traffic -- split at `brow` between the tile's two items
+          float* dsm = pool_stage;                    // [128][33]
+          const float4* wsm = reinterpret_cast<const float4*>(pool_stage + 128 * 33);
+          float* stg = pool_stage + 128 * 33 + 128 * 4;   // [rg 4][item 2][8][32]
 #pragma unroll
           for (int i = 0; i < 32; i++) {
             float x = leaky(__uint_as_float(r[i]) + params[c + i]);
             x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
-            d[i] = x - params[2 * BN + c + i];
+            dsm[et * 33 + i] = x - params[2 * BN + c + i];
           }
-          float* stg = pool_stage + ((c >> 5) & 1) * (4 * 2 * 8 * 32) + (quad * 2) * (8 * 32);
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          {
+            const int rg = et >> 5, col = et & 31, r_lo = rg * 32, r_hi = r_lo + 32;
 #pragma unroll
-          for (int sg = 0; sg < 2; sg++) {
-            if (!warp_has[sg]) {
-              for (int k = 0; k < a.pool_K; k++) {
-                stg[(sg * 8 + 2 * k) * 32 + lane] = 0.f;
-                stg[(sg * 8 + 2 * k + 1) * 32 + lane] = 0.f;
+            for (int sg = 0; sg < 2; sg++) {
+              const int lo = sg == 0 ? r_lo : max(r_lo, brow), hi = sg == 0 ? min(r_hi, brow) : r_hi;
+              float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+              for (int rr = lo; rr < hi; rr++) {
+                const float dv = dsm[rr * 33 + col];
+                const float4 w4 = wsm[rr];
+                const float a0 = w4.x * dv, a1 = w4.y * dv, a2 = w4.z * dv, a3 = w4.w * dv;
+                s1[0] += a0; s1[1] += a1; s1[2] += a2; s1[3] += a3;
+                s2[0] = fmaf(a0, dv, s2[0]); s2[1] = fmaf(a1, dv, s2[1]); s2[2] = fmaf(a2, dv, s2[2]); s2[3] = fmaf(a3, dv, s2[3]);
               }
-              continue;
-            }
-#pragma unroll 1
-            for (int k = 0; k < a.pool_K; k++) {
-              const float wsel = k == 0 ? pw.x : (k == 1 ? pw.y : (k == 2 ? pw.z : pw.w));
-              const float wv = pseg == sg ? wsel : 0.f;
 #pragma unroll
-              for (int i = 0; i < 32; i++) v[i] = wv * d[i];
-              float v2[32];
-#pragma unroll
-              for (int i = 0; i < 32; i++) v2[i] = v[i] * d[i];
-              stg[(sg * 8 + 2 * k) * 32 + lane] = warp_transpose_reduce(v, lane);
-              stg[(sg * 8 + 2 * k + 1) * 32 + lane] = warp_transpose_reduce(v2, lane);
+              for (int k = 0; k < 4; k++) {
+                stg[((rg * 2 + sg) * 8 + 2 * k) * 32 + col] = s1[k];
+                stg[((rg * 2 + sg) * 8 + 2 * k + 1) * 32 + col] = s2[k];
+              }
             }
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
-          // 2 items x K speakers x 2 sums x 32 columns: the four warps' totals are added in a fixed order
-          const float* sb = pool_stage + ((c >> 5) & 1) * (4 * 2 * 8 * 32);
+          // 2 items x K speakers x 2 sums x 32 columns: the four row groups' totals are added in a fixed order
           for (int idx = et; idx < 2 * a.pool_K * 2 * 32; idx += 128) {
             const int col = idx & 31, j = (idx >> 5) % (2 * a.pool_K), sg = idx / (64 * a.pool_K);
-            const float tot = ((sb[((0 * 2 + sg) * 8 + j) * 32 + col] + sb[((1 * 2 + sg) * 8 + j) * 32 + col]) +
-                               sb[((2 * 2 + sg) * 8 + j) * 32 + col]) + sb[((3 * 2 + sg) * 8 + j) * 32 + col];
+            const float tot = ((stg[((0 * 2 + sg) * 8 + j) * 32 + col] + stg[((1 * 2 + sg) * 8 + j) * 32 + col]) +
+                               stg[((2 * 2 + sg) * 8 + j) * 32 + col]) + stg[((3 * 2 + sg) * 8 + j) * 32 + col];
             const int n = n0 + c + col;
             if (n < a.N) a.pool_part[(((size_t)mt * 2 + sg) * 8 + j) * a.N + n] = tot;
           }
@@ -302,7 +302,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + mo * a.ldc + n0 + c);
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              const uint4 hq = rh[q], lq = rl[q];
+              const uint4 hq = c == 0 ? rh0[q] : rh[q], lq = c == 0 ? rl0[q] : rl[q];
               const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
 #pragma unroll
               for (int e = 0; e < 4; e++) {
@@ -494,7 +494,7 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
   }
   const bool wide = g.Npad % 256 == 0;
   if (g.epi == TC_CONV2D) {
-    if (g.ldc % 32 || g.N % 32 || g.Wp < 3 || g.Hp < 3 || (!g.out_hi && !g.out_f32)) {
+    if (g.ldc % 32 || g.N % 32 || g.Wp < 3 || g.Hp < 3 || (!g.out_hi && !g.out_f32) || g.M >= (1LL << 31)) {
       set_error("gemm_tc (conv2d): channel counts must be multiples of 32");
       return -1;
     }

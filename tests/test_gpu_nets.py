@@ -85,7 +85,8 @@ def test_embedding_reference_call_convention(cuda_nets, oracle_nets, audio_batch
     w_rows = w.permute(0, 2, 1).reshape(B * K, F)
     out = emb_c(rep.to(cuda_device), w_rows.to(cuda_device)).reshape(B, K, -1)
     fused = emb_c.forward_fused(x.to(cuda_device), w.to(cuda_device))
-    assert torch.equal(out, fused)
+    # same trunk; the fused path pools inside TDNN5's epilogue (per-tile partial sums), the row path reads the map back
+    assert torch.allclose(out, fused, rtol=2e-5, atol=2e-6)
     with torch.no_grad():
         ref = emb_o(rep, w_rows).reshape(B, K, -1)
     rel = ((out.cpu() - ref).norm(dim=-1) / ref.norm(dim=-1)).max().item()
