@@ -249,17 +249,18 @@ def run_ours(args):
     shared = None
 
     def run_steps(n):
-        """n pipeline steps, depth-2 pipelined (dg_pipeline_submit / collect): clustering of step i overlaps the
-        networks of step i+1; every step's results are complete when the last collect is reached on the stream"""
+        """n pipeline steps through dg_pipeline_submit / collect: the clustering of step i overlaps the networks of steps
+        i+1, i+2; every step's results are complete when the last collect is reached on the stream"""
         if args.serial:
             for i in range(n):
                 pipe.device_step(dev[i % NB])
             return
-        for i in range(n):
+        for i in range(n):           # three steps outstanding, like the host-buffer leg
             _lib.check(lib.dg_pipeline_submit(fused, dev[i % NB].data_ptr(), B, CHUNK, stream))
-            if i > 0:
+            if i > 1:
                 _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
-        _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
+        for _ in range(min(n, 2)):
+            _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
 
     run_steps(args.warmup)
     barrier()
@@ -483,9 +484,16 @@ def run_ours(args):
             torch.set_num_threads(min(16, os.cpu_count() or 1))
             o_seg = onets.make_segmentation()(torch.from_numpy(host[0][:4])[:, None, :]).numpy()
         seg_err = float(np.abs(got[0][0][:4].cpu().numpy() - o_seg).max())
+        emb_err = None
+        if args.embedding == "xvector":      # unit-norm embeddings of the same 4 windows against the oracle network
+            from oracle.pipeline import osp_block
+            with torch.no_grad():
+                o_emb = onets.make_embedding().forward_dedup(torch.from_numpy(host[0][:4])[:, None, :], osp_block(torch.from_numpy(o_seg)))
+                o_emb = (o_emb / o_emb.norm(dim=-1, keepdim=True)).numpy()
+            emb_err = float(np.abs(got[0][1][:4].cpu().numpy() - o_emb).max())
         parity = {"chunks": NB * B, "maps_equal_oracle_replay": ok, "centroids_bit_equal": centers_equal,
-                  "seg_max_abs_err_4_windows": seg_err, "first_difference": bad}
-        if not (ok and centers_equal and seg_err < 1e-4):
+                  "seg_max_abs_err_4_windows": seg_err, "emb_max_abs_err_4_windows": emb_err, "first_difference": bad}
+        if not (ok and centers_equal and seg_err < 1e-4 and (emb_err is None or emb_err < 1e-4)):
             raise SystemExit(f"bench.py: the benchmarked configuration fails its parity check: {parity}")
 
     if rank != 0:

@@ -92,9 +92,9 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
 
+    if not os.path.exists(LIB_PATH) or (_build._stale() and _build.have_nvcc()):
         _build.build()
     try:
         handle = C.CDLL(LIB_PATH)

@@ -25,12 +25,31 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found: the CUDA extension cannot be built")
 
 
+def have_nvcc() -> bool:
+    return any(c and os.path.exists(c) for c in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"))
+
+
+HASH = OUT + ".hash"
+
+
+def _source_hash() -> str:
+    import hashlib
+
+    h = hashlib.sha256()
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "diart_b200.h")]
+    for path in files:
+        if os.path.isfile(path):
+            h.update(os.path.basename(path).encode())
+            h.update(open(path, "rb").read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(OUT):
+    """content hash of the sources vs the one recorded at build time (time stamps do not survive a copy to another box)"""
+    if not os.path.exists(OUT) or not os.path.exists(HASH):
         return True
-    t = os.path.getmtime(OUT)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "diart_b200.h")]
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return open(HASH).read().strip() != _source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -59,6 +78,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(HASH, "w") as f:
+        f.write(_source_hash() + "\n")
     return OUT
 
 

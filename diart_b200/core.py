@@ -145,10 +145,13 @@ except Exception:  # noqa: BLE001
 
         @property
         def extent(self) -> Segment:
+            # pyannote.core: SlidingWindow.range_to_segment(0, n) = [start - step/2 + duration/2, ... + n * step)
             sw = self.sliding_window
             n = self.data.shape[0]
-            return Segment(sw.start, sw.start + n * sw.step) if sw.duration == sw.step else \
-                Segment(sw.start, sw.start + (n - 1) * sw.step + sw.duration)
+            if sw.duration == sw.step:
+                return Segment(sw.start, sw.start + n * sw.step)
+            start = sw.start + (0 - 0.5) * sw.step + 0.5 * sw.duration
+            return Segment(start, start + n * sw.step)
 
         def crop(self, focus: Segment, mode: str = "loose", fixed: Optional[float] = None,
                  return_data: bool = True):
@@ -223,7 +226,7 @@ except Exception:  # noqa: BLE001
                 segs = sorted(by_label[label])
                 cur = Segment(segs[0].start, segs[0].end)
                 for s in segs[1:]:
-                    if s.start - cur.end <= collar:
+                    if s.start - cur.end < collar or s.start <= cur.end:     # pyannote: gaps strictly shorter than the collar
                         cur = Segment(cur.start, max(cur.end, s.end))
                     else:
                         out._tracks[(cur, n)] = label

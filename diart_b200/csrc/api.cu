@@ -19,7 +19,7 @@ namespace dg {
 
 static thread_local std::string g_err;
 std::atomic<long long> g_launches{0};
-int g_sm_limit = 0;
+thread_local int g_sm_limit = 0;   // per host thread: distinct handles driven by distinct threads stay independent
 void set_error(const std::string& msg) { g_err = msg; }
 
 struct ProfRec {

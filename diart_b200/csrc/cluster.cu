@@ -39,9 +39,8 @@ __global__ void __launch_bounds__(128) cluster_prep_kernel(const float* __restri
     float mx = -INFINITY, sum = 0.f;
     for (int f = 0; f < F; f++) {
       const float v = s[f * K + threadIdx.x];
-      mx = fmaxf(mx, v);
+      mx = (isnan(v) || isnan(mx)) ? NAN : fmaxf(mx, v);   // np.max propagates NaN (fmaxf alone would drop it again)
       sum = __fadd_rn(sum, v);
-      if (isnan(v)) mx = v;   // np.max propagates NaN
     }
     prep[((size_t)i * K + threadIdx.x) * 3 + 0] = mx;
     prep[((size_t)i * K + threadIdx.x) * 3 + 1] = __fdiv_rn(sum, (float)F);
@@ -432,10 +431,10 @@ int launch_cluster_step(const ClusterParams& p, const float* seg, const float* e
     set_error("cluster_step: max_speakers * dim too large for the resident centroid table (limit 200 KB)");
     return -1;
   }
-  static size_t dyn_set = 0;
-  if (dyn > dyn_set) {
-    DG_CUDA(cudaFuncSetAttribute(cluster_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    dyn_set = dyn;
+  {   // per device: the opt-in above 48 KB is a property of (function, device)
+    static bool attr_done[64] = {};
+    if (first_use_on_device(attr_done))
+      DG_CUDA(cudaFuncSetAttribute(cluster_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
   cluster_seq_kernel<<<1, SEQ_THREADS, dyn, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map,
                                           permuted);

@@ -15,7 +15,7 @@ void set_error(const std::string& msg);
 extern std::atomic<long long> g_launches;
 // persistent kernels size their grid to the SM count; while two streams overlap (fused pipeline) the
 // kernels of the lower-priority stream are capped so that they never wait for SMs held by the other one
-extern int g_sm_limit;
+extern thread_local int g_sm_limit;
 inline int usable_sms() {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -31,6 +31,17 @@ inline int usable_sms() {
       return -2;                                                                        \
     }                                                                                   \
   } while (0)
+
+// cudaFuncSetAttribute is per DEVICE: `flags` is a function-local static bool[64]; returns true the first time it is asked
+// about the current device (the caller then sets the attribute)
+inline bool first_use_on_device(bool* flags) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) return true;
+  if (flags[dev]) return false;
+  flags[dev] = true;
+  return true;
+}
 
 // every kernel launch goes through this so bench.py can report `gpu_launches`
 #define DG_LAUNCHED()                                                                   \

@@ -236,7 +236,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       if (EPI == TC_POOL) {
         float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
         if (m < a.M) pw = *reinterpret_cast<const float4*>(a.pool_w + m * 4);
-        reinterpret_cast<float4*>(pool_stage + 128 * 33)[et] = pw;
+        reinterpret_cast<float4*>(pool_stage + 128 * 33)[quad * 32 + lane] = pw;     // row of the tile = TMEM lane
         const long long first = (long long)mt * TC_BM;
         const long long nxt = (first / a.pool_item_rows + 1) * a.pool_item_rows;
         brow = nxt - first < TC_BM ? (int)(nxt - first) : TC_BM;
@@ -259,7 +259,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           for (int i = 0; i < 32; i++) {
             float x = leaky(__uint_as_float(r[i]) + params[c + i]);
             x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
-            dsm[et * 33 + i] = x - params[2 * BN + c + i];
+            dsm[(quad * 32 + lane) * 33 + i] = x - params[2 * BN + c + i];
           }
           asm volatile("bar.sync 1, 128;" ::: "memory");
           {

@@ -54,12 +54,28 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t (&r)[4]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr));
+}
+template <int NC>
+__device__ __forceinline__ void tmem_ldn(uint32_t taddr, uint32_t (&r)[NC]);
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
                : "r"(taddr));
 }
-constexpr int L3_THREADS = 288;                        // 8 cell-update warps + 1 issuing warp
+template <>
+__device__ __forceinline__ void tmem_ldn<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ldn<4>(uint32_t taddr, uint32_t (&r)[4]) { tmem_ld4(taddr, r); }
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
+  asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
+}
+// NC = cells (batch rows) per cell-update thread: 8 -> 8 cell warps, 4 -> 16 cell warps (twice the warps per scheduler to hide
+// the ex2 / rcp chains of the cell update); + 1 issuing warp
+__host__ __device__ constexpr int l3_threads(int NC) { return (4 * (LT_NB / NC) + 1) * 32; }
 constexpr int L3_WS_BYTES = 2 * 128 * 128;             // W_lo of gate o: 2 k-blocks x (128 rows x 128 B)
 constexpr int L3_PLANE = 128 * LT_NB * 2;              // one plane of h_t: 128 units x 16 rows x 2 B = 4 KB
 constexpr int LT_H_BYTES = 2 * 2 * L3_PLANE;           // [buffer][plane]
@@ -91,19 +107,19 @@ struct L3Cell {
 
 // the 293 dependent cell updates of one thread; FULL = all 8 batch rows of this warp are valid (no branches: the
 // eight independent dependency chains overlap)
-template <bool F16, bool FULL, bool TIMING>
+template <bool F16, bool FULL, bool TIMING, int NC>
 __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done, uint64_t* h_ready, int lane,
                                              unsigned* dbg) {
   constexpr int f16 = F16 ? 1 : 0;
   const float L2E = 1.4426950408889634f;
-  float c[8];
+  float c[NC];
 #pragma unroll
-  for (int n = 0; n < 8; n++) c[n] = 0.f;
+  for (int n = 0; n < NC; n++) c[n] = 0.f;
   for (int step = 0; step < T; step++) {
     const int nxt = (step + 1) & 1;
-    float xg[4][8];
+    float xg[4][NC];
 #pragma unroll
-    for (int n = 0; n < 8; n++) {
+    for (int n = 0; n < NC; n++) {
       if (FULL || n < s.rows) {
 #pragma unroll
         for (int g = 0; g < 4; g++) xg[g][n] = __ldg(s.gp + n * s.row_gx + g * 128);
@@ -115,15 +131,15 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
     mbar_wait(&mma_done[0], step & 1);
     tc_fence_after();
     if (TIMING && dbg) dbg[step * 8 + 2] = (unsigned)clock();
-    uint32_t ri[8], rf[8], rg[8], ro[8];
-    tmem_ld8(s.tlane + 0 * LT_NB, ri);
-    tmem_ld8(s.tlane + 1 * LT_NB, rf);
-    tmem_ld8(s.tlane + 2 * LT_NB, rg);
+    uint32_t ri[NC], rf[NC], rg[NC], ro[NC];
+    tmem_ldn<NC>(s.tlane + 0 * LT_NB, ri);
+    tmem_ldn<NC>(s.tlane + 1 * LT_NB, rf);
+    tmem_ldn<NC>(s.tlane + 2 * LT_NB, rg);
     tmem_ld_wait();
     if (TIMING && dbg) dbg[step * 8 + 3] = (unsigned)clock();
-    float num[8], den[8];     // tanh(c') = num / den
+    float num[NC], den[NC];     // tanh(c') = num / den
 #pragma unroll
-    for (int n = 0; n < 8; n++) {
+    for (int n = 0; n < NC; n++) {
       if (FULL || n < s.rows) {
         // e^-i, e^-f, e^2g (exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127)
         const float ei = ex2_approx(fminf((__uint_as_float(ri[n]) + xg[0][n]) * -L2E, 40.f));
@@ -139,12 +155,12 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
     }
     mbar_wait(&mma_done[1], step & 1);
     tc_fence_after();
-    tmem_ld8(s.tlane + 3 * LT_NB, ro);
+    tmem_ldn<NC>(s.tlane + 3 * LT_NB, ro);
     tmem_ld_wait();
-    float h[8];
-    uint16_t hh[8], hl[8];
+    float h[NC];
+    uint16_t hh[NC], hl[NC];
 #pragma unroll
-    for (int n = 0; n < 8; n++) {
+    for (int n = 0; n < NC; n++) {
       if (FULL || n < s.rows) {
         // h = tanh(c') / (1 + e^-o)
         const float eo = ex2_approx(fminf((__uint_as_float(ro[n]) + xg[3][n]) * -L2E, 40.f));
@@ -157,9 +173,14 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
     }
     const uint32_t dst = s.h_addr + nxt * (LT_H_BYTES / 2);
     if (TIMING && dbg) dbg[step * 8 + 4] = (unsigned)clock() + (__float_as_uint(h[0]) & 0u);   // (keeps the math above the read)
-    st_shared_v4(dst, pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]), pack_u16x2(hh[4], hh[5]), pack_u16x2(hh[6], hh[7]));
-    st_shared_v4(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]), pack_u16x2(hl[2], hl[3]), pack_u16x2(hl[4], hl[5]),
-                 pack_u16x2(hl[6], hl[7]));
+    if constexpr (NC == 8) {
+      st_shared_v4(dst, pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]), pack_u16x2(hh[4], hh[5]), pack_u16x2(hh[6], hh[7]));
+      st_shared_v4(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]), pack_u16x2(hl[2], hl[3]), pack_u16x2(hl[4], hl[5]),
+                   pack_u16x2(hl[6], hl[7]));
+    } else {
+      st_shared_v2(dst, pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]));
+      st_shared_v2(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]), pack_u16x2(hl[2], hl[3]));
+    }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (TIMING && dbg) dbg[step * 8 + 5] = (unsigned)clock();
     tc_fence_before();
@@ -168,7 +189,7 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
     // the float32 copy of h_t for the next layer leaves after the hand-off: it is not on the recurrence's critical path
     if (s.php) {        // the next layer's GEMM reads h as hi/lo planes: write them directly (no float32 round trip)
 #pragma unroll
-      for (int n = 0; n < 8; n++)
+      for (int n = 0; n < NC; n++)
         if (FULL || n < s.rows) {
           s.php[n * s.row_h] = hh[n];
           s.php[n * s.row_h + s.plane_off] = hl[n];
@@ -177,7 +198,7 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
     }
     if (s.hp) {
 #pragma unroll
-      for (int n = 0; n < 8; n++)
+      for (int n = 0; n < NC; n++)
         if (FULL || n < s.rows) s.hp[n * s.row_h] = h[n];
       s.hp += s.dh;
     }
@@ -185,8 +206,8 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
   }
 }
 
-template <bool F16, bool TIMING>
-__global__ void __launch_bounds__(L3_THREADS, 1)
+template <bool F16, bool TIMING, int NC>
+__global__ void __launch_bounds__(l3_threads(NC), 1)
 lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __restrict__ w_hi,
                 const uint16_t* __restrict__ w_lo /*both [2][512][128]*/, const float* __restrict__ gx, int B, int T,
                 int stride, int groups_per_dir, float* __restrict__ hout, uint16_t* __restrict__ out_hi,
@@ -201,6 +222,8 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
   uint64_t* h_ready = bars + 3;                      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
 
+  constexpr int NCW = 4 * (LT_NB / NC);              // cell-update warps; warp NCW issues the MMAs
+  constexpr int L3_THREADS = l3_threads(NC);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int dir = blockIdx.x / groups_per_dir;
   const int b0 = (blockIdx.x - dir * groups_per_dir) * LT_NB;
@@ -209,11 +232,11 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     mbar_init(w_full, 1);
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
-    mbar_init(&h_ready[0], 8);
-    mbar_init(&h_ready[1], 8);
+    mbar_init(&h_ready[0], NCW);
+    mbar_init(&h_ready[1], NCW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 8) {
+  if (warp == NCW) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -224,7 +247,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
   tc_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
-  if (warp == 8) {
+  if (warp == NCW) {
     if (lane == 0) {
       mbar_expect_tx(w_full, L3_WS_BYTES);
       for (int kb = 0; kb < 2; kb++) tma_load_2d(wsm + kb * 16384, &tm_wlo, kb * 64, dir * 512 + 3 * 128, w_full);
@@ -257,7 +280,7 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
   __syncthreads();
   tc_fence_after();
 
-  if (warp == 8) {
+  if (warp == NCW) {
     if (elect_one()) {
       // D = f32, A K-major (TMEM / swizzled smem), B MN-major (bit 16), N = 16, M = 128
       const uint32_t idesc = (1u << 4) | idesc_ab_format(F16 ? 1 : 0) | (1u << 16) | ((uint32_t)(LT_NB >> 3) << 17) |
@@ -301,29 +324,30 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     __syncwarp();
   } else {
     // ================================================================ cell update (warps 0..7)
-    const int quad = warp & 3, ch = warp >> 2;
+    const int quad = warp & 3, ch = warp >> 2;      // ch: which NC batch columns of the 16
     const int u = quad * 32 + lane;                 // hidden unit == TMEM lane
     L3Cell s;
-    s.rows = min(8, max(0, B - (b0 + ch * 8)));     // valid batch rows of this warp's 8 columns
-    s.tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + L3_COL_D + ch * 8;
+    s.rows = min(NC, max(0, B - (b0 + ch * NC)));   // valid batch rows of this warp's NC columns
+    s.tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + L3_COL_D + ch * NC;
     s.row_gx = (size_t)stride * 1024;
     s.row_h = (size_t)stride * 256;
     const int t0 = dir == 0 ? 0 : T - 1;
-    s.gp = gx + ((size_t)(b0 + ch * 8) * stride + t0) * 1024 + dir * 512 + u;
-    const size_t e0 = ((size_t)(b0 + ch * 8) * stride + t0) * 256 + dir * 128 + u;
+    s.gp = gx + ((size_t)(b0 + ch * NC) * stride + t0) * 1024 + dir * 512 + u;
+    const size_t e0 = ((size_t)(b0 + ch * NC) * stride + t0) * 256 + dir * 128 + u;
     s.hp = hout ? hout + e0 : nullptr;
     s.php = out_hi ? out_hi + e0 : nullptr;
     s.plane_off = out_hi ? (size_t)(out_lo - out_hi) : 0;
     s.dgx = dir == 0 ? 1024 : -1024;
     s.dh = dir == 0 ? 256 : -256;
-    s.h_addr = smem_u32(hsm) + (u >> 3) * 256 + ch * 128 + (u & 7) * 16;
+    // 16-byte unit of (unit u, row group of 8); with NC = 4 two warps share a unit (8 bytes each)
+    s.h_addr = smem_u32(hsm) + (u >> 3) * 256 + ((ch * NC) >> 3) * 128 + (u & 7) * 16 + ((ch * NC) & 7) * 2;
     unsigned* my_dbg = (TIMING && blockIdx.x == 0 && threadIdx.x == 0) ? dbg : nullptr;
-    if (s.rows == 8) l3_cell_loop<F16, true, TIMING>(s, T, mma_done, h_ready, lane, my_dbg);
-    else l3_cell_loop<F16, false, TIMING>(s, T, mma_done, h_ready, lane, my_dbg);
+    if (s.rows == NC) l3_cell_loop<F16, true, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg);
+    else l3_cell_loop<F16, false, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) {
+  if (warp == NCW) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
@@ -357,14 +381,18 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     set_error("cuTensorMapEncodeTiled failed for W_hh");
     return -2;
   }
-  static bool attr_done = false;
+  static bool attr_done[64] = {};
   static bool timing = false;
-  if (!attr_done) {
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+  // DG_LSTM_CELLS=8: 8 cells per thread / 8 cell warps (the round-1 shape); default 4 cells / 16 cell warps
+  static const bool cells8 = getenv("DG_LSTM_CELLS") && getenv("DG_LSTM_CELLS")[0] == '8';
+  if (first_use_on_device(attr_done)) {
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
     timing = getenv("DG_LSTM_TIMING") && getenv("DG_LSTM_TIMING")[0] == '1';
-    attr_done = true;
   }
   if (!hout && !out_hi) {
     set_error("lstm_rec: no output buffer");
@@ -381,7 +409,8 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     unsigned* dbg = nullptr;
     DG_CUDA(cudaMalloc(&dbg, (size_t)T * 8 * sizeof(unsigned)));
     DG_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(unsigned), st));
-    lstm_tc3_kernel<true, true><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, dbg);
+    if (cells8) lstm_tc3_kernel<true, true, 8><<<2 * gpd, l3_threads(8), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, dbg);
+    else lstm_tc3_kernel<true, true, 4><<<2 * gpd, l3_threads(4), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, dbg);
     DG_CUDA(cudaStreamSynchronize(st));
     if (reported++ < 6) {
       std::vector<unsigned> hbuf((size_t)T * 8);
@@ -406,10 +435,13 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     cudaFree(dbg);
     return 0;
   }
-  if (split_f16())
-    lstm_tc3_kernel<true, false><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
-  else
-    lstm_tc3_kernel<false, false><<<2 * gpd, L3_THREADS, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
+  if (split_f16()) {
+    if (cells8) lstm_tc3_kernel<true, false, 8><<<2 * gpd, l3_threads(8), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
+    else lstm_tc3_kernel<true, false, 4><<<2 * gpd, l3_threads(4), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
+  } else {
+    if (cells8) lstm_tc3_kernel<false, false, 8><<<2 * gpd, l3_threads(8), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
+    else lstm_tc3_kernel<false, false, 4><<<2 * gpd, l3_threads(4), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
+  }
   DG_LAUNCHED();
   return 0;
 }

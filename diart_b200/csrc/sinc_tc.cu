@@ -326,11 +326,9 @@ static int sinc0_launch_common(const void* w_planes, uint64_t rows, int rpi, siz
   for (int pl = 0; pl < ST_WP; pl++)
     if (make_map2(&maps.w[pl], reinterpret_cast<const uint16_t*>(w_planes) + (size_t)pl * 80 * 256, 256, 80, 512, ST_N))
       return -2;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};
+  if (first_use_on_device(attr_done))
     DG_CUDA(cudaFuncSetAttribute(sinc0_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, ST_SMEM));
-    attr_done = true;
-  }
   const int sms = usable_sms();
   const int row_tiles = (int)((rows + ST_ROWS - 1) / ST_ROWS);
   const int tiles = row_tiles * 4;

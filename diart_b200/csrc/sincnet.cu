@@ -175,12 +175,10 @@ sinc0_kernel(const float* __restrict__ wav, const float* __restrict__ mean, cons
 int launch_sinc0(const float* wav, const float* mean, const float* rstd, float wn_gamma, float wn_beta,
                  const float* filt, int B, const Geom& g, float* p0, cudaStream_t st) {
   ProfScope _ps("sinc0", st);
-  static bool attr_done = false;
+  static bool attr_done[64] = {};
   const size_t smem = (size_t)(SINC_K * SINC_F + ((SINC_XSEG + 3) & ~3)) * sizeof(float);
-  if (!attr_done) {
+  if (first_use_on_device(attr_done))
     DG_CUDA(cudaFuncSetAttribute(sinc0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

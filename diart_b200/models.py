@@ -26,25 +26,38 @@ from . import _lib
 StateDict = Dict[str, Union[torch.Tensor, np.ndarray]]
 
 
-def _load_state(source) -> StateDict:
+def _load_pyannote(name: str, use_hf_token=True):
+    """pyannote model by name (what reference ``src/diart/models.py:41-53`` does), with the token the caller gave"""
+    try:
+        from pyannote.audio import Model  # type: ignore
+    except ImportError as e:
+        raise FileNotFoundError(
+            f"'{name}' is not a state-dict file and pyannote.audio is not installed to fetch it") from e
+    return Model.from_pretrained(name, use_auth_token=use_hf_token)
+
+
+def _load_state(source, use_hf_token=True):
+    """-> (state dict, the pyannote model it came from or None)"""
     if isinstance(source, dict):
-        return source
+        return source, None
     if isinstance(source, (str, Path)):
         path = Path(source)
         if path.suffix == ".npz":
-            return dict(np.load(path))
+            return dict(np.load(path)), None
         if path.exists():
             obj = torch.load(path, map_location="cpu", weights_only=True)
-            return obj.get("state_dict", obj) if isinstance(obj, dict) else obj
-        try:  # a pyannote model name, e.g. "pyannote/segmentation"
-            from pyannote.audio import Model  # type: ignore
-        except ImportError as e:
-            raise FileNotFoundError(
-                f"'{source}' is not a state-dict file and pyannote.audio is not installed to fetch it") from e
-        return Model.from_pretrained(str(source)).state_dict()
+            return (obj.get("state_dict", obj) if isinstance(obj, dict) else obj), None
+        model = _load_pyannote(str(source), use_hf_token)      # a pyannote model name, e.g. "pyannote/segmentation"
+        return model.state_dict(), model
     if hasattr(source, "state_dict"):
-        return source.state_dict()
+        return source.state_dict(), source
     raise ValueError("expected a state dict, a path to one, a pyannote model name or an nn.Module")
+
+
+def _powerset_classes(num_speakers: int, max_per_frame: int) -> int:
+    from math import comb
+
+    return sum(comb(num_speakers, k) for k in range(max_per_frame + 1))
 
 
 class _Handle:
@@ -218,21 +231,33 @@ class B200SegmentationLoader:
     max_speakers_per_frame)`` for powerset checkpoints given as plain state dicts (it is read from the model's
     specifications when ``source`` is a pyannote model)."""
 
-    def __init__(self, source, powerset: Optional[Tuple[int, int]] = None):
+    def __init__(self, source, powerset: Optional[Tuple[int, int]] = None, use_hf_token=True):
         self.source = source
         self.powerset = powerset
+        self.use_hf_token = use_hf_token
 
     def __call__(self) -> B200PyanNet:
-        powerset = self.powerset if self.powerset is not None else _powerset_of(self.source)
-        return B200PyanNet(_load_state(self.source), powerset=powerset)
+        # the model is loaded ONCE; its specifications (powerset or multilabel) are read from the loaded object before the
+        # state dict is taken -- a powerset checkpoint given by name must not be decoded as 7 "speakers" through the sigmoid head
+        state, model = _load_state(self.source, self.use_hf_token)
+        powerset = self.powerset if self.powerset is not None else _powerset_of(model if model is not None else self.source)
+        bias = state.get("classifier.bias")
+        if bias is not None and powerset is not None:
+            width, want = int(np.prod(tuple(bias.shape))), _powerset_classes(*powerset)
+            if width != want:
+                raise ValueError(f"classifier has {width} outputs but a powerset of {powerset[0]} speakers with at most "
+                                 f"{powerset[1]} per frame has {want} classes")
+        return B200PyanNet(state, powerset=powerset)
 
 
 class B200EmbeddingLoader:
-    def __init__(self, source, pool_mode: str = "3.1"):
-        self.source, self.pool_mode = source, pool_mode
+    def __init__(self, source, pool_mode: str = "3.1", use_hf_token=True):
+        self.source, self.pool_mode, self.use_hf_token = source, pool_mode, use_hf_token
 
     def __call__(self) -> B200XVectorSincNet:
-        return B200XVectorSincNet(_load_state(self.source), self.pool_mode)
+        """pyannote/embedding (XVectorSincNet) and pyannote/wespeaker-voxceleb-resnet34-LM (WeSpeakerResNet34, variant B) are
+        told apart by the key names of the state dict (``dg_emb_create``)."""
+        return B200XVectorSincNet(_load_state(self.source, self.use_hf_token)[0], self.pool_mode)
 
 
 class LazyModel:
@@ -271,11 +296,11 @@ class SegmentationModel(LazyModel):
 
     @staticmethod
     def from_pyannote(model, use_hf_token=True) -> "SegmentationModel":
-        return SegmentationModel(B200SegmentationLoader(model))
+        return SegmentationModel(B200SegmentationLoader(model, use_hf_token=use_hf_token))
 
     @staticmethod
     def from_pretrained(model, use_hf_token=True) -> "SegmentationModel":
-        return SegmentationModel(B200SegmentationLoader(model))
+        return SegmentationModel(B200SegmentationLoader(model, use_hf_token=use_hf_token))
 
     def __call__(self, waveform: torch.Tensor) -> torch.Tensor:
         return super().__call__(waveform)
@@ -286,11 +311,11 @@ class EmbeddingModel(LazyModel):
 
     @staticmethod
     def from_pyannote(model, use_hf_token=True, pool_mode: str = "3.1") -> "EmbeddingModel":
-        return EmbeddingModel(B200EmbeddingLoader(model, pool_mode))
+        return EmbeddingModel(B200EmbeddingLoader(model, pool_mode, use_hf_token=use_hf_token))
 
     @staticmethod
     def from_pretrained(model, use_hf_token=True, pool_mode: str = "3.1") -> "EmbeddingModel":
-        return EmbeddingModel(B200EmbeddingLoader(model, pool_mode))
+        return EmbeddingModel(B200EmbeddingLoader(model, pool_mode, use_hf_token=use_hf_token))
 
     def __call__(self, waveform: torch.Tensor, weights: Optional[torch.Tensor] = None) -> torch.Tensor:
         embeddings = super().__call__(waveform, weights)
