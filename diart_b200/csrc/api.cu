@@ -332,7 +332,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
       }
       if (prep->hop) {   // stream form: one convolution of the unique samples + a per-window affine / |.| / pool pass
         const SincStreamGeom sg = sinc_stream_geom(B, g, prep->hop);
-        if (k.craw.ensure(((size_t)sg.P + 16) * 80 * 4) || k.part.ensure(sinc_pool_part_floats(B) * 4)) return DG_ECUDA;
+        if (k.craw.ensure(((size_t)sg.P + 16) * 80 * 4) || k.part.ensure(sinc_pool_part_floats(B, g, prep->hop) * 4)) return DG_ECUDA;
         // raw convolution of the stream, then statistics and normalised operand planes straight from it (p0 is never written)
         if ((rc = launch_sinc0_tc_stream(w.filt_planes.p, B, g, prep->hop, prep->swh.p, prep->swl.p, k.craw.as<float>(),
                                          prep->flag.as<int>(), st)) ||

@@ -197,7 +197,7 @@ int launch_sinc0_tc_stream(const void* w_planes, int B, const Geom& g, int hop, 
                            float* craw, const int* flag, cudaStream_t st);
 int launch_sinc_pool(const float* craw, const float* mean, const float* rstd, const float* cf, const float* hsum, float gamma,
                      int B, const Geom& g, int hop, float* p0, const int* flag, cudaStream_t st);
-size_t sinc_pool_part_floats(int B);
+size_t sinc_pool_part_floats(int B, const Geom& g, int hop);
 int launch_sinc_pool_fused(const float* craw, const float* mean, const float* rstd, const float* cf, const float* hsum, float gamma,
                            int B, const Geom& g, int hop, const float* g0, const float* b0, float* part, float* sc, float* sh,
                            void* planes_hi, void* planes_lo, const int* flag, cudaStream_t st);

@@ -268,6 +268,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             for (int sg = 0; sg < 2; sg++) {
               const int lo = sg == 0 ? r_lo : max(r_lo, brow), hi = sg == 0 ? min(r_hi, brow) : r_hi;
               float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 8
               for (int rr = lo; rr < hi; rr++) {
                 const float dv = dsm[rr * 33 + col];
                 const float4 w4 = wsm[rr];

@@ -469,10 +469,16 @@ int launch_sinc_pool(const float* craw, const float* mean, const float* rstd, co
 // a second pass recomputes p0, applies the normalisation + LeakyReLU and writes the 16-bit hi/lo planes Conv1d(80, 60, 5) reads
 // (80-channel rows, no padding).  Replaces sinc0_pool + instnorm_stats + split16 of this layer (218 MB written and 2 x 218 MB
 // read back per network and step).
-constexpr int SP_NBLK = 32, SP_ROWL = 16;
+//
+// Both passes walk the STREAM, not the windows: a CTA stages SP_R (+2 halo) rows of the raw convolution in shared memory once
+// and serves every window that contains them (up to ceil(3 T0 / hop10) + 1 = 11), so each row leaves L2 once per pass instead
+// of ten times.  Pool groups of different windows have different phases (hop / 10 is not a multiple of 3): a CTA owns the
+// groups whose FIRST row lies in its range.
+constexpr int SP_R = 96, SP_GL = 16, SP_THREADS = 20 * SP_GL;
 
-__device__ __forceinline__ float4 sp_value(const float4* __restrict__ src, int p, int f4, float A, const float4& bias) {
-  const float4 u0 = src[(size_t)(3 * p) * 20 + f4], u1 = src[(size_t)(3 * p + 1) * 20 + f4], u2 = src[(size_t)(3 * p + 2) * 20 + f4];
+__device__ __forceinline__ float4 sp_value_sm(const float4* __restrict__ rows /*[SP_R + 2][20]*/, int r, int f4, float A,
+                                              const float4& bias) {
+  const float4 u0 = rows[r * 20 + f4], u1 = rows[(r + 1) * 20 + f4], u2 = rows[(r + 2) * 20 + f4];
   float4 v;
   v.x = fmaxf(fmaxf(fabsf(fmaf(A, u0.x, bias.x)), fabsf(fmaf(A, u1.x, bias.x))), fabsf(fmaf(A, u2.x, bias.x)));
   v.y = fmaxf(fmaxf(fabsf(fmaf(A, u0.y, bias.y)), fabsf(fmaf(A, u1.y, bias.y))), fabsf(fmaf(A, u2.y, bias.y)));
@@ -484,65 +490,109 @@ __device__ __forceinline__ float4 sp_bias(const float* cf, const float* hsum, in
   const float4 c4 = reinterpret_cast<const float4*>(cf)[f4], h4 = reinterpret_cast<const float4*>(hsum)[f4];
   return make_float4(fmaf(-Am, h4.x, c4.x), fmaf(-Am, h4.y, c4.y), fmaf(-Am, h4.z, c4.z), fmaf(-Am, h4.w, c4.w));
 }
-
-// partial sums around the pivot p0[b][0][f]: part[b][blk][0 / 1][80] = sum d, sum d^2 over the block's pooled rows
-__global__ void __launch_bounds__(20 * SP_ROWL) sinc_pool_stats_kernel(const float* __restrict__ craw, const float* __restrict__ mean,
-                                                                       const float* __restrict__ rstd, const float* __restrict__ cf,
-                                                                       const float* __restrict__ hsum, float gamma, int hop10, int T0,
-                                                                       float* __restrict__ part, const int* __restrict__ flag) {
-  if (*flag == 0) return;
-  __shared__ float4 r1[SP_ROWL][20], r2[SP_ROWL][20];
-  const int b = blockIdx.y, blk = blockIdx.x, f4 = threadIdx.x % 20, rl = threadIdx.x / 20;
-  const float A = gamma * rstd[b], Am = A * mean[b];
-  const float4* src = reinterpret_cast<const float4*>(craw + (size_t)b * hop10 * ST_N);
-  const float4 bias = sp_bias(cf, hsum, f4, Am);
-  const float4 pv = sp_value(src, 0, f4, A, bias);
-  const int per = (T0 + SP_NBLK - 1) / SP_NBLK, p_lo = blk * per, p_hi = min(T0, p_lo + per);
-  float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
-  for (int p = p_lo + rl; p < p_hi; p += SP_ROWL) {
-    const float4 v = sp_value(src, p, f4, A, bias);
-    const float dx = v.x - pv.x, dy = v.y - pv.y, dz = v.z - pv.z, dw = v.w - pv.w;
-    s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
-    s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
-  }
-  r1[rl][f4] = s1;
-  r2[rl][f4] = s2;
-  __syncthreads();
-  if (rl == 0) {
-    float4 a = r1[0][f4], q = r2[0][f4];
-    for (int i = 1; i < SP_ROWL; i++) {
-      a.x += r1[i][f4].x; a.y += r1[i][f4].y; a.z += r1[i][f4].z; a.w += r1[i][f4].w;
-      q.x += r2[i][f4].x; q.y += r2[i][f4].y; q.z += r2[i][f4].z; q.w += r2[i][f4].w;
-    }
-    float4* o = reinterpret_cast<float4*>(part + ((size_t)b * SP_NBLK + blk) * 2 * ST_N);
-    o[f4] = a;
-    o[20 + f4] = q;
+// rows [r0, r0 + SP_R + 2) of craw -> shared memory (zeros past the end of the stream)
+__device__ __forceinline__ void sp_stage(const float* __restrict__ craw, long long r0, long long P, float4* rows) {
+  for (int i = threadIdx.x; i < (SP_R + 2) * 20; i += SP_THREADS) {
+    const long long r = r0 + i / 20;
+    rows[i] = r < P ? reinterpret_cast<const float4*>(craw)[r * 20 + (i % 20)] : make_float4(0.f, 0.f, 0.f, 0.f);
   }
 }
+// windows with a pool group starting in [r0, r0 + SP_R): b_lo .. b_hi; groups p_lo .. p_hi of window b
+__device__ __forceinline__ void sp_windows(long long r0, int B, int hop10, int T0, int& b_lo, int& b_hi) {
+  const long long last_start = 3LL * (T0 - 1);
+  long long lo = (r0 - last_start + hop10 - 1) / hop10;        // ceil((r0 - last_start) / hop10) for non-negative results
+  if (r0 - last_start <= 0) lo = 0;
+  b_lo = (int)lo;
+  b_hi = (int)min((long long)B - 1, (r0 + SP_R - 1) / hop10);
+}
+__device__ __forceinline__ void sp_groups(long long r0, int b, int hop10, int T0, int& p_lo, int& p_hi) {
+  const long long off = r0 - (long long)b * hop10;             // block start relative to the window
+  p_lo = off <= 0 ? 0 : (int)((off + 2) / 3);
+  const long long e = off + SP_R;                              // groups with 3 p < e
+  p_hi = (int)min((long long)T0, (e + 2) / 3);
+}
 
-// InstanceNorm1d(80, affine) scale / shift per (window, filter) from the block partials (double, fixed order)
-__global__ void __launch_bounds__(96) sinc_pool_finalize_kernel(const float* __restrict__ craw, const float* __restrict__ mean,
-                                                                const float* __restrict__ rstd, const float* __restrict__ cf,
-                                                                const float* __restrict__ hsum, float gamma, int hop10, int T0,
-                                                                const float* __restrict__ part, const float* __restrict__ g0,
-                                                                const float* __restrict__ b0, float* __restrict__ sc,
-                                                                float* __restrict__ sh, const int* __restrict__ flag) {
+// p0[b][0][f] for every window: the pivot of the statistics
+__global__ void __launch_bounds__(96) sinc_pool_pivot_kernel(const float* __restrict__ craw, const float* __restrict__ mean,
+                                                             const float* __restrict__ rstd, const float* __restrict__ cf,
+                                                             const float* __restrict__ hsum, float gamma, int hop10,
+                                                             float* __restrict__ pv, const int* __restrict__ flag) {
   if (*flag == 0) return;
   const int b = blockIdx.x, f = threadIdx.x;
   if (f >= ST_N) return;
   const float A = gamma * rstd[b], Am = A * mean[b];
   const float bias = fmaf(-Am, hsum[f], cf[f]);
   const float* src = craw + (size_t)b * hop10 * ST_N + f;
-  const float pivot = fmaxf(fmaxf(fabsf(fmaf(A, src[0], bias)), fabsf(fmaf(A, src[ST_N], bias))), fabsf(fmaf(A, src[2 * ST_N], bias)));
+  pv[(size_t)b * ST_N + f] = fmaxf(fmaxf(fabsf(fmaf(A, src[0], bias)), fabsf(fmaf(A, src[ST_N], bias))), fabsf(fmaf(A, src[2 * ST_N], bias)));
+}
+
+// partial sums around the pivot: part[b][j][0 / 1][80], j = CTA index relative to the window's first CTA
+__global__ void __launch_bounds__(SP_THREADS) sinc_pool_stats_kernel(const float* __restrict__ craw, long long P,
+                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                     const float* __restrict__ cf, const float* __restrict__ hsum,
+                                                                     float gamma, int B, int hop10, int T0, int npart,
+                                                                     const float* __restrict__ pv, float* __restrict__ part,
+                                                                     const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  __shared__ float4 rows[(SP_R + 2) * 20];
+  __shared__ float4 r1[SP_GL][20], r2[SP_GL][20];
+  const long long r0 = (long long)blockIdx.x * SP_R;
+  sp_stage(craw, r0, P, rows);
+  const int f4 = threadIdx.x % 20, gl = threadIdx.x / 20;
+  int b_lo, b_hi;
+  sp_windows(r0, B, hop10, T0, b_lo, b_hi);
+  __syncthreads();
+  for (int b = b_lo; b <= b_hi; b++) {
+    int p_lo, p_hi;
+    sp_groups(r0, b, hop10, T0, p_lo, p_hi);
+    const float A = gamma * rstd[b], Am = A * mean[b];
+    const float4 bias = sp_bias(cf, hsum, f4, Am);
+    const float4 pvv = reinterpret_cast<const float4*>(pv + (size_t)b * ST_N)[f4];
+    float4 s1 = make_float4(0.f, 0.f, 0.f, 0.f), s2 = s1;
+    for (int p = p_lo + gl; p < p_hi; p += SP_GL) {
+      const int r = (int)((long long)b * hop10 + 3LL * p - r0);
+      const float4 v = sp_value_sm(rows, r, f4, A, bias);
+      const float dx = v.x - pvv.x, dy = v.y - pvv.y, dz = v.z - pvv.z, dw = v.w - pvv.w;
+      s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+      s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+    }
+    r1[gl][f4] = s1;
+    r2[gl][f4] = s2;
+    __syncthreads();
+    if (gl == 0) {
+      float4 a = r1[0][f4], q = r2[0][f4];
+      for (int i = 1; i < SP_GL; i++) {
+        a.x += r1[i][f4].x; a.y += r1[i][f4].y; a.z += r1[i][f4].z; a.w += r1[i][f4].w;
+        q.x += r2[i][f4].x; q.y += r2[i][f4].y; q.z += r2[i][f4].z; q.w += r2[i][f4].w;
+      }
+      const int j = (int)(blockIdx.x - ((long long)b * hop10) / SP_R);
+      float4* o = reinterpret_cast<float4*>(part + ((size_t)b * npart + j) * 2 * ST_N);
+      o[f4] = a;
+      o[20 + f4] = q;
+    }
+    __syncthreads();
+  }
+}
+
+// InstanceNorm1d(80, affine) scale / shift per (window, filter) from the CTA partials (double, fixed order)
+__global__ void __launch_bounds__(96) sinc_pool_finalize_kernel(int hop10, int T0, int npart, const float* __restrict__ pv,
+                                                                const float* __restrict__ part, const float* __restrict__ g0,
+                                                                const float* __restrict__ b0, float* __restrict__ sc,
+                                                                float* __restrict__ sh, const int* __restrict__ flag) {
+  if (*flag == 0) return;
+  const int b = blockIdx.x, f = threadIdx.x;
+  if (f >= ST_N) return;
+  const long long w0 = (long long)b * hop10;
+  const int nj = (int)((w0 + 3LL * (T0 - 1)) / SP_R - w0 / SP_R) + 1;       // CTAs that own a pool group of this window
   double t1 = 0, t2 = 0;
-  for (int i = 0; i < SP_NBLK; i++) {
-    t1 += part[((size_t)b * SP_NBLK + i) * 2 * ST_N + f];
-    t2 += part[((size_t)b * SP_NBLK + i) * 2 * ST_N + ST_N + f];
+  for (int i = 0; i < nj; i++) {
+    t1 += part[((size_t)b * npart + i) * 2 * ST_N + f];
+    t2 += part[((size_t)b * npart + i) * 2 * ST_N + ST_N + f];
   }
   const double m = t1 / T0;
   double var = t2 / T0 - m * m;
   if (var < 0) var = 0;
-  const double mu = (double)pivot + m;
+  const double mu = (double)pv[(size_t)b * ST_N + f] + m;
   const float r = (float)(1.0 / sqrt(var + 1e-5));
   const float gsc = g0[f] * r;
   sc[(size_t)b * ST_N + f] = gsc;
@@ -550,51 +600,67 @@ __global__ void __launch_bounds__(96) sinc_pool_finalize_kernel(const float* __r
 }
 
 // p0 recomputed -> leaky(p0 * sc + sh) -> 16-bit hi / lo planes [B * S0][80]
-__global__ void __launch_bounds__(256) sinc_pool_split_kernel(const float* __restrict__ craw, const float* __restrict__ mean,
-                                                              const float* __restrict__ rstd, const float* __restrict__ cf,
-                                                              const float* __restrict__ hsum, float gamma, int hop10, int T0, int S0,
-                                                              const float* __restrict__ sc, const float* __restrict__ sh,
-                                                              uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int f16,
-                                                              const int* __restrict__ flag) {
+__global__ void __launch_bounds__(SP_THREADS) sinc_pool_split_kernel(const float* __restrict__ craw, long long P,
+                                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                     const float* __restrict__ cf, const float* __restrict__ hsum,
+                                                                     float gamma, int B, int hop10, int T0, int S0,
+                                                                     const float* __restrict__ sc, const float* __restrict__ sh,
+                                                                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int f16,
+                                                                     const int* __restrict__ flag) {
   if (*flag == 0) return;
-  const int b = blockIdx.y;
-  const float A = gamma * rstd[b], Am = A * mean[b];
-  const float4* src = reinterpret_cast<const float4*>(craw + (size_t)b * hop10 * ST_N);
-  uint2* oh = reinterpret_cast<uint2*>(hi + (size_t)b * S0 * ST_N);
-  uint2* ol = reinterpret_cast<uint2*>(lo + (size_t)b * S0 * ST_N);
-  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < T0 * 20; idx += gridDim.x * blockDim.x) {
-    const int p = idx / 20, f4 = idx - p * 20;
+  __shared__ float4 rows[(SP_R + 2) * 20];
+  const long long r0 = (long long)blockIdx.x * SP_R;
+  sp_stage(craw, r0, P, rows);
+  const int f4 = threadIdx.x % 20, gl = threadIdx.x / 20;
+  int b_lo, b_hi;
+  sp_windows(r0, B, hop10, T0, b_lo, b_hi);
+  __syncthreads();
+  for (int b = b_lo; b <= b_hi; b++) {
+    int p_lo, p_hi;
+    sp_groups(r0, b, hop10, T0, p_lo, p_hi);
+    const float A = gamma * rstd[b], Am = A * mean[b];
     const float4 bias = sp_bias(cf, hsum, f4, Am);
-    const float4 v = sp_value(src, p, f4, A, bias);
     const float4 s4 = reinterpret_cast<const float4*>(sc + (size_t)b * ST_N)[f4], h4 = reinterpret_cast<const float4*>(sh + (size_t)b * ST_N)[f4];
-    uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
-    split_h16(leaky(fmaf(v.x, s4.x, h4.x)), f16, h0, l0);
-    split_h16(leaky(fmaf(v.y, s4.y, h4.y)), f16, h1, l1);
-    split_h16(leaky(fmaf(v.z, s4.z, h4.z)), f16, h2, l2);
-    split_h16(leaky(fmaf(v.w, s4.w, h4.w)), f16, h3, l3);
-    oh[(size_t)p * 20 + f4] = make_uint2(pack_u16x2(h0, h1), pack_u16x2(h2, h3));
-    ol[(size_t)p * 20 + f4] = make_uint2(pack_u16x2(l0, l1), pack_u16x2(l2, l3));
+    uint2* oh = reinterpret_cast<uint2*>(hi + (size_t)b * S0 * ST_N);
+    uint2* ol = reinterpret_cast<uint2*>(lo + (size_t)b * S0 * ST_N);
+    for (int p = p_lo + gl; p < p_hi; p += SP_GL) {
+      const int r = (int)((long long)b * hop10 + 3LL * p - r0);
+      const float4 v = sp_value_sm(rows, r, f4, A, bias);
+      uint16_t h0, h1, h2, h3, l0, l1, l2, l3;
+      split_h16(leaky(fmaf(v.x, s4.x, h4.x)), f16, h0, l0);
+      split_h16(leaky(fmaf(v.y, s4.y, h4.y)), f16, h1, l1);
+      split_h16(leaky(fmaf(v.z, s4.z, h4.z)), f16, h2, l2);
+      split_h16(leaky(fmaf(v.w, s4.w, h4.w)), f16, h3, l3);
+      oh[(size_t)p * 20 + f4] = make_uint2(pack_u16x2(h0, h1), pack_u16x2(h2, h3));
+      ol[(size_t)p * 20 + f4] = make_uint2(pack_u16x2(l0, l1), pack_u16x2(l2, l3));
+    }
   }
 }
 
-size_t sinc_pool_part_floats(int B) { return (size_t)B * SP_NBLK * 2 * ST_N; }
+static int sp_npart(const Geom& g, int hop) { return (3 * g.T0 + SP_R - 1) / SP_R + 2; }
+size_t sinc_pool_part_floats(int B, const Geom& g, int hop) { return (size_t)B * sp_npart(g, hop) * 2 * ST_N + (size_t)B * ST_N; }
 
 int launch_sinc_pool_fused(const float* craw, const float* mean, const float* rstd, const float* cf, const float* hsum, float gamma,
                            int B, const Geom& g, int hop, const float* g0, const float* b0, float* part, float* sc, float* sh,
                            void* planes_hi, void* planes_lo, const int* flag, cudaStream_t st) {
+  const SincStreamGeom sg = sinc_stream_geom(B, g, hop);
+  const int hop10 = hop / 10, npart = sp_npart(g, hop);
+  const long long last = (long long)(B - 1) * hop10 + 3LL * (g.T0 - 1);       // last pool-group start of the stream
+  const int blocks = (int)(last / SP_R) + 1;
+  float* pv = part + (size_t)B * npart * 2 * ST_N;
   {
     ProfScope _ps("sinc0_pool_stats", st);
-    dim3 grid(SP_NBLK, B);
-    sinc_pool_stats_kernel<<<grid, 20 * SP_ROWL, 0, st>>>(craw, mean, rstd, cf, hsum, gamma, hop / 10, g.T0, part, flag);
+    sinc_pool_pivot_kernel<<<B, 96, 0, st>>>(craw, mean, rstd, cf, hsum, gamma, hop10, pv, flag);
     DG_LAUNCHED();
-    sinc_pool_finalize_kernel<<<B, 96, 0, st>>>(craw, mean, rstd, cf, hsum, gamma, hop / 10, g.T0, part, g0, b0, sc, sh, flag);
+    sinc_pool_stats_kernel<<<blocks, SP_THREADS, 0, st>>>(craw, sg.P, mean, rstd, cf, hsum, gamma, B, hop10, g.T0, npart, pv, part, flag);
+    DG_LAUNCHED();
+    sinc_pool_finalize_kernel<<<B, 96, 0, st>>>(hop10, g.T0, npart, pv, part, g0, b0, sc, sh, flag);
     DG_LAUNCHED();
   }
   ProfScope _ps("sinc0_pool_split", st);
-  dim3 grid((g.T0 * 20 + 255) / 256 < 64 ? (g.T0 * 20 + 255) / 256 : 64, B);
-  sinc_pool_split_kernel<<<grid, 256, 0, st>>>(craw, mean, rstd, cf, hsum, gamma, hop / 10, g.T0, g.S0, sc, sh,
-                                               reinterpret_cast<uint16_t*>(planes_hi), reinterpret_cast<uint16_t*>(planes_lo), split_f16(),
-                                               flag);
+  sinc_pool_split_kernel<<<blocks, SP_THREADS, 0, st>>>(craw, sg.P, mean, rstd, cf, hsum, gamma, B, hop10, g.T0, g.S0, sc, sh,
+                                                        reinterpret_cast<uint16_t*>(planes_hi), reinterpret_cast<uint16_t*>(planes_lo),
+                                                        split_f16(), flag);
   DG_LAUNCHED();
   return 0;
 }
