@@ -77,6 +77,247 @@ struct TcSmem {
   static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
 };
 
+// ------------------------------------------------------------------------------------ the epilogue of one 128-row tile
+// Executed by the 128 epilogue threads of a CTA (four warps, TMEM lane quadrant = warp % 4).  `mt` = index of the 128-row tile
+// (rows mt * 128 ..), `tmem_acc` = TMEM address of the tile's accumulator (lane 0), `acc_full_bar` is waited for before the
+// accumulator is read (after the parameter staging and the residual prefetch).
+template <int BN, int EPI>
+__device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params, float* pool_stage, uint32_t tmem_acc, long long mt,
+                                                 int n0, int quad, int lane, int et, bool stage_params, uint64_t* acc_full_bar,
+                                                 int acc_phase) {
+    const long long m = mt * TC_BM + quad * 32 + lane;
+    // stage the per-column parameters of this tile (named barrier 1: the 128 epilogue threads only); with a single
+    // column tile they are the same for every tile of this CTA: staged once
+    if (stage_params) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      for (int i = et; i < BN; i += 128) {
+        const int n = n0 + i;
+        const bool ok = n < a.N;
+        params[i] = (ok && a.bias) ? a.bias[n] : 0.f;
+        params[BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_scale[n] : 1.f;
+        params[2 * BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_shift[n] : 0.f;
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    // TC_CONV2D: output position of this row, and the residual of the first 32 columns requested before the wait
+    long long mo = m;                 // output row
+    bool row_ok = m < a.M;
+    uint4 rh0[4], rl0[4];
+    if (EPI == TC_CONV2D) {
+      const unsigned mu = (unsigned)m, per = (unsigned)(a.Wp * a.Hp);     // (the launcher checks M < 2^31)
+      const unsigned item = mu / per, rem = mu - item * per;
+      const int w = (int)(rem / (unsigned)a.Hp), h = (int)(rem - (unsigned)w * (unsigned)a.Hp);
+      row_ok = row_ok && w >= 1 && w <= a.Wp - 2 && h >= 1 && h <= a.Hp - 2;     // a centre inside the un-padded map
+      if (a.stride2) {
+        row_ok = row_ok && (w & 1) && (h & 1);
+        mo = ((long long)item * a.Wop + ((w - 1) >> 1) + 1) * a.Hop + ((h - 1) >> 1) + 1;
+      }
+      if (row_ok && a.res_hi) {
+        const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + mo * a.ldc + n0);
+        const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + mo * a.ldc + n0);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          rh0[q] = rh[q];
+          rl0[q] = rl[q];
+        }
+      }
+    }
+    mbar_wait(acc_full_bar, acc_phase);
+    tc_fence_after();
+    const uint32_t taddr = tmem_acc + ((uint32_t)(quad * 32) << 16);
+    // TC_POOL: the rows' pooling weights go to shared memory; `brow` = first row of the tile that belongs to the NEXT item
+    // (a 128-row tile covers at most two items)
+    int brow = TC_BM;
+    if (EPI == TC_POOL) {
+      float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < a.M) pw = *reinterpret_cast<const float4*>(a.pool_w + m * 4);
+      reinterpret_cast<float4*>(pool_stage + 128 * 33)[quad * 32 + lane] = pw;     // row of the tile = TMEM lane
+      const long long first = (long long)mt * TC_BM;
+      const long long nxt = (first / a.pool_item_rows + 1) * a.pool_item_rows;
+      brow = nxt - first < TC_BM ? (int)(nxt - first) : TC_BM;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      uint32_t r[32];
+      tmem_ld32(taddr + c, r);
+      if (EPI != TC_POOL && n0 + c >= a.N) continue;
+      float v[32];
+      if (EPI == TC_POOL) {
+        // bias -> LeakyReLU -> BatchNorm affine, then the deviation from the per-channel pivot (the BatchNorm shift) goes to
+        // shared memory; thread (row group rg, column col) then sums its 32 rows for the K speakers -- independent
+        // accumulators, no cross-lane traffic -- split at `brow` between the tile's two items
+        float* dsm = pool_stage;                    // [128][33]
+        const float4* wsm = reinterpret_cast<const float4*>(pool_stage + 128 * 33);
+        float* stg = pool_stage + 128 * 33 + 128 * 4;   // [rg 4][item 2][8][32]
+#pragma unroll
+        for (int q4 = 0; q4 < 8; q4++) {       // parameters as 128-bit loads
+          const float4 b4 = *reinterpret_cast<const float4*>(params + c + 4 * q4);
+          const float4 s4 = *reinterpret_cast<const float4*>(params + BN + c + 4 * q4);
+          const float4 h4 = *reinterpret_cast<const float4*>(params + 2 * BN + c + 4 * q4);
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const float x = leaky(__uint_as_float(r[4 * q4 + e]) + bb[e]);
+            dsm[(quad * 32 + lane) * 33 + 4 * q4 + e] = fmaf(x, ss[e], hh[e]) - hh[e];
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        {
+          const int rg = et >> 5, col = et & 31, r_lo = rg * 32, r_hi = r_lo + 32;
+#pragma unroll
+          for (int sg = 0; sg < 2; sg++) {
+            const int lo = sg == 0 ? r_lo : max(r_lo, brow), hi = sg == 0 ? min(r_hi, brow) : r_hi;
+            float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+            if (a.pool_K <= 3) {               // the usual three local speakers: the fourth weight is not touched
+#pragma unroll 8
+              for (int rr = lo; rr < hi; rr++) {
+                const float dv = dsm[rr * 33 + col];
+                const float4 w4 = wsm[rr];
+                const float a0 = w4.x * dv, a1 = w4.y * dv, a2 = w4.z * dv;
+                s1[0] += a0; s1[1] += a1; s1[2] += a2;
+                s2[0] = fmaf(a0, dv, s2[0]); s2[1] = fmaf(a1, dv, s2[1]); s2[2] = fmaf(a2, dv, s2[2]);
+              }
+            } else {
+#pragma unroll 8
+              for (int rr = lo; rr < hi; rr++) {
+                const float dv = dsm[rr * 33 + col];
+                const float4 w4 = wsm[rr];
+                const float a0 = w4.x * dv, a1 = w4.y * dv, a2 = w4.z * dv, a3 = w4.w * dv;
+                s1[0] += a0; s1[1] += a1; s1[2] += a2; s1[3] += a3;
+                s2[0] = fmaf(a0, dv, s2[0]); s2[1] = fmaf(a1, dv, s2[1]); s2[2] = fmaf(a2, dv, s2[2]); s2[3] = fmaf(a3, dv, s2[3]);
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+              stg[((rg * 2 + sg) * 8 + 2 * k) * 32 + col] = s1[k];
+              stg[((rg * 2 + sg) * 8 + 2 * k + 1) * 32 + col] = s2[k];
+            }
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        // 2 items x K speakers x 2 sums x 32 columns: the four row groups' totals are added in a fixed order
+        {
+          const int col = et & 31, twoK = 2 * a.pool_K;
+          for (int q = et >> 5; q < 2 * twoK; q += 4) {
+            const int sg = q >= twoK ? 1 : 0, j = q - sg * twoK;
+            const float tot = ((stg[((0 * 2 + sg) * 8 + j) * 32 + col] + stg[((1 * 2 + sg) * 8 + j) * 32 + col]) +
+                               stg[((2 * 2 + sg) * 8 + j) * 32 + col]) + stg[((3 * 2 + sg) * 8 + j) * 32 + col];
+            const int n = n0 + c + col;
+            if (n < a.N && mt < a.m_tiles) a.pool_part[(((size_t)mt * 2 + sg) * 8 + j) * a.N + n] = tot;
+          }
+        }
+        continue;
+      }
+      if (EPI == TC_CONV2D) {
+        // BatchNorm2d(eval) affine -> (+ residual) -> ReLU
+#pragma unroll
+        for (int i = 0; i < 32; i++) v[i] = fmaf(__uint_as_float(r[i]), params[BN + c + i], params[2 * BN + c + i]);
+        if (row_ok && a.res_hi) {
+          const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + mo * a.ldc + n0 + c);
+          const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + mo * a.ldc + n0 + c);
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            const uint4 hq = c == 0 ? rh0[q] : rh[q], lq = c == 0 ? rl0[q] : rl[q];
+            const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              v[8 * q + 2 * e] += h16_to_f32((uint16_t)(hw[e] & 0xFFFFu), a.f16) + h16_to_f32((uint16_t)(lw[e] & 0xFFFFu), a.f16);
+              v[8 * q + 2 * e + 1] += h16_to_f32((uint16_t)(hw[e] >> 16), a.f16) + h16_to_f32((uint16_t)(lw[e] >> 16), a.f16);
+            }
+          }
+        }
+        if (a.relu) {
+#pragma unroll
+          for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (row_ok) {
+          if (a.out_f32) {
+            float* po = a.out_f32 + mo * a.ldc + n0 + c;
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              reinterpret_cast<float4*>(po)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          }
+          if (a.out_hi) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+              uint16_t h0, l0, h1, l1;
+              split_h16(v[2 * i], a.f16, h0, l0);
+              split_h16(v[2 * i + 1], a.f16, h1, l1);
+              hi[i] = pack_u16x2(h0, h1);
+              lo[i] = pack_u16x2(l0, l1);
+            }
+            uint4* ph = reinterpret_cast<uint4*>(a.out_hi + mo * a.ldc + n0 + c);
+            uint4* pl = reinterpret_cast<uint4*>(a.out_lo + mo * a.ldc + n0 + c);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          }
+        }
+        continue;
+      }
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        float x = __uint_as_float(r[i]) + params[c + i];
+        if (EPI != TC_BIAS_F32) {
+          x = leaky(x);
+          x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
+        }
+        v[i] = x;
+      }
+      if (m < a.M) {
+        if (EPI == TC_LEAKY_BN_SPLIT) {
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int i = 0; i < 16; i++) {
+            uint16_t h0, l0, h1, l1;
+            split_h16(v[2 * i], a.f16, h0, l0);
+            split_h16(v[2 * i + 1], a.f16, h1, l1);
+            hi[i] = pack_u16x2(h0, h1);
+            lo[i] = pack_u16x2(l0, l1);
+          }
+          uint4* ph = reinterpret_cast<uint4*>(a.out_hi + m * a.ldc + n0 + c);
+          uint4* pl = reinterpret_cast<uint4*>(a.out_lo + m * a.ldc + n0 + c);
+          if (a.vec8) {
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              st_global_v8(ph + 2 * i, hi[8 * i], hi[8 * i + 1], hi[8 * i + 2], hi[8 * i + 3], hi[8 * i + 4], hi[8 * i + 5],
+                           hi[8 * i + 6], hi[8 * i + 7]);
+              st_global_v8(pl + 2 * i, lo[8 * i], lo[8 * i + 1], lo[8 * i + 2], lo[8 * i + 3], lo[8 * i + 4], lo[8 * i + 5],
+                           lo[8 * i + 6], lo[8 * i + 7]);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+              ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
+              pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
+            }
+          }
+        } else {
+          float* po = a.out_f32 + m * a.ldc + n0 + c;
+          if (n0 + c + 32 <= a.N && a.vec8) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+              st_global_v8(po + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]),
+                           __float_as_uint(v[8 * i + 3]), __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]),
+                           __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
+          } else if (n0 + c + 32 <= a.N) {
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+              reinterpret_cast<float4*>(po)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; i++)
+              if (n0 + c + i < a.N) po[i] = v[i];
+          }
+        }
+      }
+    }
+}
+
 template <int BN, int EPI>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
@@ -189,218 +430,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
     int acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-      const int n0 = nt * BN;
-      const long long m = (long long)mt * TC_BM + quad * 32 + lane;
-      // stage the per-column parameters of this tile (named barrier 1: the 128 epilogue threads only); with a single
-      // column tile they are the same for every tile of this CTA: staged once
-      if (a.n_tiles > 1 || tile == (int)blockIdx.x) {
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (int i = et; i < BN; i += 128) {
-          const int n = n0 + i;
-          const bool ok = n < a.N;
-          params[i] = (ok && a.bias) ? a.bias[n] : 0.f;
-          params[BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_scale[n] : 1.f;
-          params[2 * BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_shift[n] : 0.f;
-        }
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-      // TC_CONV2D: output position of this row, and the residual of the first 32 columns requested before the wait
-      long long mo = m;                 // output row
-      bool row_ok = m < a.M;
-      uint4 rh0[4], rl0[4];
-      if (EPI == TC_CONV2D) {
-        const unsigned mu = (unsigned)m, per = (unsigned)(a.Wp * a.Hp);     // (the launcher checks M < 2^31)
-        const unsigned item = mu / per, rem = mu - item * per;
-        const int w = (int)(rem / (unsigned)a.Hp), h = (int)(rem - (unsigned)w * (unsigned)a.Hp);
-        row_ok = row_ok && w >= 1 && w <= a.Wp - 2 && h >= 1 && h <= a.Hp - 2;     // a centre inside the un-padded map
-        if (a.stride2) {
-          row_ok = row_ok && (w & 1) && (h & 1);
-          mo = ((long long)item * a.Wop + ((w - 1) >> 1) + 1) * a.Hop + ((h - 1) >> 1) + 1;
-        }
-        if (row_ok && a.res_hi) {
-          const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + mo * a.ldc + n0);
-          const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + mo * a.ldc + n0);
-#pragma unroll
-          for (int q = 0; q < 4; q++) {
-            rh0[q] = rh[q];
-            rl0[q] = rl[q];
-          }
-        }
-      }
-      mbar_wait(&acc_full[acc], acc_phase);
-      tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * BN;
-      // TC_POOL: the rows' pooling weights go to shared memory; `brow` = first row of the tile that belongs to the NEXT item
-      // (a 128-row tile covers at most two items)
-      int brow = TC_BM;
-      if (EPI == TC_POOL) {
-        float4 pw = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < a.M) pw = *reinterpret_cast<const float4*>(a.pool_w + m * 4);
-        reinterpret_cast<float4*>(pool_stage + 128 * 33)[quad * 32 + lane] = pw;     // row of the tile = TMEM lane
-        const long long first = (long long)mt * TC_BM;
-        const long long nxt = (first / a.pool_item_rows + 1) * a.pool_item_rows;
-        brow = nxt - first < TC_BM ? (int)(nxt - first) : TC_BM;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-      }
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        tmem_ld32(taddr + c, r);
-        if (EPI != TC_POOL && n0 + c >= a.N) continue;
-        float v[32];
-        if (EPI == TC_POOL) {
-          // bias -> LeakyReLU -> BatchNorm affine, then the deviation from the per-channel pivot (the BatchNorm shift) goes to
-          // shared memory; thread (row group rg, column col) then sums its 32 rows for the K speakers -- independent
-          // accumulators, no cross-lane traffic -- split at `brow` between the tile's two items
-          float* dsm = pool_stage;                    // [128][33]
-          const float4* wsm = reinterpret_cast<const float4*>(pool_stage + 128 * 33);
-          float* stg = pool_stage + 128 * 33 + 128 * 4;   // [rg 4][item 2][8][32]
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            float x = leaky(__uint_as_float(r[i]) + params[c + i]);
-            x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
-            dsm[(quad * 32 + lane) * 33 + i] = x - params[2 * BN + c + i];
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          {
-            const int rg = et >> 5, col = et & 31, r_lo = rg * 32, r_hi = r_lo + 32;
-#pragma unroll
-            for (int sg = 0; sg < 2; sg++) {
-              const int lo = sg == 0 ? r_lo : max(r_lo, brow), hi = sg == 0 ? min(r_hi, brow) : r_hi;
-              float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll 8
-              for (int rr = lo; rr < hi; rr++) {
-                const float dv = dsm[rr * 33 + col];
-                const float4 w4 = wsm[rr];
-                const float a0 = w4.x * dv, a1 = w4.y * dv, a2 = w4.z * dv, a3 = w4.w * dv;
-                s1[0] += a0; s1[1] += a1; s1[2] += a2; s1[3] += a3;
-                s2[0] = fmaf(a0, dv, s2[0]); s2[1] = fmaf(a1, dv, s2[1]); s2[2] = fmaf(a2, dv, s2[2]); s2[3] = fmaf(a3, dv, s2[3]);
-              }
-#pragma unroll
-              for (int k = 0; k < 4; k++) {
-                stg[((rg * 2 + sg) * 8 + 2 * k) * 32 + col] = s1[k];
-                stg[((rg * 2 + sg) * 8 + 2 * k + 1) * 32 + col] = s2[k];
-              }
-            }
-          }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
-          // 2 items x K speakers x 2 sums x 32 columns: the four row groups' totals are added in a fixed order
-          for (int idx = et; idx < 2 * a.pool_K * 2 * 32; idx += 128) {
-            const int col = idx & 31, j = (idx >> 5) % (2 * a.pool_K), sg = idx / (64 * a.pool_K);
-            const float tot = ((stg[((0 * 2 + sg) * 8 + j) * 32 + col] + stg[((1 * 2 + sg) * 8 + j) * 32 + col]) +
-                               stg[((2 * 2 + sg) * 8 + j) * 32 + col]) + stg[((3 * 2 + sg) * 8 + j) * 32 + col];
-            const int n = n0 + c + col;
-            if (n < a.N) a.pool_part[(((size_t)mt * 2 + sg) * 8 + j) * a.N + n] = tot;
-          }
-          continue;
-        }
-        if (EPI == TC_CONV2D) {
-          // BatchNorm2d(eval) affine -> (+ residual) -> ReLU
-#pragma unroll
-          for (int i = 0; i < 32; i++) v[i] = fmaf(__uint_as_float(r[i]), params[BN + c + i], params[2 * BN + c + i]);
-          if (row_ok && a.res_hi) {
-            const uint4* rh = reinterpret_cast<const uint4*>(a.res_hi + mo * a.ldc + n0 + c);
-            const uint4* rl = reinterpret_cast<const uint4*>(a.res_lo + mo * a.ldc + n0 + c);
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              const uint4 hq = c == 0 ? rh0[q] : rh[q], lq = c == 0 ? rl0[q] : rl[q];
-              const uint32_t hw[4] = {hq.x, hq.y, hq.z, hq.w}, lw[4] = {lq.x, lq.y, lq.z, lq.w};
-#pragma unroll
-              for (int e = 0; e < 4; e++) {
-                v[8 * q + 2 * e] += h16_to_f32((uint16_t)(hw[e] & 0xFFFFu), a.f16) + h16_to_f32((uint16_t)(lw[e] & 0xFFFFu), a.f16);
-                v[8 * q + 2 * e + 1] += h16_to_f32((uint16_t)(hw[e] >> 16), a.f16) + h16_to_f32((uint16_t)(lw[e] >> 16), a.f16);
-              }
-            }
-          }
-          if (a.relu) {
-#pragma unroll
-            for (int i = 0; i < 32; i++) v[i] = fmaxf(v[i], 0.f);
-          }
-          if (row_ok) {
-            if (a.out_f32) {
-              float* po = a.out_f32 + mo * a.ldc + n0 + c;
-#pragma unroll
-              for (int i = 0; i < 8; i++)
-                reinterpret_cast<float4*>(po)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            }
-            if (a.out_hi) {
-              uint32_t hi[16], lo[16];
-#pragma unroll
-              for (int i = 0; i < 16; i++) {
-                uint16_t h0, l0, h1, l1;
-                split_h16(v[2 * i], a.f16, h0, l0);
-                split_h16(v[2 * i + 1], a.f16, h1, l1);
-                hi[i] = pack_u16x2(h0, h1);
-                lo[i] = pack_u16x2(l0, l1);
-              }
-              uint4* ph = reinterpret_cast<uint4*>(a.out_hi + mo * a.ldc + n0 + c);
-              uint4* pl = reinterpret_cast<uint4*>(a.out_lo + mo * a.ldc + n0 + c);
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-              }
-            }
-          }
-          continue;
-        }
-#pragma unroll
-        for (int i = 0; i < 32; i++) {
-          float x = __uint_as_float(r[i]) + params[c + i];
-          if (EPI != TC_BIAS_F32) {
-            x = leaky(x);
-            x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
-          }
-          v[i] = x;
-        }
-        if (m < a.M) {
-          if (EPI == TC_LEAKY_BN_SPLIT) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-              uint16_t h0, l0, h1, l1;
-              split_h16(v[2 * i], a.f16, h0, l0);
-              split_h16(v[2 * i + 1], a.f16, h1, l1);
-              hi[i] = pack_u16x2(h0, h1);
-              lo[i] = pack_u16x2(l0, l1);
-            }
-            uint4* ph = reinterpret_cast<uint4*>(a.out_hi + m * a.ldc + n0 + c);
-            uint4* pl = reinterpret_cast<uint4*>(a.out_lo + m * a.ldc + n0 + c);
-            if (a.vec8) {
-#pragma unroll
-              for (int i = 0; i < 2; i++) {
-                st_global_v8(ph + 2 * i, hi[8 * i], hi[8 * i + 1], hi[8 * i + 2], hi[8 * i + 3], hi[8 * i + 4], hi[8 * i + 5],
-                             hi[8 * i + 6], hi[8 * i + 7]);
-                st_global_v8(pl + 2 * i, lo[8 * i], lo[8 * i + 1], lo[8 * i + 2], lo[8 * i + 3], lo[8 * i + 4], lo[8 * i + 5],
-                             lo[8 * i + 6], lo[8 * i + 7]);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 4; i++) {
-                ph[i] = make_uint4(hi[4 * i], hi[4 * i + 1], hi[4 * i + 2], hi[4 * i + 3]);
-                pl[i] = make_uint4(lo[4 * i], lo[4 * i + 1], lo[4 * i + 2], lo[4 * i + 3]);
-              }
-            }
-          } else {
-            float* po = a.out_f32 + m * a.ldc + n0 + c;
-            if (n0 + c + 32 <= a.N && a.vec8) {
-#pragma unroll
-              for (int i = 0; i < 4; i++)
-                st_global_v8(po + 8 * i, __float_as_uint(v[8 * i]), __float_as_uint(v[8 * i + 1]), __float_as_uint(v[8 * i + 2]),
-                             __float_as_uint(v[8 * i + 3]), __float_as_uint(v[8 * i + 4]), __float_as_uint(v[8 * i + 5]),
-                             __float_as_uint(v[8 * i + 6]), __float_as_uint(v[8 * i + 7]));
-            } else if (n0 + c + 32 <= a.N) {
-#pragma unroll
-              for (int i = 0; i < 8; i++)
-                reinterpret_cast<float4*>(po)[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; i++)
-                if (n0 + c + i < a.N) po[i] = v[i];
-            }
-          }
-        }
-      }
+      tc_epilogue_tile<BN, EPI>(a, params, pool_stage, tmem_base + acc * BN, mt, nt * BN, quad, lane, et,
+                                a.n_tiles > 1 || tile == (int)blockIdx.x, &acc_full[acc], acc_phase);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&acc_empty[acc]);
@@ -415,6 +446,157 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------ CTA-pair variant
+// The same GEMM on PAIRS of CTAs (cluster of two, tcgen05 cta_group::2): a pair owns a 256 x BN tile; each CTA loads the A rows of
+// its 128-row half and HALF of the W tile (BN / 2 rows), the even CTA issues M = 256 MMAs that read A from both CTAs' shared
+// memory and the two W halves as one N = BN operand, each CTA's tensor memory receives its 128 rows.  Per SM and k-block that is
+// 64 KB instead of 96 KB from L2 and 8 KB instead of 12 KB of operand reads per MMA pair -- the three-product GEMM at 128-row
+// tiles is bound by exactly these two rates -- and three pipeline stages instead of two.
+template <int BN>
+struct TcSmem2 {
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;          // 16 KB per plane (this CTA's 128 rows)
+  static constexpr int W_BYTES = (BN / 2) * TC_BK * 2;       // this CTA's half of the W tile
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int NSTAGE = BN == 256 ? 3 : 4;
+  static constexpr int PARAM_BYTES = 3 * BN * 4;
+  static constexpr int POOL_BYTES = (128 * 33 + 128 * 4 + 4 * 2 * 8 * 32) * 4;
+  static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;
+};
+
+template <int BN, int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
+                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcArgs a) {
+  using S = TcSmem2<BN>;
+  constexpr int NSTAGE = S::NSTAGE;
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* params = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES);
+  uint64_t* full = bars;                       // [NSTAGE] used in the even CTA: both CTAs' TMA -> MMA
+  uint64_t* empty = bars + NSTAGE;             // [NSTAGE] in each CTA: MMA (multicast commit) -> its TMA producer
+  uint64_t* acc_full = bars + 2 * NSTAGE;      // [2] in each CTA: MMA (multicast commit) -> its epilogue
+  uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2] used in the even CTA: epilogue warps of both CTAs -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  float* pool_stage = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES + 256);
+
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int rank = (int)cluster_ctarank();
+  const int pair = blockIdx.x >> 1, pairs = gridDim.x >> 1;
+  const int m_pairs = (a.m_tiles + 1) >> 1;
+  const int num_tiles = m_pairs * a.n_tiles;
+  const int kblocks = a.KW * a.cin_blocks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NSTAGE; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);     // four epilogue warps in each of the two CTAs
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(2 * BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // the peer's barriers are initialised before anything arrives on them
+  tc_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0, phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += pairs) {
+        const int mp = tile / a.n_tiles, nt = tile - mp * a.n_tiles;
+        const int m0 = (mp * 2 + rank) * TC_BM, n0 = nt * BN + rank * (BN / 2);
+        for (int j = 0; j < a.KW; j++) {
+          for (int cb = 0; cb < a.cin_blocks; cb++) {
+            mbar_wait(&empty[stage], phase ^ 1);
+            unsigned char* st = smem + stage * S::STAGE_BYTES;
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * S::STAGE_BYTES);       // this CTA's bytes + the peer's
+            const int kcol = (j * a.cin_blocks + cb) * TC_BK;
+            tma_load_2d_2sm(st, &tmA_hi, cb * TC_BK, m0 + a.tap_off[j], &full[stage]);
+            tma_load_2d_2sm(st + S::A_BYTES, &tmA_lo, cb * TC_BK, m0 + a.tap_off[j], &full[stage]);
+            tma_load_2d_2sm(st + 2 * S::A_BYTES, &tmW_hi, kcol, n0, &full[stage]);
+            tma_load_2d_2sm(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, kcol, n0, &full[stage]);
+            if (++stage == NSTAGE) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer (even CTA only)
+    if (rank == 0 && elect_one()) {
+      // D = f32, A = B = fp16 (or bf16), both K-major, N = BN, M = 256 across the pair
+      const uint32_t idesc = (1u << 4) | idesc_ab_format(a.f16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += pairs) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_c = tmem_base + acc * BN;
+        for (int kb = 0; kb < kblocks; kb++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + S::A_BYTES);
+          const uint64_t w_hi = umma_desc(sa + 2 * S::A_BYTES), w_lo = umma_desc(sa + 2 * S::A_BYTES + S::W_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < TC_BK / 16; ks++) {
+            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+            umma_f16_2sm(tmem_c, a_lo + adv, w_hi + adv, idesc, (kb | ks) != 0);
+            umma_f16_2sm(tmem_c, a_hi + adv, w_lo + adv, idesc, 1);
+            umma_f16_2sm(tmem_c, a_hi + adv, w_hi + adv, idesc, 1);
+          }
+          umma_commit_2sm(&empty[stage]);         // both CTAs' producers may refill the slot
+          if (++stage == NSTAGE) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit_2sm(&acc_full[acc]);          // both CTAs' epilogues
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5 of both CTAs)
+    const int quad = warp & 3;
+    const int et = threadIdx.x - 64;
+    int acc = 0, acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += pairs) {
+      const int mp = tile / a.n_tiles, nt = tile - mp * a.n_tiles;
+      tc_epilogue_tile<BN, EPI>(a, params, pool_stage, tmem_base + acc * BN, (long long)mp * 2 + rank, nt * BN, quad, lane, et,
+                                a.n_tiles > 1 || tile == pair, &acc_full[acc], acc_phase);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&acc_empty[acc]);
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                  // nothing of the peer is touched after this point
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN) : "memory");
   }
 }
 
@@ -438,6 +620,12 @@ static int make_map(CUtensorMap* m, const void* base, long long rows, int cols, 
     return -2;
   }
   return 0;
+}
+
+// DG_GEMM_1CTA=1: A/B switch, 256-wide tiles on single CTAs (the round-1 kernel) instead of CTA pairs
+static bool gemm_pairs_on() {
+  static const bool off = getenv("DG_GEMM_1CTA") && getenv("DG_GEMM_1CTA")[0] == '1';
+  return !off;
 }
 
 template <int BN, int EPI>
@@ -479,6 +667,23 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
   }
   const int sms = g.sm_limit > 0 ? std::min(g.sm_limit, usable_sms()) : usable_sms();
   const int tiles = a.m_tiles * a.n_tiles;
+  if constexpr (BN == 256 && (EPI == TC_BIAS_F32 || EPI == TC_LEAKY_BN_SPLIT || EPI == TC_LEAKY_BN_F32 || EPI == TC_POOL)) {
+    if (gemm_pairs_on() && a.m_tiles >= 4) {
+      using S2 = TcSmem2<BN>;
+      // the pair's CTAs each load HALF of the W tile: a second pair of maps with BN / 2-row boxes
+      CUtensorMap tw2_hi, tw2_lo;
+      if (make_map(&tw2_hi, g.W_hi, g.Npad, Ktot, Ktot, BN / 2) || make_map(&tw2_lo, g.W_lo, g.Npad, Ktot, Ktot, BN / 2)) return -2;
+      const int smem2 = S2::TOTAL + (EPI == TC_POOL ? S2::POOL_BYTES : 0);
+      static bool attr2_done[64] = {};
+      if (first_use_on_device(attr2_done))
+        DG_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+      const int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
+      const int pairs = std::min(pair_tiles, sms / 2);
+      gemm_tc2_kernel<BN, EPI><<<2 * pairs, TC_THREADS, smem2, st>>>(ta_hi, ta_lo, tw2_hi, tw2_lo, a);
+      DG_LAUNCHED();
+      return 0;
+    }
+  }
   const int grid = tiles < sms ? tiles : sms;
   gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL + (EPI == TC_POOL ? S::POOL_BYTES : 0), st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
   DG_LAUNCHED();

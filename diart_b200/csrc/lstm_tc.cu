@@ -206,8 +206,10 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
   }
 }
 
+// (launched as clusters of two CTAs only so that the 2 x ceil(B/16) CTAs fill whole TPCs: the GEMMs of the other streams run on
+// CTA PAIRS (gemm_tc2_kernel), which need both SMs of a TPC free)
 template <bool F16, bool TIMING, int NC>
-__global__ void __launch_bounds__(l3_threads(NC), 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(l3_threads(NC), 1)
 lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __restrict__ w_hi,
                 const uint16_t* __restrict__ w_lo /*both [2][512][128]*/, const float* __restrict__ gx, int B, int T,
                 int stride, int groups_per_dir, float* __restrict__ hout, uint16_t* __restrict__ out_hi,
