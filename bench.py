@@ -430,25 +430,30 @@ def run_ours(args):
         n_calls = max(3, min(args.steps, 10))
 
         def call_steps(n, first):
-            turns = 0
+            """the timed bracket is the reference's: `pipeline(batch)` only (inference.py:130-137); the batch objects exist before"""
+            turns, spent = 0, 0.0
             for i in range(n):
                 g0 = (first + i) * B
                 chunks = [SlidingWindowFeature(rows[i % NB][b], sw_of(g0 + b)) for b in range(B)]
+                t0 = time.perf_counter()
                 out = pipe(chunks)
+                spent += time.perf_counter() - t0
                 turns += sum(len(a) for a, _ in out)
-            return turns
+            return turns, spent
 
         call_steps(2, 0)
         barrier()
-        t0 = time.perf_counter()
-        n_turn_objs = call_steps(n_calls, 2)
-        call_s = time.perf_counter() - t0
+        pipe.call_profile = {}
+        n_turn_objs, call_s = call_steps(n_calls, 2)
+        prof = pipe.call_profile
+        pipe.call_profile = None
         t = torch.tensor([call_s], device=device, dtype=torch.float64)
         if dist is not None:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         call_line = {"value": world * n_calls * B * STEP_SECONDS / float(t.item()), "unit": UNIT,
                      "ms_per_call": 1e3 * float(t.item()) / n_calls, "calls": n_calls,
                      "h2d_bytes_per_step": B * CHUNK * 4, "d2h_bytes_per_step": B * 16 + 4 + 4 * (n_turn_objs // n_calls),
+                     "phases_ms_per_call": {k: round(1e3 * v / max(1, prof.get("calls", 1)), 3) for k, v in prof.items() if k != "calls"},
                      "api": "SpeakerDiarization.__call__(Sequence[SlidingWindowFeature]) -> Sequence[(Annotation, SlidingWindowFeature)], "
                             "synchronous per batch (dg_pipeline_call_host: threaded gather + upload of B separate pageable host "
                             "windows, fused step, device aggregation/binarisation, one D2H of the turn list)"}

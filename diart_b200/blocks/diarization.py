@@ -9,6 +9,7 @@ on the device too (``blocks/post.py``, ``csrc/post.cu``); the host only attaches
 from __future__ import annotations
 
 import ctypes as C
+import time
 from typing import Optional, Sequence, Tuple
 
 import numpy as np
@@ -83,6 +84,7 @@ class SpeakerDiarization(base.Pipeline):
         self._fused: Optional[C.c_void_p] = None
         self._pinned: Optional[torch.Tensor] = None
         self._post: Optional[DevicePostPath] = None
+        self.call_profile: Optional[dict] = None       # set to {} to accumulate seconds per phase of __call__
         self.reset()
 
     @staticmethod
@@ -220,6 +222,8 @@ class SpeakerDiarization(base.Pipeline):
         expected = int(np.rint(self.config.duration * self.config.sample_rate))
         if self._native_models() is None:
             return self._call_blockwise(waveforms, expected)
+        prof = self.call_profile          # None, or a dict of accumulated seconds per phase (bench.py)
+        t0 = time.perf_counter() if prof is not None else 0.0
         rows = []
         for w in waveforms:
             d = w.data
@@ -236,14 +240,23 @@ class SpeakerDiarization(base.Pipeline):
         header, turns = post.buffers(batch_size)
         ptrs = (C.c_void_p * batch_size)(*[r.__array_interface__["data"][0] for r in rows])
         n_turns = C.c_int()
+        t1 = time.perf_counter() if prof is not None else 0.0
         with torch.cuda.device(self.segmentation.device):
             _lib.check(_lib.lib().dg_pipeline_call_host(h, post.handle, ptrs, batch_size, expected, plan.ctypes.data,
                                                         header.ctypes.data, turns.ctypes.data, len(turns),
                                                         C.byref(n_turns), None, None))
+        t2 = time.perf_counter() if prof is not None else 0.0
         annotations = post.annotations(header, turns, n_turns.value, out_start, out_res, self.timestamp_shift)
+        t3 = time.perf_counter() if prof is not None else 0.0
         audio, self.chunk_buffer = aggregate_audio(self.chunk_buffer, waveforms, post.nw, self.config.step,
                                                    self.config.latency)
-        return list(zip(annotations, audio))
+        out = list(zip(annotations, audio))
+        if prof is not None:
+            t4 = time.perf_counter()
+            for key, dt in (("prepare", t1 - t0), ("library_call", t2 - t1), ("annotations", t3 - t2), ("audio", t4 - t3)):
+                prof[key] = prof.get(key, 0.0) + dt
+            prof["calls"] = prof.get("calls", 0) + 1
+        return out
 
     def call_stream(self, stream, batch_size: Optional[int] = None):
         """``__call__`` for the next ``batch_size`` windows (default: all available) of a

@@ -9,6 +9,11 @@
 #include <map>
 #include <memory>
 #include <sstream>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <atomic>
+#include <chrono>
 #include <thread>
 #include <vector>
 
@@ -49,6 +54,7 @@ int launch_stats_pool_ex(const float* x, int stride, int T, int C, const float* 
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
+  float wscale = 1.f;   // weight hi planes: the power-of-two factor both planes were multiplied by (upload_split)
   int ensure(size_t n) {
     if (n <= bytes) return 0;
     if (p) cudaFree(p);
@@ -114,7 +120,8 @@ static int upload_u16(DevBuf& b, const std::vector<uint16_t>& h) {
 // float32 [N][K] host weights -> zero-padded 16-bit hi/lo device planes [Npad][K]
 static int upload_split(DevBuf& hi, DevBuf& lo, const std::vector<float>& w_nk, int N, int Npad, int K) {
   std::vector<uint16_t> h((size_t)Npad * K), l((size_t)Npad * K);
-  split_weights_host(w_nk.data(), N, Npad, K, h.data(), l.data(), split_f16());
+  hi.wscale = lo.wscale = weight_plane_scale(w_nk.data(), (size_t)N * K, split_f16());
+  split_weights_host(w_nk.data(), N, Npad, K, h.data(), l.data(), split_f16(), hi.wscale);
   return (upload_u16(hi, h) || upload_u16(lo, l)) ? DG_ECUDA : 0;
 }
 
@@ -255,6 +262,7 @@ struct SincWork {
   DevBuf wmean, wrstd, p0, sc0, sh0, p1, sc1, sh1, p2, sc2, sh2;
   DevBuf a0h, a0l, c1, a1h, a1l, c2;   // tcgen05 path: 16-bit planes of the conv inputs, un-pooled conv outputs
   DevBuf craw, part;                   // stream form: raw convolution of the stream [P][80], statistics partials
+  DevBuf part3;                        // per-tile InstanceNorm partial sums of the pooling GEMM epilogues (conv1, conv2)
   SincPrep own_prep;                   // statistics + waveform planes when no shared ones are supplied
   const float* out = nullptr;          // conv2 output that the next layer normalises on load ...
   int out_pool = 0;                    // ... 1: still un-pooled (rows = 3x), MaxPool1d(3) is applied on load
@@ -355,9 +363,35 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
     if ((rc = launch_split_ex(k.p0.as<float>(), M0, 80, 80, 80, 0, g.S0, k.sc0.as<float>(), k.sh0.as<float>(),
                               k.a0h.p, k.a0l.p, st, stream_flag)))
       return rc;
+    // conv1 / conv2 with MaxPool1d(3) and the InstanceNorm partial sums in the GEMM epilogue (TC_MAXPOOL3): the un-pooled maps are
+    // never written, the statistics pass reads 2 x 2 x 64 floats per tile.  Needs items of at least 126 rows at both stages;
+    // DG_NO_POOL3_FUSE=1 = the round-1 path (un-pooled float32 map -> instnorm_stats -> split with pooling on load)
+    static const bool pool3_on = !(getenv("DG_NO_POOL3_FUSE") && getenv("DG_NO_POOL3_FUSE")[0] == '1');
+    if (pool3_on && g.S1 >= 126) {
+      if (k.part3.ensure((size_t)gemm_tc_pool3_tiles(M0) * 2 * 2 * 64 * 4)) return DG_ECUDA;
+      TcGemm t{};
+      t.A_hi = k.a0h.p; t.A_lo = k.a0l.p; t.lda = 80; t.Cin = 448; t.KW = 1; t.dil = 1; t.Mtot = M0; t.M = M0;
+      t.W_hi = w.w1_hi.p; t.w_scale = w.w1_hi.wscale; t.W_lo = w.w1_lo.p; t.Npad = 64; t.N = 64; t.bias = w.bias1.as<float>();
+      t.out_f32 = k.p1.as<float>(); t.ldc = 64; t.epi = 5; t.tag = "sinc_conv1";
+      t.pool_part = k.part3.as<float>(); t.pool_item_rows = g.S0; t.pool3_T = g.T1;
+      if ((rc = launch_gemm_tc(t, st)) ||
+          (rc = launch_instnorm_finalize(k.part3.as<float>(), B, g.S0, g.T1, 64, 64, w.bias1.as<float>(), w.g1.as<float>(),
+                                         w.b1.as<float>(), k.sc1.as<float>(), k.sh1.as<float>(), 64, st)) ||
+          (rc = launch_split_ex(k.p1.as<float>(), M1, 64, 64, 64, 0, g.S1, k.sc1.as<float>(), k.sh1.as<float>(), k.a1h.p, k.a1l.p, st)))
+        return rc;
+      t.A_hi = k.a1h.p; t.A_lo = k.a1l.p; t.lda = 64; t.Cin = 64; t.KW = 5; t.Mtot = M1; t.M = M1;
+      t.W_hi = w.w2_hi.p; t.w_scale = w.w2_hi.wscale; t.W_lo = w.w2_lo.p; t.bias = w.bias2.as<float>();
+      t.out_f32 = k.p2.as<float>(); t.tag = "sinc_conv2";
+      t.pool_item_rows = g.S1; t.pool3_T = g.T2;
+      if ((rc = launch_gemm_tc(t, st))) return rc;
+      k.out = k.p2.as<float>();
+      k.out_pool = 0;
+      return launch_instnorm_finalize(k.part3.as<float>(), B, g.S1, g.T2, 64, 64, w.bias2.as<float>(), w.g2.as<float>(),
+                                      w.b2.as<float>(), k.sc2.as<float>(), k.sh2.as<float>(), 64, st);
+    }
     TcGemm t{};
     t.A_hi = k.a0h.p; t.A_lo = k.a0l.p; t.lda = 80; t.Cin = 448; t.KW = 1; t.dil = 1; t.Mtot = M0; t.M = M0;
-    t.W_hi = w.w1_hi.p; t.W_lo = w.w1_lo.p; t.Npad = 64; t.N = 64; t.bias = w.bias1.as<float>();
+    t.W_hi = w.w1_hi.p; t.w_scale = w.w1_hi.wscale; t.W_lo = w.w1_lo.p; t.Npad = 64; t.N = 64; t.bias = w.bias1.as<float>();
     t.out_f32 = k.c1.as<float>(); t.ldc = 64; t.epi = 0; t.tag = "sinc_conv1";
     if ((rc = launch_gemm_tc(t, st))) return rc;
     if ((rc = launch_instnorm_stats(k.c1.as<float>(), B, g.S0, g.T1, 64, 64, w.g1.as<float>(), w.b1.as<float>(),
@@ -368,7 +402,7 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
                               k.a1h.p, k.a1l.p, st)))
       return rc;
     t.A_hi = k.a1h.p; t.A_lo = k.a1l.p; t.lda = 64; t.Cin = 64; t.KW = 5; t.Mtot = M1; t.M = M1;
-    t.W_hi = w.w2_hi.p; t.W_lo = w.w2_lo.p; t.bias = w.bias2.as<float>();
+    t.W_hi = w.w2_hi.p; t.w_scale = w.w2_hi.wscale; t.W_lo = w.w2_lo.p; t.bias = w.bias2.as<float>();
     t.out_f32 = k.c2.as<float>(); t.tag = "sinc_conv2";
     if ((rc = launch_gemm_tc(t, st))) return rc;
     k.out = k.c2.as<float>();
@@ -459,7 +493,7 @@ static int seg_prepare(dg_seg* h, const Tensors& t) {
     if (upload_split(h->wih_hi[L], h->wih_lo[L], w_nk, 1024, 1024, in_pad)) return DG_ECUDA;
     {
       std::vector<uint16_t> rh(lstm_tc_plane_elems()), rl(lstm_tc_plane_elems());
-      lstm_tc_pack_whh(hh[0], hh[1], rh.data(), rl.data(), split_f16());
+      h->whh_hi[L].wscale = lstm_tc_pack_whh(hh[0], hh[1], rh.data(), rl.data(), split_f16());
       if (upload_u16(h->whh_hi[L], rh) || upload_u16(h->whh_lo[L], rl)) return DG_ECUDA;
     }
   }
@@ -644,7 +678,7 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
       if (rc) return rc;
       TcGemm t{};
       t.A_hi = w.xh.p; t.A_lo = w.xl.p; t.lda = cin; t.Cin = cin; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
-      t.W_hi = h->wih_hi[L].p; t.W_lo = h->wih_lo[L].p; t.Npad = 1024; t.N = 1024; t.bias = h->bih[L].as<float>();
+      t.W_hi = h->wih_hi[L].p; t.w_scale = h->wih_hi[L].wscale; t.W_lo = h->wih_lo[L].p; t.Npad = 1024; t.N = 1024; t.bias = h->bih[L].as<float>();
       t.out_f32 = w.gx.as<float>(); t.ldc = 1024; t.epi = 0; t.tag = "lstm_inproj";
       if ((rc = launch_gemm_tc(t, st))) return rc;
       float* hout = hbuf[L & 1];
@@ -653,7 +687,7 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
       if (lstm_simt)
         rc = launch_lstm_layer(w.gx.as<float>(), h->whh[L].as<float>(), B, g.T2, g.S2, hout, st);
       else
-        rc = launch_lstm_layer_tc(w.gx.as<float>(), h->whh_hi[L].p, h->whh_lo[L].p, B, g.T2, g.S2, nullptr, w.xh.p, w.xl.p, st);
+        rc = launch_lstm_layer_tc(w.gx.as<float>(), h->whh_hi[L].p, h->whh_lo[L].p, h->whh_hi[L].wscale, B, g.T2, g.S2, nullptr, w.xh.p, w.xl.p, st);
       if (rc) return rc;
       hin = hout;
       continue;
@@ -680,12 +714,12 @@ extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* 
     if (lstm_simt2 && (rc = launch_split(hin, M, 256, g.S2, nullptr, nullptr, w.xh.p, w.xl.p, st))) return rc;
     TcGemm t{};
     t.A_hi = w.xh.p; t.A_lo = w.xl.p; t.lda = 256; t.Cin = 256; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
-    t.W_hi = h->l1_hi.p; t.W_lo = h->l1_lo.p; t.Npad = 128; t.N = 128; t.bias = h->l1b.as<float>();
+    t.W_hi = h->l1_hi.p; t.w_scale = h->l1_hi.wscale; t.W_lo = h->l1_lo.p; t.Npad = 128; t.N = 128; t.bias = h->l1b.as<float>();
     t.bn_scale = h->ones128.as<float>(); t.bn_shift = h->zeros128.as<float>();
     t.out_hi = w.y1h.p; t.out_lo = w.y1l.p; t.ldc = 128; t.epi = 1; t.tag = "seg_linear";
     if ((rc = launch_gemm_tc(t, st))) return rc;
     t.A_hi = w.y1h.p; t.A_lo = w.y1l.p; t.lda = 128; t.Cin = 128;
-    t.W_hi = h->l2_hi.p; t.W_lo = h->l2_lo.p; t.bias = h->l2b.as<float>();
+    t.W_hi = h->l2_hi.p; t.w_scale = h->l2_hi.wscale; t.W_lo = h->l2_lo.p; t.bias = h->l2b.as<float>();
     t.out_hi = nullptr; t.out_lo = nullptr; t.out_f32 = w.y2.as<float>(); t.epi = 2;
     if ((rc = launch_gemm_tc(t, st))) return rc;
     return seg_head_final(h, w.y2.as<float>(), B, g, seg, st);
@@ -961,7 +995,7 @@ static int resnet_conv(const ResConv& c, const void* in_hi, const void* in_lo, i
   TcGemm t{};
   const long long rows = (long long)U * Wp * Hp;
   t.A_hi = in_hi; t.A_lo = in_lo; t.lda = c.lda; t.Cin = c.cin_gemm; t.KW = c.KW; t.dil = 1; t.Mtot = rows; t.M = rows;
-  t.W_hi = c.w_hi.p; t.W_lo = c.w_lo.p; t.Npad = c.cout <= 64 ? c.cout : (c.cout + 127) / 128 * 128; t.N = c.cout;
+  t.W_hi = c.w_hi.p; t.w_scale = c.w_hi.wscale; t.W_lo = c.w_lo.p; t.Npad = c.cout <= 64 ? c.cout : (c.cout + 127) / 128 * 128; t.N = c.cout;
   t.bn_scale = c.sc.as<float>(); t.bn_shift = c.sh.as<float>();
   t.out_hi = out_hi; t.out_lo = out_lo; t.out_f32 = out_f32; t.ldc = c.cout; t.epi = 3; t.tag = tag;
   t.tap_off = taps; t.Wp = Wp; t.Hp = Hp; t.Wop = Wop; t.Hop = Hop; t.stride2 = c.stride == 2; t.relu = relu;
@@ -1001,7 +1035,7 @@ static int resnet_trunk(dg_emb* h, const float* wav, int U, int S, cudaStream_t 
     TcGemm t{};
     t.A_hi = r.wav_hi.p; t.A_lo = r.wav_lo.p; t.lda = 160; t.Cin = 448; t.KW = 1; t.dil = 1;
     t.Mtot = (long long)U * rpi; t.M = (long long)U * rpi;
-    t.W_hi = r.fb_hi.p; t.W_lo = r.fb_lo.p; t.Npad = 640; t.N = 640; t.out_f32 = r.spec.as<float>(); t.ldc = 640; t.epi = 0;
+    t.W_hi = r.fb_hi.p; t.w_scale = r.fb_hi.wscale; t.W_lo = r.fb_lo.p; t.Npad = 640; t.N = 640; t.out_f32 = r.spec.as<float>(); t.ldc = 640; t.epi = 0;
     t.tag = "fbank_dft";
     if ((rc = launch_gemm_tc(t, st))) return rc;
   }
@@ -1214,7 +1248,7 @@ static int emb_trunk(dg_emb* h, const float* wav, int U, const Geom& g, cudaStre
       }
       TcGemm t{};
       t.A_hi = ih; t.A_lo = il; t.lda = cin; t.Cin = cin; t.KW = TD_K[L]; t.dil = TD_DIL[L]; t.Mtot = M; t.M = M;
-      t.W_hi = h->tw_hi[L].p; t.W_lo = h->tw_lo[L].p; t.Npad = (TD_OUT[L] + 255) / 256 * 256; t.N = TD_OUT[L];
+      t.W_hi = h->tw_hi[L].p; t.w_scale = h->tw_hi[L].wscale; t.W_lo = h->tw_lo[L].p; t.Npad = (TD_OUT[L] + 255) / 256 * 256; t.N = TD_OUT[L];
       t.bias = h->tb[L].as<float>(); t.bn_scale = h->bns[L].as<float>(); t.bn_shift = h->bnh[L].as<float>();
       t.tag = kTags[L];
       if (L == 4) {
@@ -1270,7 +1304,7 @@ static int emb_tdnn5_pool(dg_emb* h, int U, const Geom& g, const float* weights,
     return rc;
   TcGemm t{};
   t.A_hi = h->t4h; t.A_lo = h->t4l; t.lda = 512; t.Cin = 512; t.KW = 1; t.dil = 1; t.Mtot = M; t.M = M;
-  t.W_hi = h->tw_hi[4].p; t.W_lo = h->tw_lo[4].p; t.Npad = 1536; t.N = 1500;
+  t.W_hi = h->tw_hi[4].p; t.w_scale = h->tw_hi[4].wscale; t.W_lo = h->tw_lo[4].p; t.Npad = 1536; t.N = 1500;
   t.bias = h->tb[4].as<float>(); t.bn_scale = h->bns[4].as<float>(); t.bn_shift = h->bnh[4].as<float>();
   t.ldc = 1500; t.epi = 4; t.tag = "tdnn5";
   t.pool_w = h->pool_rw.as<float>(); t.pool_part = h->pool_part.as<float>(); t.pool_item_rows = g.S2; t.pool_K = K;
@@ -1294,7 +1328,7 @@ static int emb_project(dg_emb* h, int rows, int normalize, float norm, float* ou
     }
     TcGemm t{};
     t.A_hi = h->ph.p; t.A_lo = h->pl.p; t.lda = kpad; t.Cin = kpad; t.KW = 1; t.dil = 1; t.Mtot = rows; t.M = rows;
-    t.W_hi = h->ew_hi.p; t.W_lo = h->ew_lo.p; t.Npad = (h->D + 255) / 256 * 256; t.N = h->D;
+    t.W_hi = h->ew_hi.p; t.w_scale = h->ew_hi.wscale; t.W_lo = h->ew_lo.p; t.Npad = (h->D + 255) / 256 * 256; t.N = h->D;
     t.bias = h->eb.as<float>(); t.out_f32 = dst; t.ldc = h->D; t.epi = 0; t.tag = "emb_linear";
     if ((rc = launch_gemm_tc(t, st))) return rc;
     return normalize ? launch_l2norm(dst, rows, h->D, norm, out, st) : 0;
@@ -1597,7 +1631,7 @@ extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int e
   if ((rc = launch_split(dA.as<float>(), Mtot, Cin, 1, nullptr, nullptr, dAh.p, dAl.p, nullptr))) return rc;
   TcGemm t{};
   t.A_hi = dAh.p; t.A_lo = dAl.p; t.lda = Cin; t.Cin = Cin; t.KW = KW; t.dil = dil; t.Mtot = Mtot; t.M = M;
-  t.W_hi = dWh.p; t.W_lo = dWl.p; t.Npad = npad; t.N = N; t.bias = dB.as<float>(); t.bn_scale = dS.as<float>();
+  t.W_hi = dWh.p; t.w_scale = dWh.wscale; t.W_lo = dWl.p; t.Npad = npad; t.N = N; t.bias = dB.as<float>(); t.bn_scale = dS.as<float>();
   t.bn_shift = dH.as<float>(); t.out_f32 = dC1.as<float>(); t.out_hi = dOh.p; t.out_lo = dOl.p; t.ldc = N;
   t.epi = epi; t.tag = "selftest_tc";
   if ((rc = launch_gemm_tc(t, nullptr))) return rc;
@@ -1642,6 +1676,64 @@ extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int e
 }
 
 // ================================================================================ fused pipeline
+// Persistent worker threads for the host-side gather of dg_pipeline_call_host (B separate pageable windows -> pinned staging):
+// created once per pipeline handle; a job is one callable that every worker runs concurrently (the callable hands out work
+// items through its own atomic counter).
+class GatherPool {
+ public:
+  explicit GatherPool(int n) {
+    for (int i = 0; i < n; i++) th_.emplace_back([this] { loop(); });
+  }
+  ~GatherPool() {
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      stop_ = true;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  int size() const { return (int)th_.size(); }
+  void start(std::function<void()> fn) {       // returns at once; wait() returns when every worker has finished fn
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      job_ = std::move(fn);
+      generation_++;
+      active_ = (int)th_.size();
+    }
+    cv_.notify_all();
+  }
+  void wait() {
+    std::unique_lock<std::mutex> lk(mu_);
+    done_.wait(lk, [this] { return active_ == 0; });
+  }
+
+ private:
+  void loop() {
+    int seen = 0;
+    for (;;) {
+      std::function<void()> fn;
+      {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+        if (stop_) return;
+        seen = generation_;
+        fn = job_;
+      }
+      fn();
+      {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (--active_ == 0) done_.notify_all();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  std::function<void()> job_;
+  int generation_ = 0, active_ = 0;
+  bool stop_ = false;
+};
+
 struct dg_pipeline {
   dg_seg* seg;
   dg_emb* emb;
@@ -1674,6 +1766,7 @@ struct dg_pipeline {
   bool overlap_known = false;     // the current dg_pipeline_step batch was formed from a dg_stream (windows overlap by construction)
   void* pin_wav = nullptr;        // pinned staging of dg_pipeline_call_host (B separate host windows -> one upload)
   size_t pin_wav_bytes = 0;
+  std::unique_ptr<GatherPool> gather;   // worker threads of the host gather (created at the first dg_pipeline_call_host)
 };
 
 extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
@@ -1749,7 +1842,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   {
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->seg->device);
-    const int lstm_ctas = 2 * ((B + 15) / 16);
+    const int lstm_ctas = lstm_tc_ctas(B);
     g_sm_limit = sms - lstm_ctas > sms / 2 ? sms - lstm_ctas : 0;
     h->emb->shared_prep = shared;
     rc = emb_trunk(h->emb, wav, B, g, h->s_emb, &T, fuse_pool);
@@ -1772,7 +1865,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     // (persistent grid capped like the trunk's: the other lane's recurrence may hold 2 x ceil(B/16) SMs at this point)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->seg->device);
-    const int lstm_ctas = 2 * ((B + 15) / 16);
+    const int lstm_ctas = lstm_tc_ctas(B);
     g_sm_limit = sms - lstm_ctas > sms / 2 ? sms - lstm_ctas : 0;
     rc = emb_tdnn5_pool(h->emb, B, g, osp.as<float>(), F, K, T, h->s_emb);
     if (!rc) rc = emb_project(h->emb, B * K, 1, 1.f, emb, h->s_emb);
@@ -2271,14 +2364,18 @@ extern "C" int dg_post_step(dg_post* h, const float* seg_dev, const int32_t* map
 //      (as rearrange_audio_stream emits them) are gathered into pinned staging by worker threads while earlier rows are
 //      already on their way to the device, then fused step + post-path, one D2H of the turn list.
 static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, float* pin, float* dst_dev, cudaStream_t st) {
-  const int R = 8;                                    // rows per work item
+  const int R = 4;                                    // rows per work item (1.3 MB at S = 80000)
   const int items = (B + R - 1) / R;
-  int nthreads = (int)std::thread::hardware_concurrency();
-  nthreads = std::max(1, std::min({nthreads, 16, items}));
+  if (!h->gather) {
+    int n = (int)std::thread::hardware_concurrency();
+    static const int env_threads = getenv("DG_GATHER_THREADS") ? atoi(getenv("DG_GATHER_THREADS")) : 0;
+    n = env_threads > 0 ? env_threads : std::max(1, std::min(n - 2, 24));
+    h->gather.reset(new GatherPool(n));
+  }
   std::vector<std::atomic<int>> done(items);
   for (auto& d : done) d.store(0, std::memory_order_relaxed);
   std::atomic<int> next{0};
-  auto work = [&]() {
+  h->gather->start([&]() {
     for (;;) {
       const int it = next.fetch_add(1, std::memory_order_relaxed);
       if (it >= items) return;
@@ -2286,16 +2383,13 @@ static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, f
       for (int r = r0; r < r1; r++) memcpy(pin + (size_t)r * S, rows[r], (size_t)S * 4);
       done[it].store(1, std::memory_order_release);
     }
-  };
-  std::vector<std::thread> pool;
-  for (int t = 1; t < nthreads; t++) pool.emplace_back(work);
+  });
+  // the calling thread forwards finished items, in order, in runs of up to 8 (~10 MB per copy)
   cudaError_t err = cudaSuccess;
-  if (nthreads == 1) work();
-  // the calling thread forwards finished items, in order, in runs of up to 4 (~10 MB per copy)
   int sent = 0;
   while (sent < items) {
     int upto = sent;
-    while (upto < items && upto - sent < 4 && done[upto].load(std::memory_order_acquire)) upto++;
+    while (upto < items && upto - sent < 8 && done[upto].load(std::memory_order_acquire)) upto++;
     if (upto == sent) {
       std::this_thread::yield();
       continue;
@@ -2305,7 +2399,7 @@ static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, f
       err = cudaMemcpyAsync(dst_dev + (size_t)r0 * S, pin + (size_t)r0 * S, (size_t)(r1 - r0) * S * 4, cudaMemcpyHostToDevice, st);
     sent = upto;
   }
-  for (auto& t : pool) t.join();
+  h->gather->wait();          // (`next` and `done` live on this frame)
   DG_CUDA(err);
   return 0;
 }
@@ -2330,6 +2424,9 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
     return DG_EINVAL;
   }
   DG_CUDA(cudaSetDevice(h->seg->device));
+  // DG_CALL_TIMING=1: host wall-clock phases of the call on stderr (diagnostic)
+  static const bool call_timing = getenv("DG_CALL_TIMING") && getenv("DG_CALL_TIMING")[0] == '1';
+  const auto tc0 = std::chrono::steady_clock::now();
   if (h->segd.ensure((size_t)B * F * K * 4) || h->mapd.ensure((size_t)B * K * 4)) return DG_ECUDA;
   const size_t bytes = (size_t)B * S * 4;
   if (bytes > h->pin_wav_bytes) {
@@ -2341,13 +2438,45 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
   // The batch runs as up to three sub-batches through the pipelined machinery (dg_pipeline_submit_host): the upload of
   // sub-batch j+1 and its front end overlap the recurrence of sub-batch j; clustering stays in chunk order on its one stream,
   // so the result is exactly that of one step over the whole batch.  DG_CALL_SPLIT = 1..3 (default 2 from 128 windows on).
-  static const int split_env = getenv("DG_CALL_SPLIT") ? atoi(getenv("DG_CALL_SPLIT")) : 0;
-  int nsplit = split_env > 0 ? std::min(split_env, DG_MAX_INFLIGHT) : (B >= 128 ? 2 : 1);
-  nsplit = std::max(1, std::min(nsplit, B / 8 > 0 ? B / 8 : 1));
-  const int Bs = (B + nsplit - 1) / nsplit;
-  int slots[DG_MAX_INFLIGHT], nbs[DG_MAX_INFLIGHT], ns = 0;
-  for (int r0 = 0; r0 < B; r0 += Bs, ns++) {
-    const int nb = std::min(Bs, B - r0);
+  // sub-batch sizes: DG_CALL_PLAN="n1,n2[,n3]" (windows; must add up to B) or DG_CALL_SPLIT = 1..3 equal parts; default
+  // from 192 windows on: three parts -- a short first one so that the device starts early and a short last one, because
+  // its dependent chain (1172 recurrence steps + its share of the clustering) is what the caller waits for at the end
+  int plan[DG_MAX_INFLIGHT] = {B, 0, 0}, ns = 1;
+  {
+    static const int split_env = getenv("DG_CALL_SPLIT") ? atoi(getenv("DG_CALL_SPLIT")) : 0;
+    static const std::string plan_env = getenv("DG_CALL_PLAN") ? getenv("DG_CALL_PLAN") : "";
+    int vals[DG_MAX_INFLIGHT] = {0, 0, 0}, nv = 0, sum = 0;
+    if (!plan_env.empty()) {
+      std::stringstream ss(plan_env);
+      std::string tok;
+      while (nv < DG_MAX_INFLIGHT && std::getline(ss, tok, ',')) {
+        vals[nv] = atoi(tok.c_str());
+        sum += vals[nv];
+        if (vals[nv++] < 1) sum = -1 << 20;
+      }
+    }
+    if (nv > 0 && sum == B) {
+      ns = nv;
+      for (int j = 0; j < nv; j++) plan[j] = vals[j];
+    } else if (split_env > 0) {
+      ns = std::max(1, std::min({split_env, DG_MAX_INFLIGHT, B / 8 > 0 ? B / 8 : 1}));
+      const int Bs = (B + ns - 1) / ns;
+      for (int j = 0, left = B; j < ns; j++, left -= Bs) plan[j] = std::min(Bs, left);
+      while (ns > 1 && plan[ns - 1] <= 0) ns--;
+    } else if (B >= 192) {
+      ns = 3;
+      plan[0] = (B * 5 / 16 + 7) / 8 * 8;
+      plan[2] = (B * 4 / 16 + 7) / 8 * 8;
+      plan[1] = B - plan[0] - plan[2];
+    } else if (B >= 64) {
+      ns = 2;
+      plan[0] = (B / 2 + 7) / 8 * 8;
+      plan[1] = B - plan[0];
+    }
+  }
+  int slots[DG_MAX_INFLIGHT], nbs[DG_MAX_INFLIGHT];
+  for (int j = 0, r0 = 0; j < ns; r0 += plan[j], j++) {
+    const int nb = plan[j];
     const int slot = (int)(h->next_step % 3);
     if ((rc = pipeline_slot_prepare(h, slot, nb, S, F, K, true))) return rc;
     DG_CUDA(cudaStreamWaitEvent(h->s_h2d, h->e_slot_done[slot], 0));
@@ -2356,8 +2485,8 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
       return rc;
     DG_CUDA(cudaEventRecord(h->e_h2d[slot], h->s_h2d));
     if ((rc = pipeline_submit_common(h, h->slot_wav[slot].as<float>(), nb, S, F, K, slot, h->e_h2d[slot]))) return rc;
-    slots[ns] = slot;
-    nbs[ns] = nb;
+    slots[j] = slot;
+    nbs[j] = nb;
   }
   for (int j = 0, r0 = 0; j < ns; r0 += nbs[j], j++) {     // gather the sub-batches' scores / maps, in order
     DG_CUDA(cudaStreamWaitEvent(h->st, h->e_slot_done[slots[j]], 0));
@@ -2367,11 +2496,28 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
                             cudaMemcpyDeviceToDevice, h->st));
     h->outstanding--;
   }
+  const auto tc1 = std::chrono::steady_clock::now();
   if ((rc = post_enqueue(post, h->segd.as<float>(), h->mapd.as<int32_t>(), B, plan_host, h->st))) return rc;
   if (seg_host) DG_CUDA(cudaMemcpyAsync(seg_host, h->segd.p, (size_t)B * F * K * 4, cudaMemcpyDeviceToHost, h->st));
   if (map_host) DG_CUDA(cudaMemcpyAsync(map_host, h->mapd.p, (size_t)B * K * 4, cudaMemcpyDeviceToHost, h->st));
   DG_CUDA(cudaStreamSynchronize(h->st));
-  return post_finish(post, B, header_host, turns_host, turn_cap_host, n_turns, h->st);
+  const auto tc2 = std::chrono::steady_clock::now();
+  rc = post_finish(post, B, header_host, turns_host, turn_cap_host, n_turns, h->st);
+  if (call_timing) {
+    static double acc[3] = {0, 0, 0};
+    static int calls = 0;
+    const auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+      return std::chrono::duration<double, std::milli>(b - a).count(); };
+    acc[0] += ms(tc0, tc1);
+    acc[1] += ms(tc1, tc2);
+    acc[2] += ms(tc2, std::chrono::steady_clock::now());
+    if (++calls % 4 == 0) {
+      fprintf(stderr, "dg_pipeline_call_host (B=%d, %d sub-batches): gather + upload + enqueue %.2f ms | wait for the device %.2f ms | "
+                      "turn list %.2f ms (mean of 4 calls)\n", B, ns, acc[0] / 4, acc[1] / 4, acc[2] / 4);
+      acc[0] = acc[1] = acc[2] = 0;
+    }
+  }
+  return rc;
 }
 
 // ---- shared-identity mode (BASELINE config 5) without leaving the pipelined flow.  After dg_pipeline_submit*:

@@ -107,6 +107,8 @@ int launch_sinc0(const float* wav, const float* mean, const float* rstd, float w
                  const float* filt /*[251][80]*/, int B, const Geom& g, float* p0 /*[B,S0,80]*/, cudaStream_t st);
 int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
                           const float* beta, float* sc, float* sh, cudaStream_t st, int pool = 0, const int* skip_flag = nullptr);
+int launch_instnorm_finalize(const float* part, int B, int item_rows, int T, int C, int N, const float* bias, const float* gamma,
+                             const float* beta, float* sc, float* sh, int ld, cudaStream_t st);
 // gemm.cu
 enum Epi { EPI_BIAS = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_LEAKY_BN = 2, EPI_BIAS_POOL3 = 3 };
 struct GemmArgs {
@@ -139,6 +141,7 @@ struct TcGemm {
   long long Mtot, M;
   const void* W_hi;    // bf16 [Npad, KW*Cin]  (n-major: row n holds its K weights, tap-major)
   const void* W_lo;
+  float w_scale;       // power-of-two factor the W planes were multiplied by (0 = 1): undone on the accumulator
   int Npad, N;
   const float* bias;
   const float* bn_scale;
@@ -162,7 +165,12 @@ struct TcGemm {
   const float* pool_w;   // [Mtot][4]
   float* pool_part;      // [m_tiles][2][4][2][N]
   int pool_item_rows, pool_K;
+  // epi 5 (SincNet Conv1d + MaxPool1d(3) + InstanceNorm statistics): out_f32 = bias + max over row triplets ([M / 3, ldc]),
+  // pool_part = per-tile partial sums [ceil(M / 126)][2][2][N] (gemm_tc_pool3_tiles), reduced by launch_instnorm_finalize;
+  // pool_item_rows = un-pooled rows per item (multiple of 3), pool3_T = valid pooled frames per item
+  int pool3_T;
 };
+inline long long gemm_tc_pool3_tiles(long long M) { return (M + 125) / 126; }
 int launch_gemm_tc(const TcGemm& g, cudaStream_t st);
 int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
                  void* lo, cudaStream_t st);
@@ -170,7 +178,8 @@ int launch_split_ex(const float* x, long long rows_out, int C, int ld_in, int ld
                     const float* sc, const float* sh, void* hi, void* lo, cudaStream_t st, const int* skip_flag = nullptr);
 // element type of the 16-bit operand planes: 1 = fp16 (default), 0 = bf16 (DG_SPLIT_BF16=1); fixed at first use
 int split_f16();
-void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo, int f16);
+void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo, int f16, float scale = 1.f);
+float weight_plane_scale(const float* w, size_t n, int f16);   // power of two that keeps the lo plane of small weights normal
 uint16_t host_f32_to_h16(float f, int f16);
 float host_h16_to_f32(uint16_t h, int f16);
 // sinc_tc.cu -- SincNet stage 0 on tcgen05 (overlapping-row TMA view of the waveform)
@@ -208,10 +217,11 @@ size_t lstm_whh_packed_floats();
 void lstm_pack_whh(const float* whh_fwd /*[512][128]*/, const float* whh_bwd, float* packed);
 // lstm_tc.cu -- recurrence on tcgen05 (W_hh hi plane in shared memory, lo plane in tensor memory)
 size_t lstm_tc_plane_elems();
-void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16);
-// `hout` (float32 [B*stride][256]) and/or the hi/lo planes `out_hi`, `out_lo` ([B*stride][256] 16-bit) receive h_t
-int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, int B, int T, int stride, float* hout,
-                         void* out_hi, void* out_lo, cudaStream_t st);
+int lstm_tc_ctas(int B);   // CTAs (= SMs) one recurrence launch occupies at batch B
+float lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16);   // -> plane scale
+// hout (float32) and / or out_hi, out_lo (16-bit planes of the next GEMM's operand) receive h_t
+int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, float w_scale, int B, int T, int stride,
+                         float* hout, void* out_hi, void* out_lo, cudaStream_t st);
 // heads.cu
 int launch_seg_final(const float* y /*[B*stride,128]*/, const float* wc /*[K][128]*/, const float* bc, int B, int T,
                      int stride, int K, float* seg /*[B,T,K]*/, cudaStream_t st);

@@ -24,6 +24,7 @@
 //               planes; overlaps the next tile's MMAs through the second accumulator.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -49,6 +50,7 @@ struct TcArgs {
   __nv_bfloat16* out_lo;
   int ldc;
   int f16;              // operand planes are fp16 (1) or bf16 (0)
+  float acc_scale;      // 1 / (power-of-two scale of the weight planes): applied to the accumulator in the epilogue
   int vec8;             // output rows are 32-byte aligned: 256-bit stores
   int tap_off[9];       // row offset of every tap (Conv1d: j * dil; Conv2d on a zero-padded map: (dw-1) * Hp + (dh-1))
   // TC_CONV2D: rows are positions (item, w, h) of a zero-padded [Wp][Hp] map; outputs go to the padded map [Wop][Hop] of the
@@ -60,9 +62,13 @@ struct TcArgs {
   const float* pool_w;     // [rows][4]: pooling weight of (row, speaker), zero for rows past an item's valid frames
   float* pool_part;        // [m_tiles][2 (item of the tile)][4 (speaker)][2 (sum w d, sum w d^2)][N]
   int pool_item_rows, pool_K;
+  // TC_MAXPOOL3: m-tiles advance by `tile_rows` = 126 rows (42 pooling windows; the MMA still covers 128), out_f32 receives
+  // bias + MaxPool1d(3) over rows ([M / 3, ldc]), pool_part the per-tile InstanceNorm partial sums of the pre-bias pooled values:
+  // [m_tiles][2 (item of the tile)][2 (sum, sum of squares)][N] over the pooled frames < pool3_T of an item
+  int tile_rows, pool3_T;
 };
 
-enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2, TC_CONV2D = 3, TC_POOL = 4 };
+enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2, TC_CONV2D = 3, TC_POOL = 4, TC_MAXPOOL3 = 5 };
 
 // ------------------------------------------------------------------------------------ the kernel
 template <int BN>
@@ -74,7 +80,10 @@ struct TcSmem {
   static constexpr int PARAM_BYTES = 3 * BN * 4;
   // TC_POOL: activation chunk [128][33] + row weights [128][4] + cross-row-group staging [4][2][8][32], all float
   static constexpr int POOL_BYTES = (128 * 33 + 128 * 4 + 4 * 2 * 8 * 32) * 4;
+  // TC_MAXPOOL3: accumulator chunk [128][33] + cross-row-group staging [4][2][2][32], all float
+  static constexpr int POOL3_BYTES = (128 * 33 + 4 * 2 * 2 * 32) * 4;
   static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int extra(int epi) { return epi == 4 ? POOL_BYTES : (epi == 5 ? POOL3_BYTES : 0); }
 };
 
 // ------------------------------------------------------------------------------------ the epilogue of one 128-row tile
@@ -85,7 +94,7 @@ template <int BN, int EPI>
 __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params, float* pool_stage, uint32_t tmem_acc, long long mt,
                                                  int n0, int quad, int lane, int et, bool stage_params, uint64_t* acc_full_bar,
                                                  int acc_phase) {
-    const long long m = mt * TC_BM + quad * 32 + lane;
+    const long long m = mt * (EPI == TC_MAXPOOL3 ? a.tile_rows : TC_BM) + quad * 32 + lane;
     // stage the per-column parameters of this tile (named barrier 1: the 128 epilogue threads only); with a single
     // column tile they are the same for every tile of this CTA: staged once
     if (stage_params) {
@@ -94,8 +103,9 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
         const int n = n0 + i;
         const bool ok = n < a.N;
         params[i] = (ok && a.bias) ? a.bias[n] : 0.f;
-        params[BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_scale[n] : 1.f;
-        params[2 * BN + i] = (ok && EPI != TC_BIAS_F32) ? a.bn_shift[n] : 0.f;
+        constexpr bool has_bn = EPI != TC_BIAS_F32 && EPI != TC_MAXPOOL3;
+        params[BN + i] = (ok && has_bn) ? a.bn_scale[n] * (EPI == TC_CONV2D ? a.acc_scale : 1.f) : 1.f;   // (2^-k: exact)
+        params[2 * BN + i] = (ok && has_bn) ? a.bn_shift[n] : 0.f;
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -141,7 +151,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
     for (int c = 0; c < BN; c += 32) {
       uint32_t r[32];
       tmem_ld32(taddr + c, r);
-      if (EPI != TC_POOL && n0 + c >= a.N) continue;
+      if (EPI != TC_POOL && EPI != TC_MAXPOOL3 && n0 + c >= a.N) continue;
       float v[32];
       if (EPI == TC_POOL) {
         // bias -> LeakyReLU -> BatchNorm affine, then the deviation from the per-channel pivot (the BatchNorm shift) goes to
@@ -158,7 +168,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
           const float bb[4] = {b4.x, b4.y, b4.z, b4.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            const float x = leaky(__uint_as_float(r[4 * q4 + e]) + bb[e]);
+            const float x = leaky(fmaf(__uint_as_float(r[4 * q4 + e]), a.acc_scale, bb[e]));
             dsm[(quad * 32 + lane) * 33 + 4 * q4 + e] = fmaf(x, ss[e], hh[e]) - hh[e];
           }
         }
@@ -207,6 +217,54 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
             if (n < a.N && mt < a.m_tiles) a.pool_part[(((size_t)mt * 2 + sg) * 8 + j) * a.N + n] = tot;
           }
         }
+        continue;
+      }
+      if (EPI == TC_MAXPOOL3) {
+        // bias + MaxPool1d(3) over the rows of the tile (42 windows of three TMEM lanes: through shared memory), and the
+        // InstanceNorm partial sums of the pooled values, split at `brow3` between the tile's two items
+        float* dsm = pool_stage;                    // [128][33]
+        float* stg = pool_stage + 128 * 33;         // [rg 4][item 2][2][32]
+#pragma unroll
+        for (int i = 0; i < 32; i++) dsm[(quad * 32 + lane) * 33 + i] = __uint_as_float(r[i]) * a.acc_scale;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        {
+          const int col = et & 31, rg = et >> 5, n = n0 + c + col;
+          const long long first = mt * (long long)a.tile_rows;                  // first un-pooled row of the tile
+          const long long item0 = first / a.pool_item_rows;
+          const long long nxt = (item0 + 1) * a.pool_item_rows;
+          const int brow3 = nxt - first < a.tile_rows ? (int)(nxt - first) / 3 : a.tile_rows / 3;   // first window of the next item
+          const long long p_first = first / 3;                                  // first pooled row of the tile
+          const int f0 = (int)(p_first - item0 * (a.pool_item_rows / 3));       // its frame index inside item0
+          const long long Mp = a.M / 3;
+          const float bias = params[c + col];
+          float s1[2] = {0.f, 0.f}, s2[2] = {0.f, 0.f};
+          for (int pr = rg; pr < a.tile_rows / 3; pr += 4) {
+            const float v = fmaxf(fmaxf(dsm[(3 * pr) * 33 + col], dsm[(3 * pr + 1) * 33 + col]), dsm[(3 * pr + 2) * 33 + col]);
+            const int sg = pr >= brow3 ? 1 : 0;
+            const int frame = sg ? pr - brow3 : f0 + pr;
+            const long long P = p_first + pr;
+            if (P < Mp) {
+              if (n < a.N) a.out_f32[P * a.ldc + n] = v + bias;
+              if (frame < a.pool3_T) {
+                s1[sg] += v;
+                s2[sg] = fmaf(v, v, s2[sg]);
+              }
+            }
+          }
+#pragma unroll
+          for (int sg = 0; sg < 2; sg++) {
+            stg[((rg * 2 + sg) * 2 + 0) * 32 + col] = s1[sg];
+            stg[((rg * 2 + sg) * 2 + 1) * 32 + col] = s2[sg];
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        {   // 2 items x 2 sums x 32 columns = 128 values, one per thread: the four row groups in a fixed order
+          const int col = et & 31, q = et >> 5, sg = q >> 1, j = q & 1, n = n0 + c + col;
+          const float tot = ((stg[((0 * 2 + sg) * 2 + j) * 32 + col] + stg[((1 * 2 + sg) * 2 + j) * 32 + col]) +
+                             stg[((2 * 2 + sg) * 2 + j) * 32 + col]) + stg[((3 * 2 + sg) * 2 + j) * 32 + col];
+          if (n < a.N) a.pool_part[(((size_t)mt * 2 + sg) * 2 + j) * a.N + n] = tot;
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");     // the chunk buffer is rewritten by the next 32 columns
         continue;
       }
       if (EPI == TC_CONV2D) {
@@ -261,7 +319,7 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
       }
 #pragma unroll
       for (int i = 0; i < 32; i++) {
-        float x = __uint_as_float(r[i]) + params[c + i];
+        float x = fmaf(__uint_as_float(r[i]), a.acc_scale, params[c + i]);
         if (EPI != TC_BIAS_F32) {
           x = leaky(x);
           x = fmaf(x, params[BN + c + i], params[2 * BN + c + i]);
@@ -333,7 +391,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* acc_full = bars + 2 * NSTAGE;      // [2] MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
-  float* pool_stage = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES + 256);   // TC_POOL only
+  float* pool_stage = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES + 256);   // TC_POOL / TC_MAXPOOL3 only
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
   const int num_tiles = a.m_tiles * a.n_tiles;
@@ -367,7 +425,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       int stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-        const int m0 = mt * TC_BM, n0 = nt * BN;
+        const int m0 = mt * (EPI == TC_MAXPOOL3 ? a.tile_rows : TC_BM), n0 = nt * BN;
         for (int j = 0; j < a.KW; j++) {
           for (int cb = 0; cb < a.cin_blocks; cb++) {
             mbar_wait(&empty[stage], phase ^ 1);
@@ -638,12 +696,16 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
       make_map(&tw_hi, g.W_hi, g.Npad, Ktot, Ktot, BN) || make_map(&tw_lo, g.W_lo, g.Npad, Ktot, Ktot, BN))
     return -2;
   TcArgs a{};
-  a.M = g.M; a.N = g.N; a.m_tiles = (int)((g.M + TC_BM - 1) / TC_BM); a.n_tiles = n_tiles;
+  a.M = g.M; a.N = g.N; a.n_tiles = n_tiles;
+  a.tile_rows = EPI == TC_MAXPOOL3 ? 126 : TC_BM;
+  a.pool3_T = g.pool3_T;
+  a.m_tiles = (int)((g.M + a.tile_rows - 1) / a.tile_rows);
   a.KW = g.KW; a.dil = g.dil; a.cin_blocks = g.Cin / TC_BK;
   a.bias = g.bias; a.bn_scale = g.bn_scale; a.bn_shift = g.bn_shift;
   a.out_f32 = g.out_f32; a.out_hi = reinterpret_cast<__nv_bfloat16*>(g.out_hi);
   a.out_lo = reinterpret_cast<__nv_bfloat16*>(g.out_lo); a.ldc = g.ldc;
   a.f16 = split_f16();
+  a.acc_scale = g.w_scale > 0.f ? 1.f / g.w_scale : 1.f;
   for (int j = 0; j < 9; j++) a.tap_off[j] = j < g.KW ? (g.tap_off ? g.tap_off[j] : j * g.dil) : 0;
   a.Wp = g.Wp; a.Hp = g.Hp; a.Wop = g.Wop; a.Hop = g.Hop; a.stride2 = g.stride2; a.relu = g.relu;
   a.res_hi = reinterpret_cast<const __nv_bfloat16*>(g.res_hi);
@@ -661,7 +723,7 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
       DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                   S::TOTAL + (EPI == TC_POOL ? S::POOL_BYTES : 0)));
+                                   S::TOTAL + S::extra(EPI)));
       if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
   }
@@ -685,7 +747,7 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
     }
   }
   const int grid = tiles < sms ? tiles : sms;
-  gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL + (EPI == TC_POOL ? S::POOL_BYTES : 0), st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
+  gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL + S::extra(EPI), st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
   DG_LAUNCHED();
   return 0;
 }
@@ -714,6 +776,13 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
       return -1;
     }
     return launch_tc<256, TC_POOL>(g, st);
+  }
+  if (g.epi == TC_MAXPOOL3) {
+    if (g.Npad != 64 || !g.out_f32 || !g.pool_part || g.pool_item_rows % 3 || g.pool_item_rows < 126 || g.M % 3 || g.pool3_T < 1) {
+      set_error("gemm_tc (maxpool3): needs 64 output channels, items whose row count is a multiple of 3 and at least 126");
+      return -1;
+    }
+    return launch_tc<64, TC_MAXPOOL3>(g, st);
   }
   if (g.Npad == 64 && g.epi == TC_BIAS_F32) return launch_tc<64, TC_BIAS_F32>(g, st);
   switch (g.epi) {
@@ -834,15 +903,35 @@ float host_h16_to_f32(uint16_t h, int f16) {
 }
 
 // host: float32 [N][K] -> zero-padded 16-bit hi/lo planes [Npad][K]
-void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo, int f16) {
+void split_weights_host(const float* w, int N, int Npad, int K, uint16_t* hi, uint16_t* lo, int f16, float scale) {
   for (size_t i = 0; i < (size_t)Npad * K; i++) hi[i] = lo[i] = 0;
   for (int n = 0; n < N; n++)
     for (int k = 0; k < K; k++) {
-      const float f = w[(size_t)n * K + k];
+      const float f = w[(size_t)n * K + k] * scale;          // power of two: exact
       const uint16_t h = host_f32_to_h16(f, f16);
       hi[(size_t)n * K + k] = h;
       lo[(size_t)n * K + k] = host_f32_to_h16(f - host_h16_to_f32(h, f16), f16);
     }
+}
+
+// Power-of-two scale of a weight tensor's fp16 planes: the largest magnitude lands in [2^12, 2^13), so that the lo plane
+// (|lo| <= 2^-11 |w|) of every weight down to 2^-15 of the largest one stays a NORMAL fp16 number (un-scaled, lo goes
+// subnormal below |w| = 0.125 and the pair keeps only an absolute 2^-25).  The accumulator is multiplied by 1 / scale in
+// the epilogue (an exact operation).  bf16 planes have float32's exponent range: scale 1.  DG_NO_WSCALE=1 disables it (A/B).
+float weight_plane_scale(const float* w, size_t n, int f16) {
+  static const bool off = getenv("DG_NO_WSCALE") && getenv("DG_NO_WSCALE")[0] == '1';
+  if (!f16 || off) return 1.f;
+  float mx = 0.f;
+  for (size_t i = 0; i < n; i++) {
+    const float v = fabsf(w[i]);
+    if (v > mx && v < 3.0e38f) mx = v;
+  }
+  if (!(mx > 0.f)) return 1.f;
+  int e = 0;
+  frexpf(mx, &e);                       // mx = m * 2^e, m in [0.5, 1)
+  int k = 13 - e;                       // mx * 2^k in [2^12, 2^13)
+  k = k > 40 ? 40 : (k < -40 ? -40 : k);
+  return ldexpf(1.f, k);
 }
 
 }  // namespace dg

@@ -34,7 +34,7 @@
 
 namespace dg {
 
-constexpr int LT_NB = 16;                               // batch rows per CTA (= N of every MMA)
+constexpr int LT_NB = 16;                               // N of every MMA (batch rows per CTA: 16, or 8 with a zero row group)
 
 __device__ __forceinline__ void umma_f16_ts(uint32_t tmem_c, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -70,12 +70,21 @@ template <>
 __device__ __forceinline__ void tmem_ldn<8>(uint32_t taddr, uint32_t (&r)[8]) { tmem_ld8(taddr, r); }
 template <>
 __device__ __forceinline__ void tmem_ldn<4>(uint32_t taddr, uint32_t (&r)[4]) { tmem_ld4(taddr, r); }
+template <>
+__device__ __forceinline__ void tmem_ldn<2>(uint32_t taddr, uint32_t (&r)[2]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
+__device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t a) {
+  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
+}
 // NC = cells (batch rows) per cell-update thread: 8 -> 8 cell warps, 4 -> 16 cell warps (twice the warps per scheduler to hide
 // the ex2 / rcp chains of the cell update); + 1 issuing warp
-__host__ __device__ constexpr int l3_threads(int NC) { return (4 * (LT_NB / NC) + 1) * 32; }
+// NR = valid batch rows per CTA (16, or 8: the MMA stays N = 16 with a zero second row group -- half the cell work per SM and
+// twice the CTAs, for the latency of a dependent step rather than for SM-time)
+__host__ __device__ constexpr int l3_threads(int NC, int NR = LT_NB) { return (4 * (NR / NC) + 1) * 32; }
 constexpr int L3_WS_BYTES = 2 * 128 * 128;             // W_lo of gate o: 2 k-blocks x (128 rows x 128 B)
 constexpr int L3_PLANE = 128 * LT_NB * 2;              // one plane of h_t: 128 units x 16 rows x 2 B = 4 KB
 constexpr int LT_H_BYTES = 2 * 2 * L3_PLANE;           // [buffer][plane]
@@ -102,14 +111,19 @@ struct L3Cell {
   ptrdiff_t dgx, dh;
   uint32_t tlane;      // TMEM address of this thread's accumulator columns
   uint32_t h_addr;     // shared address of this thread's 16-byte unit in buffer 0, hi plane
+  float inv;           // 1 / (power-of-two scale of the W_hh planes)
   int rows;
 };
 
-// the 293 dependent cell updates of one thread; FULL = all 8 batch rows of this warp are valid (no branches: the
-// eight independent dependency chains overlap)
+// the 293 dependent cell updates of one thread; FULL = all NC batch rows of this thread are valid (no branches: the
+// independent dependency chains overlap).  Three completion points per step -- gates (i, f), gate g, gate o -- so that the
+// MUFU work of a gate (the cell update is MUFU-bound: 7 per cell, 16 per clock and SM) runs under the MMAs of the next one:
+//   after i, f:  e^-i, e^-f                          (2 MUFU, under the 24 MMAs of g)
+//   after g:     e^2g, one reciprocal, e^2c'         (3 MUFU, under the 24 MMAs of o)
+//   after o:     e^-o, one reciprocal                (2 MUFU, the tail of the step)
 template <bool F16, bool FULL, bool TIMING, int NC>
 __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done, uint64_t* h_ready, int lane,
-                                             unsigned* dbg) {
+                                             unsigned* dbg, unsigned* dbg_all) {
   constexpr int f16 = F16 ? 1 : 0;
   const float L2E = 1.4426950408889634f;
   float c[NC];
@@ -117,6 +131,7 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
   for (int n = 0; n < NC; n++) c[n] = 0.f;
   for (int step = 0; step < T; step++) {
     const int nxt = (step + 1) & 1;
+    const uint32_t ph = step & 1;
     float xg[4][NC];
 #pragma unroll
     for (int n = 0; n < NC; n++) {
@@ -128,34 +143,43 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
         for (int g = 0; g < 4; g++) xg[g][n] = 0.f;
       }
     }
-    mbar_wait(&mma_done[0], step & 1);
+    uint32_t ra[NC], rb[NC];
+    float di[NC], df[NC];       // 1 + e^-i, 1 + e^-f
+    mbar_wait(&mma_done[0], ph);
     tc_fence_after();
     if (TIMING && dbg) dbg[step * 8 + 2] = (unsigned)clock();
-    uint32_t ri[NC], rf[NC], rg[NC], ro[NC];
-    tmem_ldn<NC>(s.tlane + 0 * LT_NB, ri);
-    tmem_ldn<NC>(s.tlane + 1 * LT_NB, rf);
-    tmem_ldn<NC>(s.tlane + 2 * LT_NB, rg);
+    tmem_ldn<NC>(s.tlane + 0 * LT_NB, ra);
+    tmem_ldn<NC>(s.tlane + 1 * LT_NB, rb);
     tmem_ld_wait();
     if (TIMING && dbg) dbg[step * 8 + 3] = (unsigned)clock();
+#pragma unroll
+    for (int n = 0; n < NC; n++) {
+      if (FULL || n < s.rows) {
+        // exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127
+        di[n] = 1.f + ex2_approx(fminf(fmaf(__uint_as_float(ra[n]), s.inv, xg[0][n]) * -L2E, 40.f));
+        df[n] = 1.f + ex2_approx(fminf(fmaf(__uint_as_float(rb[n]), s.inv, xg[1][n]) * -L2E, 40.f));
+      }
+    }
+    mbar_wait(&mma_done[1], ph);
+    tc_fence_after();
+    tmem_ldn<NC>(s.tlane + 2 * LT_NB, ra);
+    tmem_ld_wait();
     float num[NC], den[NC];     // tanh(c') = num / den
 #pragma unroll
     for (int n = 0; n < NC; n++) {
       if (FULL || n < s.rows) {
-        // e^-i, e^-f, e^2g (exponents capped at 2^40: sigmoid floor 9e-13, products stay below 2^127)
-        const float ei = ex2_approx(fminf((__uint_as_float(ri[n]) + xg[0][n]) * -L2E, 40.f));
-        const float ef = ex2_approx(fminf((__uint_as_float(rf[n]) + xg[1][n]) * -L2E, 40.f));
-        const float eg = ex2_approx(fminf((__uint_as_float(rg[n]) + xg[2][n]) * (2.f * L2E), 40.f));
+        const float eg = ex2_approx(fminf(fmaf(__uint_as_float(ra[n]), s.inv, xg[2][n]) * (2.f * L2E), 40.f));
         // c' = c / (1 + ef) + (eg - 1) / ((1 + ei)(1 + eg))  over one common denominator
-        const float df = 1.f + ef, p = (1.f + ei) * (1.f + eg);
-        c[n] = fmaf(c[n], p, (eg - 1.f) * df) * rcp_approx(p * df);
+        const float p = di[n] * (1.f + eg);
+        c[n] = fmaf(c[n], p, (eg - 1.f) * df[n]) * rcp_approx(p * df[n]);
         const float ec = ex2_approx(fminf(c[n] * (2.f * L2E), 40.f));
         num[n] = ec - 1.f;
         den[n] = ec + 1.f;
       }
     }
-    mbar_wait(&mma_done[1], step & 1);
+    mbar_wait(&mma_done[2], ph);
     tc_fence_after();
-    tmem_ldn<NC>(s.tlane + 3 * LT_NB, ro);
+    tmem_ldn<NC>(s.tlane + 3 * LT_NB, rb);
     tmem_ld_wait();
     float h[NC];
     uint16_t hh[NC], hl[NC];
@@ -163,7 +187,7 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
     for (int n = 0; n < NC; n++) {
       if (FULL || n < s.rows) {
         // h = tanh(c') / (1 + e^-o)
-        const float eo = ex2_approx(fminf((__uint_as_float(ro[n]) + xg[3][n]) * -L2E, 40.f));
+        const float eo = ex2_approx(fminf(fmaf(__uint_as_float(rb[n]), s.inv, xg[3][n]) * -L2E, 40.f));
         h[n] = num[n] * rcp_approx((1.f + eo) * den[n]);
         split_h16(h[n], f16, hh[n], hl[n]);
       } else {
@@ -177,16 +201,22 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
       st_shared_v4(dst, pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]), pack_u16x2(hh[4], hh[5]), pack_u16x2(hh[6], hh[7]));
       st_shared_v4(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]), pack_u16x2(hl[2], hl[3]), pack_u16x2(hl[4], hl[5]),
                    pack_u16x2(hl[6], hl[7]));
-    } else {
+    } else if constexpr (NC == 4) {
       st_shared_v2(dst, pack_u16x2(hh[0], hh[1]), pack_u16x2(hh[2], hh[3]));
       st_shared_v2(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]), pack_u16x2(hl[2], hl[3]));
+    } else {
+      st_shared_b32(dst, pack_u16x2(hh[0], hh[1]));
+      st_shared_b32(dst + L3_PLANE, pack_u16x2(hl[0], hl[1]));
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     if (TIMING && dbg) dbg[step * 8 + 5] = (unsigned)clock();
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&h_ready[nxt]);
-    // the float32 copy of h_t for the next layer leaves after the hand-off: it is not on the recurrence's critical path
+    if (lane == 0) {
+      mbar_arrive(&h_ready[nxt]);
+      if (TIMING && dbg_all) atomicMax(&dbg_all[step * 8 + 6], (unsigned)clock());   // the LAST warp's arrival
+    }
+    // the copies of h_t for the next layer leave after the hand-off: they are not on the recurrence's critical path
     if (s.php) {        // the next layer's GEMM reads h as hi/lo planes: write them directly (no float32 round trip)
 #pragma unroll
       for (int n = 0; n < NC; n++)
@@ -206,34 +236,35 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
   }
 }
 
-// (launched as clusters of two CTAs only so that the 2 x ceil(B/16) CTAs fill whole TPCs: the GEMMs of the other streams run on
+// (launched as clusters of two CTAs only so that the CTAs fill whole TPCs: the GEMMs of the other streams run on
 // CTA PAIRS (gemm_tc2_kernel), which need both SMs of a TPC free)
-template <bool F16, bool TIMING, int NC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(l3_threads(NC), 1)
+template <bool F16, bool TIMING, int NC, int NR>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(l3_threads(NC, NR), 1)
 lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __restrict__ w_hi,
                 const uint16_t* __restrict__ w_lo /*both [2][512][128]*/, const float* __restrict__ gx, int B, int T,
                 int stride, int groups_per_dir, float* __restrict__ hout, uint16_t* __restrict__ out_hi,
-                uint16_t* __restrict__ out_lo, unsigned* __restrict__ dbg) {
+                uint16_t* __restrict__ out_lo, float acc_scale, unsigned* __restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   unsigned char* wsm = smem;                         // [k-block][128 x 128 B]   (W_lo, gate o)
   unsigned char* hsm = smem + L3_WS_BYTES;           // [buffer][plane][4 KB]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L3_WS_BYTES + LT_H_BYTES);
   uint64_t* w_full = bars;
-  uint64_t* mma_done = bars + 1;                     // [2]: gates i, f, g complete / gate o complete
-  uint64_t* h_ready = bars + 3;                      // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  uint64_t* mma_done = bars + 1;                     // [3]: gates i, f complete / gate g complete / gate o complete
+  uint64_t* h_ready = bars + 4;                      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
 
-  constexpr int NCW = 4 * (LT_NB / NC);              // cell-update warps; warp NCW issues the MMAs
-  constexpr int L3_THREADS = l3_threads(NC);
+  constexpr int NCW = 4 * (NR / NC);                 // cell-update warps; warp NCW issues the MMAs
+  constexpr int L3_THREADS = l3_threads(NC, NR);
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int dir = blockIdx.x / groups_per_dir;
-  const int b0 = (blockIdx.x - dir * groups_per_dir) * LT_NB;
+  const int b0 = (blockIdx.x - dir * groups_per_dir) * NR;
 
   if (threadIdx.x == 0) {
     mbar_init(w_full, 1);
     mbar_init(&mma_done[0], 1);
     mbar_init(&mma_done[1], 1);
+    mbar_init(&mma_done[2], 1);
     mbar_init(&h_ready[0], NCW);
     mbar_init(&h_ready[1], NCW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -300,8 +331,8 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
         }
         if (TIMING && blockIdx.x == 0) dbg[step * 8 + 0] = (unsigned)clock();
         const uint64_t b0d = buf ? bb1 : bb0;
-        // gate-major order with two completion points: the cell update starts on i, f, g (72 MMAs) while the 24 MMAs
-        // of gate o -- the ones that read W_lo from shared memory -- are still in the pipe
+        // gate-major order, three completion points (see l3_cell_loop); the 24 MMAs of gate o -- the ones that read W_lo
+        // from shared memory -- come last
 #pragma unroll
         for (int g = 0; g < 4; g++) {
           const uint32_t d = tmem_base + L3_COL_D + g * LT_NB;
@@ -317,16 +348,15 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
             else umma_f16(d, a_s + (uint64_t)(kb * kTile + kk * 2), b_hi, idesc, 1);
             umma_f16_ts(d, a_hi, b_hi, idesc, 1);                                           // W_hi . h_hi
           }
-          if (g == 2) umma_commit(&mma_done[0]);
+          if (g >= 1) umma_commit(&mma_done[g - 1]);
         }
         if (TIMING && blockIdx.x == 0) dbg[step * 8 + 1] = (unsigned)clock();
-        umma_commit(&mma_done[1]);
       }
     }
     __syncwarp();
   } else {
-    // ================================================================ cell update (warps 0..7)
-    const int quad = warp & 3, ch = warp >> 2;      // ch: which NC batch columns of the 16
+    // ================================================================ cell update (warps 0 .. NCW-1)
+    const int quad = warp & 3, ch = warp >> 2;      // ch: which NC batch columns of the NR
     const int u = quad * 32 + lane;                 // hidden unit == TMEM lane
     L3Cell s;
     s.rows = min(NC, max(0, B - (b0 + ch * NC)));   // valid batch rows of this warp's NC columns
@@ -341,11 +371,13 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     s.plane_off = out_hi ? (size_t)(out_lo - out_hi) : 0;
     s.dgx = dir == 0 ? 1024 : -1024;
     s.dh = dir == 0 ? 256 : -256;
-    // 16-byte unit of (unit u, row group of 8); with NC = 4 two warps share a unit (8 bytes each)
+    s.inv = acc_scale;
+    // 16-byte unit of (unit u, row group of 8); with NC < 8 several warps share a unit (2 NC bytes each)
     s.h_addr = smem_u32(hsm) + (u >> 3) * 256 + ((ch * NC) >> 3) * 128 + (u & 7) * 16 + ((ch * NC) & 7) * 2;
     unsigned* my_dbg = (TIMING && blockIdx.x == 0 && threadIdx.x == 0) ? dbg : nullptr;
-    if (s.rows == NC) l3_cell_loop<F16, true, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg);
-    else l3_cell_loop<F16, false, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg);
+    unsigned* all_dbg = (TIMING && blockIdx.x == 0) ? dbg : nullptr;
+    if (s.rows == NC) l3_cell_loop<F16, true, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg, all_dbg);
+    else l3_cell_loop<F16, false, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg, all_dbg);
   }
   tc_fence_before();
   __syncthreads();
@@ -355,16 +387,49 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
   }
 }
 
+// (rows per CTA, cells per thread).  Default: 16 rows x 4 cells from 129 windows on (2 x ceil(B / 16) CTAs: the SM-time
+// optimum), 8 rows x 2 cells up to 128 windows -- the same <= 32 SMs, but half the cell work per SM and step: 1.10 instead of
+// 1.40 us per dependent step (profiles/r2_lstm_step_timing.log).  DG_LSTM_ROWS = 16 | 8, DG_LSTM_CELLS = 8 | 4 | 2 force a shape.
+struct LstmShape { int rows, cells; };
+static LstmShape lstm_shape(int B) {
+  static const int env_rows = getenv("DG_LSTM_ROWS") ? atoi(getenv("DG_LSTM_ROWS")) : 0;
+  static const int env_cells = getenv("DG_LSTM_CELLS") ? atoi(getenv("DG_LSTM_CELLS")) : 0;
+  LstmShape v;
+  v.rows = env_rows == 8 || env_rows == 16 ? env_rows : (B <= 128 ? 8 : 16);
+  v.cells = env_cells;
+  if (v.rows == 16 && v.cells != 8 && v.cells != 4) v.cells = 4;
+  if (v.rows == 8 && v.cells != 4 && v.cells != 2) v.cells = 2;
+  return v;
+}
+template <class Fn>
+static int lstm_dispatch(LstmShape shp, bool f16, bool timing, Fn fn) {
+#define DG_L3(F, TM, NC, NR) return fn(lstm_tc3_kernel<F, TM, NC, NR>, l3_threads(NC, NR))
+#define DG_L3_SHAPES(F, TM)                                  \
+  if (shp.rows == 16 && shp.cells == 8) DG_L3(F, TM, 8, 16);   \
+  if (shp.rows == 16) DG_L3(F, TM, 4, 16);                     \
+  if (shp.cells == 4) DG_L3(F, TM, 4, 8);                      \
+  DG_L3(F, TM, 2, 8)
+  if (timing) { DG_L3_SHAPES(true, true); }
+  if (f16) { DG_L3_SHAPES(true, false); }
+  DG_L3_SHAPES(false, false);
+#undef DG_L3_SHAPES
+#undef DG_L3
+}
+
 size_t lstm_tc_plane_elems() { return (size_t)2 * 512 * 128; }
 
 // torch weight_hh_l{L}[_reverse] ([512][128], gate order i,f,g,o) -> 16-bit hi / lo planes [2][512][128]
-void lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16) {
-  split_weights_host(whh_fwd, 512, 512, 128, hi, lo, f16);
-  split_weights_host(whh_bwd, 512, 512, 128, hi + 512 * 128, lo + 512 * 128, f16);
+// returns the power-of-two factor both planes were multiplied by (weight_plane_scale; one factor for both directions)
+float lstm_tc_pack_whh(const float* whh_fwd, const float* whh_bwd, uint16_t* hi, uint16_t* lo, int f16) {
+  const float s0 = weight_plane_scale(whh_fwd, 512 * 128, f16), s1 = weight_plane_scale(whh_bwd, 512 * 128, f16);
+  const float scale = s0 < s1 ? s0 : s1;
+  split_weights_host(whh_fwd, 512, 512, 128, hi, lo, f16, scale);
+  split_weights_host(whh_bwd, 512, 512, 128, hi + 512 * 128, lo + 512 * 128, f16, scale);
+  return scale;
 }
 
-int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, int B, int T, int stride, float* hout,
-                         void* out_hi, void* out_lo, cudaStream_t st) {
+int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo, float w_scale, int B, int T, int stride,
+                         float* hout, void* out_hi, void* out_lo, cudaStream_t st) {
   ProfScope _ps("lstm_rec", st);
   EncodeTiledFn fn = encode_fn();
   if (!fn) {
@@ -385,22 +450,23 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
   }
   static bool attr_done[64] = {};
   static bool timing = false;
-  // DG_LSTM_CELLS=8: 8 cells per thread / 8 cell warps (the round-1 shape); default 4 cells / 16 cell warps
-  static const bool cells8 = getenv("DG_LSTM_CELLS") && getenv("DG_LSTM_CELLS")[0] == '8';
+  const LstmShape shp = lstm_shape(B);
   if (first_use_on_device(attr_done)) {
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<false, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
-    DG_CUDA(cudaFuncSetAttribute(lstm_tc3_kernel<true, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM));
+    const auto opt_in = [](auto kern, int) {
+      return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM) == cudaSuccess ? 0 : -1; };
+    for (const LstmShape v : {LstmShape{16, 8}, LstmShape{16, 4}, LstmShape{8, 4}, LstmShape{8, 2}})
+      if (lstm_dispatch(v, true, false, opt_in) || lstm_dispatch(v, false, false, opt_in) || lstm_dispatch(v, true, true, opt_in)) {
+        set_error("lstm_rec: cudaFuncSetAttribute failed");
+        return -2;
+      }
     timing = getenv("DG_LSTM_TIMING") && getenv("DG_LSTM_TIMING")[0] == '1';
   }
   if (!hout && !out_hi) {
     set_error("lstm_rec: no output buffer");
     return -1;
   }
-  const int gpd = (B + LT_NB - 1) / LT_NB;
+  const int gpd = (B + shp.rows - 1) / shp.rows;
+  const float inv = w_scale > 0.f ? 1.f / w_scale : 1.f;
   const uint16_t* ph = reinterpret_cast<const uint16_t*>(whh_hi);
   const uint16_t* pl = reinterpret_cast<const uint16_t*>(whh_lo);
   uint16_t* oh = reinterpret_cast<uint16_t*>(out_hi);
@@ -411,41 +477,44 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     unsigned* dbg = nullptr;
     DG_CUDA(cudaMalloc(&dbg, (size_t)T * 8 * sizeof(unsigned)));
     DG_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(unsigned), st));
-    if (cells8) lstm_tc3_kernel<true, true, 8><<<2 * gpd, l3_threads(8), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, dbg);
-    else lstm_tc3_kernel<true, true, 4><<<2 * gpd, l3_threads(4), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, dbg);
+    lstm_dispatch(shp, true, true, [&](auto kern, int threads) {
+      kern<<<2 * gpd, threads, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, inv, dbg);
+      return 0; });
     DG_CUDA(cudaStreamSynchronize(st));
     if (reported++ < 6) {
       std::vector<unsigned> hbuf((size_t)T * 8);
       DG_CUDA(cudaMemcpy(hbuf.data(), dbg, hbuf.size() * sizeof(unsigned), cudaMemcpyDeviceToHost));
-      double acc[6] = {0, 0, 0, 0, 0, 0};
+      double acc[7] = {0, 0, 0, 0, 0, 0, 0};
       int n = 0;
       for (int s2 = 20; s2 + 1 < T; s2++, n++) {
         const unsigned* a = &hbuf[(size_t)s2 * 8];
         const unsigned* nx = &hbuf[(size_t)(s2 + 1) * 8];
         acc[0] += (double)(int)(a[1] - a[0]);     // issue of the 96 MMAs
-        acc[1] += (double)(int)(a[2] - a[1]);          // last issue -> cell threads see the FIRST completion point (negative: overlap)
+        acc[1] += (double)(int)(a[2] - a[0]);     // first issue -> cell thread 0 sees the FIRST completion point (gates i, f)
         acc[2] += (double)(int)(a[3] - a[2]);     // tcgen05.ld of the accumulators
-        acc[3] += (double)(int)(a[4] - a[3]);          // cell math incl. the wait for gate o
+        acc[3] += (double)(int)(a[4] - a[3]);     // cell math incl. the waits for gates g and o
         acc[4] += (double)(int)(a[5] - a[4]);     // shared stores + fence.proxy.async
-        acc[5] += (double)(int)(nx[0] - a[5]);    // arrive -> issuing lane resumes
+        acc[5] += (double)(int)(a[6] - a[5]);     // thread 0 done -> the LAST cell warp arrives
+        acc[6] += (double)(int)(nx[0] - a[6]);    // last arrival -> issuing lane resumes
       }
-      fprintf(stderr, "lstm_rec timing (B=%d, cycles per step, CTA 0): issue %.0f | mma->cells %.0f | tmem ld %.0f | math %.0f | "
-                      "store+fence %.0f | hand-off %.0f | total %.0f\n",
-              B, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n,
-              (acc[0] + acc[1] + acc[2] + acc[3] + acc[4] + acc[5]) / n);
+      fprintf(stderr, "lstm_rec timing (B=%d, %d rows x %d cells, cycles per step, CTA 0): issue %.0f | first issue->(i,f) seen %.0f | "
+                      "tmem ld %.0f | math+waits %.0f | store+fence %.0f | warp skew %.0f | wake-up %.0f | total %.0f\n",
+              B, shp.rows, shp.cells, acc[0] / n, acc[1] / n, acc[2] / n, acc[3] / n, acc[4] / n, acc[5] / n, acc[6] / n,
+              (acc[1] + acc[2] + acc[3] + acc[4] + acc[5] + acc[6]) / n);
     }
     cudaFree(dbg);
     return 0;
   }
-  if (split_f16()) {
-    if (cells8) lstm_tc3_kernel<true, false, 8><<<2 * gpd, l3_threads(8), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
-    else lstm_tc3_kernel<true, false, 4><<<2 * gpd, l3_threads(4), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
-  } else {
-    if (cells8) lstm_tc3_kernel<false, false, 8><<<2 * gpd, l3_threads(8), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
-    else lstm_tc3_kernel<false, false, 4><<<2 * gpd, l3_threads(4), L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, nullptr);
-  }
+  lstm_dispatch(shp, split_f16(), false, [&](auto kern, int threads) {
+    kern<<<2 * gpd, threads, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, inv, nullptr);
+    return 0; });
   DG_LAUNCHED();
   return 0;
+}
+
+int lstm_tc_ctas(int B) {
+  const LstmShape shp = lstm_shape(B);
+  return 2 * ((B + shp.rows - 1) / shp.rows);
 }
 
 }  // namespace dg
