@@ -452,11 +452,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         call_line = {"value": world * n_calls * B * STEP_SECONDS / float(t.item()), "unit": UNIT,
                      "ms_per_call": 1e3 * float(t.item()) / n_calls, "calls": n_calls,
-                     "h2d_bytes_per_step": B * CHUNK * 4, "d2h_bytes_per_step": B * 16 + 4 + 4 * (n_turn_objs // n_calls),
+                     "h2d_bytes_per_step": int(lib.dg_pipeline_last_call_h2d_bytes(pipe._fused)),
+                     "d2h_bytes_per_step": B * 16 + 4 + 4 * (n_turn_objs // n_calls),
                      "phases_ms_per_call": {k: round(1e3 * v / max(1, prof.get("calls", 1)), 3) for k, v in prof.items() if k != "calls"},
                      "api": "SpeakerDiarization.__call__(Sequence[SlidingWindowFeature]) -> Sequence[(Annotation, SlidingWindowFeature)], "
-                            "synchronous per batch (dg_pipeline_call_host: threaded gather + upload of B separate pageable host "
-                            "windows, fused step, device aggregation/binarisation, one D2H of the turn list)"}
+                            "synchronous per batch (dg_pipeline_call_host: the B separate pageable host windows are compared with "
+                            "their predecessors by worker threads and, being consecutive hops of one stream, uploaded once and re-formed on "
+                            "the device; pipelined sub-batches of the fused step, device aggregation/binarisation, one D2H of the turn list)"}
 
     # ---------------- parity of the benchmarked configuration (outside every timed region): the pipelined path over NB
     # batches of B windows from a fresh state; speaker maps against the oracle clustering replayed on the same scores /
@@ -496,9 +498,19 @@ def run_ours(args):
                 o_emb = onets.make_embedding().forward_dedup(torch.from_numpy(host[0][:4])[:, None, :], osp_block(torch.from_numpy(o_seg)))
                 o_emb = (o_emb / o_emb.norm(dim=-1, keepdim=True)).numpy()
             emb_err = float(np.abs(got[0][1][:4].cpu().numpy() - o_emb).max())
+        if os.environ.get("DG_BENCH_PARITY_DETAIL") == "1":      # diagnostic: which windows of which batch deviate
+            with torch.no_grad():
+                net = onets.make_segmentation()
+                for j in range(NB):
+                    idx = [0, 1, 2, 3, B // 2, B - 2, B - 1]
+                    o = net(torch.from_numpy(host[j][idx])[:, None, :]).numpy()
+                    g = got[j][0].cpu().numpy()[idx]
+                    print(f"parity detail: batch {j}: per-window seg max abs err " +
+                          " ".join(f"{w}:{np.abs(g[q] - o[q]).max():.1e}" for q, w in enumerate(idx)), file=sys.stderr)
         parity = {"chunks": NB * B, "maps_equal_oracle_replay": ok, "centroids_bit_equal": centers_equal,
                   "seg_max_abs_err_4_windows": seg_err, "emb_max_abs_err_4_windows": emb_err, "first_difference": bad}
         if not (ok and centers_equal and seg_err < 1e-4 and (emb_err is None or emb_err < 1e-4)):
+            print(json.dumps({"parity_failed": parity}), file=sys.stderr)
             raise SystemExit(f"bench.py: the benchmarked configuration fails its parity check: {parity}")
 
     if rank != 0:

@@ -47,6 +47,7 @@ SIGNATURES = {
     "dg_osp": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _P, _P]),
     "dg_normalize_embeddings": (C.c_int, [_P, C.c_int, C.c_int, C.c_float, _P, _P]),
     "dg_cluster_create": (C.c_int, [C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_int, C.POINTER(_P)]),
+    "dg_cluster_set_metric": (C.c_int, [_P, C.c_int]),
     "dg_cluster_step": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P, _P]),
     "dg_cluster_reset": (C.c_int, [_P]),
     "dg_cluster_get_state": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int)]),
@@ -80,6 +81,7 @@ SIGNATURES = {
     "dg_pipeline_submit_stream": (C.c_int, [_P, _P, C.c_int]),
     "dg_pipeline_call_stream": (C.c_int, [_P, _P, _P, C.c_int, _P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P]),
     "dg_pipeline_call_host": (C.c_int, [_P, _P, _P, C.c_int, C.c_int, _P, _P, _P, C.c_int, C.POINTER(C.c_int), _P, _P]),
+    "dg_pipeline_last_call_h2d_bytes": (C.c_int64, [_P]),
 }
 
 

@@ -18,12 +18,16 @@ from ..core import SlidingWindowFeature
 from ..mapping import SpeakerMap
 
 
+# scipy.spatial.distance.cdist metrics (reference mapping.py:175) evaluated in float64 by the clustering kernel
+METRICS = {"cosine": 0, "euclidean": 1, "sqeuclidean": 2, "cityblock": 3, "chebyshev": 4}
+
+
 class OnlineSpeakerClustering:
     def __init__(self, tau_active: float, rho_update: float, delta_new: float,
                  metric: Optional[str] = "cosine", max_speakers: int = 20,
                  device: Optional[torch.device] = None):
-        if metric != "cosine":
-            raise ValueError("only the cosine metric is implemented on the GPU path")
+        if metric not in METRICS:
+            raise ValueError(f"metric must be one of {sorted(METRICS)} (scipy cdist names), got {metric!r}")
         self.tau_active, self.rho_update, self.delta_new = tau_active, rho_update, delta_new
         self.metric, self.max_speakers = metric, max_speakers
         self.device = torch.device(device) if device is not None else torch.device("cuda")
@@ -40,6 +44,8 @@ class OnlineSpeakerClustering:
             h = C.c_void_p()
             _lib.check(_lib.lib().dg_cluster_create(self.max_speakers, dim, self.tau_active, self.rho_update,
                                                     self.delta_new, self.device.index, C.byref(h)))
+            if METRICS[self.metric]:
+                _lib.check(_lib.lib().dg_cluster_set_metric(h, METRICS[self.metric]))
             self._h, self._dim = h, dim
         assert dim == self._dim, "embedding dimension changed"
         return self._h

@@ -33,13 +33,18 @@ struct ProfRec {
 };
 static bool g_prof = false;
 static std::vector<ProfRec> g_recs;
+// DG_TRACE_LAUNCHES=1: every scope prints "dg-trace <tag> <first launch ordinal> <one past the last>" on stderr, so that a
+// profiler's launch list (tools/ncu_summary.py) can be labelled with the tags bench.py reports
+static const bool g_trace = getenv("DG_TRACE_LAUNCHES") && getenv("DG_TRACE_LAUNCHES")[0] == '1';
 ProfScope::ProfScope(const char* name_, cudaStream_t st_) : on(g_prof), st(st_), a(nullptr), b(nullptr), name(name_) {
+  if (g_trace) first = g_launches.load();
   if (!on) return;
   cudaEventCreate(&a);
   cudaEventCreate(&b);
   cudaEventRecord(a, st);
 }
 ProfScope::~ProfScope() {
+  if (g_trace) fprintf(stderr, "dg-trace %s %lld %lld\n", name, first, (long long)g_launches.load());
   if (!on) return;
   cudaEventRecord(b, st);
   g_recs.push_back({name, a, b});
@@ -364,29 +369,30 @@ static int run_sincnet(const SincWeights& w, SincWork& k, const float* wav, int 
                               k.a0h.p, k.a0l.p, st, stream_flag)))
       return rc;
     // conv1 / conv2 with MaxPool1d(3) and the InstanceNorm partial sums in the GEMM epilogue (TC_MAXPOOL3): the un-pooled maps are
-    // never written, the statistics pass reads 2 x 2 x 64 floats per tile.  Needs items of at least 126 rows at both stages;
+    // never written, the statistics pass reads 2 x 2 x 64 floats per tile.  Needs a tile of 96..126 rows that divides the item at both stages;
     // DG_NO_POOL3_FUSE=1 = the round-1 path (un-pooled float32 map -> instnorm_stats -> split with pooling on load)
     static const bool pool3_on = !(getenv("DG_NO_POOL3_FUSE") && getenv("DG_NO_POOL3_FUSE")[0] == '1');
-    if (pool3_on && g.S1 >= 126) {
-      if (k.part3.ensure((size_t)gemm_tc_pool3_tiles(M0) * 2 * 2 * 64 * 4)) return DG_ECUDA;
+    const int tr0 = gemm_tc_pool3_tile_rows(g.S0), tr1 = gemm_tc_pool3_tile_rows(g.S1);
+    if (pool3_on && tr0 && tr1) {
+      if (k.part3.ensure((size_t)(M0 / tr0) * 2 * 2 * 64 * 4)) return DG_ECUDA;
       TcGemm t{};
       t.A_hi = k.a0h.p; t.A_lo = k.a0l.p; t.lda = 80; t.Cin = 448; t.KW = 1; t.dil = 1; t.Mtot = M0; t.M = M0;
       t.W_hi = w.w1_hi.p; t.w_scale = w.w1_hi.wscale; t.W_lo = w.w1_lo.p; t.Npad = 64; t.N = 64; t.bias = w.bias1.as<float>();
       t.out_f32 = k.p1.as<float>(); t.ldc = 64; t.epi = 5; t.tag = "sinc_conv1";
-      t.pool_part = k.part3.as<float>(); t.pool_item_rows = g.S0; t.pool3_T = g.T1;
+      t.pool_part = k.part3.as<float>(); t.pool_item_rows = g.S0; t.pool3_T = g.T1; t.pool3_tile_rows = tr0;
       if ((rc = launch_gemm_tc(t, st)) ||
-          (rc = launch_instnorm_finalize(k.part3.as<float>(), B, g.S0, g.T1, 64, 64, w.bias1.as<float>(), w.g1.as<float>(),
+          (rc = launch_instnorm_finalize(k.part3.as<float>(), B, g.S0, tr0, g.T1, 64, 64, w.bias1.as<float>(), w.g1.as<float>(),
                                          w.b1.as<float>(), k.sc1.as<float>(), k.sh1.as<float>(), 64, st)) ||
           (rc = launch_split_ex(k.p1.as<float>(), M1, 64, 64, 64, 0, g.S1, k.sc1.as<float>(), k.sh1.as<float>(), k.a1h.p, k.a1l.p, st)))
         return rc;
       t.A_hi = k.a1h.p; t.A_lo = k.a1l.p; t.lda = 64; t.Cin = 64; t.KW = 5; t.Mtot = M1; t.M = M1;
       t.W_hi = w.w2_hi.p; t.w_scale = w.w2_hi.wscale; t.W_lo = w.w2_lo.p; t.bias = w.bias2.as<float>();
       t.out_f32 = k.p2.as<float>(); t.tag = "sinc_conv2";
-      t.pool_item_rows = g.S1; t.pool3_T = g.T2;
+      t.pool_item_rows = g.S1; t.pool3_T = g.T2; t.pool3_tile_rows = tr1;
       if ((rc = launch_gemm_tc(t, st))) return rc;
       k.out = k.p2.as<float>();
       k.out_pool = 0;
-      return launch_instnorm_finalize(k.part3.as<float>(), B, g.S1, g.T2, 64, 64, w.bias2.as<float>(), w.g2.as<float>(),
+      return launch_instnorm_finalize(k.part3.as<float>(), B, g.S1, tr1, g.T2, 64, 64, w.bias2.as<float>(), w.g2.as<float>(),
                                       w.b2.as<float>(), k.sc2.as<float>(), k.sh2.as<float>(), 64, st);
     }
     TcGemm t{};
@@ -1477,10 +1483,20 @@ extern "C" int dg_cluster_create(int max_speakers, int dim, double tau, double r
   h->p.tau_f = (float)tau;
   h->p.rho_f = (float)rho;
   h->p.delta = delta;
+  h->p.metric = 0;
   if (h->centers.ensure((size_t)max_speakers * dim * 8) || h->active.ensure(32 * 4) || h->init.ensure(2 * 4) ||
       h->base.ensure((size_t)max_speakers * dim * 8) || h->base_active.ensure(32 * 4) || h->relabel.ensure(32 * 4))
     return DG_ECUDA;
   *out = h.release();
+  return DG_OK;
+}
+
+extern "C" int dg_cluster_set_metric(dg_cluster* h, int metric) {
+  if (!h || metric < 0 || metric > 4) {
+    set_error("dg_cluster_set_metric: 0 cosine, 1 euclidean, 2 sqeuclidean, 3 cityblock, 4 chebyshev");
+    return DG_EINVAL;
+  }
+  h->p.metric = metric;
   return DG_OK;
 }
 
@@ -1767,6 +1783,8 @@ struct dg_pipeline {
   void* pin_wav = nullptr;        // pinned staging of dg_pipeline_call_host (B separate host windows -> one upload)
   size_t pin_wav_bytes = 0;
   std::unique_ptr<GatherPool> gather;   // worker threads of the host gather (created at the first dg_pipeline_call_host)
+  DevBuf call_stream;                   // device image of the stream a dg_pipeline_call_host batch was cut from
+  long long call_h2d_bytes = 0;         // bytes the last dg_pipeline_call_host uploaded
 };
 
 extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, float gamma, float beta,
@@ -1815,6 +1833,23 @@ extern "C" int dg_pipeline_create(dg_seg* seg, dg_emb* emb, dg_cluster* clu, flo
 
 // segmentation chain on s_seg and embedding chain on s_emb, both starting after `start`; on return
 // e_emb (recorded on s_emb) marks seg, osp and emb complete
+// DG_CALL_TIMING=1: device time stamps of the sub-batches of dg_pipeline_call_host (diagnostic)
+struct CallDiag {
+  cudaEvent_t t0 = nullptr, up[3], prep[3], trunk[3], seg[3], emb[3], clu[3];
+  int j = 0;
+  void create() {
+    if (t0) return;
+    cudaEventCreate(&t0);
+    for (int i = 0; i < 3; i++)
+      for (cudaEvent_t* e : {&up[i], &prep[i], &trunk[i], &seg[i], &emb[i], &clu[i]}) cudaEventCreate(e);
+  }
+};
+static thread_local CallDiag* g_diag = nullptr;
+#define DG_DIAG(field, stream)                                        \
+  do {                                                                \
+    if (g_diag) cudaEventRecord(g_diag->field[g_diag->j], stream);    \
+  } while (0)
+
 static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, int K, float* seg, float* emb,
                          cudaEvent_t start, int lane = 0, int stream_hop = 0) {
   int rc;
@@ -1833,6 +1868,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   if (!sinc_simt) {
     if ((rc = run_sinc_prep(h->prep[lane], wav, B, g, s_seg, stream_hop ? stream_hop : h->hop, stream_hop != 0))) return rc;
     DG_CUDA(cudaEventRecord(h->e_prep[lane], s_seg));
+    DG_DIAG(prep, s_seg);
     DG_CUDA(cudaStreamWaitEvent(h->s_emb, h->e_prep[lane], 0));
     shared = &h->prep[lane];
   }
@@ -1849,6 +1885,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     h->emb->shared_prep = nullptr;
     g_sm_limit = 0;
     if (rc) return rc;
+    DG_DIAG(trunk, h->s_emb);
   }
   h->seg->lane = lane;
   h->seg->shared_prep = shared;
@@ -1858,6 +1895,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   if (rc) return rc;
   if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, osp.as<float>(), s_seg))) return rc;
   DG_CUDA(cudaEventRecord(e_osp, s_seg));
+  DG_DIAG(seg, s_seg);
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, e_osp, 0));
   if ((rc = build_tables(h->emb, F, T, h->s_emb))) return rc;
   if (fuse_pool) {
@@ -1872,6 +1910,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     g_sm_limit = 0;
     if (rc) return rc;
     DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));
+    DG_DIAG(emb, h->s_emb);
     return DG_OK;
   }
   if (h->emb->pooled.ensure((size_t)B * K * 2 * h->emb->pool_C * 4)) return DG_ECUDA;
@@ -1960,6 +1999,7 @@ static int pipeline_submit_common(dg_pipeline* h, const float* wav_dev, int B, i
                             h->slot_map[slot].as<int32_t>(), nullptr, h->s_clu)))
     return rc;
   DG_CUDA(cudaEventRecord(h->e_slot_done[slot], h->s_clu));
+  DG_DIAG(clu, h->s_clu);
   h->slot_B[slot] = B;
   h->slot_S[slot] = S;
   h->next_step++;
@@ -2404,6 +2444,37 @@ static int upload_rows(dg_pipeline* h, const float* const* rows, int B, int S, f
   return 0;
 }
 
+// Windows that are consecutive hops of ONE stream -- what the reference's rearrange_audio_stream emits (operators.py:44-100) --
+// share S - hop samples with their neighbour.  The workers compare every window with its predecessor (memcmp of the shared
+// samples, exact) and pack the `hop` new samples of each into the pinned stream image; the caller then uploads
+// S + (B - 1) hop samples instead of B S and forms the windows on the device.  Returns 1 if windows [r0, r0 + nb) continue the
+// stream (pin_stream[0 .. S + (r0 + nb - 1) hop) is then valid), 0 if some window does not (the caller falls back to the
+// full gather for this and the following sub-batches).
+static int pack_stream_rows(dg_pipeline* h, const float* const* rows, int r0, int nb, int S, int hop, float* pin_stream) {
+  if (!h->gather) {
+    int n = (int)std::thread::hardware_concurrency();
+    static const int env_threads = getenv("DG_GATHER_THREADS") ? atoi(getenv("DG_GATHER_THREADS")) : 0;
+    n = env_threads > 0 ? env_threads : std::max(1, std::min(n - 2, 24));
+    h->gather.reset(new GatherPool(n));
+  }
+  std::atomic<int> next{r0}, bad{0};
+  h->gather->start([&]() {
+    for (;;) {
+      const int r = next.fetch_add(1, std::memory_order_relaxed);
+      if (r >= r0 + nb || bad.load(std::memory_order_relaxed)) return;
+      if (r == 0) {
+        memcpy(pin_stream, rows[0], (size_t)S * 4);
+      } else if (memcmp(rows[r - 1] + hop, rows[r], (size_t)(S - hop) * 4) != 0) {
+        bad.store(1, std::memory_order_relaxed);
+      } else {
+        memcpy(pin_stream + (size_t)S + (size_t)(r - 1) * hop, rows[r] + (S - hop), (size_t)hop * 4);
+      }
+    }
+  });
+  h->gather->wait();
+  return bad.load() ? 0 : 1;
+}
+
 extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float* const* rows_host, int B, int S,
                                      const int32_t* plan_host, int32_t* header_host, uint32_t* turns_host, int turn_cap_host,
                                      int* n_turns, float* seg_host, int32_t* map_host) {
@@ -2427,6 +2498,12 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
   // DG_CALL_TIMING=1: host wall-clock phases of the call on stderr (diagnostic)
   static const bool call_timing = getenv("DG_CALL_TIMING") && getenv("DG_CALL_TIMING")[0] == '1';
   const auto tc0 = std::chrono::steady_clock::now();
+  static thread_local CallDiag diag;
+  if (call_timing) {
+    diag.create();
+    cudaEventRecord(diag.t0, h->s_h2d);
+    g_diag = &diag;
+  }
   if (h->segd.ensure((size_t)B * F * K * 4) || h->mapd.ensure((size_t)B * K * 4)) return DG_ECUDA;
   const size_t bytes = (size_t)B * S * 4;
   if (bytes > h->pin_wav_bytes) {
@@ -2474,17 +2551,43 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
       plan[1] = B - plan[0];
     }
   }
+  // consecutive windows of one stream (hop known from dg_pipeline_set_hop): verified on the host, uploaded once (see
+  // pack_stream_rows); DG_CALL_NO_DEDUP=1 = always the full gather
+  static const bool no_dedup = getenv("DG_CALL_NO_DEDUP") && getenv("DG_CALL_NO_DEDUP")[0] == '1';
+  const int hop = h->hop;
+  bool as_stream = !no_dedup && hop > 0 && hop < S && hop % 4 == 0 && S % 4 == 0 && B >= 2;
+  const size_t stream_len = (size_t)S + (size_t)(B - 1) * (hop > 0 ? hop : 0);
+  if (as_stream && h->call_stream.ensure((stream_len + 64) * 4)) return DG_ECUDA;
+  float* pin = reinterpret_cast<float*>(h->pin_wav);
+  h->call_h2d_bytes = 0;
   int slots[DG_MAX_INFLIGHT], nbs[DG_MAX_INFLIGHT];
   for (int j = 0, r0 = 0; j < ns; r0 += plan[j], j++) {
     const int nb = plan[j];
     const int slot = (int)(h->next_step % 3);
     if ((rc = pipeline_slot_prepare(h, slot, nb, S, F, K, true))) return rc;
     DG_CUDA(cudaStreamWaitEvent(h->s_h2d, h->e_slot_done[slot], 0));
-    if ((rc = upload_rows(h, rows_host + r0, nb, S, reinterpret_cast<float*>(h->pin_wav) + (size_t)r0 * S,
-                          h->slot_wav[slot].as<float>(), h->s_h2d)))
-      return rc;
+    if (as_stream && !pack_stream_rows(h, rows_host, r0, nb, S, hop, pin)) as_stream = false;
+    int stream_hop = 0;
+    if (as_stream) {
+      // the samples this sub-batch adds to the device image of the stream, then its windows from that image
+      const size_t lo = r0 == 0 ? 0 : (size_t)S + (size_t)(r0 - 1) * hop, hi = (size_t)S + (size_t)(r0 + nb - 1) * hop;
+      DG_CUDA(cudaMemcpyAsync(h->call_stream.as<float>() + lo, pin + lo, (hi - lo) * 4, cudaMemcpyHostToDevice, h->s_h2d));
+      h->call_h2d_bytes += (long long)(hi - lo) * 4;
+      const long long cap = (long long)((stream_len + 3) / 4 * 4 + 4);     // linear image: the ring index never wraps
+      if ((rc = launch_expand_windows(h->call_stream.as<float>(), (long long)r0 * hop, (int)cap, hop, S, nb,
+                                      h->slot_wav[slot].as<float>(), h->s_h2d)))
+        return rc;
+      stream_hop = hop;
+    } else {
+      // (after a failed stream check the pinned buffer is reused as the [B, S] staging: earlier sub-batches are already on the device)
+      if (h->call_h2d_bytes) DG_CUDA(cudaStreamSynchronize(h->s_h2d));
+      if ((rc = upload_rows(h, rows_host + r0, nb, S, pin + (size_t)r0 * S, h->slot_wav[slot].as<float>(), h->s_h2d))) return rc;
+      h->call_h2d_bytes += (long long)nb * S * 4;
+    }
     DG_CUDA(cudaEventRecord(h->e_h2d[slot], h->s_h2d));
-    if ((rc = pipeline_submit_common(h, h->slot_wav[slot].as<float>(), nb, S, F, K, slot, h->e_h2d[slot]))) return rc;
+    if (g_diag) g_diag->j = j;
+    DG_DIAG(up, h->s_h2d);
+    if ((rc = pipeline_submit_common(h, h->slot_wav[slot].as<float>(), nb, S, F, K, slot, h->e_h2d[slot], stream_hop))) return rc;
     slots[j] = slot;
     nbs[j] = nb;
   }
@@ -2503,7 +2606,18 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
   DG_CUDA(cudaStreamSynchronize(h->st));
   const auto tc2 = std::chrono::steady_clock::now();
   rc = post_finish(post, B, header_host, turns_host, turn_cap_host, n_turns, h->st);
+  g_diag = nullptr;
   if (call_timing) {
+    static int shown = 0;
+    if (rc == 0 && shown++ % 4 == 3) {
+      for (int j = 0; j < ns; j++) {
+        float t[6] = {0, 0, 0, 0, 0, 0};
+        cudaEvent_t ev[6] = {diag.up[j], diag.prep[j], diag.trunk[j], diag.seg[j], diag.emb[j], diag.clu[j]};
+        for (int q = 0; q < 6; q++) cudaEventElapsedTime(&t[q], diag.t0, ev[q]);
+        fprintf(stderr, "  sub-batch %d (%d windows), ms after entry: uploaded %.2f | front end %.2f | embedding trunk %.2f | segmentation + "
+                        "OSP %.2f | embeddings %.2f | clustered %.2f\n", j, nbs[j], t[0], t[1], t[2], t[3], t[4], t[5]);
+      }
+    }
     static double acc[3] = {0, 0, 0};
     static int calls = 0;
     const auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
@@ -2519,6 +2633,8 @@ extern "C" int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float*
   }
   return rc;
 }
+
+extern "C" int64_t dg_pipeline_last_call_h2d_bytes(const dg_pipeline* h) { return h ? (int64_t)h->call_h2d_bytes : 0; }
 
 // ---- shared-identity mode (BASELINE config 5) without leaving the pipelined flow.  After dg_pipeline_submit*:
 //   dg_pipeline_identity_export  enqueues the export of this rank's centroid changes behind the clustering of every submitted

@@ -16,6 +16,11 @@
 //                                         the active centroids (8 warps), the assignment logic
 //                                         (warp 0), then centroid update + SpeakerMap.apply scatter
 //                                         (all threads).
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
 #include "dg_common.cuh"
 
 namespace dg {
@@ -189,7 +194,7 @@ __global__ void __launch_bounds__(SEQ_THREADS)
 cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* __restrict__ emb, int B, int F, int K,
                    double* __restrict__ centers, int* __restrict__ g_active, int* __restrict__ g_init,
                    const float* __restrict__ prep, const double* __restrict__ prep_d, int32_t* __restrict__ map_out,
-                   float* __restrict__ permuted) {
+                   float* __restrict__ permuted, unsigned* __restrict__ dbg) {
   __shared__ SeqShared sh;
   __shared__ float prs[2][CK * 3];      // per-chunk max / mean / nan flag, double buffered
   __shared__ double ens[2][CK];         // per-chunk embedding norms
@@ -222,17 +227,19 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     const float* ecur = es + (size_t)cur * K * D;
     const float* pr = prs[cur];
     const bool init = sh.initialized != 0;
+    if (dbg && tid == 0) dbg[ci * 4 + 0] = (unsigned)clock();
     if (ci + 1 < B) prefetch(ci + 1, cur ^ 1);
     // ---------------- phase A: float64 cosine distances (scipy cdist 'cosine':
     //                  1 - u.v / (|u| |v|), clipped to [-1, 1] before the subtraction).
     //                  One warp per active centroid: its norm and its K dot products in one pass.
-    if (init) {
+    if (init && p.metric == 0) {
       for (int g = warp; g < M; g += NW) {
         if (!sh.active[g]) continue;
         const double* c = cs + (size_t)g * D;
         double acc[CK + 1];
 #pragma unroll
         for (int k = 0; k <= CK; k++) acc[k] = 0.0;
+#pragma unroll 4
         for (int d = lane; d < D; d += 32) {
           const double cv = c[d];
           acc[CK] = fma(cv, cv, acc[CK]);
@@ -244,19 +251,52 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
         for (int k = 0; k <= CK; k++)
           if (k < K || k == CK)
             for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(FULL, acc[k], o);
-        const double cn = sqrt(acc[CK]);
+        // lane k finishes local speaker k: ONE float64 square root and ONE division per warp, executed by all lanes at once (a
+        // branch per k would run the three divisions one after the other: the float64 division is a long dependent chain)
+        double dot = acc[0];
+#pragma unroll
+        for (int k = 1; k < CK; k++) dot = (lane == k) ? acc[k] : dot;
+        const double en = ens[cur][lane < K ? lane : 0];
+        double cosv = dot / (en * sqrt(acc[CK]));
+        if (fabs(cosv) > 1.0) cosv = copysign(1.0, cosv);
+        if (lane < K) sh.dist[lane][g] = 1.0 - cosv;
+      }
+    } else if (init) {
+      // the other scipy.spatial.distance.cdist metrics the reference accepts through `metric` (mapping.py:175), in float64:
+      // 1 euclidean, 2 sqeuclidean, 3 cityblock, 4 chebyshev
+      for (int g = warp; g < M; g += NW) {
+        if (!sh.active[g]) continue;
+        const double* c = cs + (size_t)g * D;
+        double acc[CK];
+#pragma unroll
+        for (int k = 0; k < CK; k++) acc[k] = 0.0;
+        for (int d = lane; d < D; d += 32) {
+          const double cv = c[d];
+#pragma unroll
+          for (int k = 0; k < CK; k++)
+            if (k < K) {
+              const double df = (double)ecur[k * D + d] - cv;
+              if (p.metric <= 2) acc[k] = fma(df, df, acc[k]);
+              else if (p.metric == 3) acc[k] += fabs(df);
+              else acc[k] = fmax(acc[k], fabs(df));
+            }
+        }
 #pragma unroll
         for (int k = 0; k < CK; k++)
-          if (k < K && lane == k) {
-            double cosv = acc[k] / (ens[cur][k] * cn);
-            if (fabs(cosv) > 1.0) cosv = copysign(1.0, cosv);
-            sh.dist[k][g] = 1.0 - cosv;
-          }
+          if (k < K)
+            for (int o = 16; o > 0; o >>= 1) {
+              const double other = __shfl_xor_sync(FULL, acc[k], o);
+              acc[k] = p.metric == 4 ? fmax(acc[k], other) : acc[k] + other;
+            }
+#pragma unroll
+        for (int k = 0; k < CK; k++)
+          if (k < K && lane == k) sh.dist[k][g] = p.metric == 1 ? sqrt(acc[k]) : acc[k];
       }
     }
     __syncthreads();
     // ---------------- phase B: assignment logic, warp 0, one global speaker per lane
     if (warp == 0) {
+      if (dbg && lane == 0) dbg[ci * 4 + 1] = (unsigned)clock();
       unsigned active_spk = 0, long_spk = 0;
       for (int k = 0; k < K; k++) {
         // np.max(seg) >= tau, np.mean(seg) >= rho: float32 array vs Python float -> float32 compare
@@ -378,6 +418,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
       if (lane == 0) {
         sh.n_upd = n_upd;
         sh.n_new = n_new;
+        if (dbg) dbg[ci * 4 + 2] = (unsigned)clock();
       }
     }
     __syncthreads();
@@ -406,6 +447,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     }
     asm volatile("cp.async.wait_group 0;");
     __syncthreads();
+    if (dbg && tid == 0) dbg[ci * 4 + 3] = (unsigned)clock();
   }
   for (int i = tid; i < M * D; i += SEQ_THREADS) centers[i] = cs[i];
   if (tid < M) g_active[tid] = sh.active[tid];
@@ -436,8 +478,30 @@ int launch_cluster_step(const ClusterParams& p, const float* seg, const float* e
     if (first_use_on_device(attr_done))
       DG_CUDA(cudaFuncSetAttribute(cluster_seq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   }
+  static const bool timing = getenv("DG_CLUSTER_TIMING") && getenv("DG_CLUSTER_TIMING")[0] == '1';
+  if (timing) {   // diagnostic: SM-clock stamps per chunk (distances | assignment logic | update + hand-over), synchronises
+    unsigned* dbg = nullptr;
+    DG_CUDA(cudaMalloc(&dbg, (size_t)B * 4 * sizeof(unsigned)));
+    cluster_seq_kernel<<<1, SEQ_THREADS, dyn, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map, permuted, dbg);
+    DG_CUDA(cudaStreamSynchronize(st));
+    std::vector<unsigned> hb((size_t)B * 4);
+    DG_CUDA(cudaMemcpy(hb.data(), dbg, hb.size() * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dbg);
+    double a = 0, b = 0, c = 0;
+    for (int i = 0; i < B; i++) {
+      a += (double)(int)(hb[i * 4 + 1] - hb[i * 4 + 0]);
+      b += (double)(int)(hb[i * 4 + 2] - hb[i * 4 + 1]);
+      c += (double)(int)(hb[i * 4 + 3] - hb[i * 4 + 2]);
+    }
+    static int shown = 0;
+    if (shown++ < 8)
+      fprintf(stderr, "cluster_seq timing (B=%d, cycles per chunk): distances %.0f | assignment logic %.0f | update + hand-over %.0f | total %.0f\n",
+              B, a / B, b / B, c / B, (a + b + c) / B);
+    DG_LAUNCHED();
+    return 0;
+  }
   cluster_seq_kernel<<<1, SEQ_THREADS, dyn, st>>>(p, seg, emb, B, F, K, centers, active, initialized, prep, prep_d, map,
-                                          permuted);
+                                          permuted, nullptr);
   DG_LAUNCHED();
   return 0;
 }

@@ -62,6 +62,7 @@ struct ProfScope {
   cudaStream_t st;
   cudaEvent_t a, b;
   const char* name;
+  long long first = 0;
   ProfScope(const char* name, cudaStream_t st);
   ~ProfScope();
 };
@@ -107,8 +108,8 @@ int launch_sinc0(const float* wav, const float* mean, const float* rstd, float w
                  const float* filt /*[251][80]*/, int B, const Geom& g, float* p0 /*[B,S0,80]*/, cudaStream_t st);
 int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, int ldc, const float* gamma,
                           const float* beta, float* sc, float* sh, cudaStream_t st, int pool = 0, const int* skip_flag = nullptr);
-int launch_instnorm_finalize(const float* part, int B, int item_rows, int T, int C, int N, const float* bias, const float* gamma,
-                             const float* beta, float* sc, float* sh, int ld, cudaStream_t st);
+int launch_instnorm_finalize(const float* part, int B, int item_rows, int tile_rows, int T, int C, int N, const float* bias,
+                             const float* gamma, const float* beta, float* sc, float* sh, int ld, cudaStream_t st);
 // gemm.cu
 enum Epi { EPI_BIAS = 0, EPI_BIAS_LEAKY = 1, EPI_BIAS_LEAKY_BN = 2, EPI_BIAS_POOL3 = 3 };
 struct GemmArgs {
@@ -166,11 +167,17 @@ struct TcGemm {
   float* pool_part;      // [m_tiles][2][4][2][N]
   int pool_item_rows, pool_K;
   // epi 5 (SincNet Conv1d + MaxPool1d(3) + InstanceNorm statistics): out_f32 = bias + max over row triplets ([M / 3, ldc]),
-  // pool_part = per-tile partial sums [ceil(M / 126)][2][2][N] (gemm_tc_pool3_tiles), reduced by launch_instnorm_finalize;
+  // pool_part = per-tile partial sums [M / pool3_tile_rows][2][2][N], reduced by launch_instnorm_finalize;
   // pool_item_rows = un-pooled rows per item (multiple of 3), pool3_T = valid pooled frames per item
-  int pool3_T;
+  int pool3_T, pool3_tile_rows;
 };
-inline long long gemm_tc_pool3_tiles(long long M) { return (M + 125) / 126; }
+// rows an m-tile of the pooling epilogue advances by: the largest multiple of 3 up to 126 that divides the item's rows
+// (tiles never straddle items: an item's statistics are grouped identically wherever it sits in the batch); 0 if none >= 96
+inline int gemm_tc_pool3_tile_rows(int item_rows) {
+  for (int t = 126; t >= 96; t -= 3)
+    if (item_rows % t == 0) return t;
+  return 0;
+}
 int launch_gemm_tc(const TcGemm& g, cudaStream_t st);
 int launch_split(const float* x, long long rows, int C, int item_rows, const float* sc, const float* sh, void* hi,
                  void* lo, cudaStream_t st);
@@ -252,6 +259,7 @@ struct ClusterParams {
   int M, D;
   float tau_f, rho_f;   // thresholds as numpy compares them (float32, see cluster.cu)
   double delta;
+  int metric;           // 0 cosine (default), 1 euclidean, 2 sqeuclidean, 3 cityblock, 4 chebyshev (scipy cdist names)
 };
 int launch_cluster_step(const ClusterParams& p, const float* seg, const float* emb, int B, int F, int K,
                         double* centers, int* active, int* initialized, float* prep /*scratch*/,

@@ -62,7 +62,8 @@ struct TcArgs {
   const float* pool_w;     // [rows][4]: pooling weight of (row, speaker), zero for rows past an item's valid frames
   float* pool_part;        // [m_tiles][2 (item of the tile)][4 (speaker)][2 (sum w d, sum w d^2)][N]
   int pool_item_rows, pool_K;
-  // TC_MAXPOOL3: m-tiles advance by `tile_rows` = 126 rows (42 pooling windows; the MMA still covers 128), out_f32 receives
+  // TC_MAXPOOL3: m-tiles advance by `tile_rows` <= 126 rows (whole pooling windows, a divisor of the item's rows, so that every
+  // item is summed in the same grouping wherever it sits in the batch; the MMA still covers 128 rows), out_f32 receives
   // bias + MaxPool1d(3) over rows ([M / 3, ldc]), pool_part the per-tile InstanceNorm partial sums of the pre-bias pooled values:
   // [m_tiles][2 (item of the tile)][2 (sum, sum of squares)][N] over the pooled frames < pool3_T of an item
   int tile_rows, pool3_T;
@@ -697,7 +698,7 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
     return -2;
   TcArgs a{};
   a.M = g.M; a.N = g.N; a.n_tiles = n_tiles;
-  a.tile_rows = EPI == TC_MAXPOOL3 ? 126 : TC_BM;
+  a.tile_rows = EPI == TC_MAXPOOL3 ? g.pool3_tile_rows : TC_BM;
   a.pool3_T = g.pool3_T;
   a.m_tiles = (int)((g.M + a.tile_rows - 1) / a.tile_rows);
   a.KW = g.KW; a.dil = g.dil; a.cin_blocks = g.Cin / TC_BK;
@@ -778,8 +779,9 @@ int launch_gemm_tc(const TcGemm& g, cudaStream_t st) {
     return launch_tc<256, TC_POOL>(g, st);
   }
   if (g.epi == TC_MAXPOOL3) {
-    if (g.Npad != 64 || !g.out_f32 || !g.pool_part || g.pool_item_rows % 3 || g.pool_item_rows < 126 || g.M % 3 || g.pool3_T < 1) {
-      set_error("gemm_tc (maxpool3): needs 64 output channels, items whose row count is a multiple of 3 and at least 126");
+    if (g.Npad != 64 || !g.out_f32 || !g.pool_part || g.pool3_T < 1 || g.pool3_tile_rows < 3 || g.pool3_tile_rows > 126 ||
+        g.pool3_tile_rows % 3 || g.pool_item_rows % g.pool3_tile_rows || g.M % g.pool_item_rows) {
+      set_error("gemm_tc (maxpool3): needs 64 output channels and tiles of 3..126 rows (a multiple of 3) that divide the item");
       return -1;
     }
     return launch_tc<64, TC_MAXPOOL3>(g, st);

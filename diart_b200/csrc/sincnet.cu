@@ -250,21 +250,19 @@ int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, 
   return 0;
 }
 
-// InstanceNorm1d(affine) scale / shift from the per-tile partial sums of gemm_tc's TC_MAXPOOL3 epilogue (tiles of 126 un-pooled
-// rows; slot 0 = the item of the tile's first row, slot 1 = the next item).  The sums are of the pooled values BEFORE the
-// bias, which serves as the pivot; the <= 23 tiles of an item are added in tile order, in double.
-__global__ void __launch_bounds__(64) instnorm_finalize_kernel(const float* __restrict__ part, int item_rows, int T, int C, int N,
+// InstanceNorm1d(affine) scale / shift from the per-tile partial sums of gemm_tc's TC_MAXPOOL3 epilogue (tiles of `tile_rows`
+// un-pooled rows, a divisor of the item's rows: slot 0 of the item's own tiles).  The sums are of the pooled values BEFORE the
+// bias, which serves as the pivot; the tiles of an item are added in tile order, in double.
+__global__ void __launch_bounds__(64) instnorm_finalize_kernel(const float* __restrict__ part, int tiles_per_item, int T, int C, int N,
                                                                const float* __restrict__ bias, const float* __restrict__ gamma,
                                                                const float* __restrict__ beta, float* __restrict__ sc,
                                                                float* __restrict__ sh, int ld) {
   const int b = blockIdx.x, c = threadIdx.x;
   if (c >= C) return;
-  const long long r0 = (long long)b * item_rows, r1 = r0 + item_rows - 1;
   double t1 = 0, t2 = 0;
-  for (long long mt = r0 / 126; mt <= r1 / 126; mt++) {
-    const int sg = mt * 126 < r0 ? 1 : 0;
-    t1 += part[((mt * 2 + sg) * 2 + 0) * N + c];
-    t2 += part[((mt * 2 + sg) * 2 + 1) * N + c];
+  for (long long mt = (long long)b * tiles_per_item; mt < (long long)(b + 1) * tiles_per_item; mt++) {
+    t1 += part[((mt * 2 + 0) * 2 + 0) * N + c];
+    t2 += part[((mt * 2 + 0) * 2 + 1) * N + c];
   }
   const double m = t1 / T;
   double var = t2 / T - m * m;
@@ -276,14 +274,14 @@ __global__ void __launch_bounds__(64) instnorm_finalize_kernel(const float* __re
   sh[(size_t)b * ld + c] = beta[c] - (float)mean * gsc;
 }
 
-int launch_instnorm_finalize(const float* part, int B, int item_rows, int T, int C, int N, const float* bias, const float* gamma,
-                             const float* beta, float* sc, float* sh, int ld, cudaStream_t st) {
+int launch_instnorm_finalize(const float* part, int B, int item_rows, int tile_rows, int T, int C, int N, const float* bias,
+                             const float* gamma, const float* beta, float* sc, float* sh, int ld, cudaStream_t st) {
   ProfScope _ps("instnorm_finalize", st);
-  if (C > 64) {
-    set_error("instnorm_finalize: at most 64 channels");
+  if (C > 64 || tile_rows < 1 || item_rows % tile_rows) {
+    set_error("instnorm_finalize: at most 64 channels, tiles must divide the item");
     return -1;
   }
-  instnorm_finalize_kernel<<<B, 64, 0, st>>>(part, item_rows, T, C, N, bias, gamma, beta, sc, sh, ld);
+  instnorm_finalize_kernel<<<B, 64, 0, st>>>(part, item_rows / tile_rows, T, C, N, bias, gamma, beta, sc, sh, ld);
   DG_LAUNCHED();
   return 0;
 }

@@ -105,6 +105,9 @@ int dg_normalize_embeddings(const float* emb_dev /*[rows,D]*/, int rows, int D, 
  *      the device. ---- */
 int dg_cluster_create(int max_speakers, int dim, double tau_active, double rho_update,
                       double delta_new, int device, dg_cluster** out);
+/* Distance of the embeddings to the centroids: the `metric` argument of the reference class (clustering.py:31-46), handed to
+ * scipy's cdist at mapping.py:175.  0 cosine (default), 1 euclidean, 2 sqeuclidean, 3 cityblock, 4 chebyshev; float64. */
+int dg_cluster_set_metric(dg_cluster* h, int metric);
 /* Processes the B chunks in order (the reference's sequential loop, diarization.py:193-203).
  * map_dev  int32 [B,K]: global speaker of each local speaker, -1 if unmapped.
  * permuted_dev float32 [B,F,M] or NULL: SpeakerMap.apply output (values are float32-exact). */
@@ -177,12 +180,16 @@ int dg_post_step(dg_post* h, const float* seg_dev /*[B,F,K]*/, const int32_t* ma
 int dg_post_reset(dg_post* h);
 int dg_post_destroy(dg_post* h);
 /* The whole body of SpeakerDiarization.__call__ (reference diarization.py:172-232) in ONE call: rows_host[b] points to the
- * S float32 samples of window b (B separate host arrays, as rearrange_audio_stream emits them); they are gathered into
- * pinned staging by worker threads and uploaded while the gather is still running, then fused step + post-path; only the
- * turn list (and, if asked for, scores and maps) returns to the host.  Synchronous. */
+ * S float32 samples of window b (B separate host arrays, as rearrange_audio_stream emits them).  With a hop set
+ * (dg_pipeline_set_hop) worker threads compare every window with its predecessor (memcmp of the S - hop shared samples);
+ * windows that are consecutive hops of one stream are uploaded ONCE (S + (B-1) hop samples) and formed on the device,
+ * anything else is gathered into pinned staging and uploaded as [B,S] while the gather is still running.  Then fused step
+ * + post-path in up to three pipelined sub-batches; only the turn list (and, if asked for, scores and maps) returns to
+ * the host.  Synchronous.  dg_pipeline_last_call_h2d_bytes: what the last call uploaded. */
 int dg_pipeline_call_host(dg_pipeline* h, dg_post* post, const float* const* rows_host, int B, int S,
                           const int32_t* plan_host, int32_t* header_host, uint32_t* turns_host, int turn_cap_host,
                           int* n_turns, float* seg_host /*nullable*/, int32_t* map_host /*nullable*/);
+int64_t dg_pipeline_last_call_h2d_bytes(const dg_pipeline* h);
 
 /* ---- device-side audio stream: rearrange_audio_stream (reference src/diart/operators.py:44-100) with the ring buffer in
  *      HBM.  The host pushes every sample ONCE (step_samples new samples per chunk instead of chunk_samples: 8.2 MB

@@ -24,8 +24,8 @@ CONFIGS = [  # (max_speakers, sigma, delta, tau, rho, K)
 ]
 
 
-def _oracle_run(seg, emb, tau, rho, delta, M):
-    o = OracleClustering(tau, rho, delta, "cosine", M)
+def _oracle_run(seg, emb, tau, rho, delta, M, metric="cosine"):
+    o = OracleClustering(tau, rho, delta, metric, M)
     maps, outs = [], []
     for s, e in zip(seg, emb):
         a, out = o(s, e)
@@ -53,6 +53,24 @@ def test_cluster_stream_bit_exact(cfg, cuda_device):
     assert np.array_equal(got_out.astype(np.float64), ref_out)
     assert c.active_centers == o.active_centers
     assert np.array_equal(c.centers, o.centers), "centroids are not bit-identical"
+
+
+@pytest.mark.parametrize("metric,delta", [("euclidean", 1.3), ("sqeuclidean", 1.7), ("cityblock", 22.0), ("chebyshev", 0.16)])
+def test_cluster_other_cdist_metrics(metric, delta, cuda_device):
+    """the reference hands `metric` to scipy's cdist (mapping.py:175): the non-cosine metrics on unit-norm embeddings, thresholds
+    near the median assigned distance so that every branch (assign, create, re-assign on a full table) is reached"""
+    seg, emb = make_stream(512, 5, K=3, sigma=1.5)
+    emb = (emb / np.linalg.norm(emb, axis=-1, keepdims=True)).astype(np.float32)
+    for M in (20, 4):
+        o, ref_maps, _ = _oracle_run(seg, emb, 0.6, 0.3, delta, M, metric)
+        c = OnlineSpeakerClustering(0.6, 0.3, delta, metric, M, device=cuda_device)
+        got = np.concatenate([c.step_batch(torch.from_numpy(seg[lo:hi]), torch.from_numpy(emb[lo:hi]))[0].cpu().numpy()
+                              for lo, hi in ((0, 3), (3, 200), (200, 512))])
+        bad = np.where((got != ref_maps).any(axis=1))[0]
+        assert bad.size == 0, f"{metric}, M={M}: first differing chunk {bad[:5]}"
+        assert c.active_centers == o.active_centers
+        assert np.array_equal(c.centers, o.centers), "centroids are not bit-identical"
+        assert len(o.active_centers) > 1, "the threshold never created a second speaker"
 
 
 def test_cluster_single_chunk_api(cuda_device):

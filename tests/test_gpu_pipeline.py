@@ -103,6 +103,48 @@ def test_speaker_diarization_drop_in(oracle_nets, stream, cuda_device):
     assert pipe.clustering.centers is None
 
 
+def test_call_uploads_a_stream_once_and_falls_back_for_anything_else(oracle_nets, cuda_device):
+    """__call__ verifies on the host that the windows are consecutive hops of one stream and then uploads every sample once
+    (dg_pipeline_call_host); a batch that breaks the pattern -- here: a jump inside the second sub-batch, and a batch of
+    unrelated windows -- takes the full gather.  Both must give exactly what the fused step gives on the stacked windows."""
+    from diart_b200 import _lib
+
+    sr, step, n = 16000, 0.5, 72
+    audio = synth.synth_audio(80000 + 8000 * (n + 40), seed=5)
+    starts = [8000 * i for i in range(n)]
+    jump = list(starts)
+    for i in range(50, n):
+        jump[i] += 8000 * 17 + 4000          # window 50 does not continue window 49
+    shuffled = [starts[(7 * i) % n] for i in range(n)]
+    for name, offs, expect_stream in (("stream", starts, True), ("jump", jump, False), ("shuffled", shuffled, False)):
+        pipe = make_pipeline(oracle_nets, cuda_device)
+        ref = make_pipeline(oracle_nets, cuda_device)
+        chunks = [SlidingWindowFeature(np.ascontiguousarray(audio[o:o + 80000, None]),
+                                       SlidingWindow(start=step * i, duration=1 / sr, step=1 / sr)) for i, o in enumerate(offs)]
+        out = pipe(chunks)
+        uploaded = int(_lib.lib().dg_pipeline_last_call_h2d_bytes(pipe._fused))
+        if expect_stream:
+            assert uploaded == (80000 + 8000 * (n - 1)) * 4, f"{name}: {uploaded} bytes uploaded"
+        else:
+            assert uploaded > n * 80000 * 4 // 3, f"{name}: {uploaded} bytes uploaded"
+        x = torch.from_numpy(np.stack([audio[o:o + 80000] for o in offs])).to(cuda_device)
+        seg, _, maps = ref.device_step(x)
+        seg, maps = seg.cpu().numpy(), maps.cpu().numpy()
+        res = 5 / seg.shape[1]
+        for i in range(n):          # latency = step: every output is the binarised, permuted score of its own chunk
+            permuted = np.zeros((seg.shape[1], ref.config.max_speakers))
+            for k, g in enumerate(maps[i]):
+                if g >= 0:
+                    permuted[:, g] = seg[i][:, k]
+            swf = SlidingWindowFeature(permuted, SlidingWindow(start=step * i, duration=res, step=res))
+            want = ref.binarize(ref.pred_aggregation([swf])).to_rttm()
+            if out[i][0].to_rttm() != want:
+                # the reference step ran the whole batch through ONE form of the sinc layer, the call may have run its first
+                # sub-batch through the stream form (scores differ by ~1e-5): only a score that close to the threshold may flip
+                clearance = np.abs(permuted[permuted != 0] - ref.config.tau_active).min()
+                assert not expect_stream and clearance < 2e-4, f"{name}: chunk {i} differs, threshold clearance {clearance:.1e}"
+
+
 def test_foreign_models_behind_loader_api(oracle_nets, stream, cuda_device):
     """any Callable behind SegmentationModel / EmbeddingModel still works (block-by-block path);
     here: the oracle torch modules moved to the GPU"""
