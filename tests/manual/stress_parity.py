@@ -35,6 +35,7 @@ sw_of = lambda n: SlidingWindow(start=0.5 * n, duration=1 / 16000, step=1 / 1600
 
 
 def device_steps(n):
+    fused = pipe._ensure_fused(CHUNK)[0]       # (pipe.reset() drops the handle: never keep it across a reset)
     for i in range(n):
         _lib.check(lib.dg_pipeline_submit(fused, dev[i % NB].data_ptr(), B, CHUNK, stream))
         if i > 1:
@@ -44,6 +45,7 @@ def device_steps(n):
 
 
 def host_steps(n):
+    fused = pipe._ensure_fused(CHUNK)[0]
     for i in range(n):
         _lib.check(lib.dg_pipeline_submit_host(fused, pinned[i % NB].data_ptr(), B, CHUNK))
         if i >= 2:
