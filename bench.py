@@ -329,13 +329,14 @@ def run_ours(args):
         fused, F, K, D = pipe._ensure_fused(CHUNK)
         ident = SharedIdentity(pipe.clustering)
 
-        def ident_steps(n):
+        def ident_steps(n):          # three steps outstanding, like `value`
             for i in range(n):
                 _lib.check(lib.dg_pipeline_submit(fused, dev[i % NB].data_ptr(), B, CHUNK, stream))
                 ident.sync_submitted(fused)
-                if i > 0:
+                if i > 1:
                     _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
-            _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
+            for _ in range(min(n, 2)):
+                _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
 
         ident_steps(max(2, args.warmup))
         barrier()

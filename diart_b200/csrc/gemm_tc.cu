@@ -52,6 +52,7 @@ struct TcArgs {
   int f16;              // operand planes are fp16 (1) or bf16 (0)
   float acc_scale;      // 1 / (power-of-two scale of the weight planes): applied to the accumulator in the epilogue
   int vec8;             // output rows are 32-byte aligned: 256-bit stores
+  int tma_out;          // TC_BIAS_F32 on CTA pairs: rows leave through bulk tensor stores (tmOut)
   int tap_off[9];       // row offset of every tap (Conv1d: j * dil; Conv2d on a zero-padded map: (dw-1) * Hp + (dh-1))
   // TC_CONV2D: rows are positions (item, w, h) of a zero-padded [Wp][Hp] map; outputs go to the padded map [Wop][Hop] of the
   // next layer (stride 1: same geometry; stride 2: computed at every centre, only odd (w, h) are kept)
@@ -72,18 +73,23 @@ struct TcArgs {
 enum TcEpi { TC_BIAS_F32 = 0, TC_LEAKY_BN_SPLIT = 1, TC_LEAKY_BN_F32 = 2, TC_CONV2D = 3, TC_POOL = 4, TC_MAXPOOL3 = 5 };
 
 // ------------------------------------------------------------------------------------ the kernel
-template <int BN>
+// WRES: the whole W operand (all k-blocks, hi + lo planes) stays in shared memory for the lifetime of the persistent CTA -- the
+// 64-wide SincNet convolutions re-fetched 112 / 80 KB of W per 111-row tile and are bound by the L2->SM rate.  Layout:
+// [W: TC_WRES_KB k-blocks x (hi, lo)] [NSTAGE stages of A (hi, lo)] [parameters] [barriers] [epilogue staging]
+constexpr int TC_WRES_KB = 7;
+template <int BN, bool WRES = false>
 struct TcSmem {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;     // 16 KB per plane
   static constexpr int W_BYTES = BN * TC_BK * 2;
-  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int NSTAGE = BN == 256 ? 2 : (BN == 128 ? 3 : 4);   // BN = 64 / 32: 4 stages
+  static constexpr int WRES_BYTES = WRES ? TC_WRES_KB * 2 * W_BYTES : 0;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + (WRES ? 0 : 2 * W_BYTES);
+  static constexpr int NSTAGE = WRES ? 3 : (BN == 256 ? 2 : (BN == 128 ? 3 : 4));   // BN = 64 / 32: 4 stages
   static constexpr int PARAM_BYTES = 3 * BN * 4;
   // TC_POOL: activation chunk [128][33] + row weights [128][4] + cross-row-group staging [4][2][8][32], all float
   static constexpr int POOL_BYTES = (128 * 33 + 128 * 4 + 4 * 2 * 8 * 32) * 4;
   // TC_MAXPOOL3: accumulator chunk [128][33] + cross-row-group staging [4][2][2][32], all float
   static constexpr int POOL3_BYTES = (128 * 33 + 4 * 2 * 2 * 32) * 4;
-  static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
+  static constexpr int TOTAL = WRES_BYTES + NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;   // + barriers + alignment slack
   static constexpr int extra(int epi) { return epi == 4 ? POOL_BYTES : (epi == 5 ? POOL3_BYTES : 0); }
 };
 
@@ -91,10 +97,14 @@ struct TcSmem {
 // Executed by the 128 epilogue threads of a CTA (four warps, TMEM lane quadrant = warp % 4).  `mt` = index of the 128-row tile
 // (rows mt * 128 ..), `tmem_acc` = TMEM address of the tile's accumulator (lane 0), `acc_full_bar` is waited for before the
 // accumulator is read (after the parameter staging and the residual prefetch).
+// `tm_out` (TC_BIAS_F32 on CTA pairs): the float32 rows leave through bulk tensor stores -- each warp stages its 32 rows x 32
+// columns in shared memory (`out_stage`, 1024-byte aligned, 4 KB per warp, 128-byte swizzle) and one lane issues the store;
+// per-lane 32-byte global stores to 32 different rows kept this epilogue at 1450 cycles per 32-column chunk (lstm_inproj)
 template <int BN, int EPI>
 __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params, float* pool_stage, uint32_t tmem_acc, long long mt,
                                                  int n0, int quad, int lane, int et, bool stage_params, uint64_t* acc_full_bar,
-                                                 int acc_phase) {
+                                                 int acc_phase, const CUtensorMap* tm_out = nullptr,
+                                                 unsigned char* out_stage = nullptr) {
     const long long m = mt * (EPI == TC_MAXPOOL3 ? a.tile_rows : TC_BM) + quad * 32 + lane;
     // stage the per-column parameters of this tile (named barrier 1: the 128 epilogue threads only); with a single
     // column tile they are the same for every tile of this CTA: staged once
@@ -224,9 +234,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
         // bias + MaxPool1d(3) over the rows of the tile (42 windows of three TMEM lanes: through shared memory), and the
         // InstanceNorm partial sums of the pooled values, split at `brow3` between the tile's two items
         float* dsm = pool_stage;                    // [128][33]
-        float* stg = pool_stage + 128 * 33;         // [rg 4][item 2][2][32]
+        float* stg = pool_stage + a.tile_rows * 33; // [rg 4][item 2][2][32]
+        if (quad * 32 + lane < a.tile_rows) {        // (the staging buffer holds tile_rows rows)
 #pragma unroll
-        for (int i = 0; i < 32; i++) dsm[(quad * 32 + lane) * 33 + i] = __uint_as_float(r[i]) * a.acc_scale;
+          for (int i = 0; i < 32; i++) dsm[(quad * 32 + lane) * 33 + i] = __uint_as_float(r[i]) * a.acc_scale;
+        }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         {
           const int col = et & 31, rg = et >> 5, n = n0 + c + col;
@@ -318,6 +330,28 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
         }
         continue;
       }
+      if (EPI == TC_BIAS_F32 && tm_out) {
+        unsigned char* wst = out_stage + quad * 4096;           // this warp's [32 rows][128 B]
+        if (lane == 0) tma_store_wait_read();                   // the previous chunk's store has read the buffer
+        __syncwarp();
+        const uint32_t row_addr = smem_u32(wst) + lane * 128;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float x0 = fmaf(__uint_as_float(r[4 * j]), a.acc_scale, params[c + 4 * j]);
+          const float x1 = fmaf(__uint_as_float(r[4 * j + 1]), a.acc_scale, params[c + 4 * j + 1]);
+          const float x2 = fmaf(__uint_as_float(r[4 * j + 2]), a.acc_scale, params[c + 4 * j + 2]);
+          const float x3 = fmaf(__uint_as_float(r[4 * j + 3]), a.acc_scale, params[c + 4 * j + 3]);
+          st_shared_v4(row_addr + ((j ^ (lane & 7)) << 4), __float_as_uint(x0), __float_as_uint(x1), __float_as_uint(x2),
+                       __float_as_uint(x3));
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(tm_out, wst, n0 + c, (int)(mt * TC_BM) + quad * 32);
+          tma_store_commit();
+        }
+        continue;
+      }
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         float x = fmaf(__uint_as_float(r[i]), a.acc_scale, params[c + i]);
@@ -377,14 +411,16 @@ __device__ __forceinline__ void tc_epilogue_tile(const TcArgs& a, float* params,
     }
 }
 
-template <int BN, int EPI>
+template <int BN, int EPI, bool WRES = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcArgs a) {
-  using S = TcSmem<BN>;
+  using S = TcSmem<BN, WRES>;
   constexpr int NSTAGE = S::NSTAGE;
   extern __shared__ unsigned char smem_raw[];
-  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* smem_base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  unsigned char* wres = smem_base;                       // WRES: [k-block][hi 64 x 64 | lo 64 x 64], resident
+  unsigned char* smem = smem_base + S::WRES_BYTES;       // the stage ring
   float* params = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES);          // bias | bn_scale | bn_shift
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES);
   uint64_t* full = bars;                 // [NSTAGE] TMA -> MMA
@@ -392,6 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   uint64_t* acc_full = bars + 2 * NSTAGE;      // [2] MMA -> epilogue
   uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
+  uint64_t* w_full = bars + 2 * NSTAGE + 5;    // WRES: the resident W operand has landed
   float* pool_stage = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES + 256);   // TC_POOL / TC_MAXPOOL3 only
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform
@@ -407,6 +444,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);     // one arrive per epilogue warp
     }
+    if (WRES) mbar_init(w_full, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM: two accumulators of BN fp32 columns
@@ -423,6 +461,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
+      if (WRES) {   // the whole W operand once (a single column tile: n0 = 0)
+        mbar_expect_tx(w_full, kblocks * 2 * S::W_BYTES);
+        for (int kb = 0; kb < kblocks; kb++) {
+          tma_load_2d(wres + kb * 2 * S::W_BYTES, &tmW_hi, kb * TC_BK, 0, w_full);
+          tma_load_2d(wres + kb * 2 * S::W_BYTES + S::W_BYTES, &tmW_lo, kb * TC_BK, 0, w_full);
+        }
+      }
       int stage = 0, phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
@@ -435,8 +480,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
             const int kcol = (j * a.cin_blocks + cb) * TC_BK;
             tma_load_2d(st, &tmA_hi, cb * TC_BK, m0 + a.tap_off[j], &full[stage]);
             tma_load_2d(st + S::A_BYTES, &tmA_lo, cb * TC_BK, m0 + a.tap_off[j], &full[stage]);
-            tma_load_2d(st + 2 * S::A_BYTES, &tmW_hi, kcol, n0, &full[stage]);
-            tma_load_2d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, kcol, n0, &full[stage]);
+            if (!WRES) {
+              tma_load_2d(st + 2 * S::A_BYTES, &tmW_hi, kcol, n0, &full[stage]);
+              tma_load_2d(st + 2 * S::A_BYTES + S::W_BYTES, &tmW_lo, kcol, n0, &full[stage]);
+            }
             if (++stage == NSTAGE) {
               stage = 0;
               phase ^= 1;
@@ -452,6 +499,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
       // instruction descriptor: D=f32, A=B=fp16 (or bf16), both K-major, N = BN, M = 128
       const uint32_t idesc = (1u << 4) | idesc_ab_format(a.f16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
       int stage = 0, phase = 0, acc = 0, acc_phase = 0;
+      if (WRES) {
+        mbar_wait(w_full, 0);
+        tc_fence_after();
+      }
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         mbar_wait(&acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
@@ -460,8 +511,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant
           mbar_wait(&full[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * S::STAGE_BYTES);
+          const uint32_t sw = WRES ? smem_u32(wres + kb * 2 * S::W_BYTES) : sa + 2 * S::A_BYTES;
           const uint64_t a_hi = umma_desc(sa), a_lo = umma_desc(sa + S::A_BYTES);
-          const uint64_t w_hi = umma_desc(sa + 2 * S::A_BYTES), w_lo = umma_desc(sa + 2 * S::A_BYTES + S::W_BYTES);
+          const uint64_t w_hi = umma_desc(sw), w_lo = umma_desc(sw + S::W_BYTES);
 #pragma unroll
           for (int ks = 0; ks < TC_BK / 16; ks++) {
             const uint64_t adv = (uint64_t)((ks * 32) >> 4);   // +32 bytes per 16-element k-step
@@ -522,13 +574,15 @@ struct TcSmem2 {
   static constexpr int NSTAGE = BN == 256 ? 3 : 4;
   static constexpr int PARAM_BYTES = 3 * BN * 4;
   static constexpr int POOL_BYTES = (128 * 33 + 128 * 4 + 4 * 2 * 8 * 32) * 4;
+  static constexpr int OUT_STAGE_BYTES = 4 * 4096 + 1024;     // bulk-store epilogue: 4 warps x [32][128 B] + alignment
   static constexpr int TOTAL = NSTAGE * STAGE_BYTES + PARAM_BYTES + 256 + 1024;
 };
 
 template <int BN, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constant__ CUtensorMap tmA_lo,
-                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo, TcArgs a) {
+                const __grid_constant__ CUtensorMap tmW_hi, const __grid_constant__ CUtensorMap tmW_lo,
+                const __grid_constant__ CUtensorMap tmOut, TcArgs a) {
   using S = TcSmem2<BN>;
   constexpr int NSTAGE = S::NSTAGE;
   extern __shared__ unsigned char smem_raw[];
@@ -541,6 +595,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
   uint64_t* acc_empty = bars + 2 * NSTAGE + 2; // [2] used in the even CTA: epilogue warps of both CTAs -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NSTAGE + 4);
   float* pool_stage = reinterpret_cast<float*>(smem + NSTAGE * S::STAGE_BYTES + S::PARAM_BYTES + 256);
+  // staging of the bulk-store epilogue (TC_BIAS_F32): 4 warps x 4 KB, 1024-byte aligned (128-byte swizzle atoms)
+  unsigned char* out_stage = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(pool_stage) + 1023) & ~uintptr_t(1023));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int rank = (int)cluster_ctarank();
@@ -640,7 +696,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
     for (int tile = pair; tile < num_tiles; tile += pairs) {
       const int mp = tile / a.n_tiles, nt = tile - mp * a.n_tiles;
       tc_epilogue_tile<BN, EPI>(a, params, pool_stage, tmem_base + acc * BN, (long long)mp * 2 + rank, nt * BN, quad, lane, et,
-                                a.n_tiles > 1 || tile == pair, &acc_full[acc], acc_phase);
+                                a.n_tiles > 1 || tile == pair, &acc_full[acc], acc_phase, a.tma_out ? &tmOut : nullptr, out_stage);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_leader(&acc_empty[acc]);
@@ -649,6 +705,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA_hi, const __grid_constan
         acc_phase ^= 1;
       }
     }
+    if (EPI == TC_BIAS_F32 && a.tma_out && lane == 0) tma_store_wait_all();   // this lane's bulk stores are complete
   }
   tc_fence_before();
   __syncthreads();
@@ -736,18 +793,49 @@ static int launch_tc(const TcGemm& g, cudaStream_t st) {
       // the pair's CTAs each load HALF of the W tile: a second pair of maps with BN / 2-row boxes
       CUtensorMap tw2_hi, tw2_lo;
       if (make_map(&tw2_hi, g.W_hi, g.Npad, Ktot, Ktot, BN / 2) || make_map(&tw2_lo, g.W_lo, g.Npad, Ktot, Ktot, BN / 2)) return -2;
-      const int smem2 = S2::TOTAL + (EPI == TC_POOL ? S2::POOL_BYTES : 0);
+      // float32 rows through bulk tensor stores (DG_NO_TMA_STORE=1: per-lane 256-bit stores)
+      CUtensorMap t_out;
+      memset(&t_out, 0, sizeof(t_out));
+      if constexpr (EPI == TC_BIAS_F32) {
+        static const bool no_tma_store = getenv("DG_NO_TMA_STORE") && getenv("DG_NO_TMA_STORE")[0] == '1';
+        if (!no_tma_store && g.N % 32 == 0 && (g.ldc * 4) % 16 == 0 && (uintptr_t)g.out_f32 % 16 == 0) {
+          EncodeTiledFn fn = encode_fn();
+          cuuint64_t dims[2] = {(cuuint64_t)g.N, (cuuint64_t)g.M};
+          cuuint64_t strides[1] = {(cuuint64_t)g.ldc * 4};
+          cuuint32_t box[2] = {32, 32};
+          cuuint32_t estr[2] = {1, 1};
+          if (fn && fn(&t_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, g.out_f32, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            a.tma_out = 1;
+        }
+      }
+      const int smem2 = S2::TOTAL + (EPI == TC_POOL ? S2::POOL_BYTES : 0) + (a.tma_out ? S2::OUT_STAGE_BYTES : 0);
       static bool attr2_done[64] = {};
       if (first_use_on_device(attr2_done))
-        DG_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem2));
+        DG_CUDA(cudaFuncSetAttribute(gemm_tc2_kernel<BN, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     S2::TOTAL + (EPI == TC_POOL ? S2::POOL_BYTES : 0) + (EPI == TC_BIAS_F32 ? S2::OUT_STAGE_BYTES : 0)));
       const int pair_tiles = ((a.m_tiles + 1) / 2) * a.n_tiles;
       const int pairs = std::min(pair_tiles, sms / 2);
-      gemm_tc2_kernel<BN, EPI><<<2 * pairs, TC_THREADS, smem2, st>>>(ta_hi, ta_lo, tw2_hi, tw2_lo, a);
+      gemm_tc2_kernel<BN, EPI><<<2 * pairs, TC_THREADS, smem2, st>>>(ta_hi, ta_lo, tw2_hi, tw2_lo, t_out, a);
       DG_LAUNCHED();
       return 0;
     }
   }
   const int grid = tiles < sms ? tiles : sms;
+  if constexpr (BN == 64 && EPI == TC_MAXPOOL3) {
+    // W resident in shared memory (DG_NO_WRES=1: off): needs one column tile, <= 7 k-blocks and a staging buffer that still fits
+    static const bool no_wres = getenv("DG_NO_WRES") && getenv("DG_NO_WRES")[0] == '1';
+    using SW = TcSmem<64, true>;
+    const int smem_w = SW::WRES_BYTES + SW::NSTAGE * SW::STAGE_BYTES + SW::PARAM_BYTES + 256 + (a.tile_rows * 33 + 512) * 4 + 1024;
+    if (!no_wres && a.n_tiles == 1 && a.KW * a.cin_blocks <= TC_WRES_KB && smem_w <= 227 * 1024) {
+      static bool attrw_done[64] = {};
+      if (first_use_on_device(attrw_done))
+        DG_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<64, TC_MAXPOOL3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      gemm_tc_kernel<64, TC_MAXPOOL3, true><<<grid, TC_THREADS, smem_w, st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
+      DG_LAUNCHED();
+      return 0;
+    }
+  }
   gemm_tc_kernel<BN, EPI><<<grid, TC_THREADS, S::TOTAL + S::extra(EPI), st>>>(ta_hi, ta_lo, tw_hi, tw_lo, a);
   DG_LAUNCHED();
   return 0;

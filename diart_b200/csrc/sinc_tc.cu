@@ -306,7 +306,10 @@ int launch_sinc_prep(const float* wav, const float* mean, const float* rstd, int
   const int rpi = sinc_tc_rows_per_item(g), Lp = rpi * 120;
   const size_t plane = sinc_tc_plane_elems(B, g);
   ProfScope _ps("sinc0_prep", st);
-  dim3 grid((Lp + 8 + 255) / 256, B);
+  // (grid-stride in x: about 2048 CTAs in all -- this launch usually returns at once on the stream-form flag, and 80 k
+  // empty CTAs cost 45 us)
+  const int want_x = (2048 + B - 1) / B, max_x = (Lp + 8 + 255) / 256;
+  dim3 grid(want_x < max_x ? want_x : max_x, B);
   sinc_prep_kernel<<<grid, 256, 0, st>>>(wav, mean, rstd, g.S, Lp, plane, reinterpret_cast<uint16_t*>(planes_hi),
                                          reinterpret_cast<uint16_t*>(planes_lo), split_f16(), skip_flag);
   DG_LAUNCHED();

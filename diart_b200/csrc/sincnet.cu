@@ -253,17 +253,27 @@ int launch_instnorm_stats(const float* x, int B, int stride_rows, int T, int C, 
 // InstanceNorm1d(affine) scale / shift from the per-tile partial sums of gemm_tc's TC_MAXPOOL3 epilogue (tiles of `tile_rows`
 // un-pooled rows, a divisor of the item's rows: slot 0 of the item's own tiles).  The sums are of the pooled values BEFORE the
 // bias, which serves as the pivot; the tiles of an item are added in tile order, in double.
-__global__ void __launch_bounds__(64) instnorm_finalize_kernel(const float* __restrict__ part, int tiles_per_item, int T, int C, int N,
-                                                               const float* __restrict__ bias, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, float* __restrict__ sc,
-                                                               float* __restrict__ sh, int ld) {
-  const int b = blockIdx.x, c = threadIdx.x;
-  if (c >= C) return;
+__global__ void __launch_bounds__(256) instnorm_finalize_kernel(const float* __restrict__ part, int tiles_per_item, int T, int C, int N,
+                                                                const float* __restrict__ bias, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, float* __restrict__ sc,
+                                                                float* __restrict__ sh, int ld) {
+  // 4 tile groups x 64 channels: the loads of a group are independent, the groups are added in a fixed order
+  __shared__ double s1[4][64], s2[4][64];
+  const int b = blockIdx.x, c = threadIdx.x & 63, grp = threadIdx.x >> 6;
+  const long long mt0 = (long long)b * tiles_per_item;
+  const int per = (tiles_per_item + 3) / 4, lo = grp * per, hi = min(tiles_per_item, lo + per);
   double t1 = 0, t2 = 0;
-  for (long long mt = (long long)b * tiles_per_item; mt < (long long)(b + 1) * tiles_per_item; mt++) {
-    t1 += part[((mt * 2 + 0) * 2 + 0) * N + c];
-    t2 += part[((mt * 2 + 0) * 2 + 1) * N + c];
-  }
+  if (c < C)
+    for (int i = lo; i < hi; i++) {
+      t1 += part[(((mt0 + i) * 2 + 0) * 2 + 0) * N + c];
+      t2 += part[(((mt0 + i) * 2 + 0) * 2 + 1) * N + c];
+    }
+  s1[grp][c] = t1;
+  s2[grp][c] = t2;
+  __syncthreads();
+  if (grp != 0 || c >= C) return;
+  t1 = ((s1[0][c] + s1[1][c]) + s1[2][c]) + s1[3][c];
+  t2 = ((s2[0][c] + s2[1][c]) + s2[2][c]) + s2[3][c];
   const double m = t1 / T;
   double var = t2 / T - m * m;
   if (var < 0) var = 0;
@@ -281,7 +291,7 @@ int launch_instnorm_finalize(const float* part, int B, int item_rows, int tile_r
     set_error("instnorm_finalize: at most 64 channels, tiles must divide the item");
     return -1;
   }
-  instnorm_finalize_kernel<<<B, 64, 0, st>>>(part, item_rows / tile_rows, T, C, N, bias, gamma, beta, sc, sh, ld);
+  instnorm_finalize_kernel<<<B, 256, 0, st>>>(part, item_rows / tile_rows, T, C, N, bias, gamma, beta, sc, sh, ld);
   DG_LAUNCHED();
   return 0;
 }

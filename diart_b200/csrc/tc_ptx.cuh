@@ -80,6 +80,17 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
                : "memory");
 }
 
+// ---- bulk tensor STORE (shared -> global through a tensor map; rows / columns outside the tensor are clipped by the hardware)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the bulk stores committed so far have READ their shared-memory source (it may be rewritten)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---- 16-bit operand planes.  A float32 value travels as hi + lo; the element type is fp16 (default: |x| < 65504 and
 // 22 significand bits for the pair) or bf16 (16 bits for the pair, float32 range).  `f16` is warp-uniform.
 __device__ __forceinline__ uint16_t f32_to_h16(float x, int f16) {

@@ -104,8 +104,12 @@ class SharedIdentity:
         if getattr(self, "_rec", None) is None or self._rec.numel() != n:
             self._rec = torch.empty(n, dtype=torch.float64, device=device)
             self._gathered = torch.empty(self.world * n, dtype=torch.float64, device=device) if self.world > 1 else self._rec
-        stream = self._lib.stream_ptr(device)
-        with torch.cuda.device(device):
+        # the exchange runs on its OWN stream: on the caller's stream the all-gather of step i (which waits for the clustering
+        # of step i) would sit in front of the next submit's start event and de-pipeline the networks
+        if getattr(self, "_comm", None) is None:
+            self._comm = torch.cuda.Stream(device)
+        with torch.cuda.device(device), torch.cuda.stream(self._comm):
+            stream = self._C.c_void_p(self._comm.cuda_stream)
             self._lib.check(lib.dg_pipeline_identity_export(pipeline_handle, self._rec.data_ptr(), stream))
             if self.world > 1:
                 dist.all_gather_into_tensor(self._gathered, self._rec, group=self.group)
