@@ -90,6 +90,7 @@ class ClockSampler:
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.stamps, self.t_mark = [], None
 
     def __enter__(self):
         try:
@@ -104,6 +105,12 @@ class ClockSampler:
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
+            self.stamps.append(time.monotonic())
+
+    def mark(self):
+        """samples from here on count (the sampler is started before the warm-up: on an 8-GPU box nvidia-smi needs longer than
+        a 70 ms timed region to deliver its first line)"""
+        self.t_mark = time.monotonic()
 
     def __exit__(self, *exc):
         if self.proc is not None:
@@ -114,6 +121,13 @@ class ClockSampler:
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        window = "timed region"
+        if self.t_mark is not None:
+            inside = [r for r, t in zip(self.rows, self.stamps) if t >= self.t_mark]
+            if inside:
+                self.rows = inside
+            else:
+                window = "warm-up + timed region (same load; no sample fell inside the timed region)"
         sm = [float(r[1]) for r in self.rows if len(r) >= 9]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -124,7 +138,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(self.rows[0][2]), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def make_stream_batches(rank: int, n_batches: int, batch: int) -> np.ndarray:
@@ -262,21 +276,26 @@ def run_ours(args):
         for _ in range(min(n, 2)):
             _lib.check(lib.dg_pipeline_collect(fused, None, None, None, stream))
 
-    run_steps(args.warmup)
-    barrier()
-    lib.dg_profile_enable(1)
-    launches0 = lib.dg_launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clocks:
+        run_steps(args.warmup)
+        barrier()
+        lib.dg_profile_enable(1)
+        launches0 = lib.dg_launch_count()
+        clocks.mark()
         ev0.record()
         run_steps(args.steps)
         ev1.record()
         torch.cuda.synchronize(device)
+        lib.dg_profile_enable(0)
+        launches = lib.dg_launch_count() - launches0
+        t_wait = time.monotonic()
+        while not clocks.rows and clocks.proc is not None and time.monotonic() - t_wait < 3.0:
+            run_steps(args.steps)            # nvidia-smi has not delivered a line yet: keep the same load until it does (untimed)
+            torch.cuda.synchronize(device)
     ms = ev0.elapsed_time(ev1)
-    launches = lib.dg_launch_count() - launches0
     buf = C.create_string_buffer(1 << 16)
     lib.dg_profile_report(buf, len(buf))
-    lib.dg_profile_enable(0)
     kernels = json.loads(buf.value.decode())
     t = torch.tensor([ms], device=device, dtype=torch.float64)
     if dist is not None:
