@@ -59,6 +59,21 @@ class PipelineConfig(ABC):
         return left, right
 
 
+class WindowTiming(PipelineConfig):
+    """Chunk geometry shared by the pipeline configurations: ``duration`` / ``step`` in seconds, ``latency`` in seconds or
+    ``"min"`` (= step, the default) / ``"max"`` (= duration), as in the reference's config constructors
+    (``blocks/diarization.py:33-60``, ``blocks/vad.py:27-65``)."""
+
+    def _set_timing(self, duration: float, step: float, latency, sample_rate: int):
+        self._duration, self._step, self._sample_rate = duration, step, sample_rate
+        self._latency = step if latency in (None, "min") else (duration if latency == "max" else latency)
+
+    duration = property(lambda self: self._duration)
+    step = property(lambda self: self._step)
+    latency = property(lambda self: self._latency)
+    sample_rate = property(lambda self: self._sample_rate)
+
+
 class Pipeline(ABC):
     @staticmethod
     @abstractmethod

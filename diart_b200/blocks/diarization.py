@@ -27,7 +27,7 @@ from .segmentation import SpeakerSegmentation
 from .utils import Binarize
 
 
-class SpeakerDiarizationConfig(base.PipelineConfig):
+class SpeakerDiarizationConfig(base.WindowTiming):
     def __init__(self, segmentation: Optional[m.SegmentationModel] = None,
                  embedding: Optional[m.EmbeddingModel] = None, duration: float = 5, step: float = 0.5,
                  latency=None, tau_active: float = 0.6, rho_update: float = 0.3, delta_new: float = 1,
@@ -36,32 +36,11 @@ class SpeakerDiarizationConfig(base.PipelineConfig):
                  sample_rate: int = 16000, **kwargs):
         self.segmentation = segmentation or m.SegmentationModel.from_pyannote("pyannote/segmentation")
         self.embedding = embedding or m.EmbeddingModel.from_pyannote("pyannote/embedding")
-        self._duration, self._sample_rate, self._step = duration, sample_rate, step
-        self._latency = latency
-        if self._latency is None or self._latency == "min":
-            self._latency = self._step
-        elif self._latency == "max":
-            self._latency = self._duration
+        self._set_timing(duration, step, latency, sample_rate)
         self.tau_active, self.rho_update, self.delta_new = tau_active, rho_update, delta_new
         self.gamma, self.beta, self.max_speakers = gamma, beta, max_speakers
         self.normalize_embedding_weights = normalize_embedding_weights
         self.device = device or torch.device("cuda")
-
-    @property
-    def duration(self) -> float:
-        return self._duration
-
-    @property
-    def step(self) -> float:
-        return self._step
-
-    @property
-    def latency(self) -> float:
-        return self._latency
-
-    @property
-    def sample_rate(self) -> int:
-        return self._sample_rate
 
 
 class SpeakerDiarization(base.Pipeline):

@@ -10,6 +10,7 @@ import pytest
 import torch
 
 from diart_b200 import _lib, blocks, models, synth
+from diart_b200.blocks.utils import Binarize
 from diart_b200.core import SlidingWindow, SlidingWindowFeature
 from oracle.clustering import OracleClustering
 from oracle.pipeline import OraclePipeline
@@ -216,10 +217,28 @@ def test_voice_activity_detection_pipeline(oracle_nets, stream, cuda_device):
     res = 5 / ref.shape[1]
     for i, (annotation, audio) in enumerate(out):
         swf = SlidingWindowFeature(ref[i], SlidingWindow(start=0.5 * i, duration=res, step=res))
-        expect = vad.binarize(blocks.DelayedAggregation(0.5, 0.5, "hamming", "loose")([swf]))
+        expect = Binarize(0.6)(blocks.DelayedAggregation(0.5, 0.5, "hamming", "loose")([swf]))
         got = sorted((round(s.start, 3), round(s.end, 3)) for s, _ in annotation.itertracks())
         want = sorted((round(s.start, 3), round(s.end, 3)) for s, _ in expect.itertracks())
         assert got == want and all(lab == "speech" for _, _, lab in annotation.itertracks(yield_label=True))
+    # latency > step: the device aggregation over the 4 most recent chunks against the host mirrors of the reference's loop
+    # (vad.py:150-190) fed with the SAME device scores
+    cfg2 = blocks.VoiceActivityDetectionConfig(segmentation=config.segmentation, latency=2.0, device=cuda_device)
+    vad2 = blocks.VoiceActivityDetection(cfg2)
+    chunks2 = [SlidingWindowFeature(stream[8000 * i:8000 * i + 80000, None],
+                                    SlidingWindow(start=0.5 * i, duration=1 / sr, step=1 / sr)) for i in range(9)]
+    out2 = vad2(chunks2[:5]) + vad2(chunks2[5:])
+    scores = vad2.segmentation.forward_device(torch.from_numpy(synth.windows(stream, 9)))
+    host_scores = scores.amax(dim=-1, keepdim=True).cpu().numpy()
+    agg, binarize, buf = blocks.DelayedAggregation(0.5, 2.0, "hamming", "loose"), Binarize(0.6), []
+    for i in range(9):
+        buf.append(SlidingWindowFeature(host_scores[i], SlidingWindow(start=0.5 * i, duration=res, step=res)))
+        expect = binarize(agg(buf))
+        got = sorted((s.start, s.end) for s, _ in out2[i][0].itertracks())
+        want = sorted((s.start, s.end) for s, _ in expect.itertracks())
+        assert got == want, f"latency 2.0, chunk {i}"
+        if len(buf) == agg.num_overlapping_windows:
+            buf = buf[1:]
 
 
 def test_host_submit_collect_matches_step_host(oracle_nets, stream, cuda_device):
