@@ -81,6 +81,28 @@ struct DevBuf {
   }
 };
 
+// A model handle owns ONE set of activation buffers per scratch lane.  A new user of a lane -- another pipeline built on the same
+// handle, or a block-level call on another stream -- first waits, stream-ordered, for the previous user's last kernel; without it
+// two users in flight would silently overwrite each other's activations.  (Host threads: a handle is single-threaded.)
+struct UseGuard {
+  cudaEvent_t e = nullptr;
+  const void* owner = nullptr;
+  ~UseGuard() {
+    if (e) cudaEventDestroy(e);
+  }
+};
+static thread_local bool g_in_pipeline = false;      // the fused pipeline brackets its own uses (per lane)
+static int use_begin(UseGuard& u, const void* owner, cudaStream_t st) {
+  if (u.e && u.owner != owner) DG_CUDA(cudaStreamWaitEvent(st, u.e, 0));
+  return 0;
+}
+static int use_end(UseGuard& u, const void* owner, cudaStream_t st) {
+  if (!u.e) DG_CUDA(cudaEventCreateWithFlags(&u.e, cudaEventDisableTiming));
+  DG_CUDA(cudaEventRecord(u.e, st));
+  u.owner = owner;
+  return 0;
+}
+
 struct Tensors {
   std::map<std::string, std::pair<const float*, int64_t>> m;
   Tensors(const dg_tensor* t, int n) {
@@ -470,6 +492,7 @@ struct dg_seg {
   } scr[2];
   int lane = 0;
   const SincPrep* shared_prep = nullptr;   // set by the fused pipeline: statistics + planes computed once per step
+  UseGuard guard[2];                       // per scratch lane
 };
 
 static int seg_prepare(dg_seg* h, const Tensors& t) {
@@ -652,11 +675,22 @@ static int seg_head_final(dg_seg* h, const float* y2, int B, const Geom& g, floa
   return launch_seg_final(y2, h->cw.as<float>(), h->cb.as<float>(), B, g.T2, g.S2, h->K, seg, st);
 }
 
+static int seg_forward_impl(dg_seg* h, const float* wav, int B, int S, float* seg, void* stream);
 extern "C" int dg_seg_forward(dg_seg* h, const float* wav, int B, int S, float* seg, void* stream) {
   if (!h || !wav || !seg || B < 1 || S < 3000) {
     set_error("dg_seg_forward: bad arguments (need B >= 1, S >= 3000)");
     return DG_EINVAL;
   }
+  if (g_in_pipeline) return seg_forward_impl(h, wav, B, S, seg, stream);
+  DG_CUDA(cudaSetDevice(h->device));
+  UseGuard& u = h->guard[h->lane & 1];
+  int rc = use_begin(u, stream ? stream : (void*)h, (cudaStream_t)stream);
+  if (!rc) rc = seg_forward_impl(h, wav, B, S, seg, stream);
+  if (!rc) rc = use_end(u, stream ? stream : (void*)h, (cudaStream_t)stream);
+  return rc;
+}
+
+static int seg_forward_impl(dg_seg* h, const float* wav, int B, int S, float* seg, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   DG_CUDA(cudaSetDevice(h->device));
   dg_seg::Scratch& w = h->scr[h->lane & 1];
@@ -756,6 +790,7 @@ struct dg_emb {
   DevBuf xh, xl, aH, aL, bH, bL;         // bf16 hi/lo activation planes
   DevBuf ew, eb;
   SincWork work;
+  UseGuard guard;
   DevBuf tA, tB, t5, pooled, eraw;
   DevBuf idx0, idx1, lam1;
   int tab_F = -1, tab_T = -1;
@@ -1364,6 +1399,12 @@ extern "C" int dg_emb_forward(dg_emb* h, const float* wav, const float* weights,
   DG_CUDA(cudaSetDevice(h->device));
   const Geom g = make_geom(S);
   int rc, T = 0;
+  const void* me = stream ? stream : (void*)h;
+  struct Done {              // every exit of this call marks the end of the use
+    dg_emb* h; const void* me; cudaStream_t st; bool on;
+    ~Done() { if (on) use_end(h->guard, me, st); }
+  } done{h, me, st, !g_in_pipeline};
+  if (!g_in_pipeline && (rc = use_begin(h->guard, me, st))) return rc;
   const bool fuse = weights && h->variant == 0 && K <= 4 && g.S2 >= 128 && pool_fusion_on();
   if ((rc = emb_trunk(h, wav, B, g, st, &T, fuse))) return rc;
   if (weights && (rc = build_tables(h, F, T, st))) return rc;
@@ -1390,6 +1431,12 @@ extern "C" int dg_emb_forward_rows(dg_emb* h, const float* wav, const float* wei
   DG_CUDA(cudaSetDevice(h->device));
   const Geom g = make_geom(S);
   int rc, T = 0;
+  const void* me = stream ? stream : (void*)h;
+  struct Done {
+    dg_emb* h; const void* me; cudaStream_t st; bool on;
+    ~Done() { if (on) use_end(h->guard, me, st); }
+  } done{h, me, st, !g_in_pipeline};
+  if (!g_in_pipeline && (rc = use_begin(h->guard, me, st))) return rc;
   // consecutive identical rows (the reference repeats each waveform once per local speaker,
   // src/diart/blocks/embedding.py:57-59) share one trunk pass
   if (h->flags.ensure((size_t)N * 4)) return DG_ECUDA;
@@ -1862,6 +1909,12 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   if (osp.ensure((size_t)B * F * K * 4)) return DG_ECUDA;
   DG_CUDA(cudaStreamWaitEvent(s_seg, start, 0));
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, start, 0));
+  // another pipeline (or a block-level call) that used these model handles' scratch last: stream-ordered hand-over
+  if ((rc = use_begin(h->seg->guard[lane], h, s_seg)) || (rc = use_begin(h->emb->guard, h, h->s_emb))) return rc;
+  struct InPipeline {
+    InPipeline() { g_in_pipeline = true; }
+    ~InPipeline() { g_in_pipeline = false; }
+  } in_pipeline;
   // waveform statistics + standardised 16-bit planes once, for both networks' SincNets
   static const bool sinc_simt = getenv("DG_SINC_SIMT") && getenv("DG_SINC_SIMT")[0] == '1';
   const SincPrep* shared = nullptr;
@@ -1895,6 +1948,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
   if (rc) return rc;
   if ((rc = dg_osp(seg, B, F, K, h->gamma, h->beta, h->normalize_weights, osp.as<float>(), s_seg))) return rc;
   DG_CUDA(cudaEventRecord(e_osp, s_seg));
+  if ((rc = use_end(h->seg->guard[lane], h, s_seg))) return rc;
   DG_DIAG(seg, s_seg);
   DG_CUDA(cudaStreamWaitEvent(h->s_emb, e_osp, 0));
   if ((rc = build_tables(h->emb, F, T, h->s_emb))) return rc;
@@ -1911,7 +1965,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     if (rc) return rc;
     DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));
     DG_DIAG(emb, h->s_emb);
-    return DG_OK;
+    return use_end(h->emb->guard, h, h->s_emb);
   }
   if (h->emb->pooled.ensure((size_t)B * K * 2 * h->emb->pool_C * 4)) return DG_ECUDA;
   if ((rc = launch_stats_pool(h->emb->pool_x, B, g.S2, T, h->emb->pool_C, osp.as<float>(), F, K,
@@ -1921,7 +1975,7 @@ static int pipeline_nets(dg_pipeline* h, const float* wav, int B, int S, int F, 
     return rc;
   if ((rc = emb_project(h->emb, B * K, 1, 1.f, emb, h->s_emb))) return rc;
   DG_CUDA(cudaEventRecord(h->e_emb, h->s_emb));
-  return DG_OK;
+  return use_end(h->emb->guard, h, h->s_emb);
 }
 
 extern "C" int dg_pipeline_set_hop(dg_pipeline* h, int hop_samples) {

@@ -146,6 +146,34 @@ def test_call_uploads_a_stream_once_and_falls_back_for_anything_else(oracle_nets
                 assert not expect_stream and clearance < 2e-4, f"{name}: chunk {i} differs, threshold clearance {clearance:.1e}"
 
 
+def test_two_pipelines_on_the_same_model_handles(oracle_nets, stream, cuda_device):
+    """two SpeakerDiarization instances built on the SAME SegmentationModel / EmbeddingModel objects (two audio streams, one set
+    of weights) share the handles' activation buffers: submits of both in flight at once must hand the buffers over in stream order
+    and give what each pipeline gives on its own"""
+    seg_o, emb_o = oracle_nets
+    seg_m = models.SegmentationModel(models.B200SegmentationLoader(seg_o.state_dict()))
+    emb_m = models.EmbeddingModel(models.B200EmbeddingLoader(emb_o.state_dict()))
+    mk = lambda: blocks.SpeakerDiarization(blocks.SpeakerDiarizationConfig(segmentation=seg_m, embedding=emb_m, device=cuda_device))
+    a, b, ref = mk(), mk(), mk()
+    xs = [torch.from_numpy(synth.windows(stream, BATCH, first=i * BATCH)).to(cuda_device) for i in range(3)]
+    want = [[t.cpu().numpy() for t in ref.device_step(x)] for x in xs]          # ref sees batches 0, 1, 2 in order
+    ref.reset()
+    got_a, got_b = [], []
+    for i in range(3):                      # a and b both see batches 0, 1, 2; their steps are interleaved and overlap
+        a.submit(xs[i])
+        b.submit(xs[i])
+        if i > 0:
+            got_a.append(a.collect())
+            got_b.append(b.collect())
+    got_a.append(a.collect())
+    got_b.append(b.collect())
+    torch.cuda.synchronize()
+    for i in range(3):
+        for name, w, ga, gb in zip(("seg", "emb", "map"), want[i], got_a[i], got_b[i]):
+            assert np.array_equal(w, ga.cpu().numpy()), f"pipeline a, batch {i}: {name}"
+            assert np.array_equal(w, gb.cpu().numpy()), f"pipeline b, batch {i}: {name}"
+
+
 def test_foreign_models_behind_loader_api(oracle_nets, stream, cuda_device):
     """any Callable behind SegmentationModel / EmbeddingModel still works (block-by-block path);
     here: the oracle torch modules moved to the GPU"""
