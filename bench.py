@@ -159,6 +159,7 @@ def run_reference(args):
     from oracle import nets
     from oracle.pipeline import OraclePipeline
 
+    nets.STABLE = False       # a timing leg: one evaluation per call (the reproducibility double-check is for reference VALUES)
     pipe = OraclePipeline(nets.make_segmentation(), nets.make_embedding(), as_reference=True)
     rb = args.ref_batch
     data = torch.from_numpy(make_stream_batches(0, 1, 2 * rb)[0])
@@ -209,13 +210,17 @@ def cpu_baseline(budget_s: float = 12.0, rb: int = 32):
 
     pipe = OraclePipeline(nets.make_segmentation(), nets.make_embedding(), as_reference=True)
     data = torch.from_numpy(make_stream_batches(0, 1, 2 * rb)[0])
-    cores = pick_threads(pipe, data)
-    pipe(data[:rb])                                  # warm-up
-    n, t0 = 0, time.perf_counter()
-    while n < 2 or (time.perf_counter() - t0 < budget_s and n < 12):
-        pipe(data[(n % 2) * rb:(n % 2 + 1) * rb])
-        n += 1
-    dt = time.perf_counter() - t0
+    stable, nets.STABLE = nets.STABLE, False         # a timing leg: one evaluation per call
+    try:
+        cores = pick_threads(pipe, data)
+        pipe(data[:rb])                              # warm-up
+        n, t0 = 0, time.perf_counter()
+        while n < 2 or (time.perf_counter() - t0 < budget_s and n < 12):
+            pipe(data[(n % 2) * rb:(n % 2 + 1) * rb])
+            n += 1
+        dt = time.perf_counter() - t0
+    finally:
+        nets.STABLE = stable
     return {"value": n * rb * STEP_SECONDS / dt, "unit": UNIT, "cores": cores, "kind": "port",
             "sample": f"{n} batches x {rb} consecutive windows of the same stream, oracle pipeline (K-fold repeated "
                       f"trunk as the reference runs it), torch CPU float32, {dt:.1f} s"}
@@ -545,8 +550,9 @@ def run_ours(args):
 
         parity = measure_parity()
         if parity.get("failed"):
-            # seen twice in ~40 runs of this check on this pool (and never again in 20 targeted repetitions):
-            # measure once more; a second failure is fatal, a pass is reported together with the first attempt
+            # (round 2 traced three such reports to the torch CPU oracle's first float32 evaluation in a process, DESIGN.md section 4;
+            # the oracle now double-checks itself.)  Measure once more; a second failure is fatal, a pass is reported together
+            # with the first attempt
             first = parity
             parity = measure_parity()
             parity["first_attempt"] = first

@@ -1665,7 +1665,9 @@ extern "C" int dg_selftest_gemm_tc(int M, int Cin, int KW, int dil, int N, int e
     seed = seed * 1664525u + 1013904223u;
     return ((seed >> 8) & 0xFFFF) / 65536.f - 0.5f;
   };
-  for (auto& v : A) v = 2.f * rnd();
+  // DG_SELFTEST_AMP: amplitude of the A operand (default 2): small values put the whole lo plane into fp16's subnormal range
+  static const float amp = getenv("DG_SELFTEST_AMP") ? (float)atof(getenv("DG_SELFTEST_AMP")) : 2.f;
+  for (auto& v : A) v = amp * rnd();
   for (int k = 0; k < K; k++)
     for (int n = 0; n < N; n++) {
       const float w = rnd() * 0.25f;

@@ -31,6 +31,42 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+# The FIRST float32 evaluation of a torch CPU module for a given input shape is not reproducible on every host: on the GPU boxes
+# of this pool (2 x Xeon Platinum 8562Y+, torch 2.11) about one process in six returns a first result 6e-4 .. 1.3e-2 away from
+# every later evaluation in the same process, from every other process and from the float64 evaluation -- with oneDNN enabled or
+# not, at 16 or 64 threads -- while later evaluations are bit-identical everywhere (profiles/r2_oracle_float32_first_call.log;
+# the CUDA outputs were bit-identical in every process).  A reference value is therefore only accepted once two consecutive
+# evaluations agree bit for bit.  `STABLE = False` switches this off (the timing legs of bench.py).
+STABLE = True
+
+
+def _same(a, b) -> bool:
+    if isinstance(a, torch.Tensor):
+        return isinstance(b, torch.Tensor) and a.shape == b.shape and torch.equal(a, b)
+    if isinstance(a, (tuple, list)):
+        return len(a) == len(b) and all(_same(x, y) for x, y in zip(a, b))
+    return a == b
+
+
+def _reproduced(fn):
+    y = fn()
+    if not STABLE or torch.is_grad_enabled():
+        return y
+    for _ in range(3):
+        again = fn()
+        if _same(y, again):
+            return again
+        y = again
+    raise RuntimeError("oracle: the float32 evaluation does not reproduce itself on this host")
+
+
+class _Reproducible:
+    """mixin of the three top-level oracle networks: `net(x)` evaluates until two consecutive results agree"""
+
+    def __call__(self, *args, **kwargs):
+        return _reproduced(lambda: nn.Module.__call__(self, *args, **kwargs))
+
+
 class ParamSincFB(nn.Module):
     """asteroid_filterbanks.ParamSincFB(80, 251, stride=10, sample_rate=16000, min_low_hz=50, min_band_hz=50).
 
@@ -142,7 +178,7 @@ def to_multilabel(powerset_log_probabilities: torch.Tensor, mapping: torch.Tenso
     return hard @ mapping
 
 
-class PyanNet(nn.Module):
+class PyanNet(_Reproducible, nn.Module):
     """pyannote.audio.models.segmentation.PyanNet with the pyannote/segmentation hyper-parameters."""
 
     def __init__(self, num_speakers: int = 3, sample_rate: int = 16000, powerset_max_classes: Optional[int] = None):
@@ -211,7 +247,7 @@ class StatsPool(nn.Module):
         return torch.cat([mean, torch.sqrt(var)], dim=1)
 
 
-class XVectorSincNet(nn.Module):
+class XVectorSincNet(_Reproducible, nn.Module):
     """pyannote.audio.models.embedding.XVectorSincNet (pyannote/embedding), dimension 512."""
 
     def __init__(self, sample_rate: int = 16000, dimension: int = 512, pool_mode: str = "3.1"):
@@ -243,10 +279,12 @@ class XVectorSincNet(nn.Module):
         Arithmetically identical to the reference's K-fold repeat
         (``src/diart/blocks/embedding.py:57-59``) because the weights only enter at pooling.
         """
-        x = self.trunk(waveforms)
-        B, _, K = weights.shape
-        out = [self.embedding(self.stats_pool(x, weights[:, :, k])) for k in range(K)]
-        return torch.stack(out, dim=1)
+        def once():
+            x = self.trunk(waveforms)
+            out = [self.embedding(self.stats_pool(x, weights[:, :, k])) for k in range(weights.shape[2])]
+            return torch.stack(out, dim=1)
+
+        return _reproduced(once)
 
 
 # --------------------------------------------------------------------------------------
@@ -302,7 +340,7 @@ class _ResNet34(nn.Module):
         return self.seg_1(self.pool(x, weights))
 
 
-class WeSpeakerResNet34(nn.Module):
+class WeSpeakerResNet34(_Reproducible, nn.Module):
     """pyannote.audio.models.embedding.WeSpeakerResNet34: int16-scaled waveform -> kaldi fbank (80 mel bins, 25 ms / 10 ms,
     Hamming, no dither, no energy) -> per-item mean normalisation over time -> ResNet34 -> TSTP(weights) -> Linear(5120, 256)"""
 
@@ -327,10 +365,13 @@ class WeSpeakerResNet34(nn.Module):
     def forward_dedup(self, waveforms: torch.Tensor, weights: torch.Tensor) -> torch.Tensor:
         """Trunk once per waveform, K poolings: ``weights`` (B, F, K) -> (B, K, 256); arithmetically identical to the
         reference's K-fold repeat (``src/diart/blocks/embedding.py:57-59``) because the weights only enter at pooling."""
-        r = self.resnet
-        x = r.maps(self.compute_fbank(waveforms))
-        x = x.reshape(x.shape[0], x.shape[1] * x.shape[2], x.shape[3])
-        return torch.stack([r.seg_1(r.pool(x, weights[:, :, k])) for k in range(weights.shape[2])], dim=1)
+        def once():
+            r = self.resnet
+            x = r.maps(self.compute_fbank(waveforms))
+            x = x.reshape(x.shape[0], x.shape[1] * x.shape[2], x.shape[3])
+            return torch.stack([r.seg_1(r.pool(x, weights[:, :, k])) for k in range(weights.shape[2])], dim=1)
+
+        return _reproduced(once)
 
 
 def make_wespeaker(seed: int = 2468, pool_mode: str = "3.1") -> WeSpeakerResNet34:
