@@ -203,7 +203,9 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
   const int M = p.M, D = p.D;
   constexpr int NW = SEQ_THREADS / 32;
   double* cs = reinterpret_cast<double*>(dyn);                 // centroids [M][D], resident for the whole batch
-  float* es = reinterpret_cast<float*>(cs + (size_t)M * D);    // embeddings [2][K][D], double buffered
+  double* ed = cs + (size_t)M * D;                             // the current chunk's embeddings as float64 [K][D] (converted once
+                                                               // per chunk by all threads instead of once per centroid warp)
+  float* es = reinterpret_cast<float*>(ed + (size_t)K * D);    // embeddings [2][K][D], double buffered (cp.async landing zone)
   auto prefetch = [&](int ci, int buf) {
     const float* e = emb + (size_t)ci * K * D;
     for (int i = tid; i < K * D; i += SEQ_THREADS) cp_async4(es + (size_t)buf * K * D + i, e + i);
@@ -220,6 +222,8 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     sh.error = 0;
   }
   asm volatile("cp.async.wait_group 0;");
+  __syncthreads();
+  for (int i = tid; i < K * D; i += SEQ_THREADS) ed[i] = (double)es[i];
   __syncthreads();
 
   for (int ci = 0; ci < B; ci++) {
@@ -245,7 +249,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
           acc[CK] = fma(cv, cv, acc[CK]);
 #pragma unroll
           for (int k = 0; k < CK; k++)
-            if (k < K) acc[k] = fma((double)ecur[k * D + d], cv, acc[k]);
+            if (k < K) acc[k] = fma(ed[k * D + d], cv, acc[k]);
         }
 #pragma unroll
         for (int k = 0; k <= CK; k++)
@@ -275,7 +279,7 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
 #pragma unroll
           for (int k = 0; k < CK; k++)
             if (k < K) {
-              const double df = (double)ecur[k * D + d] - cv;
+              const double df = ed[k * D + d] - cv;
               if (p.metric <= 2) acc[k] = fma(df, df, acc[k]);
               else if (p.metric == 3) acc[k] += fabs(df);
               else acc[k] = fmax(acc[k], fabs(df));
@@ -447,6 +451,11 @@ cluster_seq_kernel(ClusterParams p, const float* __restrict__ seg, const float* 
     }
     asm volatile("cp.async.wait_group 0;");
     __syncthreads();
+    if (ci + 1 < B) {            // the next chunk's embeddings have landed: float64 copies for its distance phase
+      const float* enext = es + (size_t)(cur ^ 1) * K * D;
+      for (int i = tid; i < K * D; i += SEQ_THREADS) ed[i] = (double)enext[i];
+      __syncthreads();
+    }
     if (dbg && tid == 0) dbg[ci * 4 + 3] = (unsigned)clock();
   }
   for (int i = tid; i < M * D; i += SEQ_THREADS) centers[i] = cs[i];
@@ -468,7 +477,7 @@ int launch_cluster_step(const ClusterParams& p, const float* seg, const float* e
   if (B <= 0) return 0;
   cluster_prep_kernel<<<B, 128, 0, st>>>(seg, emb, F, K, p.D, prep, prep_d);
   DG_LAUNCHED();
-  const size_t dyn = (size_t)p.M * p.D * sizeof(double) + (size_t)2 * K * p.D * sizeof(float);
+  const size_t dyn = (size_t)p.M * p.D * sizeof(double) + (size_t)K * p.D * sizeof(double) + (size_t)2 * K * p.D * sizeof(float);
   if (dyn > 200 * 1024) {
     set_error("cluster_step: max_speakers * dim too large for the resident centroid table (limit 200 KB)");
     return -1;
