@@ -77,6 +77,11 @@ __device__ __forceinline__ void tmem_ldn<2>(uint32_t taddr, uint32_t (&r)[2]) {
 __device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t a, uint32_t b) {
   asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(a), "r"(b) : "memory");
 }
+__device__ __forceinline__ float ld_shared_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+  return v;
+}
 __device__ __forceinline__ void st_shared_b32(uint32_t addr, uint32_t a) {
   asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(a) : "memory");
 }
@@ -88,7 +93,9 @@ __host__ __device__ constexpr int l3_threads(int NC, int NR = LT_NB) { return (4
 constexpr int L3_WS_BYTES = 2 * 128 * 128;             // W_lo of gate o: 2 k-blocks x (128 rows x 128 B)
 constexpr int L3_PLANE = 128 * LT_NB * 2;              // one plane of h_t: 128 units x 16 rows x 2 B = 4 KB
 constexpr int LT_H_BYTES = 2 * 2 * L3_PLANE;           // [buffer][plane]
-constexpr int L3_SMEM = L3_WS_BYTES + LT_H_BYTES + 256 + 1024;
+constexpr int L3_XG_STAGES = 3;                        // ring of gate pre-activation rows, fetched two steps ahead by TMA
+__host__ __device__ constexpr int l3_xg_stage_bytes(int NR) { return NR * 512 * 4; }    // [half 2][row NR][256 floats]
+__host__ __device__ constexpr int l3_smem(int NR) { return L3_WS_BYTES + LT_H_BYTES + 256 + 1024 + L3_XG_STAGES * l3_xg_stage_bytes(NR); }
 constexpr uint32_t L3_COL_D = 0, L3_COL_WHI = 64, L3_COL_WLO = 320;
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -103,12 +110,13 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 struct L3Cell {
-  const float* gp;     // gate pre-activations of (first row, t, dir, u)
+  uint32_t xg_addr;    // shared address of this thread's first value in stage 0 of the gate pre-activation ring
+  uint32_t xg_stage;   // bytes per ring stage ([half 2][row NR][256 floats])
   float* hp;           // float32 output h of (first row, t, dir, u), or null
   uint16_t* php;       // 16-bit hi plane of the same element (lo plane = php + plane_off), or null
   size_t plane_off;
-  size_t row_gx, row_h;
-  ptrdiff_t dgx, dh;
+  size_t row_h;
+  ptrdiff_t dh;
   uint32_t tlane;      // TMEM address of this thread's accumulator columns
   uint32_t h_addr;     // shared address of this thread's 16-byte unit in buffer 0, hi plane
   float inv;           // 1 / (power-of-two scale of the W_hh planes)
@@ -122,40 +130,26 @@ struct L3Cell {
 //   after g:     e^2g, one reciprocal, e^2c'         (3 MUFU, under the 24 MMAs of o)
 //   after o:     e^-o, one reciprocal                (2 MUFU, the tail of the step)
 template <bool F16, bool FULL, bool TIMING, int NC>
-__device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done, uint64_t* h_ready, int lane,
-                                             unsigned* dbg, unsigned* dbg_all) {
+__device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done, uint64_t* h_ready, uint64_t* xg_full,
+                                             uint64_t* xg_empty, int lane, unsigned* dbg, unsigned* dbg_all) {
   constexpr int f16 = F16 ? 1 : 0;
   const float L2E = 1.4426950408889634f;
   float c[NC];
 #pragma unroll
   for (int n = 0; n < NC; n++) c[n] = 0.f;
-  // the gate pre-activations are fetched ONE STEP AHEAD: inside the concurrent pipeline step an HBM / L2 round trip can take
-  // longer than the ~600 cycles between the top of a step and the first use (1.71 us per step in-step against 1.40 alone)
-  float xn[4][NC];
-#pragma unroll
-  for (int n = 0; n < NC; n++) {
-#pragma unroll
-    for (int g = 0; g < 4; g++) xn[g][n] = (FULL || n < s.rows) ? __ldg(s.gp + n * s.row_gx + g * 128) : 0.f;
-  }
+  // the gate pre-activations of step t wait in shared memory (ring slot t % 3): the issuing lane fetched them two steps
+  // ahead with two bulk tensor copies ([256 floats][1 frame][NR rows] each); rows past the batch arrive as zeros
   for (int step = 0; step < T; step++) {
     const int nxt = (step + 1) & 1;
     const uint32_t ph = step & 1;
+    const int xs = step % L3_XG_STAGES;
+    const uint32_t xbase = s.xg_addr + xs * s.xg_stage;
+    mbar_wait(&xg_full[xs], (step / L3_XG_STAGES) & 1);
     float xg[4][NC];
 #pragma unroll
-    for (int n = 0; n < NC; n++) {
+    for (int g = 0; g < 2; g++)
 #pragma unroll
-      for (int g = 0; g < 4; g++) xg[g][n] = xn[g][n];
-    }
-    s.gp += s.dgx;
-    if (step + 1 < T) {
-#pragma unroll
-      for (int n = 0; n < NC; n++) {
-        if (FULL || n < s.rows) {
-#pragma unroll
-          for (int g = 0; g < 4; g++) xn[g][n] = __ldg(s.gp + n * s.row_gx + g * 128);
-        }
-      }
-    }
+      for (int n = 0; n < NC; n++) xg[g][n] = ld_shared_f32(xbase + n * 1024 + g * 512);
     uint32_t ra[NC], rb[NC];
     float di[NC], df[NC];       // 1 + e^-i, 1 + e^-f
     mbar_wait(&mma_done[0], ph);
@@ -173,6 +167,12 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
         df[n] = 1.f + ex2_approx(fminf(fmaf(__uint_as_float(rb[n]), s.inv, xg[1][n]) * -L2E, 40.f));
       }
     }
+#pragma unroll
+    for (int g = 2; g < 4; g++)
+#pragma unroll
+      for (int n = 0; n < NC; n++) xg[g][n] = ld_shared_f32(xbase + s.xg_stage / 2 + n * 1024 + (g - 2) * 512);
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&xg_empty[xs]);       // this warp has read its part of the slot
     mbar_wait(&mma_done[1], ph);
     tc_fence_after();
     tmem_ldn<NC>(s.tlane + 2 * LT_NB, ra);
@@ -252,8 +252,8 @@ __device__ __forceinline__ void l3_cell_loop(L3Cell s, int T, uint64_t* mma_done
 // CTA PAIRS (gemm_tc2_kernel), which need both SMs of a TPC free)
 template <bool F16, bool TIMING, int NC, int NR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(l3_threads(NC, NR), 1)
-lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __restrict__ w_hi,
-                const uint16_t* __restrict__ w_lo /*both [2][512][128]*/, const float* __restrict__ gx, int B, int T,
+lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const __grid_constant__ CUtensorMap tm_gx /*[item][frame][1024]*/,
+                const uint16_t* __restrict__ w_hi, const uint16_t* __restrict__ w_lo /*both [2][512][128]*/, int B, int T,
                 int stride, int groups_per_dir, float* __restrict__ hout, uint16_t* __restrict__ out_hi,
                 uint16_t* __restrict__ out_lo, float acc_scale, unsigned* __restrict__ dbg) {
   extern __shared__ unsigned char smem_raw[];
@@ -265,6 +265,10 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
   uint64_t* mma_done = bars + 1;                     // [3]: gates i, f complete / gate g complete / gate o complete
   uint64_t* h_ready = bars + 4;                      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);
+  uint64_t* xg_full = bars + 7;                      // [3] TMA -> cells: the gate pre-activation rows of a step have landed
+  uint64_t* xg_empty = bars + 10;                    // [3] cells -> TMA: every cell warp has read its part of the slot
+  unsigned char* xg_ring = smem + L3_WS_BYTES + LT_H_BYTES + 256;     // [stage][half 2][row NR][256 floats]
+  constexpr int XG_STAGE = l3_xg_stage_bytes(NR);
 
   constexpr int NCW = 4 * (NR / NC);                 // cell-update warps; warp NCW issues the MMAs
   constexpr int L3_THREADS = l3_threads(NC, NR);
@@ -279,6 +283,10 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     mbar_init(&mma_done[2], 1);
     mbar_init(&h_ready[0], NCW);
     mbar_init(&h_ready[1], NCW);
+    for (int i = 0; i < L3_XG_STAGES; i++) {
+      mbar_init(&xg_full[i], 1);
+      mbar_init(&xg_empty[i], NCW);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == NCW) {
@@ -335,8 +343,24 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
       // 128 B, one k-step (16 k) = 512 B
       const uint32_t h0 = smem_u32(hsm);
       const uint64_t bb0 = umma_desc_mn(h0, 256, 128), bb1 = umma_desc_mn(h0 + LT_H_BYTES / 2, 256, 128);
+      // gate pre-activation rows of step t: frame t (forward) / T - 1 - t (backward), this direction's 512 columns as two boxes of
+      // [256 floats][1 frame][NR items]; items past the batch are filled with zeros by the copy engine
+      auto fetch = [&](int t) {
+        const int slot = t % L3_XG_STAGES, frame = dir == 0 ? t : T - 1 - t;
+        unsigned char* dst = xg_ring + slot * XG_STAGE;
+        mbar_expect_tx(&xg_full[slot], XG_STAGE);
+        tma_load_3d(dst, &tm_gx, dir * 512, frame, b0, &xg_full[slot]);
+        tma_load_3d(dst + XG_STAGE / 2, &tm_gx, dir * 512 + 256, frame, b0, &xg_full[slot]);
+      };
+      fetch(0);
+      if (T > 1) fetch(1);
       for (int step = 0; step < T; step++) {
         const int buf = step & 1;
+        if (step + 2 < T) {        // two steps ahead; the slot was read by step - 1 (its cells arrive long before h_ready below)
+          const int use = (step + 2) / L3_XG_STAGES;
+          if (use > 0) mbar_wait(&xg_empty[(step + 2) % L3_XG_STAGES], (use - 1) & 1);
+          fetch(step + 2);
+        }
         if (step > 0) {
           mbar_wait(&h_ready[buf], ((step - 1) >> 1) & 1);
           tc_fence_after();
@@ -373,23 +397,22 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const uint16_t* __re
     L3Cell s;
     s.rows = min(NC, max(0, B - (b0 + ch * NC)));   // valid batch rows of this warp's NC columns
     s.tlane = tmem_base + ((uint32_t)(quad * 32) << 16) + L3_COL_D + ch * NC;
-    s.row_gx = (size_t)stride * 1024;
     s.row_h = (size_t)stride * 256;
     const int t0 = dir == 0 ? 0 : T - 1;
-    s.gp = gx + ((size_t)(b0 + ch * NC) * stride + t0) * 1024 + dir * 512 + u;
+    s.xg_addr = smem_u32(xg_ring) + (ch * NC) * 1024 + u * 4;
+    s.xg_stage = XG_STAGE;
     const size_t e0 = ((size_t)(b0 + ch * NC) * stride + t0) * 256 + dir * 128 + u;
     s.hp = hout ? hout + e0 : nullptr;
     s.php = out_hi ? out_hi + e0 : nullptr;
     s.plane_off = out_hi ? (size_t)(out_lo - out_hi) : 0;
-    s.dgx = dir == 0 ? 1024 : -1024;
     s.dh = dir == 0 ? 256 : -256;
     s.inv = acc_scale;
     // 16-byte unit of (unit u, row group of 8); with NC < 8 several warps share a unit (2 NC bytes each)
     s.h_addr = smem_u32(hsm) + (u >> 3) * 256 + ((ch * NC) >> 3) * 128 + (u & 7) * 16 + ((ch * NC) & 7) * 2;
     unsigned* my_dbg = (TIMING && blockIdx.x == 0 && threadIdx.x == 0) ? dbg : nullptr;
     unsigned* all_dbg = (TIMING && blockIdx.x == 0) ? dbg : nullptr;
-    if (s.rows == NC) l3_cell_loop<F16, true, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg, all_dbg);
-    else l3_cell_loop<F16, false, TIMING, NC>(s, T, mma_done, h_ready, lane, my_dbg, all_dbg);
+    if (s.rows == NC) l3_cell_loop<F16, true, TIMING, NC>(s, T, mma_done, h_ready, xg_full, xg_empty, lane, my_dbg, all_dbg);
+    else l3_cell_loop<F16, false, TIMING, NC>(s, T, mma_done, h_ready, xg_full, xg_empty, lane, my_dbg, all_dbg);
   }
   tc_fence_before();
   __syncthreads();
@@ -415,7 +438,7 @@ static LstmShape lstm_shape(int B) {
 }
 template <class Fn>
 static int lstm_dispatch(LstmShape shp, bool f16, bool timing, Fn fn) {
-#define DG_L3(F, TM, NC, NR) return fn(lstm_tc3_kernel<F, TM, NC, NR>, l3_threads(NC, NR))
+#define DG_L3(F, TM, NC, NR) return fn(lstm_tc3_kernel<F, TM, NC, NR>, l3_threads(NC, NR), l3_smem(NR))
 #define DG_L3_SHAPES(F, TM)                                  \
   if (shp.rows == 16 && shp.cells == 8) DG_L3(F, TM, 8, 16);   \
   if (shp.rows == 16) DG_L3(F, TM, 4, 16);                     \
@@ -463,9 +486,22 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
   static bool attr_done[64] = {};
   static bool timing = false;
   const LstmShape shp = lstm_shape(B);
+  // gate pre-activations as a 3-D tensor [item B][frame stride][1024 floats]; box = [256 floats][1 frame][rows of a CTA]
+  CUtensorMap tm_gx;
+  {
+    cuuint64_t gdims[3] = {1024, (cuuint64_t)stride, (cuuint64_t)B};
+    cuuint64_t gstrides[2] = {(cuuint64_t)1024 * 4, (cuuint64_t)stride * 1024 * 4};
+    cuuint32_t gbox[3] = {256, 1, (cuuint32_t)shp.rows};
+    cuuint32_t gestr[3] = {1, 1, 1};
+    if (fn(&tm_gx, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(gx), gdims, gstrides, gbox, gestr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled failed for the gate pre-activations");
+      return -2;
+    }
+  }
   if (first_use_on_device(attr_done)) {
-    const auto opt_in = [](auto kern, int) {
-      return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L3_SMEM) == cudaSuccess ? 0 : -1; };
+    const auto opt_in = [](auto kern, int, int smem) {
+      return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) == cudaSuccess ? 0 : -1; };
     for (const LstmShape v : {LstmShape{16, 8}, LstmShape{16, 4}, LstmShape{8, 4}, LstmShape{8, 2}})
       if (lstm_dispatch(v, true, false, opt_in) || lstm_dispatch(v, false, false, opt_in) || lstm_dispatch(v, true, true, opt_in)) {
         set_error("lstm_rec: cudaFuncSetAttribute failed");
@@ -489,8 +525,8 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     unsigned* dbg = nullptr;
     DG_CUDA(cudaMalloc(&dbg, (size_t)T * 8 * sizeof(unsigned)));
     DG_CUDA(cudaMemsetAsync(dbg, 0, (size_t)T * 8 * sizeof(unsigned), st));
-    lstm_dispatch(shp, true, true, [&](auto kern, int threads) {
-      kern<<<2 * gpd, threads, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, inv, dbg);
+    lstm_dispatch(shp, true, true, [&](auto kern, int threads, int smem) {
+      kern<<<2 * gpd, threads, smem, st>>>(tm, tm_gx, ph, pl, B, T, stride, gpd, hout, oh, ol, inv, dbg);
       return 0; });
     DG_CUDA(cudaStreamSynchronize(st));
     if (reported++ < 6) {
@@ -517,8 +553,8 @@ int launch_lstm_layer_tc(const float* gx, const void* whh_hi, const void* whh_lo
     cudaFree(dbg);
     return 0;
   }
-  lstm_dispatch(shp, split_f16(), false, [&](auto kern, int threads) {
-    kern<<<2 * gpd, threads, L3_SMEM, st>>>(tm, ph, pl, gx, B, T, stride, gpd, hout, oh, ol, inv, nullptr);
+  lstm_dispatch(shp, split_f16(), false, [&](auto kern, int threads, int smem) {
+    kern<<<2 * gpd, threads, smem, st>>>(tm, tm_gx, ph, pl, B, T, stride, gpd, hout, oh, ol, inv, nullptr);
     return 0; });
   DG_LAUNCHED();
   return 0;

@@ -44,6 +44,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* t
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
 // ---- CTA pairs (tcgen05 cta_group::2): the even CTA of a 2-CTA cluster issues M = 256 MMAs over both CTAs' shared / tensor
 // memory.  A shared::cta address with bit 24 cleared is the same offset in the EVEN CTA's shared memory (cute: Sm100MmaPeerBitMask).
 constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;
