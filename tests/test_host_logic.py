@@ -156,3 +156,79 @@ def test_rttm_sinks(tmp_path):
         acc.on_next("not a prediction")
     loaded = sinks.load_rttm(path)
     assert list(loaded) == ["file1"] and loaded["file1"].to_rttm() == text
+
+
+def test_pipeline_configs_share_the_reference_latency_rules():
+    """duration / step / latency of both pipeline configurations (reference blocks/diarization.py:33-60, blocks/vad.py:27-65):
+    latency None or "min" = step, "max" = duration, a number is taken as it is; get_file_padding follows from them"""
+    seg, emb = models.SegmentationModel(lambda: None), models.EmbeddingModel(lambda: None)
+    for make in (lambda **kw: blocks.SpeakerDiarizationConfig(segmentation=seg, embedding=emb, **kw),
+                 lambda **kw: blocks.VoiceActivityDetectionConfig(segmentation=seg, **kw)):
+        assert make().latency == 0.5 and make(latency="min").latency == 0.5
+        assert make(latency="max").latency == 5 and make(latency=2.5, step=0.25).latency == 2.5
+        c = make(duration=4, step=0.5, latency=2.0, sample_rate=8000)
+        assert (c.duration, c.step, c.latency, c.sample_rate) == (4, 0.5, 2.0, 8000)
+        assert c.get_file_padding(file_duration=1.0) == (1.5, 1.5)          # left = duration - (1.0 + right), right = latency - step
+        assert isinstance(c, blocks.PipelineConfig)
+
+
+def test_oracle_accepts_a_reference_value_only_when_it_reproduces():
+    """oracle/nets.py: the first float32 evaluation of a torch CPU module is not reproducible on every host (DESIGN.md section 4);
+    the oracle networks evaluate until two consecutive results agree bit for bit"""
+    from oracle import nets
+
+    class Flaky(nets._Reproducible, torch.nn.Module):
+        def __init__(self, wrong_calls):
+            super().__init__()
+            self.calls, self.wrong_calls = 0, wrong_calls
+
+        def forward(self, x):
+            self.calls += 1
+            return x + (1e-3 if self.calls in self.wrong_calls else 0.0)
+
+    x = torch.ones(3)
+    with torch.no_grad():
+        m = Flaky({1})
+        assert torch.equal(m(x), x) and m.calls == 3                 # first call off: second and third agree
+        m = Flaky(set())
+        assert torch.equal(m(x), x) and m.calls == 2
+        m = Flaky({1, 3, 5, 7})
+        with pytest.raises(RuntimeError):
+            m(x)
+        nets.STABLE = False
+        try:
+            m = Flaky({1})
+            assert not torch.equal(m(x), x) and m.calls == 1           # the timing legs of bench.py: one evaluation
+        finally:
+            nets.STABLE = True
+
+
+def test_ncu_summary_joins_launches_with_trace_tags(tmp_path):
+    """tools/ncu_summary.py: launch list of `ncu --page raw --csv` + the library's dg-trace lines -> per-tag table and traffic.json"""
+    import csv
+    import json
+    import subprocess
+    import sys
+
+    cols = ["ID", "Kernel Name", "Block Size", "Grid Size", "gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+            "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sectors_srcunit_tex.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active"]
+    units = ["", "", "", "", "us", "%", "Mbyte", "Mbyte", "sector", "%"]
+    rows = [["0", "void at::native::fill(float)", "(128, 1, 1)", "(8, 1, 1)", "1.0", "0", "0", "0", "0", "1"],
+            ["1", "gemm_tc2_kernel<256, 0>(TcArgs)", "(192, 1, 1)", "(148, 1, 1)", "100.0", "50", "20", "250", "1000", "9"],
+            ["2", "lstm_tc3_kernel<1, 0, 4, 16>()", "(544, 1, 1)", "(32, 1, 1)", "400.0", "30", "300", "60", "2000", "45"],
+            ["3", "gemm_tc2_kernel<256, 0>(TcArgs)", "(192, 1, 1)", "(148, 1, 1)", "120.0", "54", "80", "250", "3000", "9"]]
+    raw = tmp_path / "raw.csv"
+    with open(raw, "w", newline="") as f:
+        w = csv.writer(f)
+        w.writerows([cols, units] + rows)
+    trace = tmp_path / "trace.log"
+    trace.write_text("dg-trace warm 10 12\ndg-trace-begin\ndg-trace lstm_inproj 40 41\ndg-trace lstm_rec 41 42\n"
+                     "dg-trace lstm_inproj 42 43\ndg-trace-end\n")
+    tool = __import__("os").path.join(__import__("os").path.dirname(__file__), "..", "tools", "ncu_summary.py")
+    out = subprocess.run([sys.executable, tool, str(raw), str(trace), str(tmp_path / "step")], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    traffic = json.loads((tmp_path / "step.json").read_text())
+    assert traffic["lstm_inproj"] == pytest.approx((20 + 250 + 80 + 250) * 1e6 / 2) and traffic["lstm_rec"] == pytest.approx(360e6)
+    assert traffic["_step"] == pytest.approx(960e6) and traffic["_launches_per_step"] == {"lstm_inproj": 2, "lstm_rec": 1}
+    table = (tmp_path / "step.md").read_text()
+    assert "`lstm_rec`" in table and "| 400.0 |" in table and (tmp_path / "step_raw_selected.csv").exists()
