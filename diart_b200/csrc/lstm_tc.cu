@@ -356,11 +356,6 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const __grid_constan
       if (T > 1) fetch(1);
       for (int step = 0; step < T; step++) {
         const int buf = step & 1;
-        if (step + 2 < T) {        // two steps ahead; the slot was read by step - 1 (its cells arrive long before h_ready below)
-          const int use = (step + 2) / L3_XG_STAGES;
-          if (use > 0) mbar_wait(&xg_empty[(step + 2) % L3_XG_STAGES], (use - 1) & 1);
-          fetch(step + 2);
-        }
         if (step > 0) {
           mbar_wait(&h_ready[buf], ((step - 1) >> 1) & 1);
           tc_fence_after();
@@ -387,6 +382,12 @@ lstm_tc3_kernel(const __grid_constant__ CUtensorMap tm_wlo, const __grid_constan
           if (g >= 1) umma_commit(&mma_done[g - 1]);
         }
         if (TIMING && blockIdx.x == 0) dbg[step * 8 + 1] = (unsigned)clock();
+        // in the shadow of these MMAs: the rows of step + 2 into the slot step - 1 used (its cells finished before h_ready above)
+        if (step + 2 < T) {
+          const int use = (step + 2) / L3_XG_STAGES;
+          if (use > 0) mbar_wait(&xg_empty[(step + 2) % L3_XG_STAGES], (use - 1) & 1);
+          fetch(step + 2);
+        }
       }
     }
     __syncwarp();
