@@ -17,7 +17,7 @@ import torch
 
 from .. import _lib
 from .. import models as m
-from ..core import Annotation, Segment, SlidingWindow, SlidingWindowFeature
+from ..core import Annotation, Segment, SlidingWindow, SlidingWindowFeature, extent_bounds
 from . import base
 from .aggregation import DelayedAggregation
 from .clustering import OnlineSpeakerClustering
@@ -203,17 +203,18 @@ class SpeakerDiarization(base.Pipeline):
             return self._call_blockwise(waveforms, expected)
         prof = self.call_profile          # None, or a dict of accumulated seconds per phase (bench.py)
         t0 = time.perf_counter() if prof is not None else 0.0
-        rows = []
+        rows, f32 = [], np.float32
         for w in waveforms:
             d = w.data
-            assert d.shape[0] == expected, f"Expected {expected} samples per chunk, but got {d.shape[0]}"
-            assert d.ndim == 1 or d.shape[1] == 1, "expected mono audio"
-            if d.dtype != np.float32 or not d.flags.c_contiguous:
-                d = np.ascontiguousarray(d, dtype=np.float32)
+            shape = d.shape
+            assert shape[0] == expected, f"Expected {expected} samples per chunk, but got {shape[0]}"
+            assert len(shape) == 1 or shape[1] == 1, "expected mono audio"
+            if d.dtype != f32 or not d.flags.c_contiguous:
+                d = np.ascontiguousarray(d, dtype=f32)
             rows.append(d)
         h, F, K, D = self._ensure_fused(expected)
         post = self._ensure_post(F, K)
-        starts = np.array([w.extent.start for w in waveforms], dtype=np.float64)
+        starts = np.array([extent_bounds(w)[0] for w in waveforms], dtype=np.float64)
         seg_resolution = waveforms[0].extent.duration / F
         plan, out_start, out_res = post.plan(starts, seg_resolution)
         header, turns = post.buffers(batch_size)

@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .. import _lib
-from ..core import Annotation, Segment, SlidingWindow, SlidingWindowFeature
+from ..core import Annotation, Segment, SlidingWindow, SlidingWindowFeature, extent_bounds
 
 
 class DevicePostPath:
@@ -127,10 +127,11 @@ class DevicePostPath:
         labels = self.labels
         modality = "speech" if shift == 0 else None             # the reference's shifted copy drops the modality
         out = []
+        offs, cnts = header[:, 0].tolist(), header[:, 1].tolist()
         for cidx in range(B):
             ann = Annotation(uri=uri, modality=modality)
-            o = int(header[cidx, 0])
-            for i in range(o, o + int(header[cidx, 1])):
+            o = offs[cidx]
+            for i in range(o, o + cnts[cidx]):
                 ann[Segment(t_on[i], t_off[i]), g[i]] = labels[g[i]]
             out.append(ann)
         return out
@@ -158,9 +159,9 @@ def aggregate_audio(chunk_buffer: List[SlidingWindowFeature], new: Sequence[Slid
     Returns (outputs, new chunk_buffer)."""
     H, B = len(chunk_buffer), len(new)
     buf = list(chunk_buffer) + list(new)
-    ext = [w.extent for w in new]
-    w_start = np.array([e.start for e in ext])
-    w_end = np.array([e.end for e in ext])
+    bounds = [extent_bounds(w) for w in new]
+    w_start = np.array([b[0] for b in bounds])
+    w_end = np.array([b[1] for b in bounds])
     first_idx = np.maximum(H + np.arange(B) + 1 - nw, 0) if nw > 1 else H + np.arange(B)     # oldest buffer of each chunk
     nbuf = np.minimum(H + np.arange(B) + 1, nw)
     sw0 = [buf[i].sliding_window for i in first_idx]
@@ -172,23 +173,26 @@ def aggregate_audio(chunk_buffer: List[SlidingWindowFeature], new: Sequence[Slid
     fixed = np.where(end > start, end - start, 0.0)
     lo = np.rint((start - s0 - 0.5 * d0) / p0).astype(np.int64)          # SlidingWindow.closest_frame
     cnt = np.rint(fixed / p0).astype(np.int64)                           # SlidingWindow.samples(fixed, mode="center")
-    is_first = (nbuf == 1) & (w_start == 0)
+    is_first = ((nbuf == 1) & (w_start == 0)).tolist()
+    # (plain Python numbers inside the per-chunk loop: indexing numpy arrays element by element costs more than the crops)
+    first_l, lo_l, cnt_l, fixed_l, start_l = first_idx.tolist(), lo.tolist(), cnt.tolist(), fixed.tolist(), start.tolist()
     outs = []
     for c in range(B):
-        first = buf[first_idx[c]]
-        data, n = first.data, first.data.shape[0]
+        first = buf[first_l[c]]
+        data = first.data
+        n = data.shape[0]
         if is_first[c]:
             # first buffer of a stream: [0, region.end) with the region pasted over its tail (aggregation.py:188-212)
             lo1 = int(np.rint((0.0 - s0[c] - 0.5 * d0[c]) / p0[c]))
             cnt1 = int(np.rint(end[c] / p0[c]))
             out = _crop(data, lo1, cnt1, n).copy()
-            out[-int(cnt[c]):] = _crop(data, int(lo[c]), int(cnt[c]), n)
+            out[-cnt_l[c]:] = _crop(data, lo_l[c], cnt_l[c], n)
             res = end[c] / out.shape[0]
             outs.append(SlidingWindowFeature(out, SlidingWindow(start=0, duration=res, step=res)))
         else:
-            out = _crop(data, int(lo[c]), int(cnt[c]), n)
-            res = fixed[c] / out.shape[0]
-            outs.append(SlidingWindowFeature(out, SlidingWindow(start=start[c], duration=res, step=res)))
+            out = _crop(data, lo_l[c], cnt_l[c], n)
+            res = fixed_l[c] / out.shape[0]
+            outs.append(SlidingWindowFeature(out, SlidingWindow(start=start_l[c], duration=res, step=res)))
     keep = min(nw - 1, H + B)
     return outs, (buf[len(buf) - keep:] if keep else [])
 

@@ -250,3 +250,15 @@ except Exception:  # noqa: BLE001
 
 
 __all__ = ["Segment", "SlidingWindow", "SlidingWindowFeature", "Annotation", "HAVE_PYANNOTE_CORE"]
+
+
+def extent_bounds(feature) -> Tuple[float, float]:
+    """``(feature.extent.start, feature.extent.end)`` without building a ``Segment`` per window (the batch loops of the pipelines
+    do this hundreds of times per call).  With the real ``pyannote.core`` the property itself is used."""
+    if HAVE_PYANNOTE_CORE:
+        e = feature.extent
+        return e.start, e.end
+    sw, n = feature.sliding_window, feature.data.shape[0]
+    start = sw.start if sw.duration == sw.step else sw.start + (0 - 0.5) * sw.step + 0.5 * sw.duration
+    return start, start + n * sw.step
+
