@@ -289,8 +289,8 @@ class XVectorSincNet(_Reproducible, nn.Module):
 
 # --------------------------------------------------------------------------------------
 # Variant B of the embedding row (SURVEY.md section 8(a) A8', Appendix A.6): pyannote/wespeaker-voxceleb-resnet34-LM.
-# ORACLE ONLY in this round -- there is no CUDA path for it yet; this restatement (from the published WeSpeaker /
-# pyannote.audio 3.1 definitions, un-vendored by the reference: setup.cfg:34) is the checker the next round builds to.
+# Restated from the published WeSpeaker / pyannote.audio 3.1 definitions (un-vendored by the reference: setup.cfg:34); the
+# checker of the CUDA path in diart_b200/csrc/resnet.cu + gemm_tc.cu (TC_CONV2D), tests/test_zz_wespeaker.py.
 # --------------------------------------------------------------------------------------
 class _BasicBlock(nn.Module):
     """wespeaker.models.resnet.BasicBlock: conv3x3-bn-relu-conv3x3-bn + shortcut (1x1 conv + bn when the shape changes) -> relu"""
